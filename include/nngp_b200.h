@@ -1,0 +1,178 @@
+/* nngp_b200.h -- C ABI of the B200-native NNGP engine (libnngp_b200.so).
+ *
+ * Plain pointers and sizes only: no R types, no torch types.  This is the seam a maintainer of the
+ * reference binds to; every entry point names the reference interface it replaces (paths relative
+ * to the spNNGP 1.0.1 source root).  INTEGRATION.md shows the reference-side `.Call` glue.
+ *
+ * Conventions
+ *   - All matrices are column-major (R layout).  `coords` is n x 2: x = coords[0..n), y = coords[n..2n).
+ *   - Neighbour structure is the reference's ragged CSR (R/nn.R:29-40, src/util.cpp:55-70):
+ *       nnIndx[nIndx] int32 neighbour ids (0-based, ascending distance per location),
+ *       nnIndxLU[2n]: [0,n) offsets, [n,2n) counts, nIndx = (1+m)/2*m + (n-m-1)*m (src/rNNGP.cpp:218).
+ *   - Covariance model codes follow R/spNNGP.R:172-178: 0 exponential, 1 spherical, 2 matern, 3 gaussian.
+ *   - theta = (sigma.sq, tau.sq, phi[, nu]) in the reference's order (src/rNNGP.cpp:182-190).
+ *   - Every function returns an int status: 0 ok; >0 = 1-based index of the first location whose
+ *     m x m factorisation failed (the reference raises "dpotrf failed", src/rNNGP.cpp:86); <0 = NNGP_E*.
+ *     nngp_last_error() gives the text.  The library never falls back to a CPU path: without a CUDA
+ *     device every compute call returns NNGP_ENODEV.
+ *   - One context drives one GPU.  Multi-GPU = one context per process/GPU, each given a shard
+ *     [loc_begin, loc_end) of the locations; partial sums are combined by the caller (NCCL allreduce,
+ *     see spnngp_b200/dist.py).  Pointers named *_dev are device pointers, all others host pointers.
+ */
+#ifndef NNGP_B200_H
+#define NNGP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NNGP_ABI_VERSION 1
+
+enum { NNGP_COV_EXPONENTIAL = 0, NNGP_COV_SPHERICAL = 1, NNGP_COV_MATERN = 2, NNGP_COV_GAUSSIAN = 3 };
+
+enum {
+  NNGP_OK = 0,
+  NNGP_EINVAL = -1,  /* bad argument (sizes, cov model, m > NNGP_MAX_M, ...) */
+  NNGP_ENODEV = -2,  /* no usable CUDA device */
+  NNGP_ECUDA = -3,   /* CUDA runtime error, see nngp_last_error */
+  NNGP_ENOMEM = -4,
+  NNGP_ESTATE = -5   /* call order (e.g. likelihood before nngp_set_data) */
+};
+
+#define NNGP_MAX_M 32     /* neighbours per location handled by the warp-group solver */
+#define NNGP_MAX_BATCH 4  /* parameter sets evaluated per launch */
+
+/* search_type, R/spNNGP.R:304-351 */
+enum { NNGP_SEARCH_BRUTE = 0, NNGP_SEARCH_CB = 1 };
+
+typedef struct nngp_ctx nngp_ctx;
+
+/* Random-number hooks so the host sampler consumes the caller's stream (R's RNG under .Call:
+ * rnorm/runif of Rmath, bracketed by GetRNGstate/PutRNGstate as in src/rNNGP.cpp:270,390). */
+typedef double (*nngp_rnorm_fn)(double mu, double sd);
+typedef double (*nngp_runif_fn)(double a, double b);
+/* progress text hook (Rprintf); may be NULL */
+typedef void (*nngp_print_fn)(const char *msg);
+/* polled once per MCMC iteration / prediction chunk (R_CheckUserInterrupt); may be NULL */
+typedef void (*nngp_interrupt_fn)(void);
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+int nngp_abi_version(void);
+int nngp_device_count(void);
+/* device < 0: use the current CUDA device.  stream_handle: a cudaStream_t to run on, or NULL for a
+ * private non-blocking stream. */
+int nngp_create(int device, void *stream_handle, nngp_ctx **out);
+void nngp_destroy(nngp_ctx *ctx);
+const char *nngp_last_error(const nngp_ctx *ctx); /* ctx may be NULL: last global error */
+int nngp_sync(nngp_ctx *ctx);
+
+/* ---- ordered neighbour search: replaces `mkNNIndx` (src/nn.cpp:63-111) and `mkNNIndxCB`
+ *      (src/nn.cpp:214-257).  Outputs are written into the caller's arrays exactly like the reference
+ *      (R/nn.R:45,71): nnIndx[nIndx], nnDist[nIndx], nnIndxLU[2n].  Neighbour candidates of location i
+ *      are locations 0..i-1; ascending distance; distances use the reference's non-fused arithmetic
+ *      (sqrt(dx*dx+dy*dy), products rounded separately) so nnDist matches bit for bit on tie-free
+ *      data.  Locations with exact distance ties at the m-th neighbour are re-run on the host
+ *      with the reference's insertion/Shell-sort sequence (n_tie_replayed reports how many). */
+int nngp_mk_nn_indx(nngp_ctx *ctx, int n, int m, const double *coords, int search_type, int *nnIndx,
+                    double *nnDist, int *nnIndxLU, int *n_tie_replayed);
+
+/* unordered query kNN (all n sites are candidates), ascending (d^2, index): the stand-in for
+ * RANN::nn2(coords, coords.0, k=m)$nn.idx - 1 (R/generics.R:642, R/spConjNNGP.R:311).
+ * nnIndx0 is q x m column-major, 0-based. */
+int nngp_nn_query(nngp_ctx *ctx, int n, const double *coords, int q, const double *coords0, int m,
+                  int *nnIndx0);
+
+/* ---- model data: uploads what `rNNGP` / `cNNGP` read through REAL()/INTEGER()
+ *      (src/rNNGP.cpp:120-128).  X is n x p, y length n.  [loc_begin, loc_end) is this context's
+ *      shard of the locations (0, n for a single GPU).  nnIndxLU must be the closed form of
+ *      src/util.cpp:55-70 (checked). */
+int nngp_set_data(nngp_ctx *ctx, int n, int m, int p, const double *coords, const int *nnIndx,
+                  const int *nnIndxLU, const double *X, const double *y, int loc_begin, int loc_end);
+
+/* ---- the hot path: B, F and the fused log-likelihood pieces.
+ *      Replaces updateBF (src/rNNGP.cpp:46-101) + Q(B,F,r,r) (src/util.cpp:261-280) with
+ *      r = X beta - y (src/rNNGP.cpp:299-303), for `nbatch` parameter sets in ONE launch.
+ *      theta: nbatch x 4 row-major (sigma.sq, tau.sq, phi, nu); beta: nbatch x p row-major or NULL
+ *      (then only logDet is formed).  B and F of set b are kept on the device in slot slots[b]
+ *      (0 or 1) for later nngp_q_forms / nngp_get_bf calls.
+ *      out: nbatch x 2 = (sum_i log F_i, Q) over this context's shard.
+ *      The conjugate form updateConjBF (src/cNNGP.cpp:24-69) is theta = (1, alpha, phi, nu). */
+int nngp_bf_loglik(nngp_ctx *ctx, int cov_model, int nbatch, const double *theta, const double *beta,
+                   const int *slots, double *out);
+
+/* Q(B,F,r,r) only, from the B,F already stored in `slot` (the double-buffered sampler uses this for
+ * the unchanged current theta instead of re-solving, SURVEY §3.1 note).  out[0] = Q over the shard. */
+int nngp_q_resid(nngp_ctx *ctx, int slot, const double *beta, double *out);
+
+/* All cross quadratic forms of the columns [X, y] in one pass over B,F of `slot`:
+ * S = [X y]' C~^-1 [X y], (p+1) x (p+1) column-major, full symmetric.  Replaces the p + p(p+1)/2 (+1)
+ * separate Q(...) passes of src/rNNGP.cpp:281-286 and src/cNNGP.cpp:227-232,245. */
+int nngp_q_forms(nngp_ctx *ctx, int slot, double *S);
+
+/* copy B (nIndx) and F (n) of `slot` back to the host (parity tests; only this shard's range is
+ * meaningful).  Either pointer may be NULL. */
+int nngp_get_bf(nngp_ctx *ctx, int slot, double *B, double *F);
+
+/* ---- whole entry points behind the reference's `.Call` symbols ------------------------------- */
+
+/* `rNNGP` (src/rNNGP.cpp:105-420) without replicates: Metropolis-within-Gibbs for the response
+ * model.  Draw order per iteration is the reference's: p rnorm (beta), rnorm for phi, sigma.sq,
+ * tau.sq[, nu], one runif -- so a seeded chain retraces the reference's chain.
+ * mode 0 = reference-faithful (two B/F solves per iteration), 1 = double-buffered (one solve plus a
+ * Q-only pass; identical results).  Samples: betaSamples p x nSamples, thetaSamples nTheta x nSamples.
+ * Uses the data given to nngp_set_data.  accept_out: number of accepted proposals. */
+typedef struct {
+  int cov_model;
+  double sigmaSqIG[2], tauSqIG[2], phiUnif[2], nuUnif[2];
+  const double *betaStarting;
+  double sigmaSqStarting, tauSqStarting, phiStarting, nuStarting;
+  double sigmaSqTuning, tauSqTuning, phiTuning, nuTuning;
+  int nSamples;
+  int mode;
+  int verbose, nReport;
+  nngp_rnorm_fn rnorm;
+  nngp_runif_fn runif;
+  nngp_print_fn print;
+  nngp_interrupt_fn interrupt;
+  /* optional hook that sums `len` doubles across the contexts/ranks of a sharded fit in place
+   * (NCCL allreduce); NULL for a single GPU. */
+  void (*allreduce)(double *buf, int len, void *user);
+  void *allreduce_user;
+} nngp_rnngp_args;
+
+int nngp_rnngp(nngp_ctx *ctx, const nngp_rnngp_args *args, double *betaSamples, double *thetaSamples,
+               int *accept_out);
+
+/* `cNNGP` (src/cNNGP.cpp:73-357): conjugate model for g parameter sets.  thetaAlpha is nTheta x g
+ * (phi, alpha[, nu]).  Outputs as the reference: betaHat p x g, ab (written with stride 2, reference
+ * quirk src/cNNGP.cpp:242-245; allocate nTheta x g), bBInv p*p x g, bb p x g, y0Hat / y0HatVar n0 x g.
+ * X0 n0 x p, coords0 n0 x 2, nnIndx0 n0 x m column-major (may be NULL when n0 == 0). */
+int nngp_cnngp(nngp_ctx *ctx, int cov_model, int g, const double *thetaAlpha, const double sigmaSqIG[2],
+               int n0, const double *X0, const double *coords0, const int *nnIndx0, double *betaHat,
+               double *ab, double *bBInv, double *bb, double *y0Hat, double *y0HatVar);
+
+/* `rNNGPPredict` (src/rNNGPPredict.cpp:25-222): posterior predictive draws at q sites.
+ * betaSamples p x nSamples, thetaSamples nTheta x nSamples, nnIndx0 q x m column-major,
+ * z: q*nSamples standard normals in the reference's single-thread order z[i*nSamples+s]
+ * (src/rNNGPPredict.cpp:131-137,176-181); y0: q x nSamples.  Uses X, y, coords of nngp_set_data.
+ * [site_begin, site_end) is this context's shard of the sites; rows outside it are left untouched. */
+int nngp_rnngp_predict(nngp_ctx *ctx, int cov_model, int q, const double *X0, const double *coords0,
+                       const int *nnIndx0, int nSamples, const double *betaSamples,
+                       const double *thetaSamples, const double *z, double *y0, int site_begin,
+                       int site_end);
+
+/* ---- HBM-resident measurement helpers (bench.py `value`): time the likelihood launch with every
+ *      input already on the device.  Runs `iters` launches of nngp_bf_loglik's kernel back to back
+ *      on the context stream between two CUDA events and returns the mean milliseconds per launch. */
+int nngp_time_bf_loglik(nngp_ctx *ctx, int cov_model, int nbatch, const double *theta, const double *beta,
+                        int iters, int flush_l2, float *ms_per_launch);
+/* number of kernel launches issued by this context so far (bench.py `gpu_launches`) */
+long long nngp_launch_count(const nngp_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NNGP_B200_H */

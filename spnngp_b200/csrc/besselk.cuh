@@ -1,0 +1,212 @@
+// besselk.cuh -- FP64 modified Bessel function of the second kind K_nu(x) for the Matern
+// correlation, written for the device (also compiles as host code for CPU-side validation).
+//
+// Replaces Rmath's bessel_k_ex as used by spCor (reference src/util.cpp:233-237).  Algorithm:
+// Temme's series for x <= 2 and the Steed/Temme continued fraction CF2 for x > 2 give K_mu and
+// K_{mu+1} with |mu| <= 1/2, followed by the stable upward recurrence to nu = mu + nl.  Everything
+// that depends only on nu (Gamma-function pieces, reciprocals of loop constants) is computed ONCE on
+// the host per parameter set (matern_prepare) and handed to the kernel by value, so the device loops
+// contain no divisions except the one CF2 needs.
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define NNGP_HD __host__ __device__ __forceinline__
+#else
+#define NNGP_HD inline
+#endif
+
+namespace nngp {
+
+constexpr int kTemmeTerms = 24;  // (x^2/4)^i / i! < 1e-18 well before i = 24 for x <= 2
+constexpr int kCf2Tab = 64;      // tabulated reciprocals for the first CF2 iterations
+
+struct MaternConsts {
+  double nu;      // smoothness
+  double mu;      // nu - nl, in [-1/2, 1/2]
+  int nl;         // number of upward recurrence steps
+  double gam1;    // (1/Gamma(1-mu) - 1/Gamma(1+mu)) / (2 mu)
+  double gam2;    // (1/Gamma(1-mu) + 1/Gamma(1+mu)) / 2
+  double gampl;   // 1/Gamma(1+mu)
+  double gammi;   // 1/Gamma(1-mu)
+  double fact;    // pi mu / sin(pi mu)
+  double pref;    // 1 / (2^(nu-1) Gamma(nu)): Matern normalisation
+  double a1;      // 1/4 - mu^2
+  double r_i2[kTemmeTerms];  // 1/(i^2 - mu^2), i = 1..
+  double r_im[kTemmeTerms];  // 1/(i - mu)
+  double r_ip[kTemmeTerms];  // 1/(i + mu)
+  double r_i[kCf2Tab];       // 1/i (shared by both loops)
+  double r_a[kCf2Tab];       // 1/a_i of CF2, a_i = mu^2 - 1/4 - i(i-1)
+};
+
+// ---- host side: constants per nu -------------------------------------------------------------
+// Coefficients c_k of 1/Gamma(z) = sum_{k>=1} c_k z^k (Abramowitz & Stegun 6.1.34); checked
+// against mpmath in tests/test_besselk_host.py.
+inline void matern_prepare(double nu, MaternConsts *mc) {
+  static const double c[26] = {0.0,
+                               1.0000000000000000,  0.5772156649015329,  -0.6558780715202538, -0.0420026350340952,
+                               0.1665386113822915,  -0.0421977345555443, -0.0096219715278770, 0.0072189432466630,
+                               -0.0011651675918591, -0.0002152416741149, 0.0001280502823882,  -0.0000201348547807,
+                               -0.0000012504934821, 0.0000011330272320,  -0.0000002056338417, 0.0000000061160950,
+                               0.0000000050020075,  -0.0000000011812746, 0.0000000001043427,  0.0000000000077823,
+                               -0.0000000000036968, 0.0000000000005100,  -0.0000000000000206, -0.0000000000000054,
+                               0.0000000000000014};
+  const double pi = 3.14159265358979323846264338327950288;
+  mc->nu = nu;
+  int nl = (int)(nu + 0.5);
+  double mu = nu - nl;
+  mc->nl = nl;
+  mc->mu = mu;
+  double mu2 = mu * mu;
+  // Gamma1, Gamma2 from the even / odd part of the series for 1/Gamma(1+-mu) = sum c_k (+-mu)^(k-1)
+  double g1 = 0.0, g2 = 0.0, pw = 1.0;  // pw = mu^(2j)
+  for (int j = 0; j < 12; j++) {
+    g2 += c[2 * j + 1] * pw;  // c1 + c3 mu^2 + ...
+    g1 += c[2 * j + 2] * pw;  // c2 + c4 mu^2 + ...
+    pw *= mu2;
+  }
+  mc->gam1 = -g1;
+  mc->gam2 = g2;
+  // 1/Gamma(1+mu) = g2 - mu*gam1 ... : sum_k c_k mu^(k-1) = (odd k part) + mu*(even k part)
+  mc->gampl = g2 + mu * g1;
+  mc->gammi = g2 - mu * g1;
+  double pimu = pi * mu;
+  mc->fact = (fabs(pimu) < 1e-8) ? 1.0 : pimu / sin(pimu);
+  mc->pref = 1.0 / (pow(2.0, nu - 1.0) * tgamma(nu));
+  mc->a1 = 0.25 - mu2;
+  for (int i = 1; i <= kTemmeTerms; i++) {
+    mc->r_i2[i - 1] = 1.0 / ((double)i * i - mu2);
+    mc->r_im[i - 1] = 1.0 / ((double)i - mu);
+    mc->r_ip[i - 1] = 1.0 / ((double)i + mu);
+  }
+  double a = -mc->a1;
+  for (int i = 1; i <= kCf2Tab; i++) {
+    mc->r_i[i - 1] = 1.0 / (double)i;
+    if (i >= 2) a -= 2.0 * (i - 1);
+    mc->r_a[i - 1] = (a != 0.0) ? 1.0 / a : 0.0;
+  }
+}
+
+// sinh(e)/e without cancellation for small |e|
+NNGP_HD double sinhc(double e, double E /* = exp(e) */) {
+  if (fabs(e) > 0.35) return 0.5 * (E - 1.0 / E) / e;
+  double e2 = e * e;
+  // 1 + e2/6 + e2^2/120 + ... up to e^14/15!
+  double s = 1.0 / 1307674368000.0;
+  s = s * e2 + 1.0 / 6227020800.0;
+  s = s * e2 + 1.0 / 39916800.0;
+  s = s * e2 + 1.0 / 362880.0;
+  s = s * e2 + 1.0 / 5040.0;
+  s = s * e2 + 1.0 / 120.0;
+  s = s * e2 + 1.0 / 6.0;
+  s = s * e2 + 1.0;
+  return s;
+}
+
+// K_mu(x), K_{mu+1}(x) for x <= 2 (Temme).  logb = log(x/2) is also returned for the caller's x^nu.
+NNGP_HD void besselk_temme(double x, const MaternConsts &mc, double *kmu, double *kmu1, double *logb_out) {
+  const double b = 0.5 * x;
+  const double logb = log(b);
+  const double d = -logb;
+  const double e = mc.mu * d;
+  const double E = exp(e);
+  const double fact2 = sinhc(e, E);
+  const double ch = 0.5 * (E + 1.0 / E);
+  double ff = mc.fact * (mc.gam1 * ch + mc.gam2 * fact2 * d);
+  double sum = ff;
+  double p = 0.5 * E / mc.gampl;
+  double q = 0.5 / (E * mc.gammi);
+  double c = 1.0;
+  const double dd = b * b;
+  double sum1 = p;
+#pragma unroll 1
+  for (int i = 1; i <= kTemmeTerms; i++) {
+    ff = ((double)i * ff + p + q) * mc.r_i2[i - 1];
+    c *= dd * mc.r_i[i - 1];
+    p *= mc.r_im[i - 1];
+    q *= mc.r_ip[i - 1];
+    const double del = c * ff;
+    sum += del;
+    sum1 += c * (p - (double)i * ff);
+    if (fabs(del) < fabs(sum) * 1e-17) break;
+  }
+  *kmu = sum;
+  *kmu1 = sum1 * (2.0 / x);
+  *logb_out = logb;
+}
+
+// K_mu(x), K_{mu+1}(x) for x > 2 (Steed's algorithm for Temme's CF2), including the exp(-x) factor.
+NNGP_HD void besselk_cf2(double x, const MaternConsts &mc, double *kmu, double *kmu1) {
+  double b = 2.0 * (1.0 + x);
+  double d = 1.0 / b;
+  double h = d, delh = d;
+  double q1 = 0.0, q2 = 1.0;
+  const double a1 = mc.a1;
+  double q = a1, c = a1;
+  double a = -a1;
+  double s = 1.0 + q * delh;
+#pragma unroll 1
+  for (int i = 2; i < 10000; i++) {
+    a -= 2.0 * (i - 1);
+    const double ri = (i <= kCf2Tab) ? mc.r_i[i - 1] : 1.0 / (double)i;
+    const double ra = (i <= kCf2Tab) ? mc.r_a[i - 1] : 1.0 / a;
+    c = -a * c * ri;
+    const double qnew = (q1 - b * q2) * ra;
+    q1 = q2;
+    q2 = qnew;
+    q += c * qnew;
+    b += 2.0;
+    d = 1.0 / (b + a * d);
+    delh = (b * d - 1.0) * delh;
+    h += delh;
+    const double dels = q * delh;
+    s += dels;
+    if (fabs(dels) < fabs(s) * 1e-17) break;
+  }
+  h = a1 * h;
+  const double rk = sqrt(3.14159265358979323846 / (2.0 * x)) * exp(-x) / s;
+  *kmu = rk;
+  *kmu1 = rk * (mc.mu + x + 0.5 - h) / x;
+}
+
+// K_nu(x), x > 0.
+NNGP_HD double besselk(double x, const MaternConsts &mc) {
+  double k0, k1, logb;
+  if (x <= 2.0) besselk_temme(x, mc, &k0, &k1, &logb);
+  else besselk_cf2(x, mc, &k0, &k1);
+  const double xi2 = 2.0 / x;
+  double mu_j = mc.mu;
+  for (int j = 1; j <= mc.nl; j++) {  // K_{mu+j+1} = K_{mu+j-1} + 2(mu+j)/x K_{mu+j}
+    const double kn = (mu_j + 1.0) * xi2 * k1 + k0;  // at the top of step j: k0=K_{mu+j-1}, k1=K_{mu+j}
+    k0 = k1;
+    k1 = kn;
+    mu_j += 1.0;
+  }
+  return k0;
+}
+
+// Matern correlation rho(x) = x^nu K_nu(x) / (2^(nu-1) Gamma(nu)), x = D*phi; 1 at x <= 0
+// (reference src/util.cpp:233-237).
+NNGP_HD double matern_cor(double x, const MaternConsts &mc) {
+  if (!(x > 0.0)) return 1.0;
+  double k0, k1, logx;
+  if (x <= 2.0) {
+    double logb;
+    besselk_temme(x, mc, &k0, &k1, &logb);
+    logx = logb + 0.693147180559945309417232121458;
+  } else {
+    besselk_cf2(x, mc, &k0, &k1);
+    logx = log(x);
+  }
+  const double xi2 = 2.0 / x;
+  double mu_j = mc.mu;
+  for (int j = 1; j <= mc.nl; j++) {
+    const double kn = (mu_j + 1.0) * xi2 * k1 + k0;
+    k0 = k1;
+    k1 = kn;
+    mu_j += 1.0;
+  }
+  return mc.pref * exp(mc.nu * logx) * k0;
+}
+
+}  // namespace nngp

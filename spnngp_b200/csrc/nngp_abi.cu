@@ -1,0 +1,566 @@
+// nngp_abi.cu -- C ABI (include/nngp_b200.h): lifecycle, model data, the likelihood hot path and
+// the response-model sampler `rNNGP` (reference src/rNNGP.cpp:105-420) driven from the host with
+// the caller's RNG.  There is no CPU fallback anywhere in this library.
+#include <limits.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "host_linalg.h"
+#include "nngp_ctx.h"
+
+namespace nngp {
+
+static std::mutex g_err_mu;
+static std::string g_err;
+
+void set_global_error(const std::string &msg) {
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  g_err = msg;
+}
+
+int ctx_fail(nngp_ctx *ctx, int code, const std::string &msg) {
+  if (ctx) ctx->err = msg;
+  set_global_error(msg);
+  return code;
+}
+
+int ctx_cuda(nngp_ctx *ctx, cudaError_t e, const char *what) {
+  std::string msg = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+  cudaGetLastError();  // clear sticky state where possible
+  return ctx_fail(ctx, (e == cudaErrorMemoryAllocation) ? NNGP_ENOMEM : NNGP_ECUDA, msg);
+}
+
+template <typename Tp>
+static void free_dev(Tp *&p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+static void free_model(nngp_ctx *c) {
+  free_dev(c->d_coords);
+  free_dev(c->d_nnIndx);
+  free_dev(c->d_X);
+  free_dev(c->d_y);
+  for (int s = 0; s < 2; s++) {
+    free_dev(c->d_B[s]);
+    free_dev(c->d_F[s]);
+  }
+  for (int b = 0; b < NNGP_MAX_BATCH; b++) free_dev(c->d_resid[b]);
+  free_dev(c->d_beta);
+  free_dev(c->d_partials);
+  free_dev(c->d_out);
+  if (c->h_beta) cudaFreeHost(c->h_beta);
+  c->h_beta = nullptr;
+  c->n = c->m = c->p = 0;
+}
+
+}  // namespace nngp
+
+using namespace nngp;
+
+extern "C" {
+
+int nngp_abi_version(void) { return NNGP_ABI_VERSION; }
+
+int nngp_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+const char *nngp_last_error(const nngp_ctx *ctx) {
+  if (ctx) return ctx->err.c_str();
+  static thread_local std::string copy;
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  copy = g_err;
+  return copy.c_str();
+}
+
+int nngp_create(int device, void *stream_handle, nngp_ctx **out) {
+  if (!out) return ctx_fail(nullptr, NNGP_EINVAL, "nngp_create: out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return ctx_fail(nullptr, NNGP_ENODEV,
+                    "nngp_create: no CUDA device visible (this library has no CPU fallback)");
+  }
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+  }
+  if (device >= ndev) return ctx_fail(nullptr, NNGP_EINVAL, "nngp_create: device index out of range");
+  nngp_ctx *c = new nngp_ctx();
+  c->device = device;
+  NNGP_CUDA(c, cudaSetDevice(device));
+  int major = 0, sms = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  if (major < 10) {
+    delete c;
+    return ctx_fail(nullptr, NNGP_ENODEV, "nngp_create: device is not sm_100-class (kernels are built for sm_100a only)");
+  }
+  c->sms = sms > 0 ? sms : 148;
+  if (stream_handle) {
+    c->stream = (cudaStream_t)stream_handle;
+  } else {
+    NNGP_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+  }
+  NNGP_CUDA(c, cudaMalloc(&c->d_ticket, NNGP_MAX_BATCH * sizeof(unsigned int)));
+  NNGP_CUDA(c, cudaMemset(c->d_ticket, 0, NNGP_MAX_BATCH * sizeof(unsigned int)));
+  NNGP_CUDA(c, cudaMalloc(&c->d_fail, NNGP_MAX_BATCH * sizeof(int)));
+  {
+    int init[NNGP_MAX_BATCH];
+    for (int b = 0; b < NNGP_MAX_BATCH; b++) init[b] = INT_MAX;
+    NNGP_CUDA(c, cudaMemcpy(c->d_fail, init, sizeof init, cudaMemcpyHostToDevice));
+  }
+  NNGP_CUDA(c, cudaMalloc(&c->d_mat, NNGP_MAX_BATCH * sizeof(MaternConsts)));
+  NNGP_CUDA(c, cudaHostAlloc(&c->h_out, 2 * NNGP_MAX_BATCH * sizeof(double), cudaHostAllocMapped));
+  NNGP_CUDA(c, cudaHostAlloc(&c->h_fail, NNGP_MAX_BATCH * sizeof(int), cudaHostAllocMapped));
+  NNGP_CUDA(c, cudaHostAlloc(&c->h_mat, NNGP_MAX_BATCH * sizeof(MaternConsts), cudaHostAllocDefault));
+  NNGP_CUDA(c, cudaEventCreate(&c->ev0));
+  NNGP_CUDA(c, cudaEventCreate(&c->ev1));
+  *out = c;
+  return NNGP_OK;
+}
+
+void nngp_destroy(nngp_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  free_model(c);
+  free_dev(c->d_ticket);
+  free_dev(c->d_fail);
+  free_dev(c->d_mat);
+  if (c->d_flush) cudaFree(c->d_flush);
+  if (c->h_out) cudaFreeHost(c->h_out);
+  if (c->h_fail) cudaFreeHost(c->h_fail);
+  if (c->h_mat) cudaFreeHost(c->h_mat);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int nngp_sync(nngp_ctx *c) {
+  if (!c) return NNGP_EINVAL;
+  NNGP_CUDA(c, cudaSetDevice(c->device));
+  NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
+  return NNGP_OK;
+}
+
+long long nngp_launch_count(const nngp_ctx *c) { return c ? c->launches : 0; }
+
+int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const int *nnIndx, const int *nnIndxLU,
+                  const double *X, const double *y, int loc_begin, int loc_end) {
+  if (!c) return NNGP_EINVAL;
+  if (n < 1 || m < 1 || p < 0 || !coords || !nnIndx) return ctx_fail(c, NNGP_EINVAL, "nngp_set_data: bad sizes or NULL input");
+  if (m > NNGP_MAX_M) return ctx_fail(c, NNGP_EINVAL, "nngp_set_data: n.neighbors > 32 is not supported by the warp-group solver");
+  if (p > 0 && (!X || !y)) return ctx_fail(c, NNGP_EINVAL, "nngp_set_data: X / y missing");
+  if (loc_begin < 0 || loc_end > n || loc_begin > loc_end) return ctx_fail(c, NNGP_EINVAL, "nngp_set_data: bad shard range");
+  if (nnIndxLU) {  // must be the closed form of src/util.cpp:55-70
+    for (int i = 0; i < n; i++) {
+      if (i > 0 && (nnIndxLU[i] != (int)nn_offset(i, m) || nnIndxLU[n + i] != nn_count(i, m)))
+        return ctx_fail(c, NNGP_EINVAL, "nngp_set_data: nnIndxLU is not the reference's closed-form layout");
+    }
+  }
+  NNGP_CUDA(c, cudaSetDevice(c->device));
+  NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
+  free_model(c);
+  c->n = n; c->m = m; c->p = p; c->loc_begin = loc_begin; c->loc_end = loc_end;
+  c->nIndx = nn_offset(n, m);  // == (1+m)/2*m + (n-m-1)*m for n > m
+  const long long nI = c->nIndx > 0 ? c->nIndx : 1;
+  for (long long k = 0; k < c->nIndx; k++) {
+    // neighbours must precede... checked lazily: ids must at least be valid indices
+    if (nnIndx[k] < 0 || nnIndx[k] >= n) return ctx_fail(c, NNGP_EINVAL, "nngp_set_data: neighbour index out of range");
+  }
+  {
+    std::vector<double2> xy((size_t)n);
+    for (int i = 0; i < n; i++) xy[i] = make_double2(coords[i], coords[(size_t)n + i]);
+    NNGP_CUDA(c, cudaMalloc(&c->d_coords, (size_t)n * sizeof(double2)));
+    NNGP_CUDA(c, cudaMemcpy(c->d_coords, xy.data(), (size_t)n * sizeof(double2), cudaMemcpyHostToDevice));
+  }
+  NNGP_CUDA(c, cudaMalloc(&c->d_nnIndx, (size_t)nI * sizeof(int)));
+  if (c->nIndx > 0) NNGP_CUDA(c, cudaMemcpy(c->d_nnIndx, nnIndx, (size_t)c->nIndx * sizeof(int), cudaMemcpyHostToDevice));
+  if (p > 0) {
+    NNGP_CUDA(c, cudaMalloc(&c->d_X, (size_t)n * p * sizeof(double)));
+    NNGP_CUDA(c, cudaMemcpy(c->d_X, X, (size_t)n * p * sizeof(double), cudaMemcpyHostToDevice));
+    NNGP_CUDA(c, cudaMalloc(&c->d_y, (size_t)n * sizeof(double)));
+    NNGP_CUDA(c, cudaMemcpy(c->d_y, y, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+    NNGP_CUDA(c, cudaMalloc(&c->d_beta, (size_t)NNGP_MAX_BATCH * p * sizeof(double)));
+    NNGP_CUDA(c, cudaHostAlloc(&c->h_beta, (size_t)NNGP_MAX_BATCH * p * sizeof(double), cudaHostAllocDefault));
+    for (int b = 0; b < NNGP_MAX_BATCH; b++) NNGP_CUDA(c, cudaMalloc(&c->d_resid[b], (size_t)n * sizeof(double)));
+  }
+  for (int s = 0; s < 2; s++) {
+    NNGP_CUDA(c, cudaMalloc(&c->d_B[s], (size_t)nI * sizeof(double)));
+    NNGP_CUDA(c, cudaMalloc(&c->d_F[s], (size_t)n * sizeof(double)));
+  }
+  const long long nloc = (long long)loc_end - loc_begin;
+  const int K = p + 1, npairs = K * (K + 1) / 2;
+  size_t need = (size_t)2 * NNGP_MAX_BATCH * bf_grid_for(m, nloc, c->sms);
+  size_t need2 = (size_t)q_forms_grid(nloc) * npairs;
+  size_t need3 = (size_t)q_resid_grid(m, nloc, c->sms);
+  c->partials_len = need > need2 ? need : need2;
+  if (need3 > c->partials_len) c->partials_len = need3;
+  NNGP_CUDA(c, cudaMalloc(&c->d_partials, c->partials_len * sizeof(double)));
+  c->out_len = (size_t)npairs + 8;
+  NNGP_CUDA(c, cudaMalloc(&c->d_out, c->out_len * sizeof(double)));
+  return NNGP_OK;
+}
+
+// Build the launch descriptor for `nbatch` parameter sets.  resid_on: form r = X beta - y first.
+static int prepare_bf(nngp_ctx *c, int cov, int nbatch, const double *theta, const double *beta, const int *slots,
+                      bool store, BfLaunch *P, int *grid_out) {
+  if (c->n == 0) return ctx_fail(c, NNGP_ESTATE, "likelihood requested before nngp_set_data");
+  if (nbatch < 1 || nbatch > NNGP_MAX_BATCH) return ctx_fail(c, NNGP_EINVAL, "nbatch must be in 1..4");
+  if (cov < 0 || cov > 3) return ctx_fail(c, NNGP_EINVAL, "cov.model is not correctly specified");
+  if (beta && c->p == 0) return ctx_fail(c, NNGP_EINVAL, "beta given but the model has no covariates");
+  const int grid = bf_grid_for(c->m, (long long)c->loc_end - c->loc_begin, c->sms);
+  memset(P, 0, sizeof *P);
+  P->coords = c->d_coords;
+  P->nnIndx = c->d_nnIndx;
+  P->n = c->n;
+  P->m = c->m;
+  P->loc_begin = c->loc_begin;
+  P->loc_end = c->loc_end;
+  P->nbatch = nbatch;
+  double *out_dev = nullptr;
+  int *fail_dev = nullptr;
+  NNGP_CUDA(c, cudaHostGetDevicePointer((void **)&out_dev, c->h_out, 0));
+  NNGP_CUDA(c, cudaHostGetDevicePointer((void **)&fail_dev, c->h_fail, 0));
+  for (int b = 0; b < nbatch; b++) {
+    const double *t = theta + 4 * b;
+    if (!(t[0] > 0.0) || !(t[1] >= 0.0) || !(t[2] > 0.0)) return ctx_fail(c, NNGP_EINVAL, "theta out of range");
+    BfTheta &th = P->th[b];
+    th.sigmaSq = t[0];
+    th.tauSq = t[1];
+    th.phi = t[2];
+    th.mat = nullptr;
+    if (cov == NNGP_COV_MATERN) {
+      if (!(t[3] > 0.0)) return ctx_fail(c, NNGP_EINVAL, "matern nu must be > 0");
+      matern_prepare(t[3], &c->h_mat[b]);
+      th.mat = c->d_mat + b;
+    }
+    const int slot = slots ? slots[b] : (b & 1);
+    if (slot < 0 || slot > 1) return ctx_fail(c, NNGP_EINVAL, "slot must be 0 or 1");
+    th.B = store ? c->d_B[slot] : nullptr;
+    th.F = store ? c->d_F[slot] : nullptr;
+    th.resid = beta ? c->d_resid[b] : nullptr;
+    th.out = out_dev + 2 * b;
+    th.partials = c->d_partials + (size_t)2 * grid * b;
+    th.ticket = c->d_ticket + b;
+    th.fail = c->d_fail + b;
+    th.fail_out = fail_dev + b;
+  }
+  if (cov == NNGP_COV_MATERN)
+    NNGP_CUDA(c, cudaMemcpyAsync(c->d_mat, c->h_mat, nbatch * sizeof(MaternConsts), cudaMemcpyHostToDevice, c->stream));
+  if (beta) {
+    memcpy(c->h_beta, beta, (size_t)nbatch * c->p * sizeof(double));
+    NNGP_CUDA(c, cudaMemcpyAsync(c->d_beta, c->h_beta, (size_t)nbatch * c->p * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  }
+  *grid_out = grid;
+  return NNGP_OK;
+}
+
+static int enqueue_bf(nngp_ctx *c, int cov, const BfLaunch &P, int grid, bool with_resid) {
+  if (with_resid) {
+    for (int b = 0; b < P.nbatch; b++) {
+      // identical betas share one residual vector
+      bool dup = false;
+      for (int a = 0; a < b && !dup; a++)
+        if (memcmp(c->h_beta + (size_t)a * c->p, c->h_beta + (size_t)b * c->p, c->p * sizeof(double)) == 0) dup = true;
+      if (dup) continue;
+      NNGP_CUDA(c, resid_launch(c->d_X, c->d_y, c->d_beta + (size_t)b * c->p, c->n, c->p, c->d_resid[b], c->sms, c->stream));
+      c->launches++;
+    }
+  }
+  NNGP_CUDA(c, bf_launch(P, cov, grid, c->stream));
+  c->launches++;
+  return NNGP_OK;
+}
+
+// after prepare_bf: point duplicate-beta sets at the first set's residual vector
+static void share_resid(nngp_ctx *c, BfLaunch *P) {
+  for (int b = 1; b < P->nbatch; b++)
+    for (int a = 0; a < b; a++)
+      if (P->th[b].resid && memcmp(c->h_beta + (size_t)a * c->p, c->h_beta + (size_t)b * c->p, c->p * sizeof(double)) == 0) {
+        P->th[b].resid = P->th[a].resid;
+        break;
+      }
+}
+
+int nngp_bf_loglik(nngp_ctx *c, int cov, int nbatch, const double *theta, const double *beta, const int *slots,
+                   double *out) {
+  if (!c || !theta || !out) return NNGP_EINVAL;
+  NNGP_CUDA(c, cudaSetDevice(c->device));
+  BfLaunch P;
+  int grid = 0;
+  int rc = prepare_bf(c, cov, nbatch, theta, beta, slots, true, &P, &grid);
+  if (rc) return rc;
+  share_resid(c, &P);
+  rc = enqueue_bf(c, cov, P, grid, beta != nullptr);
+  if (rc) return rc;
+  NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
+  int status = 0;
+  for (int b = 0; b < nbatch; b++) {
+    out[2 * b] = c->h_out[2 * b];
+    out[2 * b + 1] = beta ? c->h_out[2 * b + 1] : 0.0;
+    if (c->h_fail[b] != INT_MAX && (status == 0 || c->h_fail[b] < status)) status = c->h_fail[b];
+  }
+  if (status > 0) return ctx_fail(c, status, "c++ error: dpotrf failed (neighbour covariance not positive definite)");
+  return NNGP_OK;
+}
+
+int nngp_time_bf_loglik(nngp_ctx *c, int cov, int nbatch, const double *theta, const double *beta, int iters,
+                        int flush_l2, float *ms_per_launch) {
+  if (!c || !theta || !ms_per_launch || iters < 1) return NNGP_EINVAL;
+  NNGP_CUDA(c, cudaSetDevice(c->device));
+  BfLaunch P;
+  int grid = 0;
+  int rc = prepare_bf(c, cov, nbatch, theta, beta, nullptr, true, &P, &grid);
+  if (rc) return rc;
+  share_resid(c, &P);
+  if (flush_l2 && !c->d_flush) {
+    c->flush_bytes = (size_t)256 << 20;  // > 126 MB L2
+    NNGP_CUDA(c, cudaMalloc(&c->d_flush, c->flush_bytes));
+  }
+  double total = 0.0;
+  if (!flush_l2) {
+    NNGP_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    for (int it = 0; it < iters; it++) {
+      rc = enqueue_bf(c, cov, P, grid, beta != nullptr);
+      if (rc) return rc;
+    }
+    NNGP_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    NNGP_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    total = ms;
+  } else {
+    for (int it = 0; it < iters; it++) {
+      NNGP_CUDA(c, cudaMemsetAsync(c->d_flush, it & 0xff, c->flush_bytes, c->stream));
+      NNGP_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+      rc = enqueue_bf(c, cov, P, grid, beta != nullptr);
+      if (rc) return rc;
+      NNGP_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+      NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
+      float ms = 0.f;
+      NNGP_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+      total += ms;
+    }
+  }
+  *ms_per_launch = (float)(total / iters);
+  return NNGP_OK;
+}
+
+int nngp_q_resid(nngp_ctx *c, int slot, const double *beta, double *out) {
+  if (!c || !beta || !out || slot < 0 || slot > 1) return NNGP_EINVAL;
+  if (c->n == 0 || c->p == 0) return ctx_fail(c, NNGP_ESTATE, "nngp_q_resid before nngp_set_data");
+  NNGP_CUDA(c, cudaSetDevice(c->device));
+  memcpy(c->h_beta, beta, c->p * sizeof(double));
+  NNGP_CUDA(c, cudaMemcpyAsync(c->d_beta, c->h_beta, c->p * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  NNGP_CUDA(c, resid_launch(c->d_X, c->d_y, c->d_beta, c->n, c->p, c->d_resid[0], c->sms, c->stream));
+  NNGP_CUDA(c, q_resid_launch(c->d_B[slot], c->d_F[slot], c->d_nnIndx, c->d_resid[0], c->m, c->loc_begin, c->loc_end,
+                              c->d_partials, c->d_out, c->sms, c->stream));
+  c->launches += 3;
+  NNGP_CUDA(c, cudaMemcpyAsync(c->h_out, c->d_out, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
+  out[0] = c->h_out[0];
+  return NNGP_OK;
+}
+
+int nngp_q_forms(nngp_ctx *c, int slot, double *S) {
+  if (!c || !S || slot < 0 || slot > 1) return NNGP_EINVAL;
+  if (c->n == 0 || c->p == 0) return ctx_fail(c, NNGP_ESTATE, "nngp_q_forms before nngp_set_data");
+  NNGP_CUDA(c, cudaSetDevice(c->device));
+  const int K = c->p + 1, npairs = K * (K + 1) / 2;
+  NNGP_CUDA(c, q_forms_launch(c->d_B[slot], c->d_F[slot], c->d_nnIndx, c->d_X, c->d_y, c->n, c->p, c->m, c->loc_begin,
+                              c->loc_end, c->d_partials, c->d_out, c->stream));
+  c->launches += 2;
+  std::vector<double> packed(npairs);
+  NNGP_CUDA(c, cudaMemcpyAsync(packed.data(), c->d_out, npairs * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
+  int e = 0;
+  for (int d = 0; d < K; d++)
+    for (int r = d; r < K; r++, e++) {
+      S[(size_t)d * K + r] = packed[e];
+      S[(size_t)r * K + d] = packed[e];
+    }
+  return NNGP_OK;
+}
+
+int nngp_get_bf(nngp_ctx *c, int slot, double *B, double *F) {
+  if (!c || slot < 0 || slot > 1) return NNGP_EINVAL;
+  if (c->n == 0) return ctx_fail(c, NNGP_ESTATE, "nngp_get_bf before nngp_set_data");
+  NNGP_CUDA(c, cudaSetDevice(c->device));
+  NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (B && c->nIndx > 0) NNGP_CUDA(c, cudaMemcpy(B, c->d_B[slot], (size_t)c->nIndx * sizeof(double), cudaMemcpyDeviceToHost));
+  if (F) NNGP_CUDA(c, cudaMemcpy(F, c->d_F[slot], (size_t)c->n * sizeof(double), cudaMemcpyDeviceToHost));
+  return NNGP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// `rNNGP`: the response-model sampler (reference src/rNNGP.cpp:255-378), host loop + device hot path.
+// ---------------------------------------------------------------------------------------------------
+
+static double logit_(double theta, double a, double b) { return log((theta - a) / (b - theta)); }  // src/util.cpp:43
+static double logit_inv_(double z, double a, double b) { return b - (b - a) / (1 + exp(z)); }      // src/util.cpp:47
+
+// src/rNNGP.cpp:317-324
+static double log_post_(double logDet, double Q, const double *th, const nngp_rnngp_args *a) {
+  double lp = -0.5 * logDet - 0.5 * Q;
+  lp += log(th[2] - a->phiUnif[0]) + log(a->phiUnif[1] - th[2]);
+  lp += -1.0 * (1.0 + a->sigmaSqIG[0]) * log(th[0]) - a->sigmaSqIG[1] / th[0] + log(th[0]);
+  lp += -1.0 * (1.0 + a->tauSqIG[0]) * log(th[1]) - a->tauSqIG[1] / th[1] + log(th[1]);
+  if (a->cov_model == NNGP_COV_MATERN) lp += log(th[3] - a->nuUnif[0]) + log(a->nuUnif[1] - th[3]);
+  return lp;
+}
+
+int nngp_rnngp(nngp_ctx *c, const nngp_rnngp_args *a, double *betaSamples, double *thetaSamples, int *accept_out) {
+  if (!c || !a || !betaSamples || !thetaSamples) return NNGP_EINVAL;
+  if (c->n == 0 || c->p == 0) return ctx_fail(c, NNGP_ESTATE, "nngp_rnngp before nngp_set_data");
+  if (!a->rnorm || !a->runif || !a->betaStarting) return ctx_fail(c, NNGP_EINVAL, "nngp_rnngp: RNG hooks / starting values missing");
+  const int p = c->p, K = p + 1, cov = a->cov_model;
+  const int nTheta = (cov == NNGP_COV_MATERN) ? 4 : 3;
+  char line[256];
+  if (a->verbose && a->print) {  // banner text of src/rNNGP.cpp:157-179
+    static const char *names[4] = {"exponential", "spherical", "matern", "gaussian"};
+    a->print("----------------------------------------\n\tModel description\n----------------------------------------\n");
+    snprintf(line, sizeof line, "NNGP Response model fit with %i observations.\n\n", c->n); a->print(line);
+    snprintf(line, sizeof line, "Number of covariates %i (including intercept if specified).\n\n", p); a->print(line);
+    snprintf(line, sizeof line, "Using the %s spatial correlation model.\n\n", names[cov]); a->print(line);
+    snprintf(line, sizeof line, "Using %i nearest neighbors.\n\n", c->m); a->print(line);
+    snprintf(line, sizeof line, "Number of MCMC samples %i.\n\n", a->nSamples); a->print(line);
+    a->print("Priors and hyperpriors:\n\tbeta flat.\n");
+    snprintf(line, sizeof line, "\tsigma.sq IG hyperpriors shape=%.5f and scale=%.5f\n", a->sigmaSqIG[0], a->sigmaSqIG[1]); a->print(line);
+    snprintf(line, sizeof line, "\ttau.sq IG hyperpriors shape=%.5f and scale=%.5f\n", a->tauSqIG[0], a->tauSqIG[1]); a->print(line);
+    snprintf(line, sizeof line, "\tphi Unif hyperpriors a=%.5f and b=%.5f\n", a->phiUnif[0], a->phiUnif[1]); a->print(line);
+    if (cov == NNGP_COV_MATERN) {
+      snprintf(line, sizeof line, "\tnu Unif hyperpriors a=%.5f and b=%.5f\n", a->nuUnif[0], a->nuUnif[1]); a->print(line);
+    }
+    snprintf(line, sizeof line, "\nSource compiled for sm_100a; model fit on CUDA device %i (%s sampler).\n", c->device,
+             a->mode ? "double-buffered" : "reference-faithful");
+    a->print(line);
+    a->print("----------------------------------------\n\t\tSampling\n----------------------------------------\n");
+  }
+
+  double theta[4] = {a->sigmaSqStarting, a->tauSqStarting, a->phiStarting, (cov == NNGP_COV_MATERN) ? a->nuStarting : 0.0};
+  double tuning[4] = {a->sigmaSqTuning, a->tauSqTuning, a->phiTuning, a->nuTuning};
+  double cand[4] = {0, 0, 0, 0};
+  std::vector<double> beta(a->betaStarting, a->betaStarting + p), S((size_t)K * K), tmp_pp((size_t)p * p), tmp_p(p),
+      mean(p);
+  int cur = 0;  // slot holding B,F of the current theta
+  double out[2 * NNGP_MAX_BATCH], red[4];
+  int slots[2];
+  int rc;
+
+  // initial B,F at the starting values (src/rNNGP.cpp:255)
+  slots[0] = cur;
+  rc = nngp_bf_loglik(c, cov, 1, theta, nullptr, slots, out);
+  if (rc) return rc;
+  double logDetCur = out[0];
+  if (a->allreduce) a->allreduce(&logDetCur, 1, a->allreduce_user);
+
+  bool thetaUpdate = true;
+  int accept = 0, batchAccept = 0, status = 0;
+  for (int s = 0; s < a->nSamples; s++) {
+    if (thetaUpdate) {  // src/rNNGP.cpp:274-292
+      thetaUpdate = false;
+      rc = nngp_q_forms(c, cur, S.data());
+      if (rc) return rc;
+      if (a->allreduce) a->allreduce(S.data(), K * K, a->allreduce_user);
+      for (int i = 0; i < p; i++) {
+        tmp_p[i] = S[(size_t)p * K + i];  // X_i' C^-1 y
+        for (int j = 0; j <= i; j++) tmp_pp[(size_t)j * p + i] = S[(size_t)j * K + i];
+      }
+      if (hl::chol(tmp_pp.data(), p)) return ctx_fail(c, NNGP_EINVAL, "c++ error: dpotrf failed (X'C^-1X)");
+      hl::chol_inverse(tmp_pp.data(), p);
+      hl::symv(tmp_pp.data(), p, tmp_p.data(), mean.data());
+      if (hl::chol(tmp_pp.data(), p)) return ctx_fail(c, NNGP_EINVAL, "c++ error: dpotrf failed (inverse of X'C^-1X)");
+    }
+    // beta ~ N(mean, (X'C^-1X)^-1): mvrnorm, src/util.cpp:28-41
+    for (int i = 0; i < p; i++) beta[i] = a->rnorm(0.0, 1.0);
+    hl::trmv_lower(tmp_pp.data(), p, beta.data());
+    for (int i = 0; i < p; i++) beta[i] += mean[i];
+
+    // proposals, in the reference's draw order phi, sigma.sq, tau.sq[, nu] (src/rNNGP.cpp:327-333)
+    cand[2] = logit_inv_(a->rnorm(logit_(theta[2], a->phiUnif[0], a->phiUnif[1]), tuning[2]), a->phiUnif[0], a->phiUnif[1]);
+    cand[0] = exp(a->rnorm(log(theta[0]), tuning[0]));
+    cand[1] = exp(a->rnorm(log(theta[1]), tuning[1]));
+    if (cov == NNGP_COV_MATERN)
+      cand[3] = logit_inv_(a->rnorm(logit_(theta[3], a->nuUnif[0], a->nuUnif[1]), tuning[3]), a->nuUnif[0], a->nuUnif[1]);
+
+    double QCur, logDetCand, QCand;
+    if (a->mode == 0) {
+      // reference-faithful: re-solve the current theta and solve the candidate, one launch
+      double th2[8], b2[2 * 64];
+      if (p > 64) return ctx_fail(c, NNGP_EINVAL, "p > 64 not supported by the batched launch");
+      memcpy(th2, theta, sizeof theta);
+      memcpy(th2 + 4, cand, sizeof cand);
+      memcpy(b2, beta.data(), p * sizeof(double));
+      memcpy(b2 + p, beta.data(), p * sizeof(double));
+      slots[0] = cur;
+      slots[1] = 1 - cur;
+      rc = nngp_bf_loglik(c, cov, 2, th2, b2, slots, out);
+      if (rc) return rc;
+      red[0] = out[0]; red[1] = out[1]; red[2] = out[2]; red[3] = out[3];
+      if (a->allreduce) a->allreduce(red, 4, a->allreduce_user);
+      logDetCur = red[0]; QCur = red[1]; logDetCand = red[2]; QCand = red[3];
+    } else {
+      // double-buffered: B,F of the current theta are still resident; only Q changes with beta
+      slots[0] = 1 - cur;
+      rc = nngp_bf_loglik(c, cov, 1, cand, beta.data(), slots, out);
+      if (rc) return rc;
+      red[2] = out[0]; red[3] = out[1];
+      rc = nngp_q_resid(c, cur, beta.data(), out);
+      if (rc) return rc;
+      red[0] = 0.0; red[1] = out[0];
+      if (a->allreduce) a->allreduce(red, 4, a->allreduce_user);
+      QCur = red[1]; logDetCand = red[2]; QCand = red[3];
+    }
+    const double lpCur = log_post_(logDetCur, QCur, theta, a);
+    const double lpCand = log_post_(logDetCand, QCand, cand, a);
+    if (a->runif(0.0, 1.0) <= exp(lpCand - lpCur)) {  // src/rNNGP.cpp:349
+      thetaUpdate = true;
+      memcpy(theta, cand, sizeof theta);
+      cur = 1 - cur;
+      logDetCur = logDetCand;
+      accept++;
+      batchAccept++;
+    }
+    memcpy(betaSamples + (size_t)s * p, beta.data(), p * sizeof(double));
+    memcpy(thetaSamples + (size_t)s * nTheta, theta, nTheta * sizeof(double));
+
+    if (status == a->nReport) {  // src/rNNGP.cpp:361-373
+      if (a->verbose && a->print) {
+        snprintf(line, sizeof line, "Sampled: %i of %i, %3.2f%%\n", s, a->nSamples, 100.0 * s / a->nSamples); a->print(line);
+        snprintf(line, sizeof line, "Report interval Metrop. Acceptance rate: %3.2f%%\n", 100.0 * batchAccept / a->nReport); a->print(line);
+        snprintf(line, sizeof line, "Overall Metrop. Acceptance rate: %3.2f%%\n", 100.0 * accept / s); a->print(line);
+        a->print("-------------------------------------------------\n");
+      }
+      batchAccept = 0;
+      status = 0;
+    }
+    status++;
+    if (a->interrupt) a->interrupt();
+  }
+  if (a->verbose && a->print) {
+    snprintf(line, sizeof line, "Sampled: %i of %i, %3.2f%%\n", a->nSamples, a->nSamples, 100.0); a->print(line);
+    snprintf(line, sizeof line, "Report interval Metrop. Acceptance rate: %3.2f%%\n", 100.0 * batchAccept / a->nReport); a->print(line);
+    snprintf(line, sizeof line, "Overall Metrop. Acceptance rate: %3.2f%%\n", 100.0 * accept / a->nSamples); a->print(line);
+    a->print("-------------------------------------------------\n");
+  }
+  if (accept_out) *accept_out = accept;
+  return NNGP_OK;
+}
+
+}  // extern "C"

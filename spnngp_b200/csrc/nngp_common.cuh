@@ -1,0 +1,41 @@
+// nngp_common.cuh -- shared declarations for the sm_100a NNGP kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/nngp_b200.h"
+#include "besselk.cuh"
+
+namespace nngp {
+
+// Closed form of the reference's ragged neighbour layout (src/util.cpp:55-70): location i has
+// min(i, m) neighbours stored at this offset.
+__host__ __device__ __forceinline__ long long nn_offset(long long i, int m) {
+  return (i < m) ? (i * (i - 1)) / 2 : ((long long)m * (m - 1)) / 2 + (i - m) * (long long)m;
+}
+__host__ __device__ __forceinline__ int nn_count(long long i, int m) { return i < m ? (int)i : m; }
+
+// One parameter set of a batched B/F launch.
+struct BfTheta {
+  double sigmaSq, tauSq, phi;
+  const MaternConsts *mat;  // device pointer (Matern only)
+  double *B;            // nIndx weights (or nullptr: do not store)
+  double *F;            // n conditional variances (or nullptr)
+  const double *resid;  // n residuals r = X beta - y (or nullptr: no quadratic form)
+  double *out;          // 2 doubles: sum log F, Q over [loc_begin, loc_end)
+  double *partials;     // 2 * gridDim.x doubles of scratch
+  unsigned int *ticket; // zero-initialised, self-resetting
+  int *fail;            // device: min over failing locations of (i + 1); INT_MAX when none; self-resetting
+  int *fail_out;        // where the last CTA publishes *fail (may be mapped host memory)
+};
+
+struct BfLaunch {
+  const double2 *coords;  // n interleaved (x, y)
+  const int *nnIndx;      // reference CSR
+  int n, m;
+  int loc_begin, loc_end;
+  int nbatch;
+  BfTheta th[NNGP_MAX_BATCH];
+};
+
+}  // namespace nngp

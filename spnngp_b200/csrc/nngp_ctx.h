@@ -1,0 +1,80 @@
+// nngp_ctx.h -- the engine context behind the C ABI (one context drives one GPU).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "nngp_common.cuh"
+
+struct nngp_ctx {
+  int device = 0;
+  int sms = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  long long launches = 0;
+
+  // model data (device)
+  int n = 0, m = 0, p = 0;
+  int loc_begin = 0, loc_end = 0;
+  long long nIndx = 0;
+  double2 *d_coords = nullptr;  // n interleaved sites
+  int *d_nnIndx = nullptr;      // reference CSR
+  double *d_X = nullptr;        // n x p column-major
+  double *d_y = nullptr;
+  double *d_B[2] = {nullptr, nullptr};  // two slots: current / candidate
+  double *d_F[2] = {nullptr, nullptr};
+  double *d_resid[NNGP_MAX_BATCH] = {};
+  double *d_beta = nullptr;             // NNGP_MAX_BATCH x p
+  nngp::MaternConsts *d_mat = nullptr;  // NNGP_MAX_BATCH
+  double *d_partials = nullptr;         // scratch for the grid reductions
+  size_t partials_len = 0;
+  unsigned int *d_ticket = nullptr;  // NNGP_MAX_BATCH
+  int *d_fail = nullptr;             // NNGP_MAX_BATCH
+  double *d_out = nullptr;           // device result slots
+  size_t out_len = 0;
+
+  // pinned host staging
+  double *h_out = nullptr;
+  int *h_fail = nullptr;
+  double *h_beta = nullptr;
+  nngp::MaternConsts *h_mat = nullptr;
+
+  // timing
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  void *d_flush = nullptr;
+  size_t flush_bytes = 0;
+};
+
+namespace nngp {
+
+// bf_kernel.cu
+int bf_tile_for_m(int m);
+int bf_locations_per_cta(int m);
+int bf_grid_for(int m, long long nloc, int sms);
+cudaError_t bf_launch(const BfLaunch &P, int cov, int grid_x, cudaStream_t stream);
+
+// q_kernels.cu
+cudaError_t resid_launch(const double *X, const double *y, const double *beta, int n, int p, double *r, int sms,
+                         cudaStream_t stream);
+int q_resid_grid(int m, long long nloc, int sms);
+cudaError_t q_resid_launch(const double *B, const double *F, const int *nnIndx, const double *resid, int m,
+                           int loc_begin, int loc_end, double *partials, double *out, int sms, cudaStream_t stream);
+int q_forms_grid(long long nloc);
+cudaError_t q_forms_launch(const double *B, const double *F, const int *nnIndx, const double *X, const double *y,
+                           int n, int p, int m, int loc_begin, int loc_end, double *partials, double *out,
+                           cudaStream_t stream);
+
+// shared helpers (nngp_abi.cu)
+int ctx_fail(nngp_ctx *ctx, int code, const std::string &msg);
+int ctx_cuda(nngp_ctx *ctx, cudaError_t e, const char *what);
+void set_global_error(const std::string &msg);
+
+}  // namespace nngp
+
+#define NNGP_CUDA(ctx, call)                                     \
+  do {                                                           \
+    cudaError_t e__ = (call);                                    \
+    if (e__ != cudaSuccess) return nngp::ctx_cuda(ctx, e__, #call); \
+  } while (0)

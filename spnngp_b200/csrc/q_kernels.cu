@@ -1,0 +1,206 @@
+// q_kernels.cu -- HBM-bound passes over stored B, F: residual formation, the quadratic form
+// Q(B,F,r,r) alone, and all cross quadratic forms of the columns [X y] in one pass.
+//
+// Replaces (reference file:line):
+//   r = X beta - y                      src/rNNGP.cpp:299-303 (dgemv + daxpy)
+//   Q(B,F,u,v)                          src/util.cpp:261-280
+//   the p + p(p+1)/2 (+1) calls of Q    src/rNNGP.cpp:281-286, src/cNNGP.cpp:227-232,245
+//
+// Layout: LP = 8/16/32 lanes cooperate on one location so that B and nnIndx (contiguous per
+// location, consecutive locations adjacent) are read fully coalesced; the u[N(i,j)] gathers hit L2.
+// Reductions are fixed-order trees (shuffle -> CTA -> per-CTA partials -> second tiny kernel), so
+// results are run-to-run deterministic.
+#include "nngp_common.cuh"
+
+namespace nngp {
+
+__global__ void __launch_bounds__(256) resid_kernel(const double *__restrict__ X, const double *__restrict__ y,
+                                                    const double *__restrict__ beta, int n, int p,
+                                                    double *__restrict__ r) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double acc = 0.0;
+    for (int c = 0; c < p; ++c) acc = fma(__ldg(&X[(size_t)c * n + i]), __ldg(&beta[c]), acc);
+    r[i] = acc - __ldg(&y[i]);
+  }
+}
+
+// ---- Q(B,F,r,r) over a shard ----------------------------------------------------------------------
+template <int LP>
+__global__ void __launch_bounds__(256) q_resid_kernel(const double *__restrict__ B, const double *__restrict__ F,
+                                                      const int *__restrict__ nnIndx,
+                                                      const double *__restrict__ resid, int m, int loc_begin,
+                                                      int loc_end, double *__restrict__ partials) {
+  constexpr int G = 256 / LP;
+  __shared__ double red[8];
+  const int tid = threadIdx.x, lane = tid % LP, g = tid / LP;
+  double qsum = 0.0;
+  for (long long base = loc_begin + (long long)blockIdx.x * G; base < loc_end; base += (long long)gridDim.x * G) {
+    const long long i = base + g;
+    const bool active = i < loc_end;
+    const int mi = active ? nn_count(i, m) : 0;
+    const long long off = active ? nn_offset(i, m) : 0;
+    double a = 0.0;
+    if (lane < mi) a = __ldg(&B[off + lane]) * __ldg(&resid[__ldg(&nnIndx[off + lane])]);
+#pragma unroll
+    for (int s = LP / 2; s >= 1; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s, LP);
+    if (lane == 0 && active) {
+      const double e = __ldg(&resid[i]) - a;
+      qsum += e * e / __ldg(&F[i]);
+    }
+  }
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) qsum += __shfl_down_sync(0xffffffffu, qsum, s);
+  if ((tid & 31) == 0) red[tid >> 5] = qsum;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    partials[blockIdx.x] = t;
+  }
+}
+
+// sums `count` partial vectors of length `len` (partials[j*len + e]) in fixed order: one CTA per entry
+__global__ void __launch_bounds__(256) sum_partials_kernel(const double *__restrict__ partials, int count, int len,
+                                                           double *__restrict__ out) {
+  __shared__ double red[8];
+  const int e = blockIdx.x, tid = threadIdx.x;
+  double a = 0.0;
+  for (int j = tid; j < count; j += 256) a += partials[(size_t)j * len + e];
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) a += __shfl_down_sync(0xffffffffu, a, s);
+  if ((tid & 31) == 0) red[tid >> 5] = a;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    out[e] = t;
+  }
+}
+
+// ---- all cross forms S = [X y]' C~^-1 [X y] ---------------------------------------------------------
+// CTA = 256 threads handles CH = 128 consecutive locations: phase 1 writes the whitened columns
+// e_c(i) = (u_c[i] - B_i . u_c[N(i)]) / sqrt(F_i) of its chunk to shared memory; phase 2 forms the
+// K(K+1)/2 cross products of the chunk; per-CTA partials are summed by sum_partials_kernel.
+template <int LP>
+__global__ void __launch_bounds__(256) q_forms_kernel(const double *__restrict__ B, const double *__restrict__ F,
+                                                      const int *__restrict__ nnIndx, const double *__restrict__ X,
+                                                      const double *__restrict__ y, int n, int p, int m,
+                                                      int loc_begin, int loc_end, double *__restrict__ partials) {
+  constexpr int CH = 128;
+  constexpr int G = 256 / LP;
+  extern __shared__ double W[];  // CH x K, column c at W[c*CH ...]
+  const int K = p + 1;
+  const int npairs = K * (K + 1) / 2;
+  const int tid = threadIdx.x, lane = tid % LP, g = tid / LP;
+  const long long chunk0 = loc_begin + (long long)blockIdx.x * CH;
+
+  for (int s0 = 0; s0 < CH; s0 += G) {
+    const int s = s0 + g;
+    const long long i = chunk0 + s;
+    const bool active = (s < CH) && (i < loc_end);
+    const int mi = active ? nn_count(i, m) : 0;
+    const long long off = active ? nn_offset(i, m) : 0;
+    double b = 0.0;
+    int idx = 0;
+    if (lane < mi) {
+      b = __ldg(&B[off + lane]);
+      idx = __ldg(&nnIndx[off + lane]);
+    }
+    const double rs = active ? rsqrt(__ldg(&F[i])) : 0.0;
+    for (int c = 0; c < K; ++c) {
+      const double *__restrict__ u = (c < p) ? (X + (size_t)c * n) : y;
+      double a = (lane < mi) ? b * __ldg(&u[idx]) : 0.0;
+#pragma unroll
+      for (int sh = LP / 2; sh >= 1; sh >>= 1) a += __shfl_xor_sync(0xffffffffu, a, sh, LP);
+      if (lane == 0 && s < CH) W[c * CH + s] = active ? (__ldg(&u[i]) - a) * rs : 0.0;
+    }
+  }
+  __syncthreads();
+  // phase 2: pair e -> (c, d), c >= d, column-major lower packing; 8 lanes per pair
+  const int sub = tid & 7;
+  for (int e0 = 0; e0 < npairs; e0 += 32) {  // uniform trip count: the shuffles below need full warps
+    const int e = e0 + (tid >> 3);
+    const bool ok = e < npairs;
+    int d = 0, rem = ok ? e : 0;
+    while (rem >= K - d) {
+      rem -= K - d;
+      ++d;
+    }
+    const int c = d + rem;
+    double a = 0.0;
+    if (ok)
+      for (int s = sub; s < CH; s += 8) a = fma(W[c * CH + s], W[d * CH + s], a);
+    a += __shfl_xor_sync(0xffffffffu, a, 4, 8);
+    a += __shfl_xor_sync(0xffffffffu, a, 2, 8);
+    a += __shfl_xor_sync(0xffffffffu, a, 1, 8);
+    if (ok && sub == 0) partials[(size_t)blockIdx.x * npairs + e] = a;
+  }
+}
+
+// ---- launchers --------------------------------------------------------------------------------------
+static int lanes_for_m(int m) { return m <= 8 ? 8 : (m <= 16 ? 16 : 32); }
+
+cudaError_t resid_launch(const double *X, const double *y, const double *beta, int n, int p, double *r, int sms,
+                         cudaStream_t stream) {
+  int grid = (n + 255) / 256;
+  if (grid > sms * 8) grid = sms * 8;
+  if (grid < 1) grid = 1;
+  resid_kernel<<<grid, 256, 0, stream>>>(X, y, beta, n, p, r);
+  return cudaGetLastError();
+}
+
+int q_resid_grid(int m, long long nloc, int sms) {
+  const int G = 256 / lanes_for_m(m);
+  long long need = (nloc + G - 1) / G;
+  long long g = (long long)sms * 8;
+  if (need < g) g = need;
+  return (int)(g < 1 ? 1 : g);
+}
+
+// partials must hold q_resid_grid() doubles; out[0] receives Q.
+cudaError_t q_resid_launch(const double *B, const double *F, const int *nnIndx, const double *resid, int m,
+                           int loc_begin, int loc_end, double *partials, double *out, int sms,
+                           cudaStream_t stream) {
+  const int grid = q_resid_grid(m, (long long)loc_end - loc_begin, sms);
+  const int lp = lanes_for_m(m);
+  if (lp == 8) q_resid_kernel<8><<<grid, 256, 0, stream>>>(B, F, nnIndx, resid, m, loc_begin, loc_end, partials);
+  else if (lp == 16) q_resid_kernel<16><<<grid, 256, 0, stream>>>(B, F, nnIndx, resid, m, loc_begin, loc_end, partials);
+  else q_resid_kernel<32><<<grid, 256, 0, stream>>>(B, F, nnIndx, resid, m, loc_begin, loc_end, partials);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  sum_partials_kernel<<<1, 256, 0, stream>>>(partials, grid, 1, out);
+  return cudaGetLastError();
+}
+
+int q_forms_grid(long long nloc) { return (int)((nloc + 127) / 128 < 1 ? 1 : (nloc + 127) / 128); }
+
+// partials must hold q_forms_grid() * (p+1)(p+2)/2 doubles; out receives the packed lower triangle
+// (column-major: (0,0),(1,0),..,(K-1,0),(1,1),...).
+cudaError_t q_forms_launch(const double *B, const double *F, const int *nnIndx, const double *X, const double *y,
+                           int n, int p, int m, int loc_begin, int loc_end, double *partials, double *out,
+                           cudaStream_t stream) {
+  const int K = p + 1, npairs = K * (K + 1) / 2;
+  const int grid = q_forms_grid((long long)loc_end - loc_begin);
+  const size_t smem = (size_t)128 * K * sizeof(double);
+  const int lp = lanes_for_m(m);
+  cudaError_t e;
+#define NNGP_QF(LPV)                                                                                         \
+  do {                                                                                                       \
+    if (smem > 48 * 1024) {                                                                                  \
+      e = cudaFuncSetAttribute(q_forms_kernel<LPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      if (e != cudaSuccess) return e;                                                                        \
+    }                                                                                                        \
+    q_forms_kernel<LPV><<<grid, 256, smem, stream>>>(B, F, nnIndx, X, y, n, p, m, loc_begin, loc_end, partials); \
+  } while (0)
+  if (lp == 8) NNGP_QF(8);
+  else if (lp == 16) NNGP_QF(16);
+  else NNGP_QF(32);
+#undef NNGP_QF
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  sum_partials_kernel<<<npairs, 256, 0, stream>>>(partials, grid, npairs, out);
+  return cudaGetLastError();
+}
+
+}  // namespace nngp

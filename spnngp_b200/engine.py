@@ -1,0 +1,184 @@
+"""Thin numpy-facing wrapper over the C ABI (include/nngp_b200.h). One Engine drives one GPU.
+
+All numerics run in libnngp_b200.so on the device; this module only marshals arrays into the
+reference's column-major layout and raises on non-zero status codes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import RnngpArgs, c_double_p, c_int_p
+
+COV_MODELS = {"exponential": 0, "spherical": 1, "matern": 2, "gaussian": 3}  # R/spNNGP.R:172-178
+
+
+class NNGPError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"nngp status {status}: {message}")
+        self.status = status
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_double_p)
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_int_p)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def colmajor(a):
+    """2-D array -> flat column-major vector (R matrix layout)."""
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim == 1:
+        return np.ascontiguousarray(a)
+    return np.ascontiguousarray(a.T).ravel()
+
+
+def n_indx(n, m):
+    """Length of nnIndx / B (reference src/rNNGP.cpp:218)."""
+    return int((1 + m) / 2 * m + (n - m - 1) * m)
+
+
+def _as_cfunc(fn, proto):
+    """Python callable, CFUNCTYPE instance or a symbol of a loaded C library -> `proto` instance."""
+    if isinstance(fn, proto):
+        return fn
+    if isinstance(fn, C._CFuncPtr):  # e.g. librshim's rnorm: pass the C address straight through
+        return proto(C.cast(fn, C.c_void_p).value)
+    return proto(fn)
+
+
+class Engine:
+    def __init__(self, device: int = -1, stream=None):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        st = self.lib.nngp_create(C.c_int(device), C.c_void_p(stream) if stream else None, C.byref(h))
+        if st != 0:
+            raise NNGPError(st, self.lib.nngp_last_error(None).decode())
+        self.h = h
+        self.n = self.m = self.p = 0
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.nngp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st):
+        if st != 0:
+            raise NNGPError(st, self.lib.nngp_last_error(self.h).decode())
+
+    # ---- data ------------------------------------------------------------------------------------
+    def set_data(self, coords, nnIndx, nnIndxLU, X, y, m, loc_range=None):
+        coords = colmajor(coords)
+        n = coords.size // 2
+        nnIndx = _i32(nnIndx)
+        lu = _i32(nnIndxLU) if nnIndxLU is not None else None
+        if X is None:
+            p = 0; Xf = None; yf = None
+        else:
+            X = np.asarray(X, dtype=np.float64).reshape(n, -1)
+            p = X.shape[1]
+            Xf = colmajor(X); yf = _f64(y)
+        lo, hi = loc_range if loc_range is not None else (0, n)
+        self._check(self.lib.nngp_set_data(self.h, n, m, p, _dp(coords), _ip(nnIndx), _ip(lu) if lu is not None else None,
+                                           _dp(Xf) if Xf is not None else None, _dp(yf) if yf is not None else None,
+                                           lo, hi))
+        self.n, self.m, self.p = n, m, p
+        self.loc_range = (lo, hi)
+
+    # ---- hot path ----------------------------------------------------------------------------------
+    def bf_loglik(self, cov, thetas, betas=None, slots=None):
+        """thetas: (nb, <=4) rows (sigma.sq, tau.sq, phi[, nu]); betas: (nb, p) or None.
+        Returns (nb, 2): sum log F and Q over this engine's shard."""
+        th = np.zeros((np.atleast_2d(thetas).shape[0], 4))
+        t2 = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
+        th[:, : t2.shape[1]] = t2
+        nb = th.shape[0]
+        bp = None
+        if betas is not None:
+            b = _f64(np.atleast_2d(betas))
+            assert b.shape == (nb, self.p)
+            bp = _dp(b)
+        sl = _i32(slots) if slots is not None else None
+        out = np.zeros((nb, 2))
+        self._check(self.lib.nngp_bf_loglik(self.h, cov, nb, _dp(th), bp, _ip(sl) if sl is not None else None, _dp(out)))
+        return out
+
+    def time_bf_loglik(self, cov, thetas, betas=None, iters=10, flush_l2=False):
+        th = np.zeros((np.atleast_2d(thetas).shape[0], 4))
+        t2 = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
+        th[:, : t2.shape[1]] = t2
+        nb = th.shape[0]
+        bp = None
+        if betas is not None:
+            b = _f64(np.atleast_2d(betas)); bp = _dp(b)
+        ms = C.c_float(0)
+        self._check(self.lib.nngp_time_bf_loglik(self.h, cov, nb, _dp(th), bp, iters, 1 if flush_l2 else 0, C.byref(ms)))
+        return float(ms.value)
+
+    def q_resid(self, slot, beta):
+        b = _f64(beta); out = np.zeros(1)
+        self._check(self.lib.nngp_q_resid(self.h, slot, _dp(b), _dp(out)))
+        return float(out[0])
+
+    def q_forms(self, slot):
+        K = self.p + 1
+        S = np.zeros(K * K)
+        self._check(self.lib.nngp_q_forms(self.h, slot, _dp(S)))
+        return S.reshape(K, K)
+
+    def get_bf(self, slot):
+        B = np.zeros(max(n_indx(self.n, self.m), 1)); F = np.zeros(self.n)
+        self._check(self.lib.nngp_get_bf(self.h, slot, _dp(B), _dp(F)))
+        return B, F
+
+    def launch_count(self):
+        return int(self.lib.nngp_launch_count(self.h))
+
+    # ---- entry points ------------------------------------------------------------------------------
+    def rnngp(self, cov, sigmaSqIG, tauSqIG, phiUnif, nuUnif, starting, tuning, n_samples, rnorm, runif, mode=0,
+              verbose=False, n_report=100, printer=None, allreduce=None):
+        """Response-model sampler on the data given to set_data (reference `rNNGP`, src/rNNGP.cpp:105).
+        rnorm/runif: ctypes function pointers or Python callables (mu, sd) / (a, b)."""
+        a = RnngpArgs()
+        a.cov_model = cov
+        a.sigmaSqIG[:] = list(sigmaSqIG); a.tauSqIG[:] = list(tauSqIG); a.phiUnif[:] = list(phiUnif)
+        a.nuUnif[:] = list(nuUnif) if nuUnif is not None else [0.0, 0.0]
+        b0 = _f64(starting["beta"]); a.betaStarting = _dp(b0)
+        a.sigmaSqStarting = starting["sigma.sq"]; a.tauSqStarting = starting["tau.sq"]; a.phiStarting = starting["phi"]
+        a.nuStarting = starting.get("nu", 0.0)
+        a.sigmaSqTuning = tuning["sigma.sq"]; a.tauSqTuning = tuning["tau.sq"]; a.phiTuning = tuning["phi"]
+        a.nuTuning = tuning.get("nu", 0.0)
+        a.nSamples = n_samples; a.mode = mode; a.verbose = int(bool(verbose)); a.nReport = n_report
+        a.rnorm = _as_cfunc(rnorm, _lib.RNORM_FN)
+        a.runif = _as_cfunc(runif, _lib.RUNIF_FN)
+        if printer is not None:
+            a.print = _lib.PRINT_FN(lambda s: printer(s.decode()))
+        if allreduce is not None:
+            def _ar(buf, n, _user):
+                arr = np.ctypeslib.as_array(buf, shape=(n,))
+                allreduce(arr)
+            a.allreduce = _lib.ALLREDUCE_FN(_ar)
+        nTheta = 4 if cov == COV_MODELS["matern"] else 3
+        bs = np.zeros(self.p * n_samples); ts = np.zeros(nTheta * n_samples)
+        acc = C.c_int(0)
+        self._check(self.lib.nngp_rnngp(self.h, C.byref(a), _dp(bs), _dp(ts), C.byref(acc)))
+        return bs.reshape(n_samples, self.p).T.copy(), ts.reshape(n_samples, nTheta).T.copy(), int(acc.value)

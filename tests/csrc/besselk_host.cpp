@@ -1,0 +1,9 @@
+// Host build of the device Bessel-K / Matern routines (spnngp_b200/csrc/besselk.cuh) so their
+// numerics can be validated against mpmath on a machine without a GPU.
+#include "../../spnngp_b200/csrc/besselk.cuh"
+extern "C" {
+double host_besselk(double x, double nu) { nngp::MaternConsts mc; nngp::matern_prepare(nu, &mc); return nngp::besselk(x, mc); }
+double host_matern(double x, double nu) { nngp::MaternConsts mc; nngp::matern_prepare(nu, &mc); return nngp::matern_cor(x, mc); }
+void host_gammas(double nu, double *out) { nngp::MaternConsts mc; nngp::matern_prepare(nu, &mc);
+  out[0]=mc.gam1; out[1]=mc.gam2; out[2]=mc.gampl; out[3]=mc.gammi; out[4]=mc.mu; out[5]=mc.pref; }
+}

@@ -1,0 +1,190 @@
+"""GPU parity: the sm_100a B/F + log-likelihood path (through the C ABI) against the CPU oracle.
+
+Tolerance (BASELINE.json north_star): B, F, logDet, Q within 1e-10 relative at tau.sq/sigma.sq = 0.2
+(SURVEY §8a tolerance budget: kappa(C) ~ 75 leaves ~3 decades of headroom).
+"""
+import numpy as np
+import pytest
+
+from tests.util import make_problem, relerr, relerr_norm
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+THETA = {0: [5.0, 1.0, 6.0], 1: [5.0, 1.0, 6.0], 2: [5.0, 1.0, 6.0, 0.75], 3: [5.0, 1.0, 6.0]}
+
+
+def _check(engine, port, prob, cov, theta, tol=TOL):
+    n, m = prob["n"], prob["m"]
+    engine.set_data(prob["coords"], prob["nnIndx"], prob["nnIndxLU"], prob["X"], prob["y"], m)
+    beta = prob["beta"]
+    out = engine.bf_loglik(cov, [theta], [beta], slots=[0])
+    B, F = engine.get_bf(0)
+    Bo, Fo, ld, info = port.update_bf(prob["coords"], prob["nnIndx"], prob["nnIndxLU"], n, m, theta, cov)
+    assert info == 0
+    r = prob["X"] @ beta - prob["y"]
+    Qo = port.q(Bo, Fo, r, r, n, prob["nnIndx"], prob["nnIndxLU"])
+    nI = len(prob["nnIndx"])
+    assert relerr(F, Fo) < tol
+    assert relerr_norm(B[:nI], Bo[:nI]) < tol
+    assert abs(out[0, 0] - ld) <= tol * max(abs(ld), 1.0)
+    assert abs(out[0, 1] - Qo) <= tol * abs(Qo)
+    return B, F, out
+
+
+@pytest.mark.parametrize("cov", [0, 1, 2, 3])
+@pytest.mark.parametrize("n,m", [(2000, 15), (300, 5), (3000, 10), (500, 32), (40, 8), (17, 16), (1500, 20), (3, 1)])
+def test_bf_parity(engine, port, cov, n, m):
+    prob = make_problem(n, m, seed=n + m, port=port, domain=np.sqrt(n / 5000.0))
+    _check(engine, port, prob, cov, THETA[cov])
+
+
+@pytest.mark.parametrize("nu", [0.3, 0.5, 1.5, 2.5, 3.2])
+def test_matern_nu(engine, port, nu):
+    prob = make_problem(1200, 15, seed=7, port=port, domain=0.5)
+    _check(engine, port, prob, 2, [2.0, 0.5, 4.0, nu])
+
+
+def test_matern_half_is_exponential(engine, port):
+    """KAT: Matern(nu = 1/2) == exponential."""
+    prob = make_problem(800, 15, seed=3, port=port, domain=0.4)
+    engine.set_data(prob["coords"], prob["nnIndx"], prob["nnIndxLU"], prob["X"], prob["y"], 15)
+    a = engine.bf_loglik(2, [[5.0, 1.0, 6.0, 0.5]], [prob["beta"]], slots=[0])
+    b = engine.bf_loglik(0, [[5.0, 1.0, 6.0]], [prob["beta"]], slots=[1])
+    assert np.allclose(a, b, rtol=1e-12)
+    Ba, Fa = engine.get_bf(0)
+    Bb, Fb = engine.get_bf(1)
+    assert relerr(Fa, Fb) < 1e-12
+
+
+def test_two_point_closed_form(engine, port):
+    """KAT n=2..: B = s2 rho/(s2+t2), F_1 = s2+t2-(s2 rho)^2/(s2+t2); F_0 = s2+t2."""
+    prob = make_problem(3, 1, seed=11, port=port)
+    s2, t2, phi = 5.0, 1.0, 6.0
+    engine.set_data(prob["coords"], prob["nnIndx"], prob["nnIndxLU"], prob["X"], prob["y"], 1)
+    engine.bf_loglik(0, [[s2, t2, phi]], None, slots=[0])
+    B, F = engine.get_bf(0)
+    c = prob["coords"]
+    assert abs(F[0] - (s2 + t2)) < 1e-14
+    j = prob["nnIndx"][0]
+    rho = np.exp(-phi * np.linalg.norm(c[1] - c[j]))
+    assert abs(B[0] - s2 * rho / (s2 + t2)) < 1e-13
+    assert abs(F[1] - (s2 + t2 - (s2 * rho) ** 2 / (s2 + t2))) < 1e-13
+
+
+def test_full_conditioning_is_exact_gp(engine, port):
+    """With m >= n-1 the NNGP is the exact GP: sum log F = log det, Q = u' C^-1 u."""
+    n, m = 30, 32
+    rng = np.random.default_rng(5)
+    coords = rng.random((n + 3, 2))[: n]
+    # n <= m: build the full lower-triangular neighbour sets by hand in the reference layout
+    nnIndx = []
+    lu = np.zeros(2 * n, dtype=np.int32)
+    off = 0
+    for i in range(n):
+        d = np.linalg.norm(coords[:i] - coords[i], axis=1)
+        order = np.argsort(d, kind="stable")
+        lu[i] = off if i > 0 else 0
+        lu[n + i] = i
+        nnIndx.extend(order.tolist())
+        off += i
+    X = np.column_stack([np.ones(n), rng.standard_normal(n)])
+    y = rng.standard_normal(n)
+    engine.set_data(coords, np.array(nnIndx, dtype=np.int32), None, X, y, m)
+    s2, t2, phi = 2.0, 0.5, 3.0
+    beta = np.array([0.3, -1.0])
+    out = engine.bf_loglik(0, [[s2, t2, phi]], [beta], slots=[0])
+    D = np.linalg.norm(coords[:, None, :] - coords[None, :, :], axis=2)
+    Cm = s2 * np.exp(-phi * D) + t2 * np.eye(n)
+    r = X @ beta - y
+    sign, logdet = np.linalg.slogdet(Cm)
+    assert abs(out[0, 0] - logdet) < 1e-10 * abs(logdet)
+    assert abs(out[0, 1] - r @ np.linalg.solve(Cm, r)) < 1e-10 * abs(out[0, 1])
+
+
+def test_batch_equals_single(engine, port):
+    prob = make_problem(2500, 15, seed=21, port=port, domain=0.7)
+    engine.set_data(prob["coords"], prob["nnIndx"], prob["nnIndxLU"], prob["X"], prob["y"], 15)
+    thetas = [[5.0, 1.0, 6.0], [4.0, 1.2, 7.5], [6.0, 0.8, 5.0], [5.5, 1.1, 6.6]]
+    betas = [prob["beta"], prob["beta"] * 1.01, prob["beta"], prob["beta"] * 0.9]
+    batch = engine.bf_loglik(0, thetas, betas, slots=[0, 1, 0, 1])
+    for b in range(4):
+        single = engine.bf_loglik(0, [thetas[b]], [betas[b]], slots=[0])
+        assert np.array_equal(single[0], batch[b])  # same launch geometry -> bit-identical sums
+
+
+def test_sharded_sums_match(port):
+    """Two contexts, each with half the locations: partial sums add up to the full result."""
+    from spnngp_b200 import Engine
+    prob = make_problem(4001, 15, seed=4, port=port, domain=0.9)
+    theta, beta = [5.0, 1.0, 6.0], prob["beta"]
+    full = Engine(); a = Engine(); b = Engine()
+    try:
+        args = (prob["coords"], prob["nnIndx"], prob["nnIndxLU"], prob["X"], prob["y"], 15)
+        full.set_data(*args)
+        a.set_data(*args, loc_range=(0, 1777))
+        b.set_data(*args, loc_range=(1777, 4001))
+        f = full.bf_loglik(0, [theta], [beta], slots=[0])
+        pa = a.bf_loglik(0, [theta], [beta], slots=[0])
+        pb = b.bf_loglik(0, [theta], [beta], slots=[0])
+        assert np.allclose(pa + pb, f, rtol=1e-12)
+        Sf = full.q_forms(0)
+        assert np.allclose(a.q_forms(0) + b.q_forms(0), Sf, rtol=1e-11)
+    finally:
+        full.close(); a.close(); b.close()
+
+
+def test_q_forms_and_q_resid(engine, port):
+    prob = make_problem(3000, 15, seed=9, port=port, p=3, domain=0.8)
+    n, m = 3000, 15
+    engine.set_data(prob["coords"], prob["nnIndx"], prob["nnIndxLU"], prob["X"], prob["y"], m)
+    theta = [5.0, 1.0, 6.0]
+    engine.bf_loglik(0, [theta], None, slots=[1])
+    Bo, Fo, _, _ = port.update_bf(prob["coords"], prob["nnIndx"], prob["nnIndxLU"], n, m, theta, 0)
+    S = engine.q_forms(1)
+    cols = [prob["X"][:, j].copy() for j in range(3)] + [prob["y"]]
+    for a in range(4):
+        for b in range(4):
+            q = port.q(Bo, Fo, cols[a], cols[b], n, prob["nnIndx"], prob["nnIndxLU"])
+            assert abs(S[a, b] - q) <= 1e-10 * max(abs(q), 1e-6 * abs(S[3, 3]))
+    beta = np.array([0.9, 5.2, -1.9])
+    r = prob["X"] @ beta - prob["y"]
+    q = port.q(Bo, Fo, r, r, n, prob["nnIndx"], prob["nnIndxLU"])
+    assert abs(engine.q_resid(1, beta) - q) <= 1e-10 * abs(q)
+
+
+def test_not_positive_definite_is_reported(engine, port):
+    """Duplicate sites with tau.sq = 0 make C singular: the reference aborts with 'dpotrf failed'
+    (src/rNNGP.cpp:86); the engine returns the 1-based location index as a positive status."""
+    from spnngp_b200 import NNGPError
+    prob = make_problem(200, 5, seed=13, port=port)
+    coords = prob["coords"].copy()
+    coords[50] = coords[49]
+    nnIndx, _, lu = port.mk_nn_indx(coords, 5)
+    engine.set_data(coords, nnIndx, lu, prob["X"], prob["y"], 5)
+    with pytest.raises(NNGPError) as ei:
+        engine.bf_loglik(0, [[5.0, 0.0, 6.0]], None, slots=[0])
+    assert ei.value.status > 0
+
+
+def test_rnngp_chain_retraces_oracle(engine, port):
+    """Same RNG stream on both sides -> same accept/reject decisions -> same chain (SURVEY §8a note)."""
+    from spnngp_b200 import _lib
+    prob = make_problem(1500, 10, seed=17, port=port, domain=0.55)
+    R = _lib.load_rshim()
+    starting = {"beta": [0.0, 0.0], "sigma.sq": 5.0, "tau.sq": 1.0, "phi": 6.0}
+    tuning = {"sigma.sq": 0.05, "tau.sq": 0.05, "phi": 0.05}
+    pri = dict(sigmaSqIG=[2.0, 5.0], tauSqIG=[2.0, 1.0], phiUnif=[3.0, 300.0], nuUnif=None)
+    S = 60
+    R.rshim_set_seed(1)
+    bo, to, acc_o = port.rnngp(prob["y"], prob["X"], prob["coords"], 0, prob["nnIndx"], prob["nnIndxLU"], 10,
+                               pri["sigmaSqIG"], pri["tauSqIG"], pri["phiUnif"], None, starting, tuning, S,
+                               lambda mu, sd: R.rnorm(mu, sd), lambda a, b: R.runif(a, b))
+    engine.set_data(prob["coords"], prob["nnIndx"], prob["nnIndxLU"], prob["X"], prob["y"], 10)
+    for mode in (0, 1):
+        R.rshim_set_seed(1)
+        bg, tg, acc_g = engine.rnngp(0, pri["sigmaSqIG"], pri["tauSqIG"], pri["phiUnif"], None, starting, tuning, S,
+                                     R.rnorm, R.runif, mode=mode)
+        assert acc_g == acc_o and 0 < acc_g < S
+        assert np.allclose(tg, to, rtol=1e-9, atol=0)
+        assert np.allclose(bg, bo, rtol=1e-7, atol=1e-9)
