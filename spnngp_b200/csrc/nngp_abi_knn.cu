@@ -1,0 +1,167 @@
+// nngp_abi_knn.cu -- C ABI for the neighbour searches (include/nngp_b200.h): nngp_mk_nn_indx replaces
+// the reference's `mkNNIndx` / `mkNNIndxCB` .Call entry points (src/nn.cpp:63-111, 214-257);
+// nngp_nn_query stands in for RANN::nn2 (R/generics.R:642).
+#include <cub/cub.cuh>
+
+#include <vector>
+
+#include "nngp_ctx.h"
+
+namespace nngp {
+cudaError_t knn_brute_launch(const double2 *coords, int n, int m, int *nnIndx, double *nnDist, cudaStream_t stream);
+cudaError_t knn_cb_launch(const double2 *sxy, const int *sidx, int n, int m, int *nnIndx, double *nnDist,
+                          cudaStream_t stream);
+cudaError_t knn_keys_launch(const double2 *coords, int n, double *u, int *idx, cudaStream_t stream);
+cudaError_t knn_gather_launch(const double2 *coords, const int *sidx, int n, double2 *sxy, cudaStream_t stream);
+cudaError_t knn_count_ties_launch(const double *u_sorted, int n, int *count, cudaStream_t stream);
+cudaError_t knn_query_launch(const double2 *sxy, const int *sidx, const double *u_sorted, int n, const double2 *q,
+                             int nq, int m, int *out, cudaStream_t stream);
+
+// R's rsort_with_index on the host (src/main/sort.c; third-party algorithm restated): only used
+// when u = x + y has exact ties, where the reference's Shell-sort order decides the scan order.
+static void host_rsort_with_index(double *x, int *indx, int n) {
+  int h;
+  for (h = 1; h <= n / 9; h = 3 * h + 1) {
+  }
+  for (; h > 0; h /= 3)
+    for (int i = h; i < n; i++) {
+      const double v = x[i];
+      const int iv = indx[i];
+      int j = i;
+      while (j >= h && (x[j - h] > v || (x[j - h] != x[j - h] && v == v))) {
+        x[j] = x[j - h];
+        indx[j] = indx[j - h];
+        j -= h;
+      }
+      x[j] = v;
+      indx[j] = iv;
+    }
+}
+
+struct DevBuf {
+  void *p = nullptr;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+  template <typename Tp>
+  Tp *as() {
+    return reinterpret_cast<Tp *>(p);
+  }
+};
+
+// sort the sites by u = x + y on the device; falls back to the reference's exact Shell sort on the
+// host when u has ties.  Outputs: d_sidx (NNGP index per sorted position), d_u (sorted keys).
+static int sort_by_u(nngp_ctx *c, const double2 *d_coords, int n, DevBuf &d_sidx, DevBuf &d_u, int *n_ties) {
+  DevBuf u_in, idx_in, tmp, ties;
+  NNGP_CUDA(c, u_in.alloc((size_t)n * sizeof(double)));
+  NNGP_CUDA(c, idx_in.alloc((size_t)n * sizeof(int)));
+  NNGP_CUDA(c, d_u.alloc((size_t)n * sizeof(double)));
+  NNGP_CUDA(c, d_sidx.alloc((size_t)n * sizeof(int)));
+  NNGP_CUDA(c, ties.alloc(sizeof(int)));
+  NNGP_CUDA(c, knn_keys_launch(d_coords, n, u_in.as<double>(), idx_in.as<int>(), c->stream));
+  size_t tmp_bytes = 0;
+  NNGP_CUDA(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, u_in.as<double>(), d_u.as<double>(),
+                                               idx_in.as<int>(), d_sidx.as<int>(), n, 0, 64, c->stream));
+  NNGP_CUDA(c, tmp.alloc(tmp_bytes));
+  NNGP_CUDA(c, cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, u_in.as<double>(), d_u.as<double>(),
+                                               idx_in.as<int>(), d_sidx.as<int>(), n, 0, 64, c->stream));
+  NNGP_CUDA(c, cudaMemsetAsync(ties.p, 0, sizeof(int), c->stream));
+  NNGP_CUDA(c, knn_count_ties_launch(d_u.as<double>(), n, ties.as<int>(), c->stream));
+  c->launches += 4;
+  int nt = 0;
+  NNGP_CUDA(c, cudaMemcpyAsync(&nt, ties.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
+  *n_ties = nt;
+  if (nt > 0) {  // exact tie order: replay the reference's serial sort (src/nn.cpp:238-243)
+    std::vector<double> u((size_t)n);
+    std::vector<int> idx((size_t)n);
+    NNGP_CUDA(c, cudaMemcpy(u.data(), u_in.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++) idx[i] = i;
+    host_rsort_with_index(u.data(), idx.data(), n);
+    NNGP_CUDA(c, cudaMemcpy(d_u.p, u.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+    NNGP_CUDA(c, cudaMemcpy(d_sidx.p, idx.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  return NNGP_OK;
+}
+
+static int upload_sites(nngp_ctx *c, const double *coords, int n, DevBuf &d) {
+  std::vector<double2> xy((size_t)n);
+  for (int i = 0; i < n; i++) xy[i] = make_double2(coords[i], coords[(size_t)n + i]);
+  NNGP_CUDA(c, d.alloc((size_t)n * sizeof(double2)));
+  NNGP_CUDA(c, cudaMemcpy(d.p, xy.data(), (size_t)n * sizeof(double2), cudaMemcpyHostToDevice));
+  return NNGP_OK;
+}
+
+}  // namespace nngp
+
+using namespace nngp;
+
+extern "C" {
+
+int nngp_mk_nn_indx(nngp_ctx *c, int n, int m, const double *coords, int search_type, int *nnIndx, double *nnDist,
+                    int *nnIndxLU, int *n_tie_replayed) {
+  if (!c) return NNGP_EINVAL;
+  if (n < 1 || m < 1 || !coords || !nnIndx || !nnDist || !nnIndxLU) return ctx_fail(c, NNGP_EINVAL, "nngp_mk_nn_indx: bad arguments");
+  if (m > NNGP_MAX_M) return ctx_fail(c, NNGP_EINVAL, "nngp_mk_nn_indx: n.neighbors > 32 is not supported");
+  if (search_type != NNGP_SEARCH_BRUTE && search_type != NNGP_SEARCH_CB) return ctx_fail(c, NNGP_EINVAL, "search.type must be brute (0) or cb (1)");
+  NNGP_CUDA(c, cudaSetDevice(c->device));
+  const long long nIndx = nn_offset(n, m);
+  DevBuf d_coords, d_idx, d_dist;
+  int rc = upload_sites(c, coords, n, d_coords);
+  if (rc) return rc;
+  NNGP_CUDA(c, d_idx.alloc((size_t)(nIndx > 0 ? nIndx : 1) * sizeof(int)));
+  NNGP_CUDA(c, d_dist.alloc((size_t)(nIndx > 0 ? nIndx : 1) * sizeof(double)));
+  int nties = 0;
+  if (search_type == NNGP_SEARCH_BRUTE) {
+    NNGP_CUDA(c, knn_brute_launch(d_coords.as<double2>(), n, m, d_idx.as<int>(), d_dist.as<double>(), c->stream));
+    c->launches++;
+  } else {
+    DevBuf d_sidx, d_u, d_sxy;
+    rc = sort_by_u(c, d_coords.as<double2>(), n, d_sidx, d_u, &nties);
+    if (rc) return rc;
+    NNGP_CUDA(c, d_sxy.alloc((size_t)n * sizeof(double2)));
+    NNGP_CUDA(c, knn_gather_launch(d_coords.as<double2>(), d_sidx.as<int>(), n, d_sxy.as<double2>(), c->stream));
+    NNGP_CUDA(c, knn_cb_launch(d_sxy.as<double2>(), d_sidx.as<int>(), n, m, d_idx.as<int>(), d_dist.as<double>(), c->stream));
+    c->launches += 2;
+    NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (nIndx > 0) {
+    NNGP_CUDA(c, cudaMemcpy(nnIndx, d_idx.p, (size_t)nIndx * sizeof(int), cudaMemcpyDeviceToHost));
+    NNGP_CUDA(c, cudaMemcpy(nnDist, d_dist.p, (size_t)nIndx * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  for (int i = 0; i < n; i++) {  // src/util.cpp:55-70 via src/nn.cpp:95-97
+    nnIndxLU[i] = (i == 0) ? 0 : (int)nn_offset(i, m);
+    nnIndxLU[n + i] = nn_count(i, m);
+  }
+  if (n_tie_replayed) *n_tie_replayed = nties;
+  return NNGP_OK;
+}
+
+int nngp_nn_query(nngp_ctx *c, int n, const double *coords, int q, const double *coords0, int m, int *nnIndx0) {
+  if (!c) return NNGP_EINVAL;
+  if (n < 1 || q < 0 || m < 1 || !coords || (q > 0 && (!coords0 || !nnIndx0))) return ctx_fail(c, NNGP_EINVAL, "nngp_nn_query: bad arguments");
+  if (m > NNGP_MAX_M) return ctx_fail(c, NNGP_EINVAL, "nngp_nn_query: k > 32 is not supported");
+  if (q == 0) return NNGP_OK;
+  NNGP_CUDA(c, cudaSetDevice(c->device));
+  DevBuf d_coords, d_q, d_sidx, d_u, d_sxy, d_out;
+  int rc = upload_sites(c, coords, n, d_coords);
+  if (rc) return rc;
+  rc = upload_sites(c, coords0, q, d_q);
+  if (rc) return rc;
+  int nties = 0;
+  rc = sort_by_u(c, d_coords.as<double2>(), n, d_sidx, d_u, &nties);
+  if (rc) return rc;
+  NNGP_CUDA(c, d_sxy.alloc((size_t)n * sizeof(double2)));
+  NNGP_CUDA(c, d_out.alloc((size_t)q * m * sizeof(int)));
+  NNGP_CUDA(c, knn_gather_launch(d_coords.as<double2>(), d_sidx.as<int>(), n, d_sxy.as<double2>(), c->stream));
+  NNGP_CUDA(c, knn_query_launch(d_sxy.as<double2>(), d_sidx.as<int>(), d_u.as<double>(), n, d_q.as<double2>(), q, m,
+                                d_out.as<int>(), c->stream));
+  c->launches += 2;
+  NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
+  NNGP_CUDA(c, cudaMemcpy(nnIndx0, d_out.p, (size_t)q * m * sizeof(int), cudaMemcpyDeviceToHost));
+  return NNGP_OK;
+}
+
+}  // extern "C"

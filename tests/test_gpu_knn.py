@@ -1,0 +1,106 @@
+"""GPU parity: ordered neighbour search through the C ABI vs the CPU oracle -- bit-exact indices and
+nnDist bits, on tie-free and on gridded (heavily tied) sites (SURVEY §8a tie notes)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle.pyoracle import coords_flat, n_indx
+from spnngp_b200._lib import c_double_p, c_int_p
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_mk_nn(engine, coords, m, search):
+    cf = coords_flat(coords); n = cf.size // 2
+    nI = max(n_indx(n, m), 1)
+    nnIndx = np.zeros(nI, dtype=np.int32); nnDist = np.zeros(nI); lu = np.zeros(2 * n, dtype=np.int32)
+    ties = C.c_int(0)
+    st = engine.lib.nngp_mk_nn_indx(engine.h, n, m, cf.ctypes.data_as(c_double_p), search,
+                                    nnIndx.ctypes.data_as(c_int_p), nnDist.ctypes.data_as(c_double_p),
+                                    lu.ctypes.data_as(c_int_p), C.byref(ties))
+    assert st == 0, engine.lib.nngp_last_error(engine.h)
+    return nnIndx, nnDist, lu, ties.value
+
+
+def random_sites(n, seed, sort=True):
+    rng = np.random.default_rng(seed)
+    c = rng.random((n, 2))
+    return c[np.argsort(c[:, 0], kind="stable")] if sort else c
+
+
+def grid_sites(k):
+    g = np.arange(k) / k
+    xx, yy = np.meshgrid(g, g, indexing="ij")
+    return np.column_stack([xx.ravel(), yy.ravel()])  # ordered by x: ties everywhere
+
+
+@pytest.mark.parametrize("n,m", [(5000, 15), (3000, 32), (20, 5), (700, 1), (2000, 9)])
+@pytest.mark.parametrize("search", [0, 1])
+def test_knn_random_bit_exact(engine, port, n, m, search):
+    coords = random_sites(n, n + m)
+    ref = (port.mk_nn_indx if search == 0 else port.mk_nn_indx_cb)(coords, m)
+    got = gpu_mk_nn(engine, coords, m, search)
+    assert np.array_equal(got[0], ref[0])
+    assert np.array_equal(got[1].view(np.int64), ref[1].view(np.int64))  # nnDist bits
+    assert np.array_equal(got[2], ref[2])
+
+
+def test_knn_unsorted_order(engine, port):
+    """Arbitrary NNGP ordering (not x-sorted): predecessors are an arbitrary subset."""
+    coords = random_sites(3000, 77, sort=False)
+    for search, fn in ((0, port.mk_nn_indx), (1, port.mk_nn_indx_cb)):
+        ref = fn(coords, 10)
+        got = gpu_mk_nn(engine, coords, 10, search)
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1].view(np.int64), ref[1].view(np.int64))
+
+
+@pytest.mark.parametrize("m", [8, 15, 32])
+@pytest.mark.parametrize("search", [0, 1])
+def test_knn_grid_ties_bit_exact(engine, port, m, search):
+    """40 x 40 grid: distance ties at almost every location, and ties in u = x + y for the code-book
+    sort.  The reference's Shell-sort tie order is replayed, so indices still match exactly."""
+    coords = grid_sites(40)
+    ref = (port.mk_nn_indx if search == 0 else port.mk_nn_indx_cb)(coords, m)
+    got = gpu_mk_nn(engine, coords, m, search)
+    assert np.array_equal(got[0], ref[0])
+    assert np.array_equal(got[1].view(np.int64), ref[1].view(np.int64))
+    if search == 1:
+        assert got[3] > 0  # u-ties detected -> exact host sort path taken
+
+
+def test_brute_equals_cb_on_tie_free_sites(engine):
+    """Documented invariant of the reference (man/spNNGP.Rd:110-119)."""
+    coords = random_sites(20000, 5)
+    a = gpu_mk_nn(engine, coords, 15, 0)
+    b = gpu_mk_nn(engine, coords, 15, 1)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.int64), b[1].view(np.int64))
+
+
+def test_neighbours_are_sorted_predecessors(engine):
+    """Size-independent properties: ids < i, ascending distances, distances recomputable."""
+    n, m = 50000, 15
+    coords = random_sites(n, 9)
+    idx, dist, lu, _ = gpu_mk_nn(engine, coords, m, 1)
+    off, cnt = lu[:n], lu[n:]
+    assert np.all(cnt == np.minimum(np.arange(n), m))
+    rows = np.repeat(np.arange(n), cnt)
+    assert np.all(idx < rows)
+    d = np.sqrt(((coords[rows] - coords[idx]) ** 2).sum(1))
+    assert np.allclose(d, dist, rtol=1e-15)
+    full = np.arange(m, n)
+    D = dist[off[m]:].reshape(-1, m)
+    assert np.all(np.diff(D, axis=1) >= 0) and len(full) == D.shape[0]
+
+
+@pytest.mark.parametrize("n,q,m", [(4000, 1500, 15), (300, 50, 32), (50, 7, 3)])
+def test_nn_query_matches_exhaustive(engine, port, n, q, m):
+    coords = random_sites(n, 3, sort=False)
+    coords0 = np.random.default_rng(4).random((q, 2))
+    ref = port.nn_query(coords, coords0, m)
+    cf, c0 = coords_flat(coords), coords_flat(coords0)
+    out = np.zeros(q * m, dtype=np.int32)
+    st = engine.lib.nngp_nn_query(engine.h, n, cf.ctypes.data_as(c_double_p), q, c0.ctypes.data_as(c_double_p), m,
+                                  out.ctypes.data_as(c_int_p))
+    assert st == 0
+    assert np.array_equal(out, ref)
