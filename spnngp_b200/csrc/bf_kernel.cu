@@ -26,6 +26,7 @@
 //     the partials in fixed order, so results are run-to-run deterministic.
 //   No tensor cores: each solve is a tiny FP64 problem (BASELINE.json north_star).
 #include <limits.h>
+#include <stdlib.h>
 
 #include "cov.cuh"
 
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(128, (M <= 16 ? 4 : 2)) bf_kernel(const __grid
   const BfTheta &th = P.th[blockIdx.y];
   const Cor<COV> cor(th);
   const int m = P.m;
+  const bool site = P.site_mode != 0;  // prediction: query sites with unordered neighbour lists
   const double sigmaSq = th.sigmaSq, tauSq = th.tauSq;
   const double *__restrict__ resid = th.resid;
 
@@ -75,14 +77,15 @@ __global__ void __launch_bounds__(128, (M <= 16 ? 4 : 2)) bf_kernel(const __grid
        base += (long long)gridDim.x * G) {
     const long long i = base + g;
     const bool active = i < P.loc_end;
-    const int mi = active ? nn_count(i, m) : 0;
-    const long long off = active ? nn_offset(i, m) : 0;
+    const int mi = active ? (site ? m : nn_count(i, m)) : 0;
+    const long long off = (active && !site) ? nn_offset(i, m) : 0;
 
     // ---- 1. gather this thread's two neighbour sites -------------------------------------------
-    const int idx_lo = (r < mi) ? __ldg(&P.nnIndx[off + r]) : -1;
-    const int idx_hi = (h < mi) ? __ldg(&P.nnIndx[off + h]) : -1;
+    int idx_lo = -1, idx_hi = -1;
+    if (r < mi) idx_lo = site ? __ldg(&P.nn0[(size_t)r * P.q + i]) : __ldg(&P.nnIndx[off + r]);
+    if (h < mi) idx_hi = site ? __ldg(&P.nn0[(size_t)h * P.q + i]) : __ldg(&P.nnIndx[off + h]);
     const double2 zero2 = make_double2(0.0, 0.0);
-    const double2 me = active ? __ldg(&P.coords[i]) : zero2;
+    const double2 me = active ? (site ? __ldg(&P.sites[i]) : __ldg(&P.coords[i])) : zero2;
     const double2 plo = (idx_lo >= 0) ? __ldg(&P.coords[idx_lo]) : zero2;
     const double2 phi_ = (idx_hi >= 0) ? __ldg(&P.coords[idx_hi]) : zero2;
     nbr[r] = plo;
@@ -212,8 +215,13 @@ __global__ void __launch_bounds__(128, (M <= 16 ? 4 : 2)) bf_kernel(const __grid
     // ---- 6. outputs and the fused likelihood terms -----------------------------------------------
     const double Fv = sigmaSq + tauSq - Fsum;
     if (th.B != nullptr) {
-      if (lo_real) th.B[off + r] = w_lo;
-      if (hi_real) th.B[off + h] = w_hi;
+      if (site) {  // q x m column-major weights
+        if (lo_real) th.B[(size_t)r * P.q + i] = w_lo;
+        if (hi_real) th.B[(size_t)h * P.q + i] = w_hi;
+      } else {
+        if (lo_real) th.B[off + r] = w_lo;
+        if (hi_real) th.B[off + h] = w_hi;
+      }
     }
     if (th.F != nullptr && r == 0 && active) th.F[i] = Fv;
     double part = 0.0;
@@ -223,7 +231,7 @@ __global__ void __launch_bounds__(128, (M <= 16 ? 4 : 2)) bf_kernel(const __grid
     }
 #pragma unroll
     for (int s = T / 2; s >= 1; s >>= 1) part += __shfl_xor_sync(0xffffffffu, part, s, T);
-    if (r == 0 && active) {
+    if (r == 0 && active && !site) {
       lsum += log(Fv);
       if (resid != nullptr) {
         const double e = __ldg(&resid[i]) - part;
@@ -320,11 +328,44 @@ int bf_grid_for(int m, long long nloc, int sms) {
   return (int)g;
 }
 
-cudaError_t bf_launch(const BfLaunch &P, int cov, int grid_x, cudaStream_t stream) {
+cudaError_t coop_launch(const BfLaunch &P, int cov, int grid_x, cudaStream_t stream) {
   const int M = bf_tile_for_m(P.m);
   if (M == 8) return launch_cov<8>(P, cov, grid_x, stream);
   if (M == 16) return launch_cov<16>(P, cov, grid_x, stream);
   return launch_cov<32>(P, cov, grid_x, stream);
+}
+
+// bf_tpl_kernel.cu
+int tpl_capacity_for_m(int m);
+int tpl_grid_for(int m, long long nloc, int sms);
+cudaError_t tpl_launch(const BfLaunch &P, int cov, int grid_x, cudaStream_t stream);
+
+// Kernel choice: thread-per-location for m <= 16, the cooperative warp-group kernel above it.
+// NNGP_FORCE_COOP=1 in the environment selects the cooperative kernel for every m (A/B profiling).
+// Matern stays on the cooperative kernel: its Bessel-K evaluation is a data-dependent loop that cannot
+// be interleaved across entries, so one-lane-per-location runs it latency-bound (measured 2.4x slower).
+static bool use_tpl(int m, int cov) {
+  static int force_coop = -1;
+  if (force_coop < 0) {
+    const char *e = getenv("NNGP_FORCE_COOP");
+    force_coop = (e && e[0] == '1') ? 1 : 0;
+  }
+  return !force_coop && cov != NNGP_COV_MATERN && tpl_capacity_for_m(m) > 0;
+}
+
+int bf_grid_any(int m, int cov, long long nloc, int sms) {
+  return use_tpl(m, cov) ? tpl_grid_for(m, nloc, sms) : bf_grid_for(m, nloc, sms);
+}
+
+// upper bound of bf_grid_any over both kernels (for sizing the partial-sum scratch)
+int bf_grid_max(int m, long long nloc, int sms) {
+  int a = bf_grid_for(m, nloc, sms);
+  int b = tpl_capacity_for_m(m) > 0 ? tpl_grid_for(m, nloc, sms) : 0;
+  return a > b ? a : b;
+}
+
+cudaError_t bf_launch(const BfLaunch &P, int cov, int grid_x, cudaStream_t stream) {
+  return use_tpl(P.m, cov) ? tpl_launch(P, cov, grid_x, stream) : coop_launch(P, cov, grid_x, stream);
 }
 
 }  // namespace nngp

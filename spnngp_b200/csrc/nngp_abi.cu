@@ -206,7 +206,7 @@ int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const 
   }
   const long long nloc = (long long)loc_end - loc_begin;
   const int K = p + 1, npairs = K * (K + 1) / 2;
-  size_t need = (size_t)2 * NNGP_MAX_BATCH * bf_grid_for(m, nloc, c->sms);
+  size_t need = (size_t)2 * NNGP_MAX_BATCH * bf_grid_max(m, nloc, c->sms);
   size_t need2 = (size_t)q_forms_grid(nloc) * npairs;
   size_t need3 = (size_t)q_resid_grid(m, nloc, c->sms);
   c->partials_len = need > need2 ? need : need2;
@@ -224,7 +224,7 @@ static int prepare_bf(nngp_ctx *c, int cov, int nbatch, const double *theta, con
   if (nbatch < 1 || nbatch > NNGP_MAX_BATCH) return ctx_fail(c, NNGP_EINVAL, "nbatch must be in 1..4");
   if (cov < 0 || cov > 3) return ctx_fail(c, NNGP_EINVAL, "cov.model is not correctly specified");
   if (beta && c->p == 0) return ctx_fail(c, NNGP_EINVAL, "beta given but the model has no covariates");
-  const int grid = bf_grid_for(c->m, (long long)c->loc_end - c->loc_begin, c->sms);
+  const int grid = bf_grid_any(c->m, cov, (long long)c->loc_end - c->loc_begin, c->sms);
   memset(P, 0, sizeof *P);
   P->coords = c->d_coords;
   P->nnIndx = c->d_nnIndx;

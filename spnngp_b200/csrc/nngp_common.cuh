@@ -35,6 +35,12 @@ struct BfLaunch {
   int n, m;
   int loc_begin, loc_end;
   int nbatch;
+  // site mode (prediction paths): "locations" are q query sites with unordered m-neighbour lists;
+  // th.B receives the kriging weights as a q x m column-major matrix, th.F the q conditional variances
+  int site_mode;
+  const double2 *sites;  // q interleaved query sites
+  const int *nn0;        // q x m column-major neighbour ids (R/generics.R:642 layout)
+  int q;
   BfTheta th[NNGP_MAX_BATCH];
 };
 

@@ -53,6 +53,8 @@ namespace nngp {
 int bf_tile_for_m(int m);
 int bf_locations_per_cta(int m);
 int bf_grid_for(int m, long long nloc, int sms);
+int bf_grid_any(int m, int cov, long long nloc, int sms);
+int bf_grid_max(int m, long long nloc, int sms);
 cudaError_t bf_launch(const BfLaunch &P, int cov, int grid_x, cudaStream_t stream);
 
 // q_kernels.cu

@@ -1,0 +1,6 @@
+// Host build of spnngp_b200/csrc/fastmath.cuh for CPU-side validation against libm.
+#include "../../spnngp_b200/csrc/fastmath.cuh"
+extern "C" {
+double host_nngp_sqrt(double x) { return nngp::nngp_sqrt(x); }
+double host_nngp_exp_nonpos(double x) { return nngp::nngp_exp_nonpos(x); }
+}
