@@ -206,7 +206,7 @@ int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const 
   }
   const long long nloc = (long long)loc_end - loc_begin;
   const int K = p + 1, npairs = K * (K + 1) / 2;
-  size_t need = (size_t)2 * NNGP_MAX_BATCH * bf_grid_max(m, nloc, c->sms);
+  size_t need = (size_t)2 * NNGP_MAX_BATCH * bf_grid_max(m, (long long)1 << 40, c->sms);  // also covers site-mode launches
   size_t need2 = (size_t)q_forms_grid(nloc) * npairs;
   size_t need3 = (size_t)q_resid_grid(m, nloc, c->sms);
   c->partials_len = need > need2 ? need : need2;

@@ -1,0 +1,283 @@
+// nngp_abi_predict.cu -- C ABI for the kNN + solve prediction paths (include/nngp_b200.h):
+//   nngp_rnngp_predict  replaces `rNNGPPredict` (reference src/rNNGPPredict.cpp:25-222)
+//   nngp_cnngp          replaces `cNNGP`        (reference src/cNNGP.cpp:73-357)
+// The m x m solves run in the B/F kernels' site mode; sites are processed in chunks so that the
+// q x nSamples normals and predictions never have to be resident at once.
+#include <limits.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <vector>
+
+#include "host_linalg.h"
+#include "nngp_ctx.h"
+
+namespace nngp {
+cudaError_t site_reduce_launch(const double *W, const int *nn0, const double *X, const double *y, const double *X0,
+                               int n, int p, int m, int cs, double *a, double *U, cudaStream_t stream);
+cudaError_t predict_emit_launch(const double *a, const double *U, const double *F, const double *beta, const double *z,
+                                const int *samples, int nsamp, int p, int cs, int S, double *y0c, cudaStream_t stream);
+cudaError_t conj_emit_launch(const double *a, const double *U, const double *F, const double *betaHat, const double *V,
+                             int p, int cs, double bIG, double aIG, double *y0Hat, double *y0HatVar,
+                             cudaStream_t stream);
+
+namespace {
+
+struct Dev {
+  void *p = nullptr;
+  ~Dev() {
+    if (p) cudaFree(p);
+  }
+  cudaError_t alloc(size_t bytes) {
+    if (p) cudaFree(p);
+    p = nullptr;
+    return cudaMalloc(&p, bytes ? bytes : 1);
+  }
+  template <typename Tp>
+  Tp *as() const {
+    return reinterpret_cast<Tp *>(p);
+  }
+};
+
+// device-side description of one chunk of query sites
+struct SiteChunk {
+  int cs = 0;
+  Dev sites, nn0, X0, W, F, a, U;
+};
+
+int upload_chunk(nngp_ctx *c, SiteChunk &ch, int q, int i0, int i1, const double *X0, const double *coords0,
+                 const int *nnIndx0) {
+  const int cs = i1 - i0, m = c->m, p = c->p;
+  ch.cs = cs;
+  std::vector<double2> xy((size_t)cs);
+  for (int i = 0; i < cs; i++) xy[i] = make_double2(coords0[i0 + i], coords0[(size_t)q + i0 + i]);
+  std::vector<int> nn((size_t)cs * m);
+  for (int k = 0; k < m; k++) {
+    const int *src = nnIndx0 + (size_t)k * q + i0;
+    for (int i = 0; i < cs; i++) {
+      if (src[i] < 0 || src[i] >= c->n) return ctx_fail(c, NNGP_EINVAL, "prediction neighbour index out of range");
+      nn[(size_t)k * cs + i] = src[i];
+    }
+  }
+  std::vector<double> x0((size_t)cs * (p > 0 ? p : 1));
+  for (int cc = 0; cc < p; cc++) memcpy(&x0[(size_t)cc * cs], X0 + (size_t)cc * q + i0, (size_t)cs * sizeof(double));
+  NNGP_CUDA(c, ch.sites.alloc((size_t)cs * sizeof(double2)));
+  NNGP_CUDA(c, ch.nn0.alloc((size_t)cs * m * sizeof(int)));
+  NNGP_CUDA(c, ch.X0.alloc((size_t)cs * (p > 0 ? p : 1) * sizeof(double)));
+  NNGP_CUDA(c, ch.W.alloc((size_t)cs * m * sizeof(double)));
+  NNGP_CUDA(c, ch.F.alloc((size_t)cs * sizeof(double)));
+  NNGP_CUDA(c, ch.a.alloc((size_t)cs * sizeof(double)));
+  NNGP_CUDA(c, ch.U.alloc((size_t)cs * (p > 0 ? p : 1) * sizeof(double)));
+  NNGP_CUDA(c, cudaMemcpy(ch.sites.p, xy.data(), (size_t)cs * sizeof(double2), cudaMemcpyHostToDevice));
+  NNGP_CUDA(c, cudaMemcpy(ch.nn0.p, nn.data(), (size_t)cs * m * sizeof(int), cudaMemcpyHostToDevice));
+  if (p > 0) NNGP_CUDA(c, cudaMemcpy(ch.X0.p, x0.data(), (size_t)cs * p * sizeof(double), cudaMemcpyHostToDevice));
+  return NNGP_OK;
+}
+
+// kriging weights W (cs x m column-major) and conditional variances F for theta = (s2, t2, phi, nu),
+// followed by the per-site reductions a = w.y_N and U = x0 - X_N'w.  Synchronises the stream.
+int site_solve(nngp_ctx *c, int cov, const double *t, SiteChunk &ch) {
+  BfLaunch P;
+  memset(&P, 0, sizeof P);
+  P.coords = c->d_coords;
+  P.n = c->n;
+  P.m = c->m;
+  P.loc_begin = 0;
+  P.loc_end = ch.cs;
+  P.nbatch = 1;
+  P.site_mode = 1;
+  P.sites = ch.sites.as<double2>();
+  P.nn0 = ch.nn0.as<int>();
+  P.q = ch.cs;
+  BfTheta &th = P.th[0];
+  th.sigmaSq = t[0];
+  th.tauSq = t[1];
+  th.phi = t[2];
+  th.mat = nullptr;
+  if (cov == NNGP_COV_MATERN) {
+    matern_prepare(t[3], &c->h_mat[0]);
+    NNGP_CUDA(c, cudaMemcpyAsync(c->d_mat, c->h_mat, sizeof(MaternConsts), cudaMemcpyHostToDevice, c->stream));
+    th.mat = c->d_mat;
+  }
+  double *out_dev = nullptr;
+  int *fail_dev = nullptr;
+  NNGP_CUDA(c, cudaHostGetDevicePointer((void **)&out_dev, c->h_out, 0));
+  NNGP_CUDA(c, cudaHostGetDevicePointer((void **)&fail_dev, c->h_fail, 0));
+  th.B = ch.W.as<double>();
+  th.F = ch.F.as<double>();
+  th.resid = nullptr;
+  th.out = out_dev;
+  th.partials = c->d_partials;
+  th.ticket = c->d_ticket;
+  th.fail = c->d_fail;
+  th.fail_out = fail_dev;
+  const int grid = bf_grid_any(c->m, cov, ch.cs, c->sms);
+  NNGP_CUDA(c, bf_launch(P, cov, grid, c->stream));
+  NNGP_CUDA(c, site_reduce_launch(ch.W.as<double>(), ch.nn0.as<int>(), c->d_X, c->d_y, ch.X0.as<double>(), c->n, c->p,
+                                  c->m, ch.cs, ch.a.as<double>(), ch.U.as<double>(), c->stream));
+  c->launches += 2;
+  NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->h_fail[0] != INT_MAX) return ctx_fail(c, c->h_fail[0], "c++ error: dpotrf failed (prediction neighbour covariance)");
+  return NNGP_OK;
+}
+
+}  // namespace
+}  // namespace nngp
+
+using namespace nngp;
+
+extern "C" {
+
+int nngp_rnngp_predict(nngp_ctx *c, int cov, int q, const double *X0, const double *coords0, const int *nnIndx0,
+                       int nSamples, const double *betaSamples, const double *thetaSamples, const double *z,
+                       double *y0, int site_begin, int site_end) {
+  if (!c) return NNGP_EINVAL;
+  if (c->n == 0 || c->p == 0) return ctx_fail(c, NNGP_ESTATE, "nngp_rnngp_predict before nngp_set_data");
+  if (q < 1 || nSamples < 1 || !X0 || !coords0 || !nnIndx0 || !betaSamples || !thetaSamples || !z || !y0)
+    return ctx_fail(c, NNGP_EINVAL, "nngp_rnngp_predict: bad arguments");
+  if (cov < 0 || cov > 3) return ctx_fail(c, NNGP_EINVAL, "cov.model is not correctly specified");
+  if (site_begin < 0 || site_end > q || site_begin > site_end) return ctx_fail(c, NNGP_EINVAL, "bad site range");
+  NNGP_CUDA(c, cudaSetDevice(c->device));
+  const int p = c->p, S = nSamples;
+  const int nTheta = (cov == NNGP_COV_MATERN) ? 4 : 3;
+
+  // group the samples by distinct theta: rejected Metropolis proposals repeat the previous column
+  std::map<std::vector<double>, int> index;
+  std::vector<std::vector<int>> groups;
+  std::vector<std::vector<double>> thetas;
+  for (int s = 0; s < S; s++) {
+    std::vector<double> key(thetaSamples + (size_t)s * nTheta, thetaSamples + (size_t)(s + 1) * nTheta);
+    auto it = index.find(key);
+    if (it == index.end()) {
+      index.emplace(key, (int)groups.size());
+      groups.emplace_back(1, s);
+      key.resize(4, 0.0);
+      thetas.push_back(key);
+    } else {
+      groups[it->second].push_back(s);
+    }
+  }
+
+  Dev d_beta, d_samples, d_z, d_y0;
+  NNGP_CUDA(c, d_beta.alloc((size_t)p * S * sizeof(double)));
+  NNGP_CUDA(c, cudaMemcpy(d_beta.p, betaSamples, (size_t)p * S * sizeof(double), cudaMemcpyHostToDevice));
+  std::vector<int> flat;
+  std::vector<int> gofs(groups.size() + 1, 0);
+  for (size_t g = 0; g < groups.size(); g++) {
+    gofs[g + 1] = gofs[g] + (int)groups[g].size();
+    flat.insert(flat.end(), groups[g].begin(), groups[g].end());
+  }
+  NNGP_CUDA(c, d_samples.alloc(flat.size() * sizeof(int)));
+  NNGP_CUDA(c, cudaMemcpy(d_samples.p, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice));
+
+  // chunk of sites: keep z and y0 of a chunk (2 x cs x S doubles) within ~2 GiB
+  long long cs_max = ((long long)1 << 30) / ((long long)8 * S);
+  if (cs_max < 1024) cs_max = 1024;
+  if (cs_max > 1 << 20) cs_max = 1 << 20;
+  for (int i0 = site_begin; i0 < site_end; i0 += (int)cs_max) {
+    const int i1 = (int)std::min<long long>(site_end, (long long)i0 + cs_max);
+    const int cs = i1 - i0;
+    SiteChunk ch;
+    int rc = upload_chunk(c, ch, q, i0, i1, X0, coords0, nnIndx0);
+    if (rc) return rc;
+    NNGP_CUDA(c, d_z.alloc((size_t)cs * S * sizeof(double)));
+    NNGP_CUDA(c, d_y0.alloc((size_t)cs * S * sizeof(double)));
+    NNGP_CUDA(c, cudaMemcpy(d_z.p, z + (size_t)i0 * S, (size_t)cs * S * sizeof(double), cudaMemcpyHostToDevice));
+    for (size_t g = 0; g < groups.size(); g++) {
+      rc = site_solve(c, cov, thetas[g].data(), ch);
+      if (rc) return rc;
+      NNGP_CUDA(c, predict_emit_launch(ch.a.as<double>(), ch.U.as<double>(), ch.F.as<double>(), d_beta.as<double>(),
+                                       d_z.as<double>(), d_samples.as<int>() + gofs[g], (int)groups[g].size(), p, cs, S,
+                                       d_y0.as<double>(), c->stream));
+      c->launches++;
+    }
+    NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
+    // y0 is q x S column-major on the host: one strided copy per chunk
+    NNGP_CUDA(c, cudaMemcpy2D(y0 + i0, (size_t)q * sizeof(double), d_y0.p, (size_t)cs * sizeof(double),
+                              (size_t)cs * sizeof(double), (size_t)S, cudaMemcpyDeviceToHost));
+  }
+  return NNGP_OK;
+}
+
+int nngp_cnngp(nngp_ctx *c, int cov, int g, const double *thetaAlpha, const double sigmaSqIG[2], int n0,
+               const double *X0, const double *coords0, const int *nnIndx0, double *betaHat, double *ab, double *bBInv,
+               double *bb, double *y0Hat, double *y0HatVar) {
+  if (!c) return NNGP_EINVAL;
+  if (c->n == 0 || c->p == 0) return ctx_fail(c, NNGP_ESTATE, "nngp_cnngp before nngp_set_data");
+  if (g < 1 || !thetaAlpha || !sigmaSqIG || !betaHat || !ab || !bBInv || !bb) return ctx_fail(c, NNGP_EINVAL, "nngp_cnngp: bad arguments");
+  if (n0 > 0 && (!X0 || !coords0 || !nnIndx0 || !y0Hat || !y0HatVar)) return ctx_fail(c, NNGP_EINVAL, "nngp_cnngp: prediction inputs missing");
+  if (cov < 0 || cov > 3) return ctx_fail(c, NNGP_EINVAL, "cov.model is not correctly specified");
+  NNGP_CUDA(c, cudaSetDevice(c->device));
+  const int p = c->p, K = p + 1, n = c->n;
+  const int nTheta = (cov == NNGP_COV_MATERN) ? 3 : 2;
+  std::vector<double> S((size_t)K * K), V((size_t)p * p), tmp_p(p);
+  Dev d_bh, d_V, d_y0, d_y0v;
+  NNGP_CUDA(c, d_bh.alloc(p * sizeof(double)));
+  NNGP_CUDA(c, d_V.alloc((size_t)p * p * sizeof(double)));
+
+  const int cs_max = 1 << 20;
+  std::vector<SiteChunk> chunks;  // the query sites do not change across parameter sets: upload once
+  if (n0 > 0) {
+    const int nchunks = (n0 + cs_max - 1) / cs_max;
+    chunks.resize(nchunks);
+    for (int k = 0; k < nchunks; k++) {
+      const int i0 = k * cs_max, i1 = std::min(n0, i0 + cs_max);
+      int rc = upload_chunk(c, chunks[k], n0, i0, i1, X0, coords0, nnIndx0);
+      if (rc) return rc;
+    }
+    NNGP_CUDA(c, d_y0.alloc((size_t)std::min(n0, cs_max) * sizeof(double)));
+    NNGP_CUDA(c, d_y0v.alloc((size_t)std::min(n0, cs_max) * sizeof(double)));
+  }
+
+  for (int k = 0; k < g; k++) {  // src/cNNGP.cpp:215-316
+    const double phi = thetaAlpha[(size_t)k * nTheta], alpha = thetaAlpha[(size_t)k * nTheta + 1];
+    const double nu = (cov == NNGP_COV_MATERN) ? thetaAlpha[(size_t)k * nTheta + 2] : 0.0;
+    const double theta[4] = {1.0, alpha, phi, nu};  // updateConjBF == updateBF with (s2, t2) = (1, alpha)
+    double out2[2];
+    int slot0 = 0;
+    int rc = nngp_bf_loglik(c, cov, 1, theta, nullptr, &slot0, out2);
+    if (rc) return rc;
+    rc = nngp_q_forms(c, 0, S.data());
+    if (rc) return rc;
+    for (int i = 0; i < p; i++) {
+      tmp_p[i] = S[(size_t)p * K + i];                                   // X'C^-1 y   (:228)
+      for (int j = 0; j <= i; j++) V[(size_t)j * p + i] = S[(size_t)j * K + i];  // X'C^-1 X (:230)
+    }
+    if (hl::chol(V.data(), p)) return ctx_fail(c, NNGP_EINVAL, "c++ error: dpotrf failed (X'C^-1X)");
+    hl::chol_inverse(V.data(), p);
+    for (int i = 0; i < p; i++)
+      for (int j = 0; j < i; j++) V[(size_t)i * p + j] = V[(size_t)j * p + i];  // full symmetric
+    double *bh = betaHat + (size_t)k * p;
+    hl::symv(V.data(), p, tmp_p.data(), bh);                               // :239
+    const double aIG = sigmaSqIG[0] + 1.0 * n / 2.0;                       // :242
+    const double bIG = sigmaSqIG[1] + 0.5 * (S[(size_t)p * K + p] - hl::dot(bh, tmp_p.data(), p));  // :245
+    ab[(size_t)k * 2] = aIG;  // stride 2 even for Matern (reference quirk, :242-245)
+    ab[(size_t)k * 2 + 1] = bIG;
+    memcpy(bBInv + (size_t)k * p * p, V.data(), (size_t)p * p * sizeof(double));
+    memcpy(bb + (size_t)k * p, tmp_p.data(), p * sizeof(double));
+
+    if (n0 > 0) {  // :252-300
+      NNGP_CUDA(c, cudaMemcpyAsync(d_bh.p, bh, p * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      NNGP_CUDA(c, cudaMemcpyAsync(d_V.p, V.data(), (size_t)p * p * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      for (size_t ck = 0; ck < chunks.size(); ck++) {
+        SiteChunk &ch = chunks[ck];
+        rc = site_solve(c, cov, theta, ch);
+        if (rc) return rc;
+        NNGP_CUDA(c, conj_emit_launch(ch.a.as<double>(), ch.U.as<double>(), ch.F.as<double>(), d_bh.as<double>(),
+                                      d_V.as<double>(), p, ch.cs, bIG, aIG, d_y0.as<double>(), d_y0v.as<double>(),
+                                      c->stream));
+        c->launches++;
+        const size_t i0 = ck * (size_t)cs_max;
+        NNGP_CUDA(c, cudaMemcpyAsync(y0Hat + (size_t)k * n0 + i0, d_y0.p, (size_t)ch.cs * sizeof(double),
+                                     cudaMemcpyDeviceToHost, c->stream));
+        NNGP_CUDA(c, cudaMemcpyAsync(y0HatVar + (size_t)k * n0 + i0, d_y0v.p, (size_t)ch.cs * sizeof(double),
+                                     cudaMemcpyDeviceToHost, c->stream));
+        NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
+      }
+    }
+  }
+  return NNGP_OK;
+}
+
+}  // extern "C"

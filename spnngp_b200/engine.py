@@ -182,3 +182,53 @@ class Engine:
         acc = C.c_int(0)
         self._check(self.lib.nngp_rnngp(self.h, C.byref(a), _dp(bs), _dp(ts), C.byref(acc)))
         return bs.reshape(n_samples, self.p).T.copy(), ts.reshape(n_samples, nTheta).T.copy(), int(acc.value)
+
+    def rnngp_predict(self, cov, X0, coords0, nnIndx0, beta_samples, theta_samples, z, site_range=None):
+        """Posterior predictive draws (reference `rNNGPPredict`, src/rNNGPPredict.cpp:25).
+        beta_samples p x S, theta_samples nTheta x S, nnIndx0 flat q*m column-major, z flat q*S (z[i*S+s]).
+        Returns q x S."""
+        X0 = np.asarray(X0, dtype=np.float64).reshape(-1, self.p); q = X0.shape[0]
+        bs = np.asarray(beta_samples, dtype=np.float64); S = bs.shape[1]
+        x0f = colmajor(X0); c0 = colmajor(coords0); nn0 = _i32(nnIndx0)
+        bsf = colmajor(bs); tsf = colmajor(np.asarray(theta_samples, dtype=np.float64)); zf = _f64(z)
+        y0 = np.zeros(q * S)
+        lo, hi = site_range if site_range is not None else (0, q)
+        self._check(self.lib.nngp_rnngp_predict(self.h, cov, q, _dp(x0f), _dp(c0), _ip(nn0), S, _dp(bsf), _dp(tsf),
+                                                _dp(zf), _dp(y0), lo, hi))
+        return y0.reshape(S, q).T.copy()
+
+    def cnngp(self, cov, theta_alpha, sigmaSqIG, X0=None, coords0=None, nnIndx0=None):
+        """Conjugate model for g parameter sets (reference `cNNGP`, src/cNNGP.cpp:73).
+        theta_alpha: nTheta x g rows (phi, alpha[, nu])."""
+        ta = np.asarray(theta_alpha, dtype=np.float64); nTheta, g = ta.shape
+        taf = colmajor(ta); ig = _f64(sigmaSqIG); p = self.p
+        if X0 is None:
+            n0 = 0; x0p = c0p = nnp = None
+        else:
+            X0 = np.asarray(X0, dtype=np.float64).reshape(-1, p); n0 = X0.shape[0]
+            x0f = colmajor(X0); c0 = colmajor(coords0); nn0 = _i32(nnIndx0)
+            x0p, c0p, nnp = _dp(x0f), _dp(c0), _ip(nn0)
+        bh = np.zeros(p * g); ab = np.zeros(nTheta * g); bBi = np.zeros(p * p * g); bb = np.zeros(p * g)
+        y0 = np.zeros(max(n0 * g, 1)); y0v = np.zeros(max(n0 * g, 1))
+        self._check(self.lib.nngp_cnngp(self.h, cov, g, _dp(taf), _dp(ig), n0, x0p, c0p, nnp, _dp(bh), _dp(ab), _dp(bBi),
+                                        _dp(bb), _dp(y0), _dp(y0v)))
+        return dict(beta_hat=bh.reshape(g, p).T.copy(), ab=ab, bB_inv=bBi.reshape(g, p * p).T.copy(),
+                    bb=bb.reshape(g, p).T.copy(), y0_hat=y0[: n0 * g].reshape(g, n0).T.copy(),
+                    y0_hat_var=y0v[: n0 * g].reshape(g, n0).T.copy())
+
+    def mk_nn_indx(self, coords, m, search_type="cb"):
+        """Ordered neighbour search (reference `mkNNIndx` / `mkNNIndxCB`, src/nn.cpp:63,214)."""
+        cf = colmajor(coords); n = cf.size // 2
+        nI = max(n_indx(n, m), 1)
+        nnIndx = np.zeros(nI, dtype=np.int32); nnDist = np.zeros(nI); lu = np.zeros(2 * n, dtype=np.int32)
+        ties = C.c_int(0)
+        st = 0 if search_type in (0, "brute") else 1
+        self._check(self.lib.nngp_mk_nn_indx(self.h, n, m, _dp(cf), st, _ip(nnIndx), _dp(nnDist), _ip(lu), C.byref(ties)))
+        return nnIndx, nnDist, lu
+
+    def nn_query(self, coords, coords0, m):
+        """Unordered query kNN, q x m column-major flat (stand-in for RANN::nn2(...)$nn.idx - 1)."""
+        cf = colmajor(coords); c0 = colmajor(coords0); n = cf.size // 2; q = c0.size // 2
+        out = np.zeros(q * m, dtype=np.int32)
+        self._check(self.lib.nngp_nn_query(self.h, n, _dp(cf), q, _dp(c0), m, _ip(out)))
+        return out

@@ -1,0 +1,82 @@
+"""GPU parity: kNN + solve prediction paths (rNNGPPredict, cNNGP) through the C ABI vs the CPU oracle."""
+import numpy as np
+import pytest
+
+from tests.util import make_problem
+
+pytestmark = pytest.mark.gpu
+
+
+def _chain_like_samples(rng, S, cov, p):
+    """theta columns with repeats (rejected proposals repeat the previous draw)."""
+    nTheta = 4 if cov == 2 else 3
+    th = np.zeros((nTheta, S)); cur = np.array([5.0, 1.0, 6.0, 0.75][:nTheta])
+    for s in range(S):
+        if rng.random() < 0.4:
+            cur = cur * np.exp(0.05 * rng.standard_normal(nTheta))
+            if cov == 2:
+                cur[3] = min(max(cur[3], 0.2), 1.9)
+        th[:, s] = cur
+    beta = np.array([1.0, 5.0, -2.0][:p])[:, None] + 0.1 * rng.standard_normal((p, S))
+    return beta, th
+
+
+@pytest.mark.parametrize("cov,m", [(0, 10), (0, 15), (2, 10), (3, 20), (1, 5)])
+def test_rnngp_predict_parity(engine, port, cov, m):
+    rng = np.random.default_rng(100 + cov + m)
+    prob = make_problem(1500, m, seed=31, port=port, domain=0.55)
+    q, S = 333, 37
+    coords0 = rng.random((q, 2)) * 0.55
+    X0 = np.column_stack([np.ones(q), rng.standard_normal(q)])
+    nn0 = port.nn_query(prob["coords"], coords0, m)
+    beta, theta = _chain_like_samples(rng, S, cov, 2)
+    z = rng.standard_normal(q * S)
+    ref, st = port.predict(prob["X"], prob["y"], prob["coords"], m, X0, coords0, nn0, beta, theta, cov, z)
+    assert st == 0
+    engine.set_data(prob["coords"], prob["nnIndx"], prob["nnIndxLU"], prob["X"], prob["y"], m)
+    got = engine.rnngp_predict(cov, X0, coords0, nn0, beta, theta, z)
+    scale = np.abs(ref).max()
+    assert np.max(np.abs(got - ref)) < 1e-10 * scale
+    # site sharding: two halves reproduce the full result
+    a = engine.rnngp_predict(cov, X0, coords0, nn0, beta, theta, z, site_range=(0, 100))
+    b = engine.rnngp_predict(cov, X0, coords0, nn0, beta, theta, z, site_range=(100, q))
+    assert np.array_equal(a[:100], got[:100]) and np.array_equal(b[100:], got[100:])
+
+
+@pytest.mark.parametrize("cov,m", [(0, 15), (2, 10), (3, 20)])
+def test_cnngp_parity(engine, port, cov, m):
+    rng = np.random.default_rng(7 + cov)
+    prob = make_problem(2000, m, seed=33, port=port, domain=0.63)
+    n0 = 400
+    coords0 = rng.random((n0, 2)) * 0.63
+    X0 = np.column_stack([np.ones(n0), rng.standard_normal(n0)])
+    nn0 = port.nn_query(prob["coords"], coords0, m)
+    phis = [3.0, 6.0, 12.0]; alphas = [0.1, 0.5]
+    rows = [[ph, al] + ([0.8] if cov == 2 else []) for ph in phis for al in alphas]
+    ta = np.array(rows).T  # nTheta x g
+    ig = [2.0, float(np.var(prob["y"]))]
+    ref = port.cnngp(prob["y"], prob["X"], prob["coords"], ta, prob["nnIndx"], prob["nnIndxLU"], X0, coords0, nn0, m, ig, cov)
+    assert ref["status"] == 0
+    engine.set_data(prob["coords"], prob["nnIndx"], prob["nnIndxLU"], prob["X"], prob["y"], m)
+    got = engine.cnngp(cov, ta, ig, X0, coords0, nn0)
+    g = ta.shape[1]
+    assert np.allclose(got["beta_hat"], ref["beta_hat"], rtol=1e-9, atol=1e-12)
+    assert np.allclose(got["ab"][: 2 * g], ref["ab"][: 2 * g], rtol=1e-10)
+    assert np.allclose(got["bb"], ref["bb"], rtol=1e-10)
+    p = 2
+    for k in range(g):  # the reference only defines the lower triangle of bB.inv
+        G = got["bB_inv"][:, k].reshape(p, p).T; R = ref["bB_inv"][:, k].reshape(p, p).T
+        assert np.allclose(np.tril(G), np.tril(R), rtol=1e-9)
+    assert np.allclose(got["y0_hat"], ref["y0_hat"], rtol=1e-9, atol=1e-10 * np.abs(ref["y0_hat"]).max())
+    assert np.allclose(got["y0_hat_var"], ref["y0_hat_var"], rtol=1e-9)
+
+
+def test_cnngp_without_prediction(engine, port):
+    prob = make_problem(900, 10, seed=35, port=port, domain=0.4)
+    ta = np.array([[6.0, 0.2], [3.0, 1.0]]).T
+    ref = port.cnngp(prob["y"], prob["X"], prob["coords"], ta, prob["nnIndx"], prob["nnIndxLU"], None, None, None, 10,
+                     [2.0, 1.0], 0)
+    engine.set_data(prob["coords"], prob["nnIndx"], prob["nnIndxLU"], prob["X"], prob["y"], 10)
+    got = engine.cnngp(0, ta, [2.0, 1.0])
+    assert np.allclose(got["beta_hat"], ref["beta_hat"], rtol=1e-9)
+    assert np.allclose(got["ab"][:4], ref["ab"][:4], rtol=1e-10)
