@@ -163,7 +163,7 @@ long long nngp_launch_count(const nngp_ctx *c) { return c ? c->launches : 0; }
 int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const int *nnIndx, const int *nnIndxLU,
                   const double *X, const double *y, int loc_begin, int loc_end) {
   if (!c) return NNGP_EINVAL;
-  if (n < 1 || m < 1 || p < 0 || !coords || !nnIndx) return ctx_fail(c, NNGP_EINVAL, "nngp_set_data: bad sizes or NULL input");
+  if (n < 1 || m < 1 || p < 0 || !coords) return ctx_fail(c, NNGP_EINVAL, "nngp_set_data: bad sizes or NULL input");
   if (m > NNGP_MAX_M) return ctx_fail(c, NNGP_EINVAL, "nngp_set_data: n.neighbors > 32 is not supported by the warp-group solver");
   if (p > 0 && (!X || !y)) return ctx_fail(c, NNGP_EINVAL, "nngp_set_data: X / y missing");
   if (loc_begin < 0 || loc_end > n || loc_begin > loc_end) return ctx_fail(c, NNGP_EINVAL, "nngp_set_data: bad shard range");
@@ -177,7 +177,8 @@ int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const 
   NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
   free_model(c);
   c->n = n; c->m = m; c->p = p; c->loc_begin = loc_begin; c->loc_end = loc_end;
-  c->nIndx = nn_offset(n, m);  // == (1+m)/2*m + (n-m-1)*m for n > m
+  c->has_nn = (nnIndx != nullptr);  // NULL: prediction-only use (sites, X, y), no B/F storage
+  c->nIndx = c->has_nn ? nn_offset(n, m) : 0;  // == (1+m)/2*m + (n-m-1)*m for n > m
   const long long nI = c->nIndx > 0 ? c->nIndx : 1;
   for (long long k = 0; k < c->nIndx; k++) {
     // neighbours must precede... checked lazily: ids must at least be valid indices
@@ -200,7 +201,7 @@ int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const 
     NNGP_CUDA(c, cudaHostAlloc(&c->h_beta, (size_t)NNGP_MAX_BATCH * p * sizeof(double), cudaHostAllocDefault));
     for (int b = 0; b < NNGP_MAX_BATCH; b++) NNGP_CUDA(c, cudaMalloc(&c->d_resid[b], (size_t)n * sizeof(double)));
   }
-  for (int s = 0; s < 2; s++) {
+  for (int s = 0; s < 2 && c->has_nn; s++) {
     NNGP_CUDA(c, cudaMalloc(&c->d_B[s], (size_t)nI * sizeof(double)));
     NNGP_CUDA(c, cudaMalloc(&c->d_F[s], (size_t)n * sizeof(double)));
   }
@@ -220,7 +221,7 @@ int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const 
 // Build the launch descriptor for `nbatch` parameter sets.  resid_on: form r = X beta - y first.
 static int prepare_bf(nngp_ctx *c, int cov, int nbatch, const double *theta, const double *beta, const int *slots,
                       bool store, BfLaunch *P, int *grid_out) {
-  if (c->n == 0) return ctx_fail(c, NNGP_ESTATE, "likelihood requested before nngp_set_data");
+  if (c->n == 0 || !c->has_nn) return ctx_fail(c, NNGP_ESTATE, "likelihood requested before nngp_set_data (with neighbours)");
   if (nbatch < 1 || nbatch > NNGP_MAX_BATCH) return ctx_fail(c, NNGP_EINVAL, "nbatch must be in 1..4");
   if (cov < 0 || cov > 3) return ctx_fail(c, NNGP_EINVAL, "cov.model is not correctly specified");
   if (beta && c->p == 0) return ctx_fail(c, NNGP_EINVAL, "beta given but the model has no covariates");
@@ -364,7 +365,7 @@ int nngp_time_bf_loglik(nngp_ctx *c, int cov, int nbatch, const double *theta, c
 
 int nngp_q_resid(nngp_ctx *c, int slot, const double *beta, double *out) {
   if (!c || !beta || !out || slot < 0 || slot > 1) return NNGP_EINVAL;
-  if (c->n == 0 || c->p == 0) return ctx_fail(c, NNGP_ESTATE, "nngp_q_resid before nngp_set_data");
+  if (c->n == 0 || c->p == 0 || !c->has_nn) return ctx_fail(c, NNGP_ESTATE, "nngp_q_resid before nngp_set_data");
   NNGP_CUDA(c, cudaSetDevice(c->device));
   memcpy(c->h_beta, beta, c->p * sizeof(double));
   NNGP_CUDA(c, cudaMemcpyAsync(c->d_beta, c->h_beta, c->p * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -380,7 +381,7 @@ int nngp_q_resid(nngp_ctx *c, int slot, const double *beta, double *out) {
 
 int nngp_q_forms(nngp_ctx *c, int slot, double *S) {
   if (!c || !S || slot < 0 || slot > 1) return NNGP_EINVAL;
-  if (c->n == 0 || c->p == 0) return ctx_fail(c, NNGP_ESTATE, "nngp_q_forms before nngp_set_data");
+  if (c->n == 0 || c->p == 0 || !c->has_nn) return ctx_fail(c, NNGP_ESTATE, "nngp_q_forms before nngp_set_data");
   NNGP_CUDA(c, cudaSetDevice(c->device));
   const int K = c->p + 1, npairs = K * (K + 1) / 2;
   NNGP_CUDA(c, q_forms_launch(c->d_B[slot], c->d_F[slot], c->d_nnIndx, c->d_X, c->d_y, c->n, c->p, c->m, c->loc_begin,
@@ -400,7 +401,7 @@ int nngp_q_forms(nngp_ctx *c, int slot, double *S) {
 
 int nngp_get_bf(nngp_ctx *c, int slot, double *B, double *F) {
   if (!c || slot < 0 || slot > 1) return NNGP_EINVAL;
-  if (c->n == 0) return ctx_fail(c, NNGP_ESTATE, "nngp_get_bf before nngp_set_data");
+  if (c->n == 0 || !c->has_nn) return ctx_fail(c, NNGP_ESTATE, "nngp_get_bf before nngp_set_data");
   NNGP_CUDA(c, cudaSetDevice(c->device));
   NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
   if (B && c->nIndx > 0) NNGP_CUDA(c, cudaMemcpy(B, c->d_B[slot], (size_t)c->nIndx * sizeof(double), cudaMemcpyDeviceToHost));

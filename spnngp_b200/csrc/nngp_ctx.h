@@ -19,6 +19,7 @@ struct nngp_ctx {
   int n = 0, m = 0, p = 0;
   int loc_begin = 0, loc_end = 0;
   long long nIndx = 0;
+  bool has_nn = false;  // false when only sites/X/y were given (prediction-only use)
   double2 *d_coords = nullptr;  // n interleaved sites
   int *d_nnIndx = nullptr;      // reference CSR
   double *d_X = nullptr;        // n x p column-major

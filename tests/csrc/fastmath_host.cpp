@@ -4,3 +4,4 @@ extern "C" {
 double host_nngp_sqrt(double x) { return nngp::nngp_sqrt(x); }
 double host_nngp_exp_nonpos(double x) { return nngp::nngp_exp_nonpos(x); }
 }
+extern "C" double host_nngp_sqrt_eps(double x) { return nngp::nngp_sqrt_eps(x); }

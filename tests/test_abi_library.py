@@ -1,0 +1,63 @@
+"""CPU: the C-ABI shared library loads, exports every symbol include/nngp_b200.h declares, and refuses to
+compute without a CUDA device (no CPU fallback).  No compute calls are made here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "nngp_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(nngp_[a-z0-9_]+)\s*\(", txt)) - {"nngp_ctx"})
+
+
+def test_every_declared_symbol_is_exported():
+    from spnngp_b200 import _lib
+    lib = _lib.load()
+    syms = header_symbols()
+    assert len(syms) >= 18
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/nngp_b200.h but not exported"
+    assert sorted(_lib.ABI_SYMBOLS) == syms
+    assert lib.nngp_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    from spnngp_b200 import _lib
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible; the no-device path cannot be exercised")
+    lib = _lib.load()
+    h = C.c_void_p()
+    st = lib.nngp_create(-1, None, C.byref(h))
+    assert st == -2 and not h.value  # NNGP_ENODEV
+    assert b"no CPU fallback" in lib.nngp_last_error(None)
+    from spnngp_b200 import Engine, NNGPError
+    with pytest.raises(NNGPError):
+        Engine()
+
+
+def test_r_glue_exports_the_reference_call_symbols():
+    path = os.path.join(ROOT, "spnngp_b200", "libspNNGP_b200.so")
+    assert os.path.exists(path), "run __graft_entry__.build()"
+    glue = C.CDLL(path)
+    for s in ("rNNGP", "cNNGP", "rNNGPPredict", "mkNNIndx", "mkNNIndxCB",  # accelerated (src/spNNGP.h, src/nn.h)
+              "sNNGP", "sNNGPLogit", "cSLGP", "sNNGPPredict", "PGLogit", "rNNGPReplicated", "mkUIndx",  # stubs
+              "R_init_spNNGP"):
+        assert hasattr(glue, s)
+
+
+def test_product_code_never_touches_the_oracle():
+    """Nothing under spnngp_b200/ may import, link or execute oracle/ (task rule)."""
+    bad = []
+    for dp, _, files in os.walk(os.path.join(ROOT, "spnngp_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                if re.search(r"oracle[/.]|liboracle|pyoracle|_ref/", txt):
+                    bad.append(os.path.join(dp, f))
+    assert not bad, bad

@@ -1,0 +1,113 @@
+"""GPU: (1) the CUDA path against the committed golden vectors (outputs of the reference's own C++);
+(2) the drop-in `.Call` layer (libspNNGP_b200.so: rNNGP, cNNGP, rNNGPPredict, mkNNIndx, mkNNIndxCB with the
+reference's SEXP signatures) driven exactly like the reference's entry points, same seeds."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from tests.util import make_problem, relerr, relerr_norm
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def glue():
+    lib = C.CDLL(os.path.join(ROOT, "spnngp_b200", "libspNNGP_b200.so"))
+    return po._Sexp(lib)
+
+
+def test_bf_against_golden(engine):
+    d = np.load(os.path.join(G, "bf_n400_m10.npz"))
+    m = int(d["m"])
+    engine.set_data(d["coords"], d["nnIndx"], d["nnIndxLU"], d["X"], d["y"], m)
+    for cov in range(4):
+        out = engine.bf_loglik(cov, [d[f"theta{cov}"]], [d["beta"]], slots=[0])
+        B, F = engine.get_bf(0)
+        assert relerr(F, d[f"F{cov}"]) < 1e-10 and relerr_norm(B[: len(d["nnIndx"])], d[f"B{cov}"][: len(d["nnIndx"])]) < 1e-10
+        assert abs(out[0, 0] - float(d[f"logDet{cov}"])) < 1e-10 * abs(out[0, 0])
+        assert abs(out[0, 1] - float(d[f"Q{cov}"])) < 1e-10 * abs(out[0, 1])
+
+
+def test_knn_against_golden(engine):
+    d = np.load(os.path.join(G, "knn.npz"))
+    for kind, ms in (("rand", (5, 15)), ("grid", (8, 15, 32))):
+        c = d[f"{kind}_coords"]
+        for m in ms:
+            for name, st in (("brute", "brute"), ("cb", "cb")):
+                idx, dist, _ = engine.mk_nn_indx(c, m, st)
+                assert np.array_equal(idx, d[f"{kind}_{name}_m{m}_idx"])
+                assert np.array_equal(dist.view(np.int64), d[f"{kind}_{name}_m{m}_dist"].view(np.int64))
+
+
+def test_glue_rnngp_chain_against_golden(glue):
+    """`rNNGP` .Call symbol, set.seed(1): retraces the reference's chain (golden = reference output)."""
+    d = np.load(os.path.join(G, "chain_n300_m10.npz"))
+    starting = {"beta": [0.0, 0.0], "sigma.sq": 5.0, "tau.sq": 1.0, "phi": 6.0, "nu": 0.75}
+    tuning = {"sigma.sq": 0.05, "tau.sq": 0.05, "phi": 0.05, "nu": 0.05}
+    for cov, name in ((0, "exp"), (2, "matern")):
+        for mode in ("0", "1"):
+            os.environ["NNGP_SAMPLER_MODE"] = mode
+            glue.lib.rshim_set_seed(1)
+            out = po.call_rnngp(glue, d["y"], d["X"], d["coords"], cov, d["nnIndx"], d["nnIndxLU"], int(d["m"]),
+                                [2.0, 5.0], [2.0, 1.0], [3.0, 300.0], [0.1, 2.0] if cov == 2 else None, starting,
+                                tuning, 40)
+            assert np.allclose(out["p_theta_samples"], d[f"{name}_theta"], rtol=1e-9)
+            assert np.allclose(out["p_beta_samples"], d[f"{name}_beta"], rtol=1e-7, atol=1e-9)
+    os.environ.pop("NNGP_SAMPLER_MODE", None)
+
+
+def test_glue_cnngp_and_predict_against_golden(glue):
+    d = np.load(os.path.join(G, "conj_predict_n500_m10.npz"))
+    m = int(d["m"])
+    for cov, name in ((0, "exp"), (3, "gauss")):
+        out = po.call_cnngp(glue, d["y"], d["X"], d["coords"], d["thetaAlpha"], d["nnIndx"], d["nnIndxLU"], d["X0"],
+                            d["coords0"], d["nn0"], m, d["sigmaSqIG"], cov)
+        assert np.allclose(out["beta.hat"], d[f"conj_{name}_beta_hat"], rtol=1e-9)
+        assert np.allclose(out["ab"], d[f"conj_{name}_ab"], rtol=1e-10)
+        assert np.allclose(out["bb"], d[f"conj_{name}_bb"], rtol=1e-10)
+        assert np.allclose(out["y.0.hat"], d[f"conj_{name}_y_0_hat"], rtol=1e-9, atol=1e-10)
+        assert np.allclose(out["y.0.hat.var"], d[f"conj_{name}_y_0_hat_var"], rtol=1e-9)
+    glue.lib.rshim_set_seed(7)
+    y0 = po.call_predict(glue, d["X"], d["y"], d["coords"], m, d["X0"], d["coords0"], d["nn0"], d["pred_beta"],
+                         d["pred_theta"], 0)
+    assert np.allclose(y0, d["pred_y0_seed7"], rtol=1e-9, atol=1e-10)
+
+
+def test_glue_mk_nn_in_place(glue, port):
+    """mkNNIndx / mkNNIndxCB write into their arguments and return R_NilValue (R/nn.R:45,71)."""
+    c = np.random.default_rng(2).random((1500, 2)); c = c[np.argsort(c[:, 0])]
+    for sym, fn in (("mkNNIndx", port.mk_nn_indx), ("mkNNIndxCB", port.mk_nn_indx_cb)):
+        got = po.call_mk_nn(glue, c, 15, symbol=sym)
+        ref = fn(c, 15)
+        assert all(np.array_equal(a, b) for a, b in zip(got, ref))
+
+
+def test_glue_error_text_matches_reference(glue, port):
+    prob = make_problem(60, 5, seed=6, port=port)
+    coords = prob["coords"].copy(); coords[30] = coords[29]; coords[31] = coords[29]
+    nnIndx, _, lu = port.mk_nn_indx(coords, 5)
+    starting = {"beta": [0.0, 0.0], "sigma.sq": 5.0, "tau.sq": 0.0, "phi": 6.0}
+    tuning = {"sigma.sq": 0.05, "tau.sq": 0.05, "phi": 0.05}
+    with pytest.raises(RuntimeError, match="dpotrf failed"):
+        po.call_rnngp(glue, prob["y"], prob["X"], coords, 0, nnIndx, lu, 5, [2.0, 5.0], [2.0, 1.0], [3.0, 300.0], None,
+                      starting, tuning, 3)
+    with pytest.raises(RuntimeError, match="outside the hot path"):
+        glue.call("mkUIndx", [glue.scalar_int(1)] * 8)
+
+
+def test_glue_vs_live_reference_when_built(glue, ref, port):
+    """Where oracle/_ref exists: the two `.Call` libraries side by side on a fresh problem."""
+    prob = make_problem(1200, 15, seed=8, port=port, domain=0.5)
+    starting = {"beta": [0.0, 0.0], "sigma.sq": 5.0, "tau.sq": 1.0, "phi": 6.0}
+    tuning = {"sigma.sq": 0.1, "tau.sq": 0.1, "phi": 0.1}
+    args = (prob["y"], prob["X"], prob["coords"], 0, prob["nnIndx"], prob["nnIndxLU"], 15, [2.0, 5.0], [2.0, 1.0],
+            [3.0, 300.0], None, starting, tuning, 80)
+    ref.set_seed(5); a = ref.rnngp(*args)
+    glue.lib.rshim_set_seed(5); b = po.call_rnngp(glue, *args)
+    assert np.allclose(a["p_theta_samples"], b["p_theta_samples"], rtol=1e-9)
+    assert np.allclose(a["p_beta_samples"], b["p_beta_samples"], rtol=1e-7, atol=1e-9)

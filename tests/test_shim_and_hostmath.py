@@ -1,0 +1,141 @@
+"""CPU: the libR stand-in (RNG, sort, BLAS/LAPACK subset) and the host builds of the device math."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def rshim():
+    from spnngp_b200 import _lib
+    return _lib.load_rshim()
+
+
+def test_rng_matches_known_r_values(rshim):
+    """set.seed(1); runif(1) -> 0.2655087, rnorm(1) -> -0.6264538; set.seed(42); runif(1) -> 0.914806
+    (R's default Mersenne-Twister / Inversion; well-known values)."""
+    rshim.rshim_set_seed(1); assert abs(rshim.unif_rand() - 0.2655087) < 5e-8
+    rshim.rshim_set_seed(1); assert abs(rshim.norm_rand() - (-0.6264538)) < 5e-8
+    rshim.rshim_set_seed(42); assert abs(rshim.unif_rand() - 0.914806) < 5e-7
+    rshim.rshim_set_seed(123); x = [rshim.rnorm(0.0, 1.0) for _ in range(3)]
+    assert np.allclose(x, [-0.56047565, -0.23017749, 1.55870831], atol=5e-8)  # set.seed(123); rnorm(3)
+
+
+def test_qnorm_accuracy(rshim):
+    from scipy.stats import norm
+    rshim.qnorm.restype = C.c_double
+    rshim.qnorm.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
+    p = np.concatenate([np.linspace(1e-12, 1 - 1e-12, 2001), 10.0 ** -np.arange(1, 300, 7)])
+    got = np.array([rshim.qnorm(float(x), 0.0, 1.0, 1, 0) for x in p])
+    assert np.allclose(got, norm.ppf(p), rtol=1e-13, atol=1e-14)
+
+
+def test_rsort_with_index_semantics(rshim, port):
+    """Shell sort with R's gap rule: n <= 8 is a stable insertion sort, larger n is unstable."""
+    rshim.rsort_with_index.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 8, 9, 15, 32, 200):
+        x = rng.integers(0, 5, n).astype(np.float64); idx = np.arange(n, dtype=np.int32)
+        xs, ids = port.rsort_with_index(x, idx)
+        x2, i2 = x.copy(), idx.copy()
+        rshim.rsort_with_index(x2.ctypes.data_as(C.POINTER(C.c_double)), i2.ctypes.data_as(C.POINTER(C.c_int)), n)
+        assert np.array_equal(xs, np.sort(x)) and np.array_equal(x2, xs) and np.array_equal(i2, ids)
+        if n <= 8:
+            assert np.array_equal(ids, np.argsort(x, kind="stable"))
+    x = np.array([2.0, np.nan, 1.0, np.inf, -1.0]); xs, ids = port.rsort_with_index(x, np.arange(5))
+    assert np.isnan(xs[-1]) and np.array_equal(xs[:4], [-1.0, 1.0, 2.0, np.inf])
+
+
+def test_minilapack_against_numpy(rshim):
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    rng = np.random.default_rng(1)
+    for n in (1, 2, 5, 15, 32):
+        A = rng.standard_normal((n, n)); A = A @ A.T + n * np.eye(n)
+        a = np.asfortranarray(A).ravel(order="F").copy()
+        info = C.c_int(0); nn = C.c_int(n); lo = C.c_char_p(b"L")
+        rshim.dpotrf_(lo, C.byref(nn), a.ctypes.data_as(dp), C.byref(nn), C.byref(info))
+        assert info.value == 0
+        Lc = np.tril(a.reshape(n, n, order="F"))
+        assert np.allclose(Lc, np.linalg.cholesky(A), rtol=1e-12, atol=1e-13)
+        rshim.dpotri_(lo, C.byref(nn), a.ctypes.data_as(dp), C.byref(nn), C.byref(info))
+        Ai = np.tril(a.reshape(n, n, order="F"))
+        assert np.allclose(Ai, np.tril(np.linalg.inv(A)), rtol=1e-10, atol=1e-13)
+        x = rng.standard_normal(n); y = np.zeros(n); one = C.c_double(1.0); zero = C.c_double(0.0); inc = C.c_int(1)
+        rshim.dsymv_(lo, C.byref(nn), C.byref(one), a.ctypes.data_as(dp), C.byref(nn), x.ctypes.data_as(dp), C.byref(inc),
+                     C.byref(zero), y.ctypes.data_as(dp), C.byref(inc))
+        assert np.allclose(y, np.linalg.inv(A) @ x, rtol=1e-10)
+    bad = np.array([1.0, 2.0, 2.0, 1.0]); info = C.c_int(0); two = C.c_int(2)
+    rshim.dpotrf_(C.c_char_p(b"L"), C.byref(two), bad.ctypes.data_as(dp), C.byref(two), C.byref(info))
+    assert info.value == 2  # not positive definite: the reference turns this into "dpotrf failed"
+
+
+def _build_host(src, out):
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-mfma",
+                    os.path.join(ROOT, "tests", "csrc", src), "-o", out], check=True)
+    return C.CDLL(out)
+
+
+def test_device_besselk_on_host_vs_mpmath(tmp_path):
+    """spnngp_b200/csrc/besselk.cuh compiled for the host: K_nu and the Matern correlation vs mpmath."""
+    import mpmath as mp
+    L = _build_host("besselk_host.cpp", str(tmp_path / "libbk.so"))
+    for f in (L.host_besselk, L.host_matern):
+        f.restype = C.c_double; f.argtypes = [C.c_double, C.c_double]
+    mp.mp.dps = 40
+    worst = 0.0
+    for nu in (0.05, 0.25, 0.49, 0.5, 0.51, 0.75, 1.0, 1.5, 2.3, 2.5, 3.7, 4.5, 5.0):
+        for x in (1e-8, 1e-4, 0.01, 0.1, 0.5, 1.0, 1.99, 2.0, 2.01, 3.0, 8.0, 20.0, 100.0, 600.0):
+            k = mp.besselk(nu, x)
+            worst = max(worst, float(abs((mp.mpf(L.host_besselk(x, nu)) - k) / k)))
+            rho = mp.mpf(x) ** nu * k / (mp.mpf(2) ** (nu - 1) * mp.gamma(nu))
+            if rho > 1e-290:
+                worst = max(worst, float(abs((mp.mpf(L.host_matern(x, nu)) - rho) / rho)))
+    assert worst < 5e-14
+    for x in (0.01, 0.3, 1.7, 4.0):  # closed forms, SURVEY §8c KATs
+        assert abs(L.host_matern(x, 0.5) - np.exp(-x)) < 1e-15
+        assert abs(L.host_matern(x, 1.5) - (1 + x) * np.exp(-x)) < 2e-15
+        assert abs(L.host_matern(x, 2.5) - (1 + x + x * x / 3) * np.exp(-x)) < 3e-15
+
+
+def test_device_fastmath_on_host(tmp_path):
+    """Branch-free sqrt / exp of spnngp_b200/csrc/fastmath.cuh (host build) vs libm."""
+    L = _build_host("fastmath_host.cpp", str(tmp_path / "libfm.so"))
+    for f in (L.host_nngp_sqrt, L.host_nngp_exp_nonpos, L.host_nngp_sqrt_eps):
+        f.restype = C.c_double; f.argtypes = [C.c_double]
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([10 ** rng.uniform(-12, 8, 20000), rng.random(10000)])
+    s = np.array([L.host_nngp_sqrt(float(x)) for x in xs]); se = np.array([L.host_nngp_sqrt_eps(float(x)) for x in xs])
+    assert np.max(np.abs(s - np.sqrt(xs)) / np.spacing(np.sqrt(xs))) <= 1.0
+    assert np.max(np.abs(se - np.sqrt(xs)) / np.spacing(np.sqrt(xs))) <= 1.0
+    assert L.host_nngp_sqrt(0.0) == 0.0 and abs(L.host_nngp_sqrt_eps(0.0) - 1e-150) < 1e-160
+    xe = -np.concatenate([10 ** rng.uniform(-10, 2.85, 20000), rng.random(10000) * 5])
+    e = np.array([L.host_nngp_exp_nonpos(float(x)) for x in xe]); r = np.exp(xe)
+    assert np.max(np.abs(e - r) / r) < 3e-16
+    assert L.host_nngp_exp_nonpos(0.0) == 1.0 and L.host_nngp_exp_nonpos(-800.0) == 0.0
+
+
+def test_kats_on_the_oracle(port):
+    """Analytic known answers on the CPU oracle itself."""
+    s2, t2, phi = 5.0, 1.0, 6.0
+    coords = np.array([[0.1, 0.2], [0.4, 0.6]])
+    idx, _, lu = port.mk_nn_indx(coords, 1)
+    B, F, ld, info = port.update_bf(coords, idx, lu, 2, 1, [s2, t2, phi], 0)
+    rho = np.exp(-phi * 0.5)
+    assert abs(F[0] - 6.0) < 1e-15 and abs(B[0] - s2 * rho / 6.0) < 1e-15
+    assert abs(F[1] - (6.0 - (s2 * rho) ** 2 / 6.0)) < 1e-14 and abs(ld - np.log(F).sum()) < 1e-14
+    # tau.sq = 0, exponential, collinear equally spaced: Markov -> one weight e^{-phi h}, F = s2 (1 - e^{-2 phi h})
+    h = 0.05; c = np.column_stack([np.arange(8) * h, np.zeros(8)])
+    idx, _, lu = port.mk_nn_indx(c, 3)
+    B, F, _, info = port.update_bf(c, idx, lu, 8, 3, [s2, 0.0, phi], 0)
+    assert info == 0
+    off, cnt = lu[7], lu[8 + 7]
+    w = B[off:off + cnt]
+    assert abs(w[0] - np.exp(-phi * h)) < 1e-9 and np.all(np.abs(w[1:]) < 1e-9)
+    assert abs(F[7] - s2 * (1 - np.exp(-2 * phi * h))) < 1e-9
+    # spherical: rho = 0 beyond the range, 1 at 0; Matern(1/2) == exponential
+    assert port.sp_cor(1.0, 6.0, 0, 1) == 0.0 and port.sp_cor(0.0, 6.0, 0, 1) == 1.0
+    assert abs(port.sp_cor(0.3, 6.0, 0.5, 2) - np.exp(-1.8)) < 1e-15
