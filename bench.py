@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of BASELINE.json on B200:
+
+    rNNGP (spNNGP method="response") MCMC iterations/s at n = 1,000,000 locations, m = 15 neighbours,
+    plus updateBF locations/s of the dominant kernel against the measured FP64 / HBM roofline.
+
+A "step" is one Metropolis iteration of the reference's `rNNGP` sampler (src/rNNGP.cpp:272-378): draw
+beta, evaluate the log-likelihood (B/F solve + Q) at the current and at the proposed theta, accept/reject.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a engine
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path (oracle/_ref)
+
+Prints ONE JSON line on rank 0.  N > 1 is launched with torchrun (one rank per GPU): the locations are
+sharded over the ranks (strong scaling, total work fixed) and the likelihood partials are summed with an
+NCCL allreduce of 4 doubles per iteration.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+COV = {"exponential": 0, "spherical": 1, "matern": 2, "gaussian": 3}
+
+
+def flops_per_location(m: int, fused: bool = True) -> float:
+    """Algorithmic FLOPs per location: distance 6P + correlation 3P + nugget m + Cholesky
+    (m^3/3 + m^2/2 + m/6) + solves 2m^2 + F (2m+2) + log 1 [+ fused Q 2m+4], P = m(m+1)/2."""
+    P = m * (m + 1) / 2
+    f = 6 * P + 3 * P + m + (m ** 3 / 3 + m ** 2 / 2 + m / 6) + 2 * m * m + (2 * m + 2) + 1
+    return f + (2 * m + 4 if fused else 0)
+
+
+def bytes_per_location(m: int) -> float:
+    """Algorithmic bytes per location with B, F stored: coords 16 + nnIndx 4m + B 8m + F 8 + resid 8."""
+    return 32 + 12 * m
+
+
+def make_workload(n: int, m: int, seed: int = 1):
+    """coords ~ U(0,1)^2 * sqrt(n/5000) (constant density), ordered by x; X = [1, N(0,1)];
+    y = X beta + smooth field + noise.  numpy default_rng(seed); identical on every rank."""
+    rng = np.random.default_rng(seed)
+    coords = rng.random((n, 2)) * np.sqrt(n / 5000.0)
+    coords = coords[np.argsort(coords[:, 0], kind="stable")]
+    X = np.column_stack([np.ones(n), rng.standard_normal(n)])
+    beta = np.array([1.0, 5.0])
+    w = np.sin(3.0 * coords[:, 0]) + np.cos(2.0 * coords[:, 1])
+    y = X @ beta + np.sqrt(5.0) * w + rng.standard_normal(n)
+    return dict(n=n, m=m, p=2, coords=coords, X=X, y=y, beta=beta)
+
+
+def sampler_settings(cov: int):
+    starting = {"beta": [0.0, 0.0], "sigma.sq": 5.0, "tau.sq": 1.0, "phi": 6.0, "nu": 0.75}
+    # well-mixing proposal sd; at n = 1e6 the posterior is sharp, so keep it small
+    tuning = {"sigma.sq": 0.002, "tau.sq": 0.002, "phi": 0.002, "nu": 0.002}
+    priors = dict(sigmaSqIG=[2.0, 5.0], tauSqIG=[2.0, 1.0], phiUnif=[3.0, 300.0], nuUnif=[0.1, 2.0] if cov == 2 else None)
+    return starting, tuning, priors
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        try:
+            rows = [r.strip().split(",") for r in open(self.path) if r.strip()]
+            sm = [float(r[0]) for r in rows if r[0].strip().replace(".", "").isdigit()]
+            mx = [float(r[1]) for r in rows if r[1].strip().replace(".", "").isdigit()]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            reasons = set()
+            for r in rows:
+                for k, nm in enumerate(names):
+                    if len(r) > 4 + k and r[4 + k].strip().lower() == "active":
+                        reasons.add(nm)
+            if sm:
+                out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                       "samples": len(sm)}
+        except Exception:
+            pass
+        finally:
+            try:
+                os.unlink(self.path)
+            except Exception:
+                pass
+        return out
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def traffic_from_profile(n, m, cov_name):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if one matches."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        for row in json.load(open(p)):
+            if row["n"] == n and row["m"] == m and row["cov"] == cov_name:
+                return row["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
+# =====================================================================================================
+# reference arm: the reference's own CPU implementation on the box's host cores
+# =====================================================================================================
+def run_reference(args, rank, world):
+    if rank != 0:
+        return 0
+    from oracle import pyoracle as po
+    cov = COV[args.cov]
+    cores = os.cpu_count() or 1
+    have_ref = po.Ref.available()
+    port = po.Port()
+    port.set_threads(cores)
+    ref = po.Ref() if have_ref else None
+    kind = "reference" if have_ref else "port"
+    starting, tuning, pri = sampler_settings(cov)
+
+    # size the per-step sample so that (W + K) iterations finish in a few minutes: probe one B/F pass
+    n_full, m = args.n, args.m
+    probe_n = min(n_full, 50000)
+    wl = make_workload(probe_n, m)
+    idx, _, lu = port.mk_nn_indx_cb(wl["coords"], m)
+    theta = [5.0, 1.0, 6.0, 0.75][: 4 if cov == 2 else 3]
+    t0 = time.perf_counter()
+    if ref is not None:
+        ref.update_bf(wl["coords"], idx, lu, probe_n, m, theta, cov, threads=cores)
+    else:
+        port.update_bf(wl["coords"], idx, lu, probe_n, m, theta, cov)
+    t_loc = (time.perf_counter() - t0) / probe_n  # seconds per location per B/F pass
+    budget = float(args.ref_budget_s)
+    iters = args.steps + args.warmup
+    n_s = int(min(n_full, max(2000, budget / (iters * 2.2 * t_loc))))
+    if n_s < n_full:
+        wl = make_workload(n_s, m)
+        idx, _, lu = port.mk_nn_indx_cb(wl["coords"], m)
+    elif probe_n != n_full:
+        wl = make_workload(n_full, m)
+        idx, _, lu = port.mk_nn_indx_cb(wl["coords"], m)
+
+    def run(k):
+        if ref is not None:
+            ref.set_seed(1)
+            t0 = time.perf_counter()
+            ref.rnngp(wl["y"], wl["X"], wl["coords"], cov, idx, lu, m, pri["sigmaSqIG"], pri["tauSqIG"], pri["phiUnif"],
+                      pri["nuUnif"], starting, tuning, k, nThreads=cores)
+            return time.perf_counter() - t0
+        from spnngp_b200 import _lib
+        R = _lib.load_rshim(); R.rshim_set_seed(1)
+        t0 = time.perf_counter()
+        port.rnngp(wl["y"], wl["X"], wl["coords"], cov, idx, lu, m, pri["sigmaSqIG"], pri["tauSqIG"], pri["phiUnif"],
+                   pri["nuUnif"], starting, tuning, k, lambda a, b: R.rnorm(a, b), lambda a, b: R.runif(a, b))
+        return time.perf_counter() - t0
+
+    if args.warmup > 0:
+        run(args.warmup)
+    dt = run(args.steps)
+    iter_s_sample = args.steps / dt
+    value = iter_s_sample * (n_s / n_full)  # work per iteration is linear in n (2 x updateBF + 2 x Q)
+    sample = (f"{args.steps} iterations of the reference's rNNGP (2 x updateBF + 2 x Q each) on the first-built "
+              f"n_s={n_s} locations of the workload, OpenMP {cores} threads; "
+              + ("full size" if n_s == n_full else f"scaled to n={n_full} by n_s/n (work is linear in n)"))
+    line = {
+        "impl": "reference", "metric": "rNNGP_mcmc_iter_per_s", "value": value, "unit": "iter/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"rNNGP response model n={n_full} m={m} p=2 cov={args.cov}", "n": n_full, "m": m,
+                   "cov_model": args.cov, "sampler": "reference (src/rNNGP.cpp), OpenMP"},
+        "cpu_baseline": {"value": value, "unit": "iter/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# =====================================================================================================
+# this repo's arm
+# =====================================================================================================
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from spnngp_b200 import Engine, _lib
+    from spnngp_b200.dist import make_allreduce, shard_range
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device visible; spnngp_b200 has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cov = COV[args.cov]
+    n, m = args.n, args.m
+    wl = make_workload(n, m)
+    starting, tuning, pri = sampler_settings(cov)
+    R = _lib.load_rshim()
+
+    stream = torch.cuda.Stream(dev)  # a real (non-default) stream: the engine and the timing events share it
+    torch.cuda.set_stream(stream)
+    eng = Engine(local_rank, stream=stream.cuda_stream)
+    t0 = time.perf_counter()
+    nnIndx, nnDist, lu = eng.mk_nn_indx(wl["coords"], m, "cb")  # setup, not timed: the sampler reuses neighbours
+    t_knn = time.perf_counter() - t0
+    lo, hi = shard_range(n, m, rank, world)
+    allreduce = make_allreduce(device=dev) if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def chain(k, mode):
+        R.rshim_set_seed(1)  # same stream on every rank -> identical accept decisions
+        return eng.rnngp(cov, pri["sigmaSqIG"], pri["tauSqIG"], pri["phiUnif"], pri["nuUnif"], starting, tuning, k,
+                         R.rnorm, R.runif, mode=mode, allreduce=allreduce)
+
+    def timed_chain(k, mode):
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        l0 = eng.launch_count()
+        e0.record(stream)
+        _, _, acc = chain(k, mode)
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), acc, eng.launch_count() - l0
+
+    # ---- HBM-resident: data uploaded once, then W warm-up and K timed iterations -----------------------
+    eng.set_data(wl["coords"], nnIndx, lu, wl["X"], wl["y"], m, loc_range=(lo, hi))
+    chain(max(args.warmup, 3), args.mode)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ms, acc, launches = timed_chain(args.steps, args.mode)
+    ms_alt, _, _ = timed_chain(args.steps, 1 - args.mode)
+    clk = clocks.stop() if rank == 0 else {}
+    value = args.steps / (ms * 1e-3)
+
+    # ---- end to end: host buffers in, samples out (H2D of the data set inside the timed region) ---------
+    barrier()
+    t0 = time.perf_counter()
+    eng.set_data(wl["coords"], nnIndx, lu, wl["X"], wl["y"], m, loc_range=(lo, hi))
+    _, _, acc_e = chain(args.steps, args.mode)
+    torch.cuda.synchronize(dev)
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s.item())
+    data_bytes = wl["coords"].nbytes + nnIndx.nbytes + wl["X"].nbytes + wl["y"].nbytes
+    nb = 2 if args.mode == 0 else 1
+    h2d_step = data_bytes / args.steps + nb * (2 * 8 + 0)           # data set amortised + beta per launch
+    d2h_step = nb * (2 * 8 + 4) + (acc_e / args.steps) * 9 * 8 + (2 + 3) * 8  # partials, S on accepts, samples
+
+    launches_t = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(launches_t)
+    line = None
+    if rank == 0:
+        # ---- dominant kernel: the fused B/F + log-likelihood launch over this rank's shard ----------------
+        theta = [5.0, 1.0, 6.0, 0.75][: 4 if cov == 2 else 3]
+        eng.time_bf_loglik(cov, [theta], [wl["beta"]], iters=3)
+        k_ms = eng.time_bf_loglik(cov, [theta], [wl["beta"]], iters=20)
+        nloc = hi - lo
+        loc_s = nloc / (k_ms * 1e-3)
+        fp64_peak = eng.fp64_peak_tflops()
+        peaks, peak_src = measured_peaks()
+        fl = flops_per_location(m)
+        ach_tf = loc_s * fl / 1e12
+        ach_gbs = loc_s * bytes_per_location(m) / 1e9
+        roofline = {
+            "bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
+            "traffic": traffic_from_profile(n, m, args.cov),
+            "kernel": "bf_tpl_kernel" if (cov != 2 and m <= 16) else "bf_kernel",
+            "kernel_ms": k_ms, "locations_per_launch": nloc, "updateBF_loc_per_s": loc_s,
+            "flops_per_location": fl, "bytes_per_location": bytes_per_location(m),
+            "peak_source": "FP64 FMA peak measured live by nngp_fp64_peak (DFMA micro-benchmark; MEASURED_PEAKS.json has no "
+                           "FP64 figure); transcendentals count as 1 flop (SURVEY §8d)",
+            "hbm_view": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"],
+                         "peak_source": peak_src},
+        }
+        # also the other common covariance at the same size (one line each, kernel only)
+        other = "exponential" if args.cov != "exponential" else "matern"
+        th_o = [5.0, 1.0, 6.0, 0.75][: 4 if COV[other] == 2 else 3]
+        eng.time_bf_loglik(COV[other], [th_o], [wl["beta"]], iters=3)
+        k_ms_o = eng.time_bf_loglik(COV[other], [th_o], [wl["beta"]], iters=10)
+
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu_baseline = cpu_baseline_leg(args, wl, nnIndx, lu, cov, starting, tuning, pri)
+        line = {
+            "metric": "rNNGP_mcmc_iter_per_s", "value": value, "unit": "iter/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": f"rNNGP response model n={n} m={m} p=2 cov={args.cov} (BASELINE.json configs[2])",
+                "n": n, "m": m, "cov_model": args.cov, "p": 2,
+                "sampler": "reference-faithful: 2 B/F solves + 2 Q per iteration, one batched launch" if args.mode == 0
+                else "double-buffered: 1 B/F solve + 1 Q-only pass per iteration",
+                "l2": f"inputs larger than L2: {bytes_per_location(m) * (hi - lo) / 1e6:.0f} MB touched per launch vs 126 MB L2"
+                if bytes_per_location(m) * (hi - lo) > 126e6 else "working set fits L2 at this shard size (no flush; strong scaling)",
+                "parallelism": f"locations sharded over {world} GPU(s); allreduce of 4 doubles per iteration",
+                "acceptance_rate": acc / args.steps, "rng": "R-compatible Mersenne-Twister + inversion (librshim), seed 1",
+            },
+            "e2e": {"value": args.steps / e2e_s, "unit": "iter/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
+                    "note": "nngp_set_data from host buffers + K iterations + samples back, wall clock, max over ranks"},
+            "gpu_launches": int(launches_t.item()),
+            "clocks": clk,
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "extra": {
+                "alt_sampler_iter_per_s": args.steps / (ms_alt * 1e-3),
+                "alt_sampler": "double-buffered" if args.mode == 0 else "reference-faithful",
+                f"updateBF_loc_per_s_{other}": (hi - lo) / (k_ms_o * 1e-3),
+                "knn_cb_setup_s": t_knn,
+            },
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def cpu_baseline_leg(args, wl, nnIndx, lu, cov, starting, tuning, pri):
+    """The reference's own OpenMP path on this box's host cores, bounded to ~10-30 s (rank 0, N = 1)."""
+    from oracle import pyoracle as po
+    cores = os.cpu_count() or 1
+    n, m = wl["n"], wl["m"]
+    theta = [5.0, 1.0, 6.0, 0.75][: 4 if cov == 2 else 3]
+    if po.Ref.available():
+        ref = po.Ref()
+        t0 = time.perf_counter()
+        ref.update_bf(wl["coords"], nnIndx, lu, n, m, theta, cov, threads=cores)
+        t_bf = time.perf_counter() - t0
+        k = int(min(20, max(1, round(15.0 / (2.2 * t_bf)))))
+        ref.set_seed(1)
+        t0 = time.perf_counter()
+        ref.rnngp(wl["y"], wl["X"], wl["coords"], cov, nnIndx, lu, m, pri["sigmaSqIG"], pri["tauSqIG"], pri["phiUnif"],
+                  pri["nuUnif"], starting, tuning, k, nThreads=cores)
+        dt = time.perf_counter() - t0
+        return {"value": k / dt, "unit": "iter/s", "cores": cores, "kind": "reference",
+                "sample": f"{k} iterations of the reference's rNNGP at full n={n} (plus its initial updateBF), OpenMP {cores} threads",
+                "updateBF_loc_per_s": n / t_bf}
+    port = po.Port(); port.set_threads(cores)
+    t0 = time.perf_counter()
+    port.update_bf(wl["coords"], nnIndx, lu, n, m, theta, cov)
+    t_bf = time.perf_counter() - t0
+    return {"value": 1.0 / (2.2 * t_bf), "unit": "iter/s", "cores": cores, "kind": "port",
+            "sample": f"one updateBF pass of the C oracle port at full n={n}; iteration = 2 x updateBF + 2 x Q",
+            "updateBF_loc_per_s": n / t_bf}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=1000000)
+    ap.add_argument("--m", type=int, default=15)
+    ap.add_argument("--cov", default="matern", choices=list(COV))
+    ap.add_argument("--mode", type=int, default=0, help="0 reference-faithful sampler, 1 double-buffered")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    return run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -73,9 +73,11 @@ int nngp_sync(nngp_ctx *ctx);
  *      (src/nn.cpp:214-257).  Outputs are written into the caller's arrays exactly like the reference
  *      (R/nn.R:45,71): nnIndx[nIndx], nnDist[nIndx], nnIndxLU[2n].  Neighbour candidates of location i
  *      are locations 0..i-1; ascending distance; distances use the reference's non-fused arithmetic
- *      (sqrt(dx*dx+dy*dy), products rounded separately) so nnDist matches bit for bit on tie-free
- *      data.  Locations with exact distance ties at the m-th neighbour are re-run on the host
- *      with the reference's insertion/Shell-sort sequence (n_tie_replayed reports how many). */
+ *      (sqrt(dx*dx+dy*dy), products rounded separately) so nnDist matches bit for bit.  Every query
+ *      runs the reference's own acceptance sequence (strict '<', overwrite-last-then-rsort_with_index)
+ *      in one GPU thread, so distance ties resolve exactly as in the reference.  For search_type cb the
+ *      u = x + y sort runs on the device; if u has exact ties the reference's serial Shell sort is
+ *      replayed on the host instead (n_tie_replayed = number of tied adjacent keys that forced this). */
 int nngp_mk_nn_indx(nngp_ctx *ctx, int n, int m, const double *coords, int search_type, int *nnIndx,
                     double *nnDist, int *nnIndxLU, int *n_tie_replayed);
 
@@ -88,7 +90,8 @@ int nngp_nn_query(nngp_ctx *ctx, int n, const double *coords, int q, const doubl
 /* ---- model data: uploads what `rNNGP` / `cNNGP` read through REAL()/INTEGER()
  *      (src/rNNGP.cpp:120-128).  X is n x p, y length n.  [loc_begin, loc_end) is this context's
  *      shard of the locations (0, n for a single GPU).  nnIndxLU must be the closed form of
- *      src/util.cpp:55-70 (checked). */
+ *      src/util.cpp:55-70 (checked; may be NULL).  nnIndx may be NULL for prediction-only use
+ *      (`rNNGPPredict` receives no fit neighbours): then only sites, X and y are uploaded. */
 int nngp_set_data(nngp_ctx *ctx, int n, int m, int p, const double *coords, const int *nnIndx,
                   const int *nnIndxLU, const double *X, const double *y, int loc_begin, int loc_end);
 
@@ -169,6 +172,9 @@ int nngp_rnngp_predict(nngp_ctx *ctx, int cov_model, int q, const double *X0, co
  *      on the context stream between two CUDA events and returns the mean milliseconds per launch. */
 int nngp_time_bf_loglik(nngp_ctx *ctx, int cov_model, int nbatch, const double *theta, const double *beta,
                         int iters, int flush_l2, float *ms_per_launch);
+/* FP64 FMA throughput of this device measured with a DFMA micro-benchmark (TFLOP/s, FMA = 2 flops):
+ * the roofline denominator for the B/F kernels (MEASURED_PEAKS.json has no FP64 figure). */
+int nngp_fp64_peak(nngp_ctx *ctx, double *tflops);
 /* number of kernel launches issued by this context so far (bench.py `gpu_launches`) */
 long long nngp_launch_count(const nngp_ctx *ctx);
 

@@ -43,6 +43,7 @@ ABI_SYMBOLS = [
     "nngp_abi_version", "nngp_device_count", "nngp_create", "nngp_destroy", "nngp_last_error", "nngp_sync",
     "nngp_mk_nn_indx", "nngp_nn_query", "nngp_set_data", "nngp_bf_loglik", "nngp_q_resid", "nngp_q_forms",
     "nngp_get_bf", "nngp_rnngp", "nngp_cnngp", "nngp_rnngp_predict", "nngp_time_bf_loglik", "nngp_launch_count",
+    "nngp_fp64_peak",
 ]
 
 _lib = None
@@ -78,6 +79,7 @@ def load():
     L.nngp_rnngp.argtypes = [vp, C.POINTER(RnngpArgs), c_double_p, c_double_p, c_int_p]
     L.nngp_time_bf_loglik.argtypes = [vp, C.c_int, C.c_int, c_double_p, c_double_p, C.c_int, C.c_int,
                                       C.POINTER(C.c_float)]
+    L.nngp_fp64_peak.argtypes = [vp, c_double_p]
     L.nngp_launch_count.restype = C.c_longlong
     L.nngp_launch_count.argtypes = [vp]
     if hasattr(L, "nngp_mk_nn_indx"):

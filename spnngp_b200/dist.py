@@ -1,0 +1,58 @@
+"""Multi-GPU plumbing: one process per GPU (torch.distributed), locations / prediction sites /
+parameter sets sharded across ranks; the only collective on the fit path is a sum of a handful of
+FP64 partials (sum log F, Q, or the (p+1)^2 cross forms) -- SURVEY §8e.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def nn_offset(i: int, m: int) -> int:
+    """Offset of location i in the reference's ragged neighbour layout (src/util.cpp:55-70)."""
+    return (i * (i - 1)) // 2 if i < m else (m * (m - 1)) // 2 + (i - m) * m
+
+
+def shard_range(n: int, m: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous location range of `rank`, balanced by neighbour count (sum of m_i), so the ragged
+    first m locations do not unbalance small problems.  Ranges of all ranks partition [0, n)."""
+    total = nn_offset(n, m) + n  # weight m_i + 1 per location
+    def boundary(r):
+        if r <= 0:
+            return 0
+        if r >= world:
+            return n
+        target = total * r // world
+        lo, hi = 0, n
+        while lo < hi:  # first i with cumulative weight >= target
+            mid = (lo + hi) // 2
+            if nn_offset(mid, m) + mid < target:
+                lo = mid + 1
+            else:
+                hi = mid
+        return lo
+    return boundary(rank), boundary(rank + 1)
+
+
+def split_even(count: int, rank: int, world: int) -> tuple[int, int]:
+    """Even contiguous split (prediction sites, theta.alpha sets)."""
+    return count * rank // world, count * (rank + 1) // world
+
+
+def make_allreduce(device=None, group=None):
+    """In-place sum over ranks of a small float64 numpy vector.  NCCL when `device` is a CUDA device
+    (one staging tensor, reused), gloo otherwise.  Returns None when not running distributed."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return None
+    use_cuda = device is not None and str(device).startswith("cuda")
+    staging = torch.zeros(256, dtype=torch.float64, device=device if use_cuda else "cpu")
+
+    def allreduce(buf: np.ndarray) -> None:
+        k = buf.shape[0]
+        t = staging[:k]
+        t.copy_(torch.from_numpy(buf))
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        buf[:] = t.cpu().numpy()
+
+    return allreduce

@@ -150,6 +150,11 @@ class Engine:
         self._check(self.lib.nngp_get_bf(self.h, slot, _dp(B), _dp(F)))
         return B, F
 
+    def fp64_peak_tflops(self):
+        out = np.zeros(1)
+        self._check(self.lib.nngp_fp64_peak(self.h, _dp(out)))
+        return float(out[0])
+
     def launch_count(self):
         return int(self.lib.nngp_launch_count(self.h))
 

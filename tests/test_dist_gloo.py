@@ -1,0 +1,64 @@
+"""CPU, world_size = 2 over gloo: the host-side logic of the multi-GPU path -- shard ranges partition the
+locations, per-shard partial sums reduce to the single-process result through the allreduce hook."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_ranges_partition():
+    from spnngp_b200.dist import shard_range, split_even, nn_offset
+    for n, m in ((1, 1), (5, 15), (100, 15), (5000, 15), (1000003, 32)):
+        for world in (1, 2, 3, 8):
+            r = [shard_range(n, m, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == n and all(r[k][1] == r[k + 1][0] for k in range(world - 1))
+            if n > 100 * world:
+                w = [nn_offset(b, m) + b - nn_offset(a, m) - a for a, b in r]
+                assert max(w) - min(w) <= 2 * (m + 1)
+    assert [split_even(10, k, 3) for k in range(3)] == [(0, 3), (3, 6), (6, 10)]
+
+
+def _worker(rank, world, port_file, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from oracle import pyoracle as po
+    from spnngp_b200.dist import make_allreduce, shard_range
+    from tests.util import make_problem
+    dist.init_process_group("gloo", init_method=f"file://{port_file}", rank=rank, world_size=world)
+    port = po.Port(); port.set_threads(1)
+    prob = make_problem(3000, 10, seed=5, port=port, domain=0.8)
+    n, m = 3000, 10
+    B, F, ld, _ = port.update_bf(prob["coords"], prob["nnIndx"], prob["nnIndxLU"], n, m, [5.0, 1.0, 6.0], 0)
+    r = prob["X"] @ prob["beta"] - prob["y"]
+    lo, hi = shard_range(n, m, rank, world)
+    # per-location terms of sum log F and Q (src/util.cpp:261-280), restricted to this rank's shard
+    off, cnt = prob["nnIndxLU"][:n], prob["nnIndxLU"][n:]
+    part = np.zeros(2)
+    for i in range(lo, hi):
+        a = B[off[i]:off[i] + cnt[i]] @ r[prob["nnIndx"][off[i]:off[i] + cnt[i]]]
+        part[0] += np.log(F[i]); part[1] += (r[i] - a) ** 2 / F[i]
+    ar = make_allreduce(device=None)
+    assert ar is not None
+    ar(part)
+    full_q = port.q(B, F, r, r, n, prob["nnIndx"], prob["nnIndxLU"])
+    q.put((rank, abs(part[0] - ld) / abs(ld), abs(part[1] - full_q) / abs(full_q)))
+    dist.destroy_process_group()
+
+
+def test_sharded_partials_allreduce_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    f = str(tmp_path / "rdzv")
+    procs = [ctx.Process(target=_worker, args=(k, 2, f, q)) for k in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, e1, e2 in res:
+        assert e1 < 1e-13 and e2 < 1e-13
