@@ -20,6 +20,7 @@ namespace nngp {
 
 constexpr int kTemmeTerms = 24;  // (x^2/4)^i / i! < 1e-18 well before i = 24 for x <= 2
 constexpr int kCf2Tab = 64;      // tabulated reciprocals for the first CF2 iterations
+constexpr int kMatSeriesTerms = 14;  // t^k/(k!)^2-like decay: 1e-17 relative at t = 1 by k = 13
 
 struct MaternConsts {
   double nu;      // smoothness
@@ -37,6 +38,13 @@ struct MaternConsts {
   double r_ip[kTemmeTerms];  // 1/(i + mu)
   double r_i[kCf2Tab];       // 1/i (shared by both loops)
   double r_a[kCf2Tab];       // 1/a_i of CF2, a_i = mu^2 - 1/4 - i(i-1)
+  // Power-series form of the Matern correlation for x <= 2 (t = x^2/4 <= 1), see matern_series():
+  //   rho = sum_k sa[k] t^k - t^nu sum_k sb[k] t^k,
+  //   sa[k] = Gamma(1-nu) / (k! Gamma(k+1-nu)),  sb[k] = Gamma(1-nu) / (k! Gamma(k+1+nu)).
+  // Only used when nu is not within 1e-3 of an integer (the two sums cancel there): use_series.
+  int use_series;
+  double sa[kMatSeriesTerms];
+  double sb[kMatSeriesTerms];
 };
 
 // ---- host side: constants per nu -------------------------------------------------------------
@@ -78,6 +86,25 @@ inline void matern_prepare(double nu, MaternConsts *mc) {
     mc->r_i2[i - 1] = 1.0 / ((double)i * i - mu2);
     mc->r_im[i - 1] = 1.0 / ((double)i - mu);
     mc->r_ip[i - 1] = 1.0 / ((double)i + mu);
+  }
+  {
+    // series coefficients in extended precision; Gamma(1-nu)/Gamma(k+1-/+nu) built by recurrence from k = 0
+    const long double lnu = (long double)nu;
+    const long double frac = lnu - roundl(lnu);
+    mc->use_series = (fabsl(frac) > 1e-3L && nu < 20.0) ? 1 : 0;
+    if (mc->use_series) {
+      const long double G = tgammal(1.0L - lnu);
+      long double ca = G / tgammal(1.0L - lnu);  // = 1
+      long double cb = G / tgammal(1.0L + lnu);
+      for (int k = 0; k < kMatSeriesTerms; k++) {
+        mc->sa[k] = (double)ca;
+        mc->sb[k] = (double)cb;
+        ca /= (long double)(k + 1) * ((long double)(k + 1) - lnu);  // Gamma(k+2-nu) = (k+1-nu) Gamma(k+1-nu)
+        cb /= (long double)(k + 1) * ((long double)(k + 1) + lnu);
+      }
+    } else {
+      for (int k = 0; k < kMatSeriesTerms; k++) mc->sa[k] = mc->sb[k] = 0.0;
+    }
   }
   double a = -mc->a1;
   for (int i = 1; i <= kCf2Tab; i++) {

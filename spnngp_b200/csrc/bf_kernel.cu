@@ -293,6 +293,10 @@ static cudaError_t launch_one(const BfLaunch &P, int grid_x, cudaStream_t stream
     if (e != cudaSuccess) return e;
     configured = true;
   }
+  if (COV == NNGP_COV_MATERN) {
+    cudaError_t e = upload_matern_consts(P.h_mat, P.nbatch, stream);
+    if (e != cudaSuccess) return e;
+  }
   dim3 grid(grid_x, P.nbatch, 1);
   bf_kernel<M, COV><<<grid, Geo::kThreads, Geo::kSmemBytes, stream>>>(P);
   return cudaGetLastError();
@@ -342,14 +346,14 @@ cudaError_t tpl_launch(const BfLaunch &P, int cov, int grid_x, cudaStream_t stre
 
 // Kernel choice: thread-per-location for m <= 16, the cooperative warp-group kernel above it.
 // NNGP_FORCE_COOP=1 in the environment selects the cooperative kernel for every m (A/B profiling).
-// Matern stays on the cooperative kernel: its Bessel-K evaluation is a data-dependent loop that cannot
-// be interleaved across entries, so one-lane-per-location runs it latency-bound (measured 2.4x slower).
 static bool use_tpl(int m, int cov) {
   static int force_coop = -1;
   if (force_coop < 0) {
     const char *e = getenv("NNGP_FORCE_COOP");
     force_coop = (e && e[0] == '1') ? 1 : 0;
   }
+  // Matern stays on the cooperative kernel for now: measured 1.79 ms vs 2.87 ms per 10^6 locations at
+  // m = 15 (its ~100-flop correlation likes the 16 resident warps more than the 5 of the one-lane kernel)
   return !force_coop && cov != NNGP_COV_MATERN && tpl_capacity_for_m(m) > 0;
 }
 

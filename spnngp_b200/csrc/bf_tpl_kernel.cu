@@ -53,7 +53,7 @@ constexpr int kTplMaxEnt = 144;
 template <int COV>
 __device__ __noinline__ void tpl_build(int off_co, int off_a, const unsigned *ent, int nent_pad, double sigmaSq,
                                        double phi, const MaternConsts *mat) {
-  constexpr int UNR = (COV == NNGP_COV_MATERN) ? 1 : 8;
+  constexpr int UNR = (COV == NNGP_COV_MATERN) ? 4 : 8;
   const int lane = threadIdx.x;
   const unsigned char *cob = tpl_smem + off_co + lane * 16;
   unsigned char *ab = tpl_smem + off_a + lane * 8;
@@ -71,7 +71,17 @@ __device__ __noinline__ void tpl_build(int off_co, int off_a, const unsigned *en
       d2[u] = dx * dx + dy * dy;
     }
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) v[u] = sigmaSq * cor(d2[u]);
+    for (int u = 0; u < UNR; ++u) v[u] = sigmaSq * cor.fast(d2[u]);
+    if (COV == NNGP_COV_MATERN) {  // rare arguments outside the straight-line path (phi D > 2, integer nu)
+      bool any = false;
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) any |= cor.needs_slow(d2[u]);
+      if (any) {
+#pragma unroll
+        for (int u = 0; u < UNR; ++u)
+          if (cor.needs_slow(d2[u])) v[u] = sigmaSq * cor.slow(d2[u]);
+      }
+    }
 #pragma unroll
     for (int u = 0; u < UNR; ++u) *reinterpret_cast<double *>(ab + dst[u] * 256u) = v[u];
   }
@@ -204,7 +214,7 @@ __global__ void __launch_bounds__(32) bf_tpl_kernel(const __grid_constant__ BfLa
   // work list of phase A (see tpl_build)
   __shared__ unsigned ent[kTplMaxEnt];
   const int ne = m * (m - 1) / 2;
-  constexpr int kBatch = (COV == NNGP_COV_MATERN) ? 1 : 8;
+  constexpr int kBatch = (COV == NNGP_COV_MATERN) ? 4 : 8;
   const int nent_pad = ((ne + m + kBatch - 1) / kBatch) * kBatch;
   for (int e = lane; e < nent_pad; e += 32) {
     unsigned w;
@@ -388,6 +398,10 @@ static cudaError_t tpl_launch_one(const BfLaunch &P, int grid_x, cudaStream_t st
                                          Geo::kWarpBytes);
     if (e != cudaSuccess) return e;
     if (dev < 16) configured[dev] = true;
+  }
+  if (COV == NNGP_COV_MATERN) {
+    cudaError_t e = upload_matern_consts(P.h_mat, P.nbatch, stream);
+    if (e != cudaSuccess) return e;
   }
   dim3 grid(grid_x, P.nbatch, 1);
   bf_tpl_kernel<MC, COV><<<grid, 32, Geo::kWarpBytes, stream>>>(P);

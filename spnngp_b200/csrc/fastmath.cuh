@@ -97,4 +97,59 @@ NNGP_FM double nngp_exp_nonpos(double x) {
   return (x < -708.0) ? 0.0 : p * s;
 }
 
+
+// natural log for positive normal x, branch-free (fdlibm's e_log.c scheme: x = 2^k (1+f), s = f/(2+f),
+// log(1+f) = f - hfsq + s (hfsq + R(s^2)); the division is a MUFU.RCP64H seed + two Newton steps).
+NNGP_FM double nngp_log_pos(double x) {
+  const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
+  const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
+               Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+               Lg7 = 1.479819860511658591e-01;
+#if defined(__CUDA_ARCH__)
+  int hx = __double2hiint(x);
+  const int lx = __double2loint(x);
+#else
+  uint64_t bits;
+  memcpy(&bits, &x, sizeof bits);
+  int hx = (int)(bits >> 32);
+  const int lx = (int)(bits & 0xffffffffu);
+#endif
+  int k = (hx >> 20) - 1023;
+  hx &= 0x000fffff;
+  const int i = (hx + 0x95f64) & 0x100000;  // 1 when the mantissa exceeds sqrt(2): use m/2, k+1
+  hx |= (i ^ 0x3ff00000);
+  k += (i >> 20);
+#if defined(__CUDA_ARCH__)
+  const double m = __hiloint2double(hx, lx);
+#else
+  const uint64_t mb = ((uint64_t)(uint32_t)hx << 32) | (uint32_t)lx;
+  double m;
+  memcpy(&m, &mb, sizeof m);
+#endif
+  const double f = m - 1.0;
+  const double den = 2.0 + f;
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+#else
+  double r = (double)(1.0f / (float)den);
+#endif
+  double e = fma(-den, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-den, r, 1.0);
+  r = fma(r, e, r);
+  double sv = f * r;
+  sv = fma(fma(-den, sv, f), r, sv);  // one residual correction: s = f/den to < 1 ulp
+  const double dk = (double)k;
+  const double z = sv * sv, w = z * z;
+  const double t1 = w * fma(w, fma(w, Lg6, Lg4), Lg2);
+  const double t2 = z * fma(w, fma(w, fma(w, Lg7, Lg5), Lg3), Lg1);
+  const double R = t2 + t1;
+  const double hfsq = 0.5 * f * f;
+  return dk * ln2_hi - ((hfsq - (sv * (hfsq + R) + dk * ln2_lo)) - f);
+}
+
+// exp for any x <= 700 (no overflow handling), flushing to 0 below -708: same kernel as nngp_exp_nonpos
+NNGP_FM double nngp_exp(double x) { return nngp_exp_nonpos(x); }
+
 }  // namespace nngp

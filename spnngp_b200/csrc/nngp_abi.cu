@@ -41,6 +41,20 @@ static void free_dev(Tp *&p) {
   p = nullptr;
 }
 
+// grow-only device buffer: reallocates when `count` elements no longer fit
+template <typename Tp>
+static int ensure_dev(nngp_ctx *c, Tp *&p, size_t &cap_bytes, size_t count) {
+  const size_t bytes = (count ? count : 1) * sizeof(Tp);
+  if (p && bytes <= cap_bytes) return NNGP_OK;
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap_bytes = 0;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return ctx_cuda(c, e, "cudaMalloc (model buffer)");
+  cap_bytes = bytes;
+  return NNGP_OK;
+}
+
 static void free_model(nngp_ctx *c) {
   free_dev(c->d_coords);
   free_dev(c->d_nnIndx);
@@ -56,6 +70,8 @@ static void free_model(nngp_ctx *c) {
   free_dev(c->d_out);
   if (c->h_beta) cudaFreeHost(c->h_beta);
   c->h_beta = nullptr;
+  c->h_beta_cap = 0;
+  for (size_t &x : c->cap) x = 0;
   c->n = c->m = c->p = 0;
 }
 
@@ -175,35 +191,50 @@ int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const 
   }
   NNGP_CUDA(c, cudaSetDevice(c->device));
   NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
-  free_model(c);
+  // device buffers are kept across calls and only grown (cudaMalloc/cudaFree of the ~0.5 GB working set
+  // would otherwise dominate a short fit: the whole-call path is measured end to end by bench.py)
   c->n = n; c->m = m; c->p = p; c->loc_begin = loc_begin; c->loc_end = loc_end;
   c->has_nn = (nnIndx != nullptr);  // NULL: prediction-only use (sites, X, y), no B/F storage
   c->nIndx = c->has_nn ? nn_offset(n, m) : 0;  // == (1+m)/2*m + (n-m-1)*m for n > m
   const long long nI = c->nIndx > 0 ? c->nIndx : 1;
   for (long long k = 0; k < c->nIndx; k++) {
-    // neighbours must precede... checked lazily: ids must at least be valid indices
     if (nnIndx[k] < 0 || nnIndx[k] >= n) return ctx_fail(c, NNGP_EINVAL, "nngp_set_data: neighbour index out of range");
   }
+  int rc;
+#define NNGP_ENSURE(ptr, slot, count)                                     \
+  do {                                                                    \
+    rc = ensure_dev(c, ptr, c->cap[slot], (size_t)(count));               \
+    if (rc) return rc;                                                    \
+  } while (0)
+  NNGP_ENSURE(c->d_coords, 0, n);
   {
-    std::vector<double2> xy((size_t)n);
+    // interleave (x, y) through pinned memory so the upload is a single DMA
+    double2 *xy = nullptr;
+    NNGP_CUDA(c, cudaMallocHost(&xy, (size_t)n * sizeof(double2)));
     for (int i = 0; i < n; i++) xy[i] = make_double2(coords[i], coords[(size_t)n + i]);
-    NNGP_CUDA(c, cudaMalloc(&c->d_coords, (size_t)n * sizeof(double2)));
-    NNGP_CUDA(c, cudaMemcpy(c->d_coords, xy.data(), (size_t)n * sizeof(double2), cudaMemcpyHostToDevice));
+    cudaError_t e = cudaMemcpy(c->d_coords, xy, (size_t)n * sizeof(double2), cudaMemcpyHostToDevice);
+    cudaFreeHost(xy);
+    NNGP_CUDA(c, e);
   }
-  NNGP_CUDA(c, cudaMalloc(&c->d_nnIndx, (size_t)nI * sizeof(int)));
+  NNGP_ENSURE(c->d_nnIndx, 1, nI);
   if (c->nIndx > 0) NNGP_CUDA(c, cudaMemcpy(c->d_nnIndx, nnIndx, (size_t)c->nIndx * sizeof(int), cudaMemcpyHostToDevice));
   if (p > 0) {
-    NNGP_CUDA(c, cudaMalloc(&c->d_X, (size_t)n * p * sizeof(double)));
+    NNGP_ENSURE(c->d_X, 2, (size_t)n * p);
     NNGP_CUDA(c, cudaMemcpy(c->d_X, X, (size_t)n * p * sizeof(double), cudaMemcpyHostToDevice));
-    NNGP_CUDA(c, cudaMalloc(&c->d_y, (size_t)n * sizeof(double)));
+    NNGP_ENSURE(c->d_y, 3, n);
     NNGP_CUDA(c, cudaMemcpy(c->d_y, y, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
-    NNGP_CUDA(c, cudaMalloc(&c->d_beta, (size_t)NNGP_MAX_BATCH * p * sizeof(double)));
-    NNGP_CUDA(c, cudaHostAlloc(&c->h_beta, (size_t)NNGP_MAX_BATCH * p * sizeof(double), cudaHostAllocDefault));
-    for (int b = 0; b < NNGP_MAX_BATCH; b++) NNGP_CUDA(c, cudaMalloc(&c->d_resid[b], (size_t)n * sizeof(double)));
+    NNGP_ENSURE(c->d_beta, 4, (size_t)NNGP_MAX_BATCH * p);
+    if (c->h_beta_cap < (size_t)NNGP_MAX_BATCH * p) {
+      if (c->h_beta) cudaFreeHost(c->h_beta);
+      c->h_beta = nullptr;
+      NNGP_CUDA(c, cudaHostAlloc(&c->h_beta, (size_t)NNGP_MAX_BATCH * p * sizeof(double), cudaHostAllocDefault));
+      c->h_beta_cap = (size_t)NNGP_MAX_BATCH * p;
+    }
+    for (int b = 0; b < NNGP_MAX_BATCH; b++) NNGP_ENSURE(c->d_resid[b], 5 + b, n);
   }
   for (int s = 0; s < 2 && c->has_nn; s++) {
-    NNGP_CUDA(c, cudaMalloc(&c->d_B[s], (size_t)nI * sizeof(double)));
-    NNGP_CUDA(c, cudaMalloc(&c->d_F[s], (size_t)n * sizeof(double)));
+    NNGP_ENSURE(c->d_B[s], 9 + s, nI);
+    NNGP_ENSURE(c->d_F[s], 11 + s, n);
   }
   const long long nloc = (long long)loc_end - loc_begin;
   const int K = p + 1, npairs = K * (K + 1) / 2;
@@ -212,9 +243,10 @@ int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const 
   size_t need3 = (size_t)q_resid_grid(m, nloc, c->sms);
   c->partials_len = need > need2 ? need : need2;
   if (need3 > c->partials_len) c->partials_len = need3;
-  NNGP_CUDA(c, cudaMalloc(&c->d_partials, c->partials_len * sizeof(double)));
+  NNGP_ENSURE(c->d_partials, 13, c->partials_len);
   c->out_len = (size_t)npairs + 8;
-  NNGP_CUDA(c, cudaMalloc(&c->d_out, c->out_len * sizeof(double)));
+  NNGP_ENSURE(c->d_out, 14, c->out_len);
+#undef NNGP_ENSURE
   return NNGP_OK;
 }
 
@@ -234,6 +266,7 @@ static int prepare_bf(nngp_ctx *c, int cov, int nbatch, const double *theta, con
   P->loc_begin = c->loc_begin;
   P->loc_end = c->loc_end;
   P->nbatch = nbatch;
+  P->h_mat = (cov == NNGP_COV_MATERN) ? c->h_mat : nullptr;
   double *out_dev = nullptr;
   int *fail_dev = nullptr;
   NNGP_CUDA(c, cudaHostGetDevicePointer((void **)&out_dev, c->h_out, 0));
@@ -249,7 +282,6 @@ static int prepare_bf(nngp_ctx *c, int cov, int nbatch, const double *theta, con
     if (cov == NNGP_COV_MATERN) {
       if (!(t[3] > 0.0)) return ctx_fail(c, NNGP_EINVAL, "matern nu must be > 0");
       matern_prepare(t[3], &c->h_mat[b]);
-      th.mat = c->d_mat + b;
     }
     const int slot = slots ? slots[b] : (b & 1);
     if (slot < 0 || slot > 1) return ctx_fail(c, NNGP_EINVAL, "slot must be 0 or 1");
@@ -262,8 +294,6 @@ static int prepare_bf(nngp_ctx *c, int cov, int nbatch, const double *theta, con
     th.fail = c->d_fail + b;
     th.fail_out = fail_dev + b;
   }
-  if (cov == NNGP_COV_MATERN)
-    NNGP_CUDA(c, cudaMemcpyAsync(c->d_mat, c->h_mat, nbatch * sizeof(MaternConsts), cudaMemcpyHostToDevice, c->stream));
   if (beta) {
     memcpy(c->h_beta, beta, (size_t)nbatch * c->p * sizeof(double));
     NNGP_CUDA(c, cudaMemcpyAsync(c->d_beta, c->h_beta, (size_t)nbatch * c->p * sizeof(double), cudaMemcpyHostToDevice, c->stream));

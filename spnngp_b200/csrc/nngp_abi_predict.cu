@@ -97,8 +97,7 @@ int site_solve(nngp_ctx *c, int cov, const double *t, SiteChunk &ch) {
   th.mat = nullptr;
   if (cov == NNGP_COV_MATERN) {
     matern_prepare(t[3], &c->h_mat[0]);
-    NNGP_CUDA(c, cudaMemcpyAsync(c->d_mat, c->h_mat, sizeof(MaternConsts), cudaMemcpyHostToDevice, c->stream));
-    th.mat = c->d_mat;
+    P.h_mat = c->h_mat;
   }
   double *out_dev = nullptr;
   int *fail_dev = nullptr;

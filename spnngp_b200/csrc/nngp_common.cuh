@@ -35,6 +35,7 @@ struct BfLaunch {
   int n, m;
   int loc_begin, loc_end;
   int nbatch;
+  const MaternConsts *h_mat;  // HOST array [nbatch] (pinned), Matern only; uploaded by the launcher
   // site mode (prediction paths): "locations" are q query sites with unordered m-neighbour lists;
   // th.B receives the kriging weights as a q x m column-major matrix, th.F the q conditional variances
   int site_mode;

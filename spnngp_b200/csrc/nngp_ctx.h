@@ -40,6 +40,8 @@ struct nngp_ctx {
   double *h_out = nullptr;
   int *h_fail = nullptr;
   double *h_beta = nullptr;
+  size_t h_beta_cap = 0;
+  size_t cap[16] = {};  // capacities (bytes) of the grow-only model buffers, see nngp_set_data
   nngp::MaternConsts *h_mat = nullptr;
 
   // timing

@@ -7,3 +7,13 @@ double host_matern(double x, double nu) { nngp::MaternConsts mc; nngp::matern_pr
 void host_gammas(double nu, double *out) { nngp::MaternConsts mc; nngp::matern_prepare(nu, &mc);
   out[0]=mc.gam1; out[1]=mc.gam2; out[2]=mc.gampl; out[3]=mc.gammi; out[4]=mc.mu; out[5]=mc.pref; }
 }
+#include "../../spnngp_b200/csrc/matern_series.cuh"
+extern "C" {
+// Matern correlation through the series path (x <= 2) exactly as the device evaluates it
+double host_matern_series(double x, double nu) {
+  nngp::MaternConsts mc; nngp::matern_prepare(nu, &mc);
+  if (!mc.use_series) return -1.0;
+  return nngp::matern_series(0.25 * x * x, mc);
+}
+double host_nngp_log_pos(double x) { return nngp::nngp_log_pos(x); }
+}

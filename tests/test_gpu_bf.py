@@ -39,10 +39,19 @@ def test_bf_parity(engine, port, cov, n, m):
     _check(engine, port, prob, cov, THETA[cov])
 
 
-@pytest.mark.parametrize("nu", [0.3, 0.5, 1.5, 2.5, 3.2])
+@pytest.mark.parametrize("nu", [0.1, 0.3, 0.5, 0.999, 1.0, 1.0005, 1.5, 2.0, 2.5, 3.2])
 def test_matern_nu(engine, port, nu):
+    """Series path (generic nu), and the Temme/CF2 path (nu within 1e-3 of an integer)."""
     prob = make_problem(1200, 15, seed=7, port=port, domain=0.5)
     _check(engine, port, prob, 2, [2.0, 0.5, 4.0, nu])
+
+
+@pytest.mark.parametrize("m", [10, 20])
+@pytest.mark.parametrize("phi", [40.0, 150.0])
+def test_matern_large_phi_mixes_series_and_cf2(engine, port, phi, m):
+    """phi D straddles 2: entries switch between the power series and the continued fraction."""
+    prob = make_problem(900, m, seed=19, port=port, domain=0.6)
+    _check(engine, port, prob, 2, [2.0, 0.5, phi, 0.8])
 
 
 def test_matern_half_is_exponential(engine, port):
