@@ -69,55 +69,70 @@ def sampler_settings(cov: int):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML polled from a
+    background thread every ~2 ms (the timed region can be shorter than one nvidia-smi -lms period)."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index: int):
         self.index = index
-        self.proc = None
-        self.path = None
+        self.samples = []
+        self.masks = set()
+        self.sm_max = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
 
     def start(self):
         try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-                 "clocks_event_reasons.sw_power_cap")
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            # CUDA_VISIBLE_DEVICES remaps indices: resolve through the UUID when possible
+            h = None
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if self.index < len(ids):
+                    tok = ids[self.index]
+                    h = pynvml.nvmlDeviceGetHandleByUUID(tok) if tok.startswith("GPU-") else \
+                        pynvml.nvmlDeviceGetHandleByIndex(int(tok))
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self._h = h
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            self._nvml = None
+            return
+
+        def loop():
+            nv = self._nvml
+            while not self._stop.is_set():
+                try:
+                    self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                    try:
+                        m = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                    except Exception:
+                        m = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                    for bit in self.REASONS:
+                        if m & bit:
+                            self.masks.add(self.REASONS[bit])
+                except Exception:
+                    pass
+                time.sleep(0.002)
+
+        self._thread = threading.Thread(target=loop, daemon=True)
+        self._thread.start()
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.proc is None:
-            return out
-        try:
-            self.proc.terminate()
-            self.proc.wait(timeout=5)
-        except Exception:
-            pass
-        try:
-            rows = [r.strip().split(",") for r in open(self.path) if r.strip()]
-            sm = [float(r[0]) for r in rows if r[0].strip().replace(".", "").isdigit()]
-            mx = [float(r[1]) for r in rows if r[1].strip().replace(".", "").isdigit()]
-            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-            reasons = set()
-            for r in rows:
-                for k, nm in enumerate(names):
-                    if len(r) > 4 + k and r[4 + k].strip().lower() == "active":
-                        reasons.add(nm)
-            if sm:
-                out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                       "samples": len(sm)}
-        except Exception:
-            pass
-        finally:
-            try:
-                os.unlink(self.path)
-            except Exception:
-                pass
+        out = {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": []}
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+        if self.samples:
+            out = {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.sm_max, "reasons": sorted(self.masks),
+                   "samples": len(self.samples), "source": "NVML, 2 ms polling inside the timed region"}
         return out
 
 
@@ -245,7 +260,14 @@ def run_b200(args, rank, world, local_rank):
     nnIndx, nnDist, lu = eng.mk_nn_indx(wl["coords"], m, "cb")  # setup, not timed: the sampler reuses neighbours
     t_knn = time.perf_counter() - t0
     lo, hi = shard_range(n, m, rank, world)
-    allreduce = make_allreduce(device=dev) if world > 1 else None
+    # the engine's own NCCL communicator: likelihood partials are summed on the device right behind the
+    # kernel (python-level hook `make_allreduce` is the slower, backend-agnostic alternative)
+    allreduce = None
+    if world > 1:
+        if args.py_allreduce:
+            allreduce = make_allreduce(device=dev)
+        else:
+            eng.comm_init_from_torch()
 
     def barrier():
         if world > 1:
@@ -285,6 +307,7 @@ def run_b200(args, rank, world, local_rank):
     barrier()
     t0 = time.perf_counter()
     eng.set_data(wl["coords"], nnIndx, lu, wl["X"], wl["y"], m, loc_range=(lo, hi))
+    t_set = time.perf_counter() - t0
     _, _, acc_e = chain(args.steps, args.mode)
     torch.cuda.synchronize(dev)
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
@@ -343,10 +366,11 @@ def run_b200(args, rank, world, local_rank):
                 else "double-buffered: 1 B/F solve + 1 Q-only pass per iteration",
                 "l2": f"inputs larger than L2: {bytes_per_location(m) * (hi - lo) / 1e6:.0f} MB touched per launch vs 126 MB L2"
                 if bytes_per_location(m) * (hi - lo) > 126e6 else "working set fits L2 at this shard size (no flush; strong scaling)",
-                "parallelism": f"locations sharded over {world} GPU(s); allreduce of 4 doubles per iteration",
+                "parallelism": f"locations sharded over {world} GPU(s); NCCL allreduce of 6 doubles per iteration on the kernel's stream",
                 "acceptance_rate": acc / args.steps, "rng": "R-compatible Mersenne-Twister + inversion (librshim), seed 1",
             },
             "e2e": {"value": args.steps / e2e_s, "unit": "iter/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
+                    "set_data_s": t_set,
                     "note": "nngp_set_data from host buffers + K iterations + samples back, wall clock, max over ranks"},
             "gpu_launches": int(launches_t.item()),
             "clocks": clk,
@@ -408,6 +432,7 @@ def main():
     ap.add_argument("--mode", type=int, default=0, help="0 reference-faithful sampler, 1 double-buffered")
     ap.add_argument("--ref-budget-s", type=float, default=150.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--py-allreduce", action="store_true", help="sum partials through torch.distributed in Python")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

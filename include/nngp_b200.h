@@ -167,6 +167,19 @@ int nngp_rnngp_predict(nngp_ctx *ctx, int cov_model, int q, const double *X0, co
                        const double *thetaSamples, const double *z, double *y0, int site_begin,
                        int site_end);
 
+/* ---- multi-GPU: one process (context) per GPU, the locations sharded with nngp_set_data's range.
+ *      After nngp_comm_init the results of nngp_bf_loglik, nngp_q_resid and nngp_q_forms are summed
+ *      over the ranks ON THE DEVICE (NCCL allreduce of <= 12 / (p+1)(p+2)/2 doubles over NVLink, issued
+ *      on the context stream right behind the producing kernel), so every rank receives the full
+ *      log-likelihood pieces and nngp_rnngp / nngp_cnngp run unchanged and in lock-step on every rank
+ *      (same RNG seed on every rank).  The id comes from rank 0 (nngp_comm_unique_id) and is
+ *      distributed by the launcher (torch.distributed broadcast in spnngp_b200/dist.py, MPI, files...).
+ *      libnccl is loaded lazily; single-GPU use needs no NCCL. */
+int nngp_comm_unique_id(char id[128]);
+int nngp_comm_init(nngp_ctx *ctx, const char id[128], int rank, int nranks);
+int nngp_comm_allreduce_sum(nngp_ctx *ctx, double *buf, int len); /* host buffer, len <= 12; for tests/tools */
+void nngp_comm_destroy(nngp_ctx *ctx);
+
 /* ---- HBM-resident measurement helpers (bench.py `value`): time the likelihood launch with every
  *      input already on the device.  Runs `iters` launches of nngp_bf_loglik's kernel back to back
  *      on the context stream between two CUDA events and returns the mean milliseconds per launch. */

@@ -43,7 +43,7 @@ ABI_SYMBOLS = [
     "nngp_abi_version", "nngp_device_count", "nngp_create", "nngp_destroy", "nngp_last_error", "nngp_sync",
     "nngp_mk_nn_indx", "nngp_nn_query", "nngp_set_data", "nngp_bf_loglik", "nngp_q_resid", "nngp_q_forms",
     "nngp_get_bf", "nngp_rnngp", "nngp_cnngp", "nngp_rnngp_predict", "nngp_time_bf_loglik", "nngp_launch_count",
-    "nngp_fp64_peak",
+    "nngp_fp64_peak", "nngp_comm_unique_id", "nngp_comm_init", "nngp_comm_allreduce_sum", "nngp_comm_destroy",
 ]
 
 _lib = None
@@ -80,6 +80,11 @@ def load():
     L.nngp_time_bf_loglik.argtypes = [vp, C.c_int, C.c_int, c_double_p, c_double_p, C.c_int, C.c_int,
                                       C.POINTER(C.c_float)]
     L.nngp_fp64_peak.argtypes = [vp, c_double_p]
+    L.nngp_comm_unique_id.argtypes = [C.c_char_p]
+    L.nngp_comm_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
+    L.nngp_comm_allreduce_sum.argtypes = [vp, c_double_p, C.c_int]
+    L.nngp_comm_destroy.restype = None
+    L.nngp_comm_destroy.argtypes = [vp]
     L.nngp_launch_count.restype = C.c_longlong
     L.nngp_launch_count.argtypes = [vp]
     if hasattr(L, "nngp_mk_nn_indx"):

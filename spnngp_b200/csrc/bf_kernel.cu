@@ -275,7 +275,9 @@ __global__ void __launch_bounds__(128, (M <= 16 ? 4 : 2)) bf_kernel(const __grid
     if (tid == 0) {
       th.out[0] = a;
       th.out[1] = b;
-      *th.fail_out = atomicExch(th.fail, INT_MAX);
+      const int fv = atomicExch(th.fail, INT_MAX);
+      th.out[2] = (fv != INT_MAX) ? 1.0 : 0.0;  // summed across ranks so that every rank sees a failure
+      *th.fail_out = fv;
       *th.ticket = 0u;
     }
   }

@@ -380,7 +380,9 @@ __global__ void __launch_bounds__(32) bf_tpl_kernel(const __grid_constant__ BfLa
     if (lane == 0) {
       th.out[0] = a;
       th.out[1] = b;
-      *th.fail_out = atomicExch(th.fail, INT_MAX);
+      const int fv = atomicExch(th.fail, INT_MAX);
+      th.out[2] = (fv != INT_MAX) ? 1.0 : 0.0;  // summed across ranks so that every rank sees a failure
+      *th.fail_out = fv;
       *th.ticket = 0u;
     }
   }

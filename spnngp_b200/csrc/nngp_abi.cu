@@ -140,7 +140,9 @@ int nngp_create(int device, void *stream_handle, nngp_ctx **out) {
     NNGP_CUDA(c, cudaMemcpy(c->d_fail, init, sizeof init, cudaMemcpyHostToDevice));
   }
   NNGP_CUDA(c, cudaMalloc(&c->d_mat, NNGP_MAX_BATCH * sizeof(MaternConsts)));
-  NNGP_CUDA(c, cudaHostAlloc(&c->h_out, 2 * NNGP_MAX_BATCH * sizeof(double), cudaHostAllocMapped));
+  NNGP_CUDA(c, cudaHostAlloc(&c->h_out, 3 * NNGP_MAX_BATCH * sizeof(double), cudaHostAllocMapped));
+  NNGP_CUDA(c, cudaMalloc(&c->d_red, 3 * NNGP_MAX_BATCH * sizeof(double)));
+  NNGP_CUDA(c, cudaHostAlloc(&c->h_red, 3 * NNGP_MAX_BATCH * sizeof(double), cudaHostAllocDefault));
   NNGP_CUDA(c, cudaHostAlloc(&c->h_fail, NNGP_MAX_BATCH * sizeof(int), cudaHostAllocMapped));
   NNGP_CUDA(c, cudaHostAlloc(&c->h_mat, NNGP_MAX_BATCH * sizeof(MaternConsts), cudaHostAllocDefault));
   NNGP_CUDA(c, cudaEventCreate(&c->ev0));
@@ -159,6 +161,8 @@ void nngp_destroy(nngp_ctx *c) {
   free_dev(c->d_mat);
   if (c->d_flush) cudaFree(c->d_flush);
   if (c->h_out) cudaFreeHost(c->h_out);
+  if (c->h_red) cudaFreeHost(c->h_red);
+  free_dev(c->d_red);
   if (c->h_fail) cudaFreeHost(c->h_fail);
   if (c->h_mat) cudaFreeHost(c->h_mat);
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -288,7 +292,7 @@ static int prepare_bf(nngp_ctx *c, int cov, int nbatch, const double *theta, con
     th.B = store ? c->d_B[slot] : nullptr;
     th.F = store ? c->d_F[slot] : nullptr;
     th.resid = beta ? c->d_resid[b] : nullptr;
-    th.out = out_dev + 2 * b;
+    th.out = (c->comm ? c->d_red : out_dev) + 3 * b;  // device buffer when the result is reduced over ranks
     th.partials = c->d_partials + (size_t)2 * grid * b;
     th.ticket = c->d_ticket + b;
     th.fail = c->d_fail + b;
@@ -340,13 +344,23 @@ int nngp_bf_loglik(nngp_ctx *c, int cov, int nbatch, const double *theta, const 
   share_resid(c, &P);
   rc = enqueue_bf(c, cov, P, grid, beta != nullptr);
   if (rc) return rc;
+  const double *res = c->h_out;
+  if (c->comm) {  // sum (logDet, Q, fail flag) over the ranks on the device, then one small copy back
+    rc = comm_allreduce_dev(c, c->d_red, 3 * nbatch);
+    if (rc) return rc;
+    NNGP_CUDA(c, cudaMemcpyAsync(c->h_red, c->d_red, 3 * nbatch * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    res = c->h_red;
+  }
   NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
   int status = 0;
+  bool any_rank_failed = false;
   for (int b = 0; b < nbatch; b++) {
-    out[2 * b] = c->h_out[2 * b];
-    out[2 * b + 1] = beta ? c->h_out[2 * b + 1] : 0.0;
+    out[2 * b] = res[3 * b];
+    out[2 * b + 1] = beta ? res[3 * b + 1] : 0.0;
+    if (res[3 * b + 2] > 0.0) any_rank_failed = true;
     if (c->h_fail[b] != INT_MAX && (status == 0 || c->h_fail[b] < status)) status = c->h_fail[b];
   }
+  if (status == 0 && any_rank_failed) status = INT_MAX;  // the failing location lives on another rank
   if (status > 0) return ctx_fail(c, status, "c++ error: dpotrf failed (neighbour covariance not positive definite)");
   return NNGP_OK;
 }
@@ -403,6 +417,10 @@ int nngp_q_resid(nngp_ctx *c, int slot, const double *beta, double *out) {
   NNGP_CUDA(c, q_resid_launch(c->d_B[slot], c->d_F[slot], c->d_nnIndx, c->d_resid[0], c->m, c->loc_begin, c->loc_end,
                               c->d_partials, c->d_out, c->sms, c->stream));
   c->launches += 3;
+  if (c->comm) {
+    int rc = comm_allreduce_dev(c, c->d_out, 1);
+    if (rc) return rc;
+  }
   NNGP_CUDA(c, cudaMemcpyAsync(c->h_out, c->d_out, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
   out[0] = c->h_out[0];
@@ -417,6 +435,10 @@ int nngp_q_forms(nngp_ctx *c, int slot, double *S) {
   NNGP_CUDA(c, q_forms_launch(c->d_B[slot], c->d_F[slot], c->d_nnIndx, c->d_X, c->d_y, c->n, c->p, c->m, c->loc_begin,
                               c->loc_end, c->d_partials, c->d_out, c->stream));
   c->launches += 2;
+  if (c->comm) {
+    int rc = comm_allreduce_dev(c, c->d_out, npairs);
+    if (rc) return rc;
+  }
   std::vector<double> packed(npairs);
   NNGP_CUDA(c, cudaMemcpyAsync(packed.data(), c->d_out, npairs * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   NNGP_CUDA(c, cudaStreamSynchronize(c->stream));

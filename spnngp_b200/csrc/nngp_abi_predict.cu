@@ -106,7 +106,7 @@ int site_solve(nngp_ctx *c, int cov, const double *t, SiteChunk &ch) {
   th.B = ch.W.as<double>();
   th.F = ch.F.as<double>();
   th.resid = nullptr;
-  th.out = out_dev;
+  th.out = out_dev;  // 3 doubles, unused in site mode
   th.partials = c->d_partials;
   th.ticket = c->d_ticket;
   th.fail = c->d_fail;

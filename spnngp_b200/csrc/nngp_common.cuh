@@ -22,7 +22,7 @@ struct BfTheta {
   double *B;            // nIndx weights (or nullptr: do not store)
   double *F;            // n conditional variances (or nullptr)
   const double *resid;  // n residuals r = X beta - y (or nullptr: no quadratic form)
-  double *out;          // 2 doubles: sum log F, Q over [loc_begin, loc_end)
+  double *out;          // 3 doubles: sum log F, Q over [loc_begin, loc_end), 1.0 if a factorisation failed
   double *partials;     // 2 * gridDim.x doubles of scratch
   unsigned int *ticket; // zero-initialised, self-resetting
   int *fail;            // device: min over failing locations of (i + 1); INT_MAX when none; self-resetting

@@ -44,6 +44,13 @@ struct nngp_ctx {
   size_t cap[16] = {};  // capacities (bytes) of the grow-only model buffers, see nngp_set_data
   nngp::MaternConsts *h_mat = nullptr;
 
+  // multi-GPU: NCCL communicator over the ranks of a sharded fit (nngp_comm_init); when set, the
+  // results of nngp_bf_loglik / nngp_q_resid / nngp_q_forms are summed over the ranks on the device
+  void *comm = nullptr;
+  int comm_rank = 0, comm_size = 1;
+  double *d_red = nullptr;  // 3 * NNGP_MAX_BATCH doubles: kernel results, reduced in place
+  double *h_red = nullptr;  // pinned copy
+
   // timing
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   void *d_flush = nullptr;
@@ -75,6 +82,8 @@ cudaError_t q_forms_launch(const double *B, const double *F, const int *nnIndx, 
 int ctx_fail(nngp_ctx *ctx, int code, const std::string &msg);
 int ctx_cuda(nngp_ctx *ctx, cudaError_t e, const char *what);
 void set_global_error(const std::string &msg);
+// nngp_abi_misc.cu: in-place sum over ranks of `len` doubles in device memory, on the context stream
+int comm_allreduce_dev(nngp_ctx *ctx, double *d_buf, int len);
 
 }  // namespace nngp
 

@@ -72,6 +72,7 @@ class Engine:
 
     def close(self):
         if getattr(self, "h", None):
+            self.lib.nngp_comm_destroy(self.h)
             self.lib.nngp_destroy(self.h)
             self.h = None
 
@@ -149,6 +150,27 @@ class Engine:
         B = np.zeros(max(n_indx(self.n, self.m), 1)); F = np.zeros(self.n)
         self._check(self.lib.nngp_get_bf(self.h, slot, _dp(B), _dp(F)))
         return B, F
+
+    def comm_init_from_torch(self, group=None):
+        """Create the engine's NCCL communicator over the ranks of torch.distributed's default (or given)
+        group: rank 0 makes the id, torch broadcasts it.  Afterwards likelihood results are rank-summed."""
+        import torch.distributed as dist
+        world = dist.get_world_size(group); rank = dist.get_rank(group)
+        if world == 1:
+            return
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            st = self.lib.nngp_comm_unique_id(buf)
+            if st != 0:
+                raise NNGPError(st, self.lib.nngp_last_error(None).decode())
+        obj = [buf.raw if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0, group=group)
+        self._check(self.lib.nngp_comm_init(self.h, obj[0], rank, world))
+
+    def comm_allreduce(self, arr):
+        a = _f64(arr).copy()
+        self._check(self.lib.nngp_comm_allreduce_sum(self.h, _dp(a), a.size))
+        return a
 
     def fp64_peak_tflops(self):
         out = np.zeros(1)

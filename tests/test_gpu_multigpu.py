@@ -1,0 +1,72 @@
+"""GPU, >= 2 devices: two ranks (one process per GPU), locations sharded, likelihood pieces summed by the
+engine's NCCL communicator -- equal to the single-GPU result; sampler chains identical on both ranks."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, rdzv, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from oracle import pyoracle as po
+    from spnngp_b200 import Engine, _lib
+    from spnngp_b200.dist import shard_range
+    from tests.util import make_problem
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"file://{rdzv}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    port = po.Port(); port.set_threads(2)
+    prob = make_problem(6000, 15, seed=5, port=port, domain=1.1)
+    n, m = 6000, 15
+    eng = Engine(rank)
+    eng.comm_init_from_torch()
+    lo, hi = shard_range(n, m, rank, world)
+    eng.set_data(prob["coords"], prob["nnIndx"], prob["nnIndxLU"], prob["X"], prob["y"], m, loc_range=(lo, hi))
+    out = eng.bf_loglik(0, [[5.0, 1.0, 6.0], [4.0, 1.1, 7.0]], [prob["beta"], prob["beta"]], slots=[0, 1])
+    S = eng.q_forms(0)
+    qr = eng.q_resid(1, prob["beta"])
+    R = _lib.load_rshim(); R.rshim_set_seed(3)
+    starting = {"beta": [0.0, 0.0], "sigma.sq": 5.0, "tau.sq": 1.0, "phi": 6.0}
+    tuning = {"sigma.sq": 0.03, "tau.sq": 0.03, "phi": 0.03}
+    bs, ts, acc = eng.rnngp(0, [2.0, 5.0], [2.0, 1.0], [3.0, 300.0], None, starting, tuning, 25, R.rnorm, R.runif)
+    q.put((rank, out, S, qr, ts, acc))
+    eng.close()
+    dist.destroy_process_group()
+
+
+def test_two_rank_nccl_matches_single_gpu(tmp_path, port):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    from spnngp_b200 import Engine, _lib
+    from tests.util import make_problem
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(k, 2, str(tmp_path / "rdzv"), q)) for k in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in procs], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    prob = make_problem(6000, 15, seed=5, port=port, domain=1.1)
+    eng = Engine(0)
+    eng.set_data(prob["coords"], prob["nnIndx"], prob["nnIndxLU"], prob["X"], prob["y"], 15)
+    out = eng.bf_loglik(0, [[5.0, 1.0, 6.0], [4.0, 1.1, 7.0]], [prob["beta"], prob["beta"]], slots=[0, 1])
+    S = eng.q_forms(0); qr = eng.q_resid(1, prob["beta"])
+    R = _lib.load_rshim(); R.rshim_set_seed(3)
+    starting = {"beta": [0.0, 0.0], "sigma.sq": 5.0, "tau.sq": 1.0, "phi": 6.0}
+    tuning = {"sigma.sq": 0.03, "tau.sq": 0.03, "phi": 0.03}
+    bs, ts, acc = eng.rnngp(0, [2.0, 5.0], [2.0, 1.0], [3.0, 300.0], None, starting, tuning, 25, R.rnorm, R.runif)
+    for r in res:
+        assert np.allclose(r[1], out, rtol=1e-12) and np.allclose(r[2], S, rtol=1e-11) and abs(r[3] - qr) < 1e-11 * abs(qr)
+        assert r[5] == acc and np.allclose(r[4], ts, rtol=1e-10)
+    assert np.array_equal(res[0][4], res[1][4])  # both ranks hold the same chain
+    eng.close()
