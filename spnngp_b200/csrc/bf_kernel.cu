@@ -27,6 +27,7 @@
 //   No tensor cores: each solve is a tiny FP64 problem (BASELINE.json north_star).
 #include <limits.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "cov.cuh"
 
@@ -341,37 +342,60 @@ cudaError_t coop_launch(const BfLaunch &P, int cov, int grid_x, cudaStream_t str
   return launch_cov<32>(P, cov, grid_x, stream);
 }
 
-// bf_tpl_kernel.cu
+// bf_tpl_kernel.cu / bf_ws_kernel.cu
 int tpl_capacity_for_m(int m);
 int tpl_grid_for(int m, long long nloc, int sms);
 cudaError_t tpl_launch(const BfLaunch &P, int cov, int grid_x, cudaStream_t stream);
+int ws_grid_for(int m, long long nloc, int sms);
+cudaError_t ws_launch(const BfLaunch &P, int cov, int grid_x, cudaStream_t stream);
 
-// Kernel choice: thread-per-location for m <= 16, the cooperative warp-group kernel above it.
-// NNGP_FORCE_COOP=1 in the environment selects the cooperative kernel for every m (A/B profiling).
-static bool use_tpl(int m, int cov) {
-  static int force_coop = -1;
-  if (force_coop < 0) {
-    const char *e = getenv("NNGP_FORCE_COOP");
-    force_coop = (e && e[0] == '1') ? 1 : 0;
+// Kernel choice.  m <= 16: the warp-specialised one-lane-per-location kernel (bf_ws_kernel.cu);
+// larger m: the cooperative warp-group kernel above.  NNGP_KERNEL=coop|tpl|ws forces one (A/B profiling;
+// tpl = the single-role one-lane-per-location kernel of bf_tpl_kernel.cu).
+enum { KERNEL_COOP = 0, KERNEL_TPL = 1, KERNEL_WS = 2 };
+
+static int kernel_for(int m, int cov) {
+  static int forced = -2;
+  if (forced == -2) {
+    const char *e = getenv("NNGP_KERNEL");
+    forced = -1;
+    if (e) {
+      if (!strcmp(e, "coop")) forced = KERNEL_COOP;
+      else if (!strcmp(e, "tpl")) forced = KERNEL_TPL;
+      else if (!strcmp(e, "ws")) forced = KERNEL_WS;
+    }
   }
-  // Matern stays on the cooperative kernel for now: measured 1.79 ms vs 2.87 ms per 10^6 locations at
-  // m = 15 (its ~100-flop correlation likes the 16 resident warps more than the 5 of the one-lane kernel)
-  return !force_coop && cov != NNGP_COV_MATERN && tpl_capacity_for_m(m) > 0;
+  (void)cov;
+  const bool small = tpl_capacity_for_m(m) > 0;
+  if (forced >= 0 && (forced == KERNEL_COOP || small)) return forced;
+  return small ? KERNEL_WS : KERNEL_COOP;
 }
 
 int bf_grid_any(int m, int cov, long long nloc, int sms) {
-  return use_tpl(m, cov) ? tpl_grid_for(m, nloc, sms) : bf_grid_for(m, nloc, sms);
+  switch (kernel_for(m, cov)) {
+    case KERNEL_WS: return ws_grid_for(m, nloc, sms);
+    case KERNEL_TPL: return tpl_grid_for(m, nloc, sms);
+    default: return bf_grid_for(m, nloc, sms);
+  }
 }
 
-// upper bound of bf_grid_any over both kernels (for sizing the partial-sum scratch)
+// upper bound of bf_grid_any over all kernels (for sizing the partial-sum scratch)
 int bf_grid_max(int m, long long nloc, int sms) {
   int a = bf_grid_for(m, nloc, sms);
-  int b = tpl_capacity_for_m(m) > 0 ? tpl_grid_for(m, nloc, sms) : 0;
-  return a > b ? a : b;
+  if (tpl_capacity_for_m(m) > 0) {
+    const int b = tpl_grid_for(m, nloc, sms), c = ws_grid_for(m, nloc, sms);
+    if (b > a) a = b;
+    if (c > a) a = c;
+  }
+  return a;
 }
 
 cudaError_t bf_launch(const BfLaunch &P, int cov, int grid_x, cudaStream_t stream) {
-  return use_tpl(P.m, cov) ? tpl_launch(P, cov, grid_x, stream) : coop_launch(P, cov, grid_x, stream);
+  switch (kernel_for(P.m, cov)) {
+    case KERNEL_WS: return ws_launch(P, cov, grid_x, stream);
+    case KERNEL_TPL: return tpl_launch(P, cov, grid_x, stream);
+    default: return coop_launch(P, cov, grid_x, stream);
+  }
 }
 
 }  // namespace nngp

@@ -1,0 +1,311 @@
+// bf_ws_kernel.cu -- warp-specialised B/F + log-likelihood kernel for m <= 16.
+//
+// Same mathematics as bf_tpl_kernel.cu (one lane owns one location; reference sites: updateBF
+// src/rNNGP.cpp:46-101, updateConjBF src/cNNGP.cpp:24-69, Q src/util.cpp:261-280, prediction solves
+// src/rNNGPPredict.cpp:154-169 / src/cNNGP.cpp:260-275), different execution structure.  ncu on the
+// single-role kernel showed its three phases have opposite needs: the covariance build (70% of the
+// instructions) runs at the FP64 pipe's cadence, while the gathers and the Cholesky chain are latency-
+// bound, and with ~1 warp per scheduler nothing overlaps them (FP64 pipe 32% busy overall).  Here a CTA
+// of 4 warps pipelines TILES of 32 locations through two shared-memory stages:
+//
+//   producer warps 1..3 : gather neighbour ids -> cp.async sites and residuals into the stage, then
+//                         each evaluates one third of the tile's m(m-1)/2 + m correlations
+//   consumer warp 0     : Cholesky + solves of the previous tile, B/F stores, sum log F / Q terms
+//
+// hand-off with named barriers (bar.arrive / bar.sync, ids 1..4 = full/empty per stage, id 5 = producers'
+// own rendezvous).  Two CTAs per SM (2 x 2 stages x 46 KB) put two latency-bound consumers on one
+// scheduler and two FP64-bound producers on each of the other three.
+#include <stdlib.h>
+
+#include "tpl_device.cuh"
+
+namespace nngp {
+
+template <int MC>
+struct WsGeo {
+  using T = TplGeo<MC>;
+  static constexpr int OFF_RR = T::kWarpBytes;                   // double[MC+1][32]: residuals of neighbours, own
+  static constexpr int kStageBytes = OFF_RR + (MC + 1) * 32 * 8;
+  static constexpr int kStages = 2;
+  static constexpr int kSmemBytes = kStages * kStageBytes;
+  static constexpr int kProducerWarps = 3;
+  static constexpr int kThreads = 32 * (1 + kProducerWarps);
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+template <int MC, int COV>
+__global__ void __launch_bounds__(128, 2) bf_ws_kernel(const __grid_constant__ BfLaunch P) {
+  using Geo = TplGeo<MC>;
+  using Ws = WsGeo<MC>;
+  constexpr int kBatch = kTplBatch<COV>;
+  constexpr int NP = Ws::kProducerWarps;
+  __shared__ unsigned ent[kTplMaxEnt];
+  __shared__ int last_flag;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+
+  const BfTheta &th = P.th[blockIdx.y];
+  const int m = P.m;
+  const bool site = P.site_mode != 0;
+  const double sigmaSq = th.sigmaSq, tauSq = th.tauSq;
+  const double diag = sigmaSq + tauSq;
+  const double *__restrict__ resid = th.resid;
+
+  // ---- one-time setup: work list, zero padding of both stages --------------------------------------
+  const int ne = m * (m - 1) / 2;
+  const int nent_pad = ((ne + m + NP * kBatch - 1) / (NP * kBatch)) * (NP * kBatch);
+  for (int e = tid; e < nent_pad; e += Ws::kThreads) {
+    unsigned w;
+    if (e < ne) {
+      int k = 1;
+      while ((k + 1) * k / 2 <= e) ++k;
+      const int l = e - k * (k - 1) / 2;
+      w = (unsigned)k | ((unsigned)l << 8) | ((unsigned)e << 16);
+    } else if (e < ne + m) {
+      const int k = e - ne;
+      w = (unsigned)k | ((unsigned)MC << 8) | ((unsigned)((Geo::OFF_CV - Geo::OFF_A) / 256 + k) << 16);
+    } else {
+      w = 0u | ((unsigned)MC << 8) | ((unsigned)((Geo::OFF_DV - Geo::OFF_A) / 256) << 16);  // padding -> dv row 0
+    }
+    ent[e] = w;
+  }
+  for (int s = 0; s < Ws::kStages; ++s) {
+    unsigned char *st = tpl_smem + s * Ws::kStageBytes;
+    double *A = reinterpret_cast<double *>(st + Geo::OFF_A);
+    double *cv = reinterpret_cast<double *>(st + Geo::OFF_CV);
+    double *rr = reinterpret_cast<double *>(st + Ws::OFF_RR);
+    for (int x = tid; x < (Geo::NE - ne) * 32; x += Ws::kThreads) A[ne * 32 + x] = 0.0;  // identity padding, m < MC
+    for (int x = tid; x < (MC - m) * 32; x += Ws::kThreads) cv[m * 32 + x] = 0.0;
+    for (int x = tid; x < (MC + 1) * 32; x += Ws::kThreads) rr[x] = 0.0;
+  }
+  __syncthreads();
+
+  const long long ntiles = ((long long)P.loc_end - P.loc_begin + 31) / 32;
+  double qsum = 0.0, lsum = 0.0;
+  int failed = INT_MAX;
+
+  if (warp > 0) {
+    // ================================ producers ========================================================
+    const int pw = warp - 1;          // producer warp index
+    const int pl = tid - 32;          // producer lane 0..95
+    int j = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++j) {
+      const int s = j & 1;
+      unsigned char *st = tpl_smem + s * Ws::kStageBytes;
+      double2 *co = reinterpret_cast<double2 *>(st + Geo::OFF_CO);
+      double *rr = reinterpret_cast<double *>(st + Ws::OFF_RR);
+      const long long base = P.loc_begin + tile * 32;
+      if (j >= Ws::kStages) named_bar_sync(3 + s, Ws::kThreads);  // stage released by the consumer
+      // ---- phase 0: ids -> asynchronous gathers of sites and residuals into the stage -------------------
+      for (int t = pl; t < m * 32; t += 32 * NP) {
+        const int k = t >> 5, loc = t & 31;
+        long long i = base + loc;
+        if (i >= P.loc_end) i = (long long)P.loc_end - 1;  // tail lanes redo the last location
+        const int mi = site ? m : nn_count(i, m);
+        if (k < mi) {
+          const int id = site ? __ldg(&P.nn0[(size_t)k * P.q + i]) : __ldg(&P.nnIndx[nn_offset(i, m) + k]);
+          cp_async16(&co[k * 32 + loc], &P.coords[id]);
+          if (resid != nullptr) cp_async8(&rr[k * 32 + loc], &resid[id]);
+        } else {
+          co[k * 32 + loc] = make_double2(0.0, 0.0);
+          rr[k * 32 + loc] = 0.0;
+        }
+      }
+      if (pl < 32) {
+        long long i = base + pl;
+        if (i >= P.loc_end) i = (long long)P.loc_end - 1;
+        cp_async16(&co[MC * 32 + pl], site ? &P.sites[i] : &P.coords[i]);
+        if (resid != nullptr && !site) cp_async8(&rr[MC * 32 + pl], &resid[i]);
+      }
+      cp_async_wait_all();
+      named_bar_sync(5, 32 * NP);  // all sites of the tile visible to the three producer warps
+      // ---- phase A: this warp's third of the correlations (lane = location) --------------------------------
+      tpl_build<COV>(lane, s * Ws::kStageBytes + Geo::OFF_CO, s * Ws::kStageBytes + Geo::OFF_A, ent, pw * kBatch,
+                     NP * kBatch, nent_pad, sigmaSq, th.phi, th.mat);
+      named_bar_arrive(1 + s, Ws::kThreads);  // stage full
+    }
+  } else {
+    // ================================ consumer ==========================================================
+    int j = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++j) {
+      const int s = j & 1;
+      unsigned char *st = tpl_smem + s * Ws::kStageBytes;
+      double *A = reinterpret_cast<double *>(st + Geo::OFF_A) + lane;
+      double *cv = reinterpret_cast<double *>(st + Geo::OFF_CV);
+      double *dv = reinterpret_cast<double *>(st + Geo::OFF_DV) + lane;
+      const double *rr = reinterpret_cast<const double *>(st + Ws::OFF_RR);
+      const long long base = P.loc_begin + tile * 32;
+      const bool active = base + lane < P.loc_end;
+      const long long i = active ? base + lane : (long long)P.loc_end - 1;
+      const int mi = site ? m : nn_count(i, m);
+      const long long off = site ? 0 : nn_offset(i, m);
+      named_bar_sync(1 + s, Ws::kThreads);  // wait for the producers
+      if (mi < m) {  // ragged start of the ordering: identity-pad rows >= m_i
+        for (int k = mi; k < m; ++k) {
+          cv[k * 32 + lane] = 0.0;
+          for (int l = 0; l < k; ++l) A[(k * (k - 1) / 2 + l) * 32] = 0.0;
+        }
+      }
+      double Fsum;
+      const bool ok = tpl_solve<MC>(A, cv + lane, dv, mi, diag, &Fsum);
+      if (!ok && active) failed = min(failed, (int)min(i + 1, (long long)INT_MAX - 1));
+      const double Fv = diag - Fsum;
+      double part = 0.0;
+      if (resid != nullptr) {
+#pragma unroll
+        for (int k = 0; k < MC; ++k) part = fma(cv[k * 32 + lane], rr[k * 32 + lane], part);
+      }
+      const double r_own = rr[MC * 32 + lane];
+      if (th.B != nullptr) {
+        if (site) {
+          if (active) {
+#pragma unroll
+            for (int k = 0; k < MC; ++k)
+              if (k < m) th.B[(size_t)k * P.q + i] = cv[k * 32 + lane];
+          }
+        } else {
+          const bool full = (base >= m) && (base + 32 <= P.loc_end);  // 32 complete rows, contiguous in B
+          if (full) {
+            __syncwarp();
+            double *dst = th.B + nn_offset(base, m);
+            const float rm = 1.0f / (float)m;
+            for (int t = lane; t < 32 * m; t += 32) {
+              const int loc = (int)(((float)t + 0.5f) * rm);
+              const int k = t - loc * m;
+              dst[t] = cv[k * 32 + loc];
+            }
+          } else if (active) {
+#pragma unroll
+            for (int k = 0; k < MC; ++k)
+              if (k < mi) th.B[off + k] = cv[k * 32 + lane];
+          }
+        }
+      }
+      __syncwarp();
+      if (tile + (long long)Ws::kStages * gridDim.x < ntiles) named_bar_arrive(3 + s, Ws::kThreads);  // stage free
+      if (th.F != nullptr && active) th.F[i] = Fv;
+      if (!site && active) {
+        lsum += log(Fv);
+        if (resid != nullptr) {
+          const double e = r_own - part;
+          qsum += e * e / Fv;
+        }
+      }
+    }
+    // ---- grid reduction by the consumer warp: per-CTA partials, last CTA adds them in fixed order -----------
+#pragma unroll
+    for (int sft = 16; sft >= 1; sft >>= 1) {
+      lsum += __shfl_down_sync(0xffffffffu, lsum, sft);
+      qsum += __shfl_down_sync(0xffffffffu, qsum, sft);
+    }
+    if (failed != INT_MAX) atomicMin(th.fail, failed);
+    __syncwarp();
+    if (lane == 0) {
+      th.partials[2 * blockIdx.x] = lsum;
+      th.partials[2 * blockIdx.x + 1] = qsum;
+      __threadfence();
+      const unsigned int tk = atomicAdd(th.ticket, 1u);
+      last_flag = (tk == gridDim.x - 1);
+    }
+    __syncwarp();
+    if (last_flag) {
+      __threadfence();
+      double a = 0.0, b = 0.0;
+      for (unsigned int jj = lane; jj < gridDim.x; jj += 32) {
+        a += __ldcg(&th.partials[2 * jj]);
+        b += __ldcg(&th.partials[2 * jj + 1]);
+      }
+#pragma unroll
+      for (int sft = 16; sft >= 1; sft >>= 1) {
+        a += __shfl_down_sync(0xffffffffu, a, sft);
+        b += __shfl_down_sync(0xffffffffu, b, sft);
+      }
+      if (lane == 0) {
+        th.out[0] = a;
+        th.out[1] = b;
+        const int fv = atomicExch(th.fail, INT_MAX);
+        th.out[2] = (fv != INT_MAX) ? 1.0 : 0.0;
+        *th.fail_out = fv;
+        *th.ticket = 0u;
+      }
+    }
+  }
+}
+
+// ---- launcher ---------------------------------------------------------------------------------------
+int tpl_capacity_for_m(int m);
+
+template <int MC, int COV>
+static cudaError_t ws_launch_one(const BfLaunch &P, int grid_x, cudaStream_t stream) {
+  using Ws = WsGeo<MC>;
+  static bool configured[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 16 || !configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(bf_ws_kernel<MC, COV>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ws::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    if (dev < 16) configured[dev] = true;
+  }
+  if (COV == NNGP_COV_MATERN) {
+    cudaError_t e = upload_matern_consts(P.h_mat, P.nbatch, stream);
+    if (e != cudaSuccess) return e;
+  }
+  dim3 grid(grid_x, P.nbatch, 1);
+  bf_ws_kernel<MC, COV><<<grid, Ws::kThreads, Ws::kSmemBytes, stream>>>(P);
+  return cudaGetLastError();
+}
+
+template <int MC>
+static cudaError_t ws_launch_cov(const BfLaunch &P, int cov, int grid_x, cudaStream_t stream) {
+  switch (cov) {
+    case NNGP_COV_EXPONENTIAL: return ws_launch_one<MC, NNGP_COV_EXPONENTIAL>(P, grid_x, stream);
+    case NNGP_COV_SPHERICAL: return ws_launch_one<MC, NNGP_COV_SPHERICAL>(P, grid_x, stream);
+    case NNGP_COV_MATERN: return ws_launch_one<MC, NNGP_COV_MATERN>(P, grid_x, stream);
+    case NNGP_COV_GAUSSIAN: return ws_launch_one<MC, NNGP_COV_GAUSSIAN>(P, grid_x, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+static int ws_stage_bytes(int MC) {
+  return (MC + 1) * 32 * 16 + (MC * (MC - 1) / 2) * 32 * 8 + 2 * MC * 32 * 8 + (MC + 1) * 32 * 8;
+}
+
+int ws_ctas_per_sm(int m) {
+  const int MC = tpl_capacity_for_m(m);
+  int c = (227 * 1024) / (2 * ws_stage_bytes(MC) + 2048);
+  static int override_ctas = -1;
+  if (override_ctas < 0) {
+    const char *e = getenv("NNGP_WS_CTAS");
+    override_ctas = e ? atoi(e) : 0;
+  }
+  if (override_ctas > 0) c = override_ctas;
+  if (c > 4) c = 4;
+  return c < 1 ? 1 : c;
+}
+
+int ws_grid_for(int m, long long nloc, int sms) {
+  long long need = (nloc + 31) / 32;
+  long long g = (long long)sms * ws_ctas_per_sm(m);
+  if (need < g) g = need;
+  return (int)(g < 1 ? 1 : g);
+}
+
+cudaError_t ws_launch(const BfLaunch &P, int cov, int grid_x, cudaStream_t stream) {
+  switch (tpl_capacity_for_m(P.m)) {
+    case 5: return ws_launch_cov<5>(P, cov, grid_x, stream);
+    case 8: return ws_launch_cov<8>(P, cov, grid_x, stream);
+    case 10: return ws_launch_cov<10>(P, cov, grid_x, stream);
+    case 12: return ws_launch_cov<12>(P, cov, grid_x, stream);
+    case 15: return ws_launch_cov<15>(P, cov, grid_x, stream);
+    case 16: return ws_launch_cov<16>(P, cov, grid_x, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace nngp

@@ -1,0 +1,181 @@
+// tpl_device.cuh -- device building blocks shared by the one-lane-per-location kernels
+// (bf_tpl_kernel.cu: every warp does all phases; bf_ws_kernel.cu: warp-specialised producer/consumer).
+// All per-location state lives in shared memory laid out [entry][lane] (32 lanes = 32 locations).
+#pragma once
+#include <limits.h>
+
+#include "cov.cuh"
+
+namespace nngp {
+
+template <int MC>
+struct TplGeo {
+  static constexpr int NE = MC * (MC - 1) / 2;
+  static constexpr int OFF_CO = 0;                          // bytes; row MC holds the location's own site
+  static constexpr int OFF_A = OFF_CO + (MC + 1) * 32 * 16;
+  static constexpr int OFF_CV = OFF_A + NE * 32 * 8;
+  static constexpr int OFF_DV = OFF_CV + MC * 32 * 8;
+  static constexpr int kWarpBytes = OFF_DV + MC * 32 * 8;
+};
+
+extern __shared__ __align__(16) unsigned char tpl_smem[];
+
+// ---- phase A: correlations ----------------------------------------------------------------------
+// Work list shared by all lanes: entry w = k | l << 8 | dst << 16 means "rho between co[k] and co[l]
+// goes to row dst (256-byte rows counted from the start of A)".  It holds the m(m-1)/2 pairs of the
+// strict lower triangle (dst = packed index), the m entries of c (l = MC: the location's own site,
+// dst = a row of cv) and is padded to a multiple of the batch width with harmless duplicates that
+// write into dv (overwritten by the factorisation afterwards).
+constexpr int kTplMaxEnt = 160;
+template <int COV>
+constexpr int kTplBatch = (COV == NNGP_COV_MATERN) ? 4 : 8;  // entries evaluated together (independent chains)
+
+// Batches of UNR entries: all loads, then UNR independent evaluation chains, then all stores.
+// (A plain unrolled loop is serialised by ptxas: it cannot prove that the store of entry e does not
+// alias the site loads of entry e+1, so the chains never overlap -- seen in SASS.)
+template <int COV>
+__device__ __noinline__ void tpl_build(int lane, int off_co, int off_a, const unsigned *ent, int e_begin, int e_step,
+                                       int nent_pad, double sigmaSq, double phi, const MaternConsts *mat) {
+  constexpr int UNR = kTplBatch<COV>;
+  const unsigned char *cob = tpl_smem + off_co + lane * 16;
+  unsigned char *ab = tpl_smem + off_a + lane * 8;
+  const Cor<COV> cor(phi, mat);
+  for (int e0 = e_begin; e0 < nent_pad; e0 += e_step) {  // e_begin, e_step: multiples of the batch width
+    double d2[UNR], v[UNR];
+    unsigned dst[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const unsigned w = ent[e0 + u];
+      dst[u] = w >> 16;
+      const double2 pk = *reinterpret_cast<const double2 *>(cob + (w & 0xffu) * 512u);
+      const double2 pl = *reinterpret_cast<const double2 *>(cob + ((w >> 8) & 0xffu) * 512u);
+      const double dx = pk.x - pl.x, dy = pk.y - pl.y;
+      d2[u] = dx * dx + dy * dy;
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) v[u] = sigmaSq * cor.fast(d2[u]);
+    if (COV == NNGP_COV_MATERN) {  // rare arguments outside the straight-line path (phi D > 2, integer nu)
+      bool any = false;
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) any |= cor.needs_slow(d2[u]);
+      if (any) {
+#pragma unroll
+        for (int u = 0; u < UNR; ++u)
+          if (cor.needs_slow(d2[u])) v[u] = sigmaSq * cor.slow(d2[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) *reinterpret_cast<double *>(ab + dst[u] * 256u) = v[u];
+  }
+}
+
+// ---- phase B: Cholesky + solves, fully unrolled -----------------------------------------------------
+// Left-looking C = V V' two columns at a time; V(i,j) overwrites A, the right-hand side rides along
+// as row MC (cv[j] becomes y_j = (V^-1 c)_j), 1/V(j,j) goes to dv[j].  Then V' B = y.
+// On return: Bout[0..MC) kriging weights, *Fsum = c' C^-1 c = |y|^2; false if a pivot is not positive.
+#define V_(i, j) A[((i) * ((i)-1) / 2 + (j)) * 32]
+
+// columns J0 and J0+1 (compile-time), then recurse; the memory clobber between pairs keeps ptxas from
+// hoisting the next pair's loads across this pair's stores (which would blow up register pressure).
+template <int MC, int J0>
+__device__ __forceinline__ void tpl_chol_pair(double *A, double *cv, double *dv, int mi, double diag, double &Fsum,
+                                              bool &ok) {
+  constexpr bool two = (J0 + 1 < MC);
+  constexpr int J1 = J0 + 1;
+  double a0[MC + 1], a1[MC + 1];  // rows J0..MC of columns J0 and J1 (row MC: right-hand side)
+#pragma unroll
+  for (int i = J0; i <= MC; ++i) {
+    if (i == J0) a0[i] = (J0 < mi) ? diag : 1.0;
+    else if (i < MC) a0[i] = V_(i, J0);
+    else a0[i] = cv[J0 * 32];
+  }
+  if (two) {
+#pragma unroll
+    for (int i = J1; i <= MC; ++i) {
+      if (i == J1) a1[i] = (J1 < mi) ? diag : 1.0;
+      else if (i < MC) a1[i] = V_(i, J1);
+      else a1[i] = cv[J1 * 32];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < J0; ++k) {
+    const double v0 = V_(J0, k);
+    a0[J0] = fma(-v0, v0, a0[J0]);
+    double v1 = 0.0;
+    if (two) {
+      v1 = V_(J1, k);
+      a0[J1] = fma(-v1, v0, a0[J1]);
+      a1[J1] = fma(-v1, v1, a1[J1]);
+    }
+#pragma unroll
+    for (int i = J0 + (two ? 2 : 1); i <= MC; ++i) {  // remaining rows; row MC = right-hand side
+      const double v = (i < MC) ? V_(i, k) : cv[k * 32];
+      a0[i] = fma(-v, v0, a0[i]);
+      if (two) a1[i] = fma(-v, v1, a1[i]);
+    }
+  }
+  // finalise column J0
+  const double d0 = a0[J0];
+  if (J0 < mi && !(d0 > 0.0)) ok = false;
+  const double r0 = rsqrt(d0);
+  dv[J0 * 32] = r0;
+#pragma unroll
+  for (int i = J0 + 1; i <= MC; ++i) a0[i] *= r0;
+  Fsum = fma(a0[MC], a0[MC], Fsum);
+  cv[J0 * 32] = a0[MC];
+#pragma unroll
+  for (int i = J0 + 1; i < MC; ++i) V_(i, J0) = a0[i];
+  if (two) {
+    const double v = a0[J1];  // V(J1, J0), still in registers
+#pragma unroll
+    for (int i = J1; i <= MC; ++i) a1[i] = fma(-a0[i], v, a1[i]);
+    const double d1 = a1[J1];
+    if (J1 < mi && !(d1 > 0.0)) ok = false;
+    const double r1 = rsqrt(d1);
+    dv[J1 * 32] = r1;
+#pragma unroll
+    for (int i = J1 + 1; i <= MC; ++i) a1[i] *= r1;
+    Fsum = fma(a1[MC], a1[MC], Fsum);
+    cv[J1 * 32] = a1[MC];
+#pragma unroll
+    for (int i = J1 + 1; i < MC; ++i) V_(i, J1) = a1[i];
+  }
+  asm volatile("" ::: "memory");
+  if constexpr (J0 + 2 < MC) tpl_chol_pair<MC, J0 + 2>(A, cv, dv, mi, diag, Fsum, ok);
+}
+
+// On return cv[k] holds the kriging weight B_k (k < MC), *Fsum_out = c' C^-1 c; false if a pivot <= 0.
+template <int MC>
+__device__ __forceinline__ bool tpl_solve(double *A, double *cv, double *dv, int mi, double diag, double *Fsum_out) {
+  double Fsum = 0.0;
+  bool ok = true;
+  tpl_chol_pair<MC, 0>(A, cv, dv, mi, diag, Fsum, ok);
+  // back substitution V' B = y: B_k = (y_k - sum_{i>k} V(i,k) B_i) / V(k,k)
+  double w[MC];
+#pragma unroll
+  for (int k = MC - 1; k >= 0; --k) {
+    double acc = cv[k * 32];
+#pragma unroll
+    for (int i = MC - 1; i > k; --i) acc = fma(-V_(i, k), w[i], acc);
+    w[k] = acc * dv[k * 32];
+  }
+#pragma unroll
+  for (int k = 0; k < MC; ++k) cv[k * 32] = w[k];
+  *Fsum_out = Fsum;
+  return ok;
+}
+#undef V_
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc) : "memory");
+}
+
+}  // namespace nngp
