@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(32) bf_tpl_kernel(const __grid_constant__ BfLa
     cp_async_wait_all();  // this pass's neighbour sites have landed in co
     co[MC * 32] = me;
     // ---- phase A: correlations ------------------------------------------------------------------------
-    tpl_build<COV>(lane, Geo::OFF_CO, Geo::OFF_A, ent, 0, kTplBatch<COV>, nent_pad, sigmaSq, th.phi, th.mat);
+    tpl_build<COV, kTplBatch<COV>>(lane, Geo::OFF_CO, Geo::OFF_A, ent, 0, kTplBatch<COV>, nent_pad, sigmaSq, th.phi, th.mat);
     if (mi < m) {  // ragged start of the ordering (only the first m locations): identity-pad rows >= m_i
       for (int k = mi; k < m; ++k) {
         cv[k * 32 + lane] = 0.0;

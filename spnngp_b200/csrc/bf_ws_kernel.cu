@@ -15,6 +15,14 @@
 // hand-off with named barriers (bar.arrive / bar.sync, ids 1..4 = full/empty per stage, id 5 = producers'
 // own rendezvous).  Two CTAs per SM (2 x 2 stages x 46 KB) put two latency-bound consumers on one
 // scheduler and two FP64-bound producers on each of the other three.
+//
+// Measured at n = 10^6, m = 15 (ms per launch; exponential / Matern): cooperative kernel 1.11 / 1.79,
+// single-role one-lane kernel 0.90 / 2.63, this kernel 0.72 / 1.63.  It is consumer-bound: the Cholesky
+// chain of one tile takes ~13k cycles against ~11k for its build.  Variants tried and rejected (all
+// ~0.91-1.01 ms): one 8-warp CTA with a consumer and a producer on every scheduler (the producer's DFMA
+// stream starves the consumer's dependent chain); 2-4 consumers packed on scheduler 0 with 6 producers on
+// schedulers 1-3 (the fully unrolled solve, 30 KB of code per consumer, thrashes the instruction cache:
+// ncu stall_no_instruction 40-49% in the solve).
 #include <stdlib.h>
 
 #include "tpl_device.cuh"
@@ -126,7 +134,7 @@ __global__ void __launch_bounds__(128, 2) bf_ws_kernel(const __grid_constant__ B
       cp_async_wait_all();
       named_bar_sync(5, 32 * NP);  // all sites of the tile visible to the three producer warps
       // ---- phase A: this warp's third of the correlations (lane = location) --------------------------------
-      tpl_build<COV>(lane, s * Ws::kStageBytes + Geo::OFF_CO, s * Ws::kStageBytes + Geo::OFF_A, ent, pw * kBatch,
+      tpl_build<COV, kBatch>(lane, s * Ws::kStageBytes + Geo::OFF_CO, s * Ws::kStageBytes + Geo::OFF_A, ent, pw * kBatch,
                      NP * kBatch, nent_pad, sigmaSq, th.phi, th.mat);
       named_bar_arrive(1 + s, Ws::kThreads);  // stage full
     }

@@ -33,10 +33,9 @@ constexpr int kTplBatch = (COV == NNGP_COV_MATERN) ? 4 : 8;  // entries evaluate
 // Batches of UNR entries: all loads, then UNR independent evaluation chains, then all stores.
 // (A plain unrolled loop is serialised by ptxas: it cannot prove that the store of entry e does not
 // alias the site loads of entry e+1, so the chains never overlap -- seen in SASS.)
-template <int COV>
+template <int COV, int UNR>
 __device__ __noinline__ void tpl_build(int lane, int off_co, int off_a, const unsigned *ent, int e_begin, int e_step,
                                        int nent_pad, double sigmaSq, double phi, const MaternConsts *mat) {
-  constexpr int UNR = kTplBatch<COV>;
   const unsigned char *cob = tpl_smem + off_co + lane * 16;
   unsigned char *ab = tpl_smem + off_a + lane * 8;
   const Cor<COV> cor(phi, mat);
