@@ -18,9 +18,20 @@
 
 namespace nngp {
 
+constexpr int kMatSeriesTerms = 14;  // t^k/(k!)^2-like decay: 1e-17 relative at t = 1 by k = 13
+constexpr int kMatExtTerms = 32;     // 6.25^k / (k!)^2 < 1e-19 by k = 31
 constexpr int kTemmeTerms = 24;  // (x^2/4)^i / i! < 1e-18 well before i = 24 for x <= 2
 constexpr int kCf2Tab = 64;      // tabulated reciprocals for the first CF2 iterations
-constexpr int kMatSeriesTerms = 14;  // t^k/(k!)^2-like decay: 1e-17 relative at t = 1 by k = 13
+
+// The part of the constants the straight-line series path needs; small enough to travel as kernel
+// parameters (constant bank, no upload, static operand addresses).
+struct MaternSeriesParams {
+  double nu;
+  double t_ext_max;  // largest t = (phi D / 2)^2 served by the extended series (beyond: Steed CF2)
+  int use_series;
+  double sa[kMatSeriesTerms];
+  double sb[kMatSeriesTerms];
+};
 
 struct MaternConsts {
   double nu;      // smoothness
@@ -45,6 +56,10 @@ struct MaternConsts {
   int use_series;
   double sa[kMatSeriesTerms];
   double sb[kMatSeriesTerms];
+  // the same series carried to kMatExtTerms terms: valid for 2 < phi D <= 5 (1 < t <= 6.25), where the
+  // cancellation against K's decay still leaves ~1e-12; evaluated by a short loop (matern_series_ext)
+  double ea[kMatExtTerms];
+  double eb[kMatExtTerms];
 };
 
 // ---- host side: constants per nu -------------------------------------------------------------
@@ -96,14 +111,19 @@ inline void matern_prepare(double nu, MaternConsts *mc) {
       const long double G = tgammal(1.0L - lnu);
       long double ca = G / tgammal(1.0L - lnu);  // = 1
       long double cb = G / tgammal(1.0L + lnu);
-      for (int k = 0; k < kMatSeriesTerms; k++) {
-        mc->sa[k] = (double)ca;
-        mc->sb[k] = (double)cb;
+      for (int k = 0; k < kMatExtTerms; k++) {
+        if (k < kMatSeriesTerms) {
+          mc->sa[k] = (double)ca;
+          mc->sb[k] = (double)cb;
+        }
+        mc->ea[k] = (double)ca;
+        mc->eb[k] = (double)cb;
         ca /= (long double)(k + 1) * ((long double)(k + 1) - lnu);  // Gamma(k+2-nu) = (k+1-nu) Gamma(k+1-nu)
         cb /= (long double)(k + 1) * ((long double)(k + 1) + lnu);
       }
     } else {
       for (int k = 0; k < kMatSeriesTerms; k++) mc->sa[k] = mc->sb[k] = 0.0;
+      for (int k = 0; k < kMatExtTerms; k++) mc->ea[k] = mc->eb[k] = 0.0;
     }
   }
   double a = -mc->a1;
@@ -234,6 +254,19 @@ NNGP_HD double matern_cor(double x, const MaternConsts &mc) {
     mu_j += 1.0;
   }
   return mc.pref * exp(mc.nu * logx) * k0;
+}
+
+
+inline void matern_series_params(const MaternConsts &mc, MaternSeriesParams *ms) {
+  ms->nu = mc.nu;
+  ms->use_series = mc.use_series;
+  // cancellation of the two sums grows like e^(2 phi D) / |sin(nu pi)|: keep ~1e-12 absolute
+  const double snp = fabs(sin(3.14159265358979323846 * mc.nu));
+  ms->t_ext_max = !mc.use_series ? 0.0 : (snp > 0.1 ? 4.0 : 2.25);
+  for (int k = 0; k < kMatSeriesTerms; k++) {
+    ms->sa[k] = mc.sa[k];
+    ms->sb[k] = mc.sb[k];
+  }
 }
 
 }  // namespace nngp

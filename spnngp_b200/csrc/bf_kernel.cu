@@ -87,8 +87,9 @@ __global__ void __launch_bounds__(128, (M <= 16 ? 4 : 2)) bf_kernel(const __grid
     if (h < mi) idx_hi = site ? __ldg(&P.nn0[(size_t)h * P.q + i]) : __ldg(&P.nnIndx[off + h]);
     const double2 zero2 = make_double2(0.0, 0.0);
     const double2 me = active ? (site ? __ldg(&P.sites[i]) : __ldg(&P.coords[i])) : zero2;
-    const double2 plo = (idx_lo >= 0) ? __ldg(&P.coords[idx_lo]) : zero2;
-    const double2 phi_ = (idx_hi >= 0) ? __ldg(&P.coords[idx_hi]) : zero2;
+    // a missing neighbour is stood in by the location's own site: masked entries stay on the cheap path
+    const double2 plo = (idx_lo >= 0) ? __ldg(&P.coords[idx_lo]) : me;
+    const double2 phi_ = (idx_hi >= 0) ? __ldg(&P.coords[idx_hi]) : me;
     nbr[r] = plo;
     nbr[h] = phi_;
     __syncwarp();
@@ -295,10 +296,6 @@ static cudaError_t launch_one(const BfLaunch &P, int grid_x, cudaStream_t stream
                                          (int)Geo::kSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
-  }
-  if (COV == NNGP_COV_MATERN) {
-    cudaError_t e = upload_matern_consts(P.h_mat, P.nbatch, stream);
-    if (e != cudaSuccess) return e;
   }
   dim3 grid(grid_x, P.nbatch, 1);
   bf_kernel<M, COV><<<grid, Geo::kThreads, Geo::kSmemBytes, stream>>>(P);

@@ -88,10 +88,14 @@ __global__ void __launch_bounds__(32) bf_tpl_kernel(const __grid_constant__ BfLa
     }
   };
   // asynchronous gather of the neighbour sites straight into shared memory
-  auto fetch_sites = [&](const int *ids) {
+  // (a missing neighbour -- ragged start of the ordering -- is stood in by the location's own site so that the
+  // masked entries stay on the straight-line correlation path)
+  auto fetch_sites = [&](const int *ids, long long i) {
 #pragma unroll
-    for (int k = 0; k < MC; ++k)
+    for (int k = 0; k < MC; ++k) {
       if (ids[k] >= 0) cp_async16(&co[k * 32], &P.coords[ids[k]]);
+      else if (k < m) cp_async16(&co[k * 32], site ? &P.sites[i] : &P.coords[i]);
+    }
   };
 
   const long long stride = (long long)gridDim.x * 32;
@@ -102,7 +106,7 @@ __global__ void __launch_bounds__(32) bf_tpl_kernel(const __grid_constant__ BfLa
     const long long i0 = loc_of(base);
     load_ids(i0, nid);
     nme = site ? __ldg(&P.sites[i0]) : __ldg(&P.coords[i0]);
-    fetch_sites(nid);
+    fetch_sites(nid, i0);
   }
 
   double qsum = 0.0, lsum = 0.0;
@@ -126,7 +130,7 @@ __global__ void __launch_bounds__(32) bf_tpl_kernel(const __grid_constant__ BfLa
     cp_async_wait_all();  // this pass's neighbour sites have landed in co
     co[MC * 32] = me;
     // ---- phase A: correlations ------------------------------------------------------------------------
-    tpl_build<COV, kTplBatch<COV>>(lane, Geo::OFF_CO, Geo::OFF_A, ent, 0, kTplBatch<COV>, nent_pad, sigmaSq, th.phi, th.mat);
+    tpl_build<COV, kTplBatch<COV>>(P, lane, Geo::OFF_CO, Geo::OFF_A, ent, 0, kTplBatch<COV>, nent_pad);
     if (mi < m) {  // ragged start of the ordering (only the first m locations): identity-pad rows >= m_i
       for (int k = mi; k < m; ++k) {
         cv[k * 32 + lane] = 0.0;
@@ -134,7 +138,7 @@ __global__ void __launch_bounds__(32) bf_tpl_kernel(const __grid_constant__ BfLa
       }
     }
     // ---- prefetch stage 2: next pass's neighbour sites (co is free now), this pass's residuals ----------
-    if (has_next) fetch_sites(nid);
+    if (has_next) fetch_sites(nid, loc_of(base + stride));
     double rr[MC];
     if (resid != nullptr) {
 #pragma unroll
@@ -179,10 +183,10 @@ __global__ void __launch_bounds__(32) bf_tpl_kernel(const __grid_constant__ BfLa
     }
     if (th.F != nullptr && active) th.F[i] = Fv;
     if (!site && active) {
-      lsum += log(Fv);
+      lsum += (Fv > 0.0) ? nngp_log_pos(Fv) : log(Fv);  // straight-line log on the normal path
       if (resid != nullptr) {
         const double e = __ldg(&resid[i]) - part;
-        qsum += e * e / Fv;
+        qsum += e * e * nngp_rcp_pos(Fv);
       }
     }
   }
@@ -238,10 +242,6 @@ static cudaError_t tpl_launch_one(const BfLaunch &P, int grid_x, cudaStream_t st
                                          Geo::kWarpBytes);
     if (e != cudaSuccess) return e;
     if (dev < 16) configured[dev] = true;
-  }
-  if (COV == NNGP_COV_MATERN) {
-    cudaError_t e = upload_matern_consts(P.h_mat, P.nbatch, stream);
-    if (e != cudaSuccess) return e;
   }
   dim3 grid(grid_x, P.nbatch, 1);
   bf_tpl_kernel<MC, COV><<<grid, 32, Geo::kWarpBytes, stream>>>(P);

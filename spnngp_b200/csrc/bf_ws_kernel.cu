@@ -54,6 +54,8 @@ __global__ void __launch_bounds__(128, 2) bf_ws_kernel(const __grid_constant__ B
   constexpr int kBatch = kTplBatch<COV>;
   constexpr int NP = Ws::kProducerWarps;
   __shared__ unsigned ent[kTplMaxEnt];
+  __shared__ long long next_tile[Ws::kStages];  // tile handed to each stage (>= ntiles: no more work)
+  __shared__ double red[2][4];
   __shared__ int last_flag;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -95,21 +97,29 @@ __global__ void __launch_bounds__(128, 2) bf_ws_kernel(const __grid_constant__ B
   __syncthreads();
 
   const long long ntiles = ((long long)P.loc_end - P.loc_begin + 31) / 32;
-  double qsum = 0.0, lsum = 0.0;
   int failed = INT_MAX;
 
   if (warp > 0) {
     // ================================ producers ========================================================
     const int pw = warp - 1;          // producer warp index
     const int pl = tid - 32;          // producer lane 0..95
-    int j = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++j) {
+    // Tiles are handed out dynamically (one atomic per tile): the first tiles of an ordering have far-apart
+    // neighbours (few predecessors), which sends Matern through its slow branches -- with a static split the
+    // CTAs that drew them finished 0.3-0.5 ms after everybody else.
+    for (int j = 0;; ++j) {
       const int s = j & 1;
       unsigned char *st = tpl_smem + s * Ws::kStageBytes;
       double2 *co = reinterpret_cast<double2 *>(st + Geo::OFF_CO);
       double *rr = reinterpret_cast<double *>(st + Ws::OFF_RR);
-      const long long base = P.loc_begin + tile * 32;
       if (j >= Ws::kStages) named_bar_sync(3 + s, Ws::kThreads);  // stage released by the consumer
+      if (pl == 0) next_tile[s] = (long long)atomicAdd(th.tile_counter, 1u);
+      named_bar_sync(5, 32 * NP);
+      const long long tile = next_tile[s];
+      if (tile >= ntiles) {
+        named_bar_arrive(1 + s, Ws::kThreads);  // hands the consumer the end-of-work marker
+        break;
+      }
+      const long long base = P.loc_begin + tile * 32;
       // ---- phase 0: ids -> asynchronous gathers of sites and residuals into the stage -------------------
       for (int t = pl; t < m * 32; t += 32 * NP) {
         const int k = t >> 5, loc = t & 31;
@@ -121,7 +131,9 @@ __global__ void __launch_bounds__(128, 2) bf_ws_kernel(const __grid_constant__ B
           cp_async16(&co[k * 32 + loc], &P.coords[id]);
           if (resid != nullptr) cp_async8(&rr[k * 32 + loc], &resid[id]);
         } else {
-          co[k * 32 + loc] = make_double2(0.0, 0.0);
+          // missing neighbour (ragged start of the ordering): stand in the location's own site, so the masked
+          // entries stay on the straight-line correlation path
+          cp_async16(&co[k * 32 + loc], site ? &P.sites[i] : &P.coords[i]);
           rr[k * 32 + loc] = 0.0;
         }
       }
@@ -134,26 +146,27 @@ __global__ void __launch_bounds__(128, 2) bf_ws_kernel(const __grid_constant__ B
       cp_async_wait_all();
       named_bar_sync(5, 32 * NP);  // all sites of the tile visible to the three producer warps
       // ---- phase A: this warp's third of the correlations (lane = location) --------------------------------
-      tpl_build<COV, kBatch>(lane, s * Ws::kStageBytes + Geo::OFF_CO, s * Ws::kStageBytes + Geo::OFF_A, ent, pw * kBatch,
-                     NP * kBatch, nent_pad, sigmaSq, th.phi, th.mat);
+      tpl_build<COV, kBatch>(P, lane, s * Ws::kStageBytes + Geo::OFF_CO, s * Ws::kStageBytes + Geo::OFF_A, ent,
+                             pw * kBatch, NP * kBatch, nent_pad);
       named_bar_arrive(1 + s, Ws::kThreads);  // stage full
     }
   } else {
     // ================================ consumer ==========================================================
-    int j = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++j) {
+    for (int j = 0;; ++j) {
       const int s = j & 1;
       unsigned char *st = tpl_smem + s * Ws::kStageBytes;
       double *A = reinterpret_cast<double *>(st + Geo::OFF_A) + lane;
       double *cv = reinterpret_cast<double *>(st + Geo::OFF_CV);
       double *dv = reinterpret_cast<double *>(st + Geo::OFF_DV) + lane;
       const double *rr = reinterpret_cast<const double *>(st + Ws::OFF_RR);
+      named_bar_sync(1 + s, Ws::kThreads);  // wait for the producers
+      const long long tile = next_tile[s];
+      if (tile >= ntiles) break;
       const long long base = P.loc_begin + tile * 32;
       const bool active = base + lane < P.loc_end;
       const long long i = active ? base + lane : (long long)P.loc_end - 1;
       const int mi = site ? m : nn_count(i, m);
       const long long off = site ? 0 : nn_offset(i, m);
-      named_bar_sync(1 + s, Ws::kThreads);  // wait for the producers
       if (mi < m) {  // ragged start of the ordering: identity-pad rows >= m_i
         for (int k = mi; k < m; ++k) {
           cv[k * 32 + lane] = 0.0;
@@ -196,52 +209,62 @@ __global__ void __launch_bounds__(128, 2) bf_ws_kernel(const __grid_constant__ B
         }
       }
       __syncwarp();
-      if (tile + (long long)Ws::kStages * gridDim.x < ntiles) named_bar_arrive(3 + s, Ws::kThreads);  // stage free
+      named_bar_arrive(3 + s, Ws::kThreads);  // stage free
       if (th.F != nullptr && active) th.F[i] = Fv;
+      // per-tile partial sums (fixed lane order), so the grand total does not depend on which CTA drew the tile
+      double lt = 0.0, qt = 0.0;
       if (!site && active) {
-        lsum += log(Fv);
+        lt = (Fv > 0.0) ? nngp_log_pos(Fv) : log(Fv);  // straight-line log on the normal path
         if (resid != nullptr) {
           const double e = r_own - part;
-          qsum += e * e / Fv;
+          qt = e * e * nngp_rcp_pos(Fv);
         }
-      }
-    }
-    // ---- grid reduction by the consumer warp: per-CTA partials, last CTA adds them in fixed order -----------
-#pragma unroll
-    for (int sft = 16; sft >= 1; sft >>= 1) {
-      lsum += __shfl_down_sync(0xffffffffu, lsum, sft);
-      qsum += __shfl_down_sync(0xffffffffu, qsum, sft);
-    }
-    if (failed != INT_MAX) atomicMin(th.fail, failed);
-    __syncwarp();
-    if (lane == 0) {
-      th.partials[2 * blockIdx.x] = lsum;
-      th.partials[2 * blockIdx.x + 1] = qsum;
-      __threadfence();
-      const unsigned int tk = atomicAdd(th.ticket, 1u);
-      last_flag = (tk == gridDim.x - 1);
-    }
-    __syncwarp();
-    if (last_flag) {
-      __threadfence();
-      double a = 0.0, b = 0.0;
-      for (unsigned int jj = lane; jj < gridDim.x; jj += 32) {
-        a += __ldcg(&th.partials[2 * jj]);
-        b += __ldcg(&th.partials[2 * jj + 1]);
       }
 #pragma unroll
       for (int sft = 16; sft >= 1; sft >>= 1) {
-        a += __shfl_down_sync(0xffffffffu, a, sft);
-        b += __shfl_down_sync(0xffffffffu, b, sft);
+        lt += __shfl_down_sync(0xffffffffu, lt, sft);
+        qt += __shfl_down_sync(0xffffffffu, qt, sft);
       }
       if (lane == 0) {
-        th.out[0] = a;
-        th.out[1] = b;
-        const int fv = atomicExch(th.fail, INT_MAX);
-        th.out[2] = (fv != INT_MAX) ? 1.0 : 0.0;
-        *th.fail_out = fv;
-        *th.ticket = 0u;
+        th.partials[2 * tile] = lt;
+        th.partials[2 * tile + 1] = qt;
       }
+    }
+    if (failed != INT_MAX) atomicMin(th.fail, failed);
+  }
+  // ---- grid reduction: the last CTA to finish adds the per-tile partials in fixed order --------------------
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    const unsigned int tk = atomicAdd(th.ticket, 1u);
+    last_flag = (tk == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last_flag) {
+    __threadfence();
+    double a = 0.0, b = 0.0;
+    for (long long t = tid; t < ntiles; t += Ws::kThreads) {  // thread t: tiles t, t + 128, ... in order
+      a += __ldcg(&th.partials[2 * t]);
+      b += __ldcg(&th.partials[2 * t + 1]);
+    }
+#pragma unroll
+    for (int sft = 16; sft >= 1; sft >>= 1) {
+      a += __shfl_down_sync(0xffffffffu, a, sft);
+      b += __shfl_down_sync(0xffffffffu, b, sft);
+    }
+    if (lane == 0) {
+      red[0][warp] = a;
+      red[1][warp] = b;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      th.out[0] = (red[0][0] + red[0][1]) + (red[0][2] + red[0][3]);
+      th.out[1] = (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]);
+      const int fv = atomicExch(th.fail, INT_MAX);
+      th.out[2] = (fv != INT_MAX) ? 1.0 : 0.0;
+      *th.fail_out = fv;
+      *th.tile_counter = 0u;
+      *th.ticket = 0u;
     }
   }
 }
@@ -259,10 +282,6 @@ static cudaError_t ws_launch_one(const BfLaunch &P, int grid_x, cudaStream_t str
     cudaError_t e = cudaFuncSetAttribute(bf_ws_kernel<MC, COV>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ws::kSmemBytes);
     if (e != cudaSuccess) return e;
     if (dev < 16) configured[dev] = true;
-  }
-  if (COV == NNGP_COV_MATERN) {
-    cudaError_t e = upload_matern_consts(P.h_mat, P.nbatch, stream);
-    if (e != cudaSuccess) return e;
   }
   dim3 grid(grid_x, P.nbatch, 1);
   bf_ws_kernel<MC, COV><<<grid, Ws::kThreads, Ws::kSmemBytes, stream>>>(P);

@@ -8,15 +8,6 @@
 
 namespace nngp {
 
-// Matern constants of the parameter sets of the current launch (one copy per translation unit;
-// uploaded stream-ordered by the launchers: FMA operands then come straight from the constant bank).
-static __constant__ MaternConsts c_mat[NNGP_MAX_BATCH];
-
-static inline cudaError_t upload_matern_consts(const MaternConsts *h_mat, int nbatch, cudaStream_t stream) {
-  if (h_mat == nullptr) return cudaSuccess;
-  return cudaMemcpyToSymbolAsync(c_mat, h_mat, (size_t)nbatch * sizeof(MaternConsts), 0, cudaMemcpyHostToDevice, stream);
-}
-
 // Every functor maps the SQUARED distance to the correlation.  fast() is straight-line code valid for
 // most arguments; needs_slow() flags the rare arguments that must be re-evaluated with slow().
 template <int COV>
@@ -49,17 +40,27 @@ struct Cor<NNGP_COV_SPHERICAL> {  // src/util.cpp:221-227
   __device__ __forceinline__ double slow(double d2) const { return (*this)(d2); }
 };
 
+// Matern (src/util.cpp:233-237) with device Bessel-K code (matern_series.cuh, besselk.cuh).  `ms` refers to
+// the series coefficients inside the kernel's __grid_constant__ parameter block: when the functor is built
+// from P.th[B] with a compile-time B (one-lane kernels) the 28 coefficients are constant-bank operands of the
+// FMAs with static addresses; with a run-time index they cost an LDC plus register moves each (~35% of the
+// build's instructions in the ncu source view).
 template <>
-struct Cor<NNGP_COV_MATERN> {  // src/util.cpp:233-237 with device Bessel-K code (matern_series.cuh, besselk.cuh)
+struct Cor<NNGP_COV_MATERN> {
   double phi, q4;  // q4 = phi^2 / 4: t = q4 d2 = (phi D / 2)^2
-  int b;           // parameter set of this CTA (index into c_mat)
-  __device__ __forceinline__ Cor(const BfTheta &t) : phi(t.phi), q4(0.25 * t.phi * t.phi), b(blockIdx.y) {}
-  __device__ __forceinline__ Cor(double phi_, const MaternConsts *) : phi(phi_), q4(0.25 * phi_ * phi_), b(blockIdx.y) {}
+  const MaternSeriesParams &ms;
+  const MaternConsts *mc;  // global memory: Temme / CF2 tables for the slow path
+  __device__ __forceinline__ Cor(const BfTheta &t) : phi(t.phi), q4(0.25 * t.phi * t.phi), ms(t.ms), mc(t.mat) {}
   // power series in t for phi D <= 2 (clamped beyond: the caller re-evaluates those with slow())
-  __device__ __forceinline__ double fast(double d2) const { return matern_series(fmin(q4 * d2, 1.0), c_mat[b]); }
-  __device__ __forceinline__ bool needs_slow(double d2) const { return !c_mat[b].use_series || q4 * d2 > 1.0; }
-  // Temme / Steed CF2 (data-dependent loops): phi D > 2, or nu within 1e-3 of an integer
-  __device__ __noinline__ double slow(double d2) const { return matern_cor(nngp_sqrt(d2) * phi, c_mat[b]); }
+  __device__ __forceinline__ double fast(double d2) const { return matern_series(fmin(q4 * d2, 1.0), ms); }
+  __device__ __forceinline__ bool needs_slow(double d2) const { return !ms.use_series || q4 * d2 > 1.0; }
+  // phi D in (2, 4]: the extended series; otherwise Temme / Steed CF2 (data-dependent loops): phi D > 4, or nu
+  // within 1e-3 of an integer
+  __device__ __noinline__ double slow(double d2) const {
+    const double t = q4 * d2;
+    if (t <= ms.t_ext_max) return matern_series_ext(t, *mc);
+    return matern_cor(nngp_sqrt(d2) * phi, *mc);
+  }
   __device__ __forceinline__ double operator()(double d2) const { return needs_slow(d2) ? slow(d2) : fast(d2); }
 };
 

@@ -98,6 +98,41 @@ NNGP_FM double nngp_exp_nonpos(double x) {
 }
 
 
+// 1/sqrt(x) for positive normal x, straight-line (hardware seed + two coupled Goldschmidt steps), ~1 ulp.
+// Used for the Cholesky pivots: the library rsqrt() carries special-case branches that lengthen the
+// dependent chain of the latency-bound solve.
+NNGP_FM double nngp_rsqrt_pos(double x) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#else
+  double y = (double)(1.0f / sqrtf((float)x));
+#endif
+  double g = x * y, h = 0.5 * y;
+  double r = fma(-g, h, 0.5);
+  g = fma(g, r, g);
+  h = fma(h, r, h);
+  r = fma(-g, h, 0.5);
+  h = fma(h, r, h);
+  return h + h;
+}
+
+// 1/x for positive normal x, straight-line (hardware seed + two Newton steps + residual), < 1 ulp
+NNGP_FM double nngp_rcp_pos(double x) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#else
+  double r = (double)(1.0f / (float)x);
+#endif
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+
 // natural log for positive normal x, branch-free (fdlibm's e_log.c scheme: x = 2^k (1+f), s = f/(2+f),
 // log(1+f) = f - hfsq + s (hfsq + R(s^2)); the division is a MUFU.RCP64H seed + two Newton steps).
 NNGP_FM double nngp_log_pos(double x) {

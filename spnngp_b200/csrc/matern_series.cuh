@@ -17,7 +17,7 @@
 namespace nngp {
 
 // t = (phi^2/4) d2 in (0, 1]; returns rho.  t == 0 gives exactly sa[0] = 1.
-NNGP_FM double matern_series(double t, const MaternConsts &mc) {
+NNGP_FM double matern_series(double t, const MaternSeriesParams &mc) {
   const double L = nngp_log_pos(t + 1e-300);
   const double pw = nngp_exp(mc.nu * L);  // t^nu
   double pa = mc.sa[kMatSeriesTerms - 1], pb = mc.sb[kMatSeriesTerms - 1];
@@ -25,6 +25,19 @@ NNGP_FM double matern_series(double t, const MaternConsts &mc) {
   for (int k = kMatSeriesTerms - 2; k >= 0; --k) {
     pa = fma(pa, t, mc.sa[k]);
     pb = fma(pb, t, mc.sb[k]);
+  }
+  return fma(-pw, pb, pa);
+}
+
+// The same series with kMatExtTerms terms from the global-memory tables, for 1 < t <= 4 (2 < phi D <= 4; 3 when nu is within ~0.03 of an integer):
+// a 32-trip loop instead of the 40-90 divisions-in-the-loop iterations Steed's CF2 needs in that range.
+NNGP_HD double matern_series_ext(double t, const MaternConsts &mc) {
+  const double pw = exp(mc.nu * log(t));
+  double pa = mc.ea[kMatExtTerms - 1], pb = mc.eb[kMatExtTerms - 1];
+#pragma unroll 4
+  for (int k = kMatExtTerms - 2; k >= 0; --k) {
+    pa = fma(pa, t, mc.ea[k]);
+    pb = fma(pb, t, mc.eb[k]);
   }
   return fma(-pw, pb, pa);
 }

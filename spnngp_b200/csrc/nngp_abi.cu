@@ -131,8 +131,8 @@ int nngp_create(int device, void *stream_handle, nngp_ctx **out) {
     NNGP_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
   }
-  NNGP_CUDA(c, cudaMalloc(&c->d_ticket, NNGP_MAX_BATCH * sizeof(unsigned int)));
-  NNGP_CUDA(c, cudaMemset(c->d_ticket, 0, NNGP_MAX_BATCH * sizeof(unsigned int)));
+  NNGP_CUDA(c, cudaMalloc(&c->d_ticket, 2 * NNGP_MAX_BATCH * sizeof(unsigned int)));  // tickets, tile counters
+  NNGP_CUDA(c, cudaMemset(c->d_ticket, 0, 2 * NNGP_MAX_BATCH * sizeof(unsigned int)));
   NNGP_CUDA(c, cudaMalloc(&c->d_fail, NNGP_MAX_BATCH * sizeof(int)));
   {
     int init[NNGP_MAX_BATCH];
@@ -242,7 +242,11 @@ int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const 
   }
   const long long nloc = (long long)loc_end - loc_begin;
   const int K = p + 1, npairs = K * (K + 1) / 2;
-  size_t need = (size_t)2 * NNGP_MAX_BATCH * bf_grid_max(m, (long long)1 << 40, c->sms);  // also covers site-mode launches
+  // per parameter set: 2 doubles per CTA or per 32-location tile, whichever is more (site-mode chunks are <= 2^20)
+  const long long tiles_max = ((nloc > (1 << 20) ? nloc : (1 << 20)) + 31) / 32;
+  const long long per_set = 2 * (tiles_max > bf_grid_max(m, (long long)1 << 40, c->sms) ? tiles_max : bf_grid_max(m, (long long)1 << 40, c->sms));
+  c->partials_stride = (size_t)per_set;
+  size_t need = (size_t)NNGP_MAX_BATCH * per_set;
   size_t need2 = (size_t)q_forms_grid(nloc) * npairs;
   size_t need3 = (size_t)q_resid_grid(m, nloc, c->sms);
   c->partials_len = need > need2 ? need : need2;
@@ -270,7 +274,6 @@ static int prepare_bf(nngp_ctx *c, int cov, int nbatch, const double *theta, con
   P->loc_begin = c->loc_begin;
   P->loc_end = c->loc_end;
   P->nbatch = nbatch;
-  P->h_mat = (cov == NNGP_COV_MATERN) ? c->h_mat : nullptr;
   double *out_dev = nullptr;
   int *fail_dev = nullptr;
   NNGP_CUDA(c, cudaHostGetDevicePointer((void **)&out_dev, c->h_out, 0));
@@ -286,6 +289,8 @@ static int prepare_bf(nngp_ctx *c, int cov, int nbatch, const double *theta, con
     if (cov == NNGP_COV_MATERN) {
       if (!(t[3] > 0.0)) return ctx_fail(c, NNGP_EINVAL, "matern nu must be > 0");
       matern_prepare(t[3], &c->h_mat[b]);
+      matern_series_params(c->h_mat[b], &th.ms);
+      th.mat = c->d_mat + b;
     }
     const int slot = slots ? slots[b] : (b & 1);
     if (slot < 0 || slot > 1) return ctx_fail(c, NNGP_EINVAL, "slot must be 0 or 1");
@@ -293,11 +298,14 @@ static int prepare_bf(nngp_ctx *c, int cov, int nbatch, const double *theta, con
     th.F = store ? c->d_F[slot] : nullptr;
     th.resid = beta ? c->d_resid[b] : nullptr;
     th.out = (c->comm ? c->d_red : out_dev) + 3 * b;  // device buffer when the result is reduced over ranks
-    th.partials = c->d_partials + (size_t)2 * grid * b;
+    th.partials = c->d_partials + c->partials_stride * b;
     th.ticket = c->d_ticket + b;
+    th.tile_counter = c->d_ticket + NNGP_MAX_BATCH + b;
     th.fail = c->d_fail + b;
     th.fail_out = fail_dev + b;
   }
+  if (cov == NNGP_COV_MATERN)  // full tables for the rare Temme / CF2 path (the series coefficients travel as parameters)
+    NNGP_CUDA(c, cudaMemcpyAsync(c->d_mat, c->h_mat, nbatch * sizeof(MaternConsts), cudaMemcpyHostToDevice, c->stream));
   if (beta) {
     memcpy(c->h_beta, beta, (size_t)nbatch * c->p * sizeof(double));
     NNGP_CUDA(c, cudaMemcpyAsync(c->d_beta, c->h_beta, (size_t)nbatch * c->p * sizeof(double), cudaMemcpyHostToDevice, c->stream));

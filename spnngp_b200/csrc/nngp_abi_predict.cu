@@ -97,7 +97,9 @@ int site_solve(nngp_ctx *c, int cov, const double *t, SiteChunk &ch) {
   th.mat = nullptr;
   if (cov == NNGP_COV_MATERN) {
     matern_prepare(t[3], &c->h_mat[0]);
-    P.h_mat = c->h_mat;
+    matern_series_params(c->h_mat[0], &th.ms);
+    NNGP_CUDA(c, cudaMemcpyAsync(c->d_mat, c->h_mat, sizeof(MaternConsts), cudaMemcpyHostToDevice, c->stream));
+    th.mat = c->d_mat;
   }
   double *out_dev = nullptr;
   int *fail_dev = nullptr;
@@ -109,6 +111,7 @@ int site_solve(nngp_ctx *c, int cov, const double *t, SiteChunk &ch) {
   th.out = out_dev;  // 3 doubles, unused in site mode
   th.partials = c->d_partials;
   th.ticket = c->d_ticket;
+  th.tile_counter = c->d_ticket + NNGP_MAX_BATCH;
   th.fail = c->d_fail;
   th.fail_out = fail_dev;
   const int grid = bf_grid_any(c->m, cov, ch.cs, c->sms);

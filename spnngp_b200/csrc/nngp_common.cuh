@@ -18,13 +18,15 @@ __host__ __device__ __forceinline__ int nn_count(long long i, int m) { return i 
 // One parameter set of a batched B/F launch.
 struct BfTheta {
   double sigmaSq, tauSq, phi;
-  const MaternConsts *mat;  // device pointer (Matern only)
+  const MaternConsts *mat;  // device pointer (Matern only): full constants for the Temme / CF2 slow path
+  MaternSeriesParams ms;    // Matern only: series coefficients, read as constant-bank kernel parameters
   double *B;            // nIndx weights (or nullptr: do not store)
   double *F;            // n conditional variances (or nullptr)
   const double *resid;  // n residuals r = X beta - y (or nullptr: no quadratic form)
   double *out;          // 3 doubles: sum log F, Q over [loc_begin, loc_end), 1.0 if a factorisation failed
-  double *partials;     // 2 * gridDim.x doubles of scratch
+  double *partials;     // scratch: 2 doubles per CTA (static kernels) or per 32-location tile (dynamic tiles)
   unsigned int *ticket; // zero-initialised, self-resetting
+  unsigned int *tile_counter;  // zero-initialised, self-resetting: next tile to hand out (bf_ws_kernel)
   int *fail;            // device: min over failing locations of (i + 1); INT_MAX when none; self-resetting
   int *fail_out;        // where the last CTA publishes *fail (may be mapped host memory)
 };
@@ -35,7 +37,6 @@ struct BfLaunch {
   int n, m;
   int loc_begin, loc_end;
   int nbatch;
-  const MaternConsts *h_mat;  // HOST array [nbatch] (pinned), Matern only; uploaded by the launcher
   // site mode (prediction paths): "locations" are q query sites with unordered m-neighbour lists;
   // th.B receives the kriging weights as a q x m column-major matrix, th.F the q conditional variances
   int site_mode;

@@ -31,6 +31,7 @@ struct nngp_ctx {
   nngp::MaternConsts *d_mat = nullptr;  // NNGP_MAX_BATCH
   double *d_partials = nullptr;         // scratch for the grid reductions
   size_t partials_len = 0;
+  size_t partials_stride = 0;  // doubles per parameter set
   unsigned int *d_ticket = nullptr;  // NNGP_MAX_BATCH
   int *d_fail = nullptr;             // NNGP_MAX_BATCH
   double *d_out = nullptr;           // device result slots

@@ -33,12 +33,11 @@ constexpr int kTplBatch = (COV == NNGP_COV_MATERN) ? 4 : 8;  // entries evaluate
 // Batches of UNR entries: all loads, then UNR independent evaluation chains, then all stores.
 // (A plain unrolled loop is serialised by ptxas: it cannot prove that the store of entry e does not
 // alias the site loads of entry e+1, so the chains never overlap -- seen in SASS.)
-template <int COV, int UNR>
-__device__ __noinline__ void tpl_build(int lane, int off_co, int off_a, const unsigned *ent, int e_begin, int e_step,
-                                       int nent_pad, double sigmaSq, double phi, const MaternConsts *mat) {
+template <int COV, int UNR, typename CorT>
+__device__ __forceinline__ void tpl_build_body(const CorT &cor, int lane, int off_co, int off_a, const unsigned *ent,
+                                               int e_begin, int e_step, int nent_pad, double sigmaSq) {
   const unsigned char *cob = tpl_smem + off_co + lane * 16;
   unsigned char *ab = tpl_smem + off_a + lane * 8;
-  const Cor<COV> cor(phi, mat);
   for (int e0 = e_begin; e0 < nent_pad; e0 += e_step) {  // e_begin, e_step: multiples of the batch width
     double d2[UNR], v[UNR];
     unsigned dst[UNR];
@@ -65,6 +64,24 @@ __device__ __noinline__ void tpl_build(int lane, int off_co, int off_a, const un
     }
 #pragma unroll
     for (int u = 0; u < UNR; ++u) *reinterpret_cast<double *>(ab + dst[u] * 256u) = v[u];
+  }
+}
+
+// The parameter set of this CTA is P.th[blockIdx.y]; Matern specialises on the index so that its series
+// coefficients become constant-bank operands with static addresses (see Cor<NNGP_COV_MATERN>).
+template <int COV, int UNR>
+__device__ __forceinline__ void tpl_build(const BfLaunch &P, int lane, int off_co, int off_a, const unsigned *ent,
+                                          int e_begin, int e_step, int nent_pad) {
+  if constexpr (COV == NNGP_COV_MATERN) {
+    switch (blockIdx.y) {  // uniform over the CTA
+      case 0: tpl_build_body<COV, UNR>(Cor<COV>(P.th[0]), lane, off_co, off_a, ent, e_begin, e_step, nent_pad, P.th[0].sigmaSq); break;
+      case 1: tpl_build_body<COV, UNR>(Cor<COV>(P.th[1]), lane, off_co, off_a, ent, e_begin, e_step, nent_pad, P.th[1].sigmaSq); break;
+      case 2: tpl_build_body<COV, UNR>(Cor<COV>(P.th[2]), lane, off_co, off_a, ent, e_begin, e_step, nent_pad, P.th[2].sigmaSq); break;
+      default: tpl_build_body<COV, UNR>(Cor<COV>(P.th[3]), lane, off_co, off_a, ent, e_begin, e_step, nent_pad, P.th[3].sigmaSq); break;
+    }
+  } else {
+    const BfTheta &th = P.th[blockIdx.y];
+    tpl_build_body<COV, UNR>(Cor<COV>(th), lane, off_co, off_a, ent, e_begin, e_step, nent_pad, th.sigmaSq);
   }
 }
 
@@ -116,7 +133,7 @@ __device__ __forceinline__ void tpl_chol_pair(double *A, double *cv, double *dv,
   // finalise column J0
   const double d0 = a0[J0];
   if (J0 < mi && !(d0 > 0.0)) ok = false;
-  const double r0 = rsqrt(d0);
+  const double r0 = nngp_rsqrt_pos(d0);
   dv[J0 * 32] = r0;
 #pragma unroll
   for (int i = J0 + 1; i <= MC; ++i) a0[i] *= r0;
@@ -130,7 +147,7 @@ __device__ __forceinline__ void tpl_chol_pair(double *A, double *cv, double *dv,
     for (int i = J1; i <= MC; ++i) a1[i] = fma(-a0[i], v, a1[i]);
     const double d1 = a1[J1];
     if (J1 < mi && !(d1 > 0.0)) ok = false;
-    const double r1 = rsqrt(d1);
+    const double r1 = nngp_rsqrt_pos(d1);
     dv[J1 * 32] = r1;
 #pragma unroll
     for (int i = J1 + 1; i <= MC; ++i) a1[i] *= r1;
@@ -153,10 +170,13 @@ __device__ __forceinline__ bool tpl_solve(double *A, double *cv, double *dv, int
   double w[MC];
 #pragma unroll
   for (int k = MC - 1; k >= 0; --k) {
-    double acc = cv[k * 32];
+    double acc0 = cv[k * 32], acc1 = 0.0;  // two chains: halves the dependent FMA depth of the sweep
 #pragma unroll
-    for (int i = MC - 1; i > k; --i) acc = fma(-V_(i, k), w[i], acc);
-    w[k] = acc * dv[k * 32];
+    for (int i = MC - 1; i > k; --i) {
+      if ((MC - 1 - i) & 1) acc1 = fma(-V_(i, k), w[i], acc1);
+      else acc0 = fma(-V_(i, k), w[i], acc0);
+    }
+    w[k] = (acc0 + acc1) * dv[k * 32];
   }
 #pragma unroll
   for (int k = 0; k < MC; ++k) cv[k * 32] = w[k];

@@ -13,7 +13,13 @@ extern "C" {
 double host_matern_series(double x, double nu) {
   nngp::MaternConsts mc; nngp::matern_prepare(nu, &mc);
   if (!mc.use_series) return -1.0;
-  return nngp::matern_series(0.25 * x * x, mc);
+  nngp::MaternSeriesParams ms; nngp::matern_series_params(mc, &ms);
+  return nngp::matern_series(0.25 * x * x, ms);
 }
 double host_nngp_log_pos(double x) { return nngp::nngp_log_pos(x); }
+}
+extern "C" double host_matern_series_ext(double x, double nu) {
+  nngp::MaternConsts mc; nngp::matern_prepare(nu, &mc);
+  if (!mc.use_series) return -1.0;
+  return nngp::matern_series_ext(0.25 * x * x, mc);
 }

@@ -5,3 +5,5 @@ double host_nngp_sqrt(double x) { return nngp::nngp_sqrt(x); }
 double host_nngp_exp_nonpos(double x) { return nngp::nngp_exp_nonpos(x); }
 }
 extern "C" double host_nngp_sqrt_eps(double x) { return nngp::nngp_sqrt_eps(x); }
+extern "C" double host_nngp_rsqrt_pos(double x) { return nngp::nngp_rsqrt_pos(x); }
+extern "C" double host_nngp_rcp_pos(double x) { return nngp::nngp_rcp_pos(x); }
