@@ -29,14 +29,14 @@
 
 namespace nngp {
 
-template <int MC>
+template <int MC, int NP>
 struct WsGeo {
   using T = TplGeo<MC>;
   static constexpr int OFF_RR = T::kWarpBytes;                   // double[MC+1][32]: residuals of neighbours, own
   static constexpr int kStageBytes = OFF_RR + (MC + 1) * 32 * 8;
   static constexpr int kStages = 2;
   static constexpr int kSmemBytes = kStages * kStageBytes;
-  static constexpr int kProducerWarps = 3;
+  static constexpr int kProducerWarps = NP;
   static constexpr int kThreads = 32 * (1 + kProducerWarps);
 };
 
@@ -47,15 +47,14 @@ __device__ __forceinline__ void named_bar_arrive(int id, int count) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
-template <int MC, int COV>
-__global__ void __launch_bounds__(128, 2) bf_ws_kernel(const __grid_constant__ BfLaunch P) {
+template <int MC, int COV, int NP>
+__global__ void __launch_bounds__(32 * (1 + NP), 2) bf_ws_kernel(const __grid_constant__ BfLaunch P) {
   using Geo = TplGeo<MC>;
-  using Ws = WsGeo<MC>;
+  using Ws = WsGeo<MC, NP>;
   constexpr int kBatch = kTplBatch<COV>;
-  constexpr int NP = Ws::kProducerWarps;
   __shared__ unsigned ent[kTplMaxEnt];
   __shared__ long long next_tile[Ws::kStages];  // tile handed to each stage (>= ntiles: no more work)
-  __shared__ double red[2][4];
+  __shared__ double red[2][1 + NP];
   __shared__ int last_flag;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -102,7 +101,7 @@ __global__ void __launch_bounds__(128, 2) bf_ws_kernel(const __grid_constant__ B
   if (warp > 0) {
     // ================================ producers ========================================================
     const int pw = warp - 1;          // producer warp index
-    const int pl = tid - 32;          // producer lane 0..95
+    const int pl = tid - 32;          // producer lane 0..32 NP - 1
     // Tiles are handed out dynamically (one atomic per tile): the first tiles of an ordering have far-apart
     // neighbours (few predecessors), which sends Matern through its slow branches -- with a static split the
     // CTAs that drew them finished 0.3-0.5 ms after everybody else.
@@ -243,7 +242,7 @@ __global__ void __launch_bounds__(128, 2) bf_ws_kernel(const __grid_constant__ B
   if (last_flag) {
     __threadfence();
     double a = 0.0, b = 0.0;
-    for (long long t = tid; t < ntiles; t += Ws::kThreads) {  // thread t: tiles t, t + 128, ... in order
+    for (long long t = tid; t < ntiles; t += Ws::kThreads) {  // thread t: tiles t, t + blockDim, ... in order
       a += __ldcg(&th.partials[2 * t]);
       b += __ldcg(&th.partials[2 * t + 1]);
     }
@@ -258,8 +257,14 @@ __global__ void __launch_bounds__(128, 2) bf_ws_kernel(const __grid_constant__ B
     }
     __syncthreads();
     if (tid == 0) {
-      th.out[0] = (red[0][0] + red[0][1]) + (red[0][2] + red[0][3]);
-      th.out[1] = (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]);
+      double o0 = red[0][0], o1 = red[1][0];
+#pragma unroll
+      for (int w = 1; w <= NP; ++w) {
+        o0 += red[0][w];
+        o1 += red[1][w];
+      }
+      th.out[0] = o0;
+      th.out[1] = o1;
       const int fv = atomicExch(th.fail, INT_MAX);
       th.out[2] = (fv != INT_MAX) ? 1.0 : 0.0;
       *th.fail_out = fv;
@@ -272,29 +277,40 @@ __global__ void __launch_bounds__(128, 2) bf_ws_kernel(const __grid_constant__ B
 // ---- launcher ---------------------------------------------------------------------------------------
 int tpl_capacity_for_m(int m);
 
-template <int MC, int COV>
+template <int MC, int COV, int NP>
 static cudaError_t ws_launch_one(const BfLaunch &P, int grid_x, cudaStream_t stream) {
-  using Ws = WsGeo<MC>;
+  using Ws = WsGeo<MC, NP>;
   static bool configured[16] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 16 || !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(bf_ws_kernel<MC, COV>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ws::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(bf_ws_kernel<MC, COV, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ws::kSmemBytes);
     if (e != cudaSuccess) return e;
     if (dev < 16) configured[dev] = true;
   }
   dim3 grid(grid_x, P.nbatch, 1);
-  bf_ws_kernel<MC, COV><<<grid, Ws::kThreads, Ws::kSmemBytes, stream>>>(P);
+  bf_ws_kernel<MC, COV, NP><<<grid, Ws::kThreads, Ws::kSmemBytes, stream>>>(P);
   return cudaGetLastError();
+}
+
+static int ws_matern_producers() {
+  static int np = -1;
+  if (np < 0) {
+    const char *e = getenv("NNGP_WS_NP");
+    np = (e && atoi(e) == 3) ? 3 : 5;
+  }
+  return np;
 }
 
 template <int MC>
 static cudaError_t ws_launch_cov(const BfLaunch &P, int cov, int grid_x, cudaStream_t stream) {
   switch (cov) {
-    case NNGP_COV_EXPONENTIAL: return ws_launch_one<MC, NNGP_COV_EXPONENTIAL>(P, grid_x, stream);
-    case NNGP_COV_SPHERICAL: return ws_launch_one<MC, NNGP_COV_SPHERICAL>(P, grid_x, stream);
-    case NNGP_COV_MATERN: return ws_launch_one<MC, NNGP_COV_MATERN>(P, grid_x, stream);
-    case NNGP_COV_GAUSSIAN: return ws_launch_one<MC, NNGP_COV_GAUSSIAN>(P, grid_x, stream);
+    case NNGP_COV_EXPONENTIAL: return ws_launch_one<MC, NNGP_COV_EXPONENTIAL, 3>(P, grid_x, stream);
+    case NNGP_COV_SPHERICAL: return ws_launch_one<MC, NNGP_COV_SPHERICAL, 3>(P, grid_x, stream);
+    case NNGP_COV_MATERN:
+      return ws_matern_producers() == 5 ? ws_launch_one<MC, NNGP_COV_MATERN, 5>(P, grid_x, stream)
+                                        : ws_launch_one<MC, NNGP_COV_MATERN, 3>(P, grid_x, stream);
+    case NNGP_COV_GAUSSIAN: return ws_launch_one<MC, NNGP_COV_GAUSSIAN, 3>(P, grid_x, stream);
     default: return cudaErrorInvalidValue;
   }
 }
