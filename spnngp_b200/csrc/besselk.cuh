@@ -22,12 +22,13 @@ constexpr int kMatSeriesTerms = 14;  // t^k/(k!)^2-like decay: 1e-17 relative at
 constexpr int kMatExtTerms = 32;     // 6.25^k / (k!)^2 < 1e-19 by k = 31
 constexpr int kTemmeTerms = 24;  // (x^2/4)^i / i! < 1e-18 well before i = 24 for x <= 2
 constexpr int kCf2Tab = 64;      // tabulated reciprocals for the first CF2 iterations
+constexpr int kGlNodes = 16;     // generalised Gauss-Laguerre rule for phi D > 2 (see matern_gl)
 
 // The part of the constants the straight-line series path needs; small enough to travel as kernel
 // parameters (constant bank, no upload, static operand addresses).
 struct MaternSeriesParams {
   double nu;
-  double t_ext_max;  // largest t = (phi D / 2)^2 served by the extended series (beyond: Steed CF2)
+  double t_ext_max;  // largest t = (phi D / 2)^2 served by the extended series (beyond: Gauss-Laguerre, matern_gl)
   int use_series;
   double sa[kMatSeriesTerms];
   double sb[kMatSeriesTerms];
@@ -60,7 +61,68 @@ struct MaternConsts {
   // cancellation against K's decay still leaves ~1e-12; evaluated by a short loop (matern_series_ext)
   double ea[kMatExtTerms];
   double eb[kMatExtTerms];
+  // Gauss-Laguerre rule for the weight t^(nu-1/2) e^-t (nodes, weights normalised to sum 1) and
+  // gl_c = sqrt(pi/2) / (2^(nu-1) Gamma(nu)): the large-argument path, see matern_gl()
+  double gl_t[kGlNodes];
+  double gl_w[kGlNodes];
+  double gl_c;
 };
+
+// Nodes and normalised weights of the n-point Gauss-Laguerre rule for t^a e^-t, a > -1 (Golub-Welsch:
+// eigenvalues of the Jacobi matrix by implicit QL in long double; weight = squared first component of
+// the eigenvector).
+inline void gauss_laguerre_rule(int n, long double a, double *t, double *w) {
+  long double d[64], e[64], z[64];
+  for (int i = 0; i < n; i++) {
+    d[i] = 2.0L * i + a + 1.0L;
+    e[i] = (i + 1 < n) ? sqrtl((long double)(i + 1) * ((long double)(i + 1) + a)) : 0.0L;  // couples i, i+1
+    z[i] = (i == 0) ? 1.0L : 0.0L;
+  }
+  for (int l = 0; l < n; l++) {
+    for (int iter = 0; iter < 300; iter++) {
+      int mm = l;
+      for (; mm < n - 1; mm++) {
+        const long double dd = fabsl(d[mm]) + fabsl(d[mm + 1]);
+        if (fabsl(e[mm]) <= 1e-22L * dd) break;
+      }
+      if (mm == l) break;
+      long double g = (d[l + 1] - d[l]) / (2.0L * e[l]);
+      long double r = hypotl(g, 1.0L);
+      g = d[mm] - d[l] + e[l] / (g + copysignl(r, g));
+      long double sn = 1.0L, cs = 1.0L, pp = 0.0L;
+      int i = mm - 1;
+      for (; i >= l; i--) {
+        long double f = sn * e[i];
+        const long double b = cs * e[i];
+        r = hypotl(f, g);
+        e[i + 1] = r;
+        if (r == 0.0L) {
+          d[i + 1] -= pp;
+          e[mm] = 0.0L;
+          break;
+        }
+        sn = f / r;
+        cs = g / r;
+        g = d[i + 1] - pp;
+        r = (d[i] - g) * sn + 2.0L * cs * b;
+        pp = sn * r;
+        d[i + 1] = g + pp;
+        g = cs * r - b;
+        f = z[i + 1];
+        z[i + 1] = sn * z[i] + cs * f;
+        z[i] = cs * z[i] - sn * f;
+      }
+      if (r == 0.0L && i >= l) continue;
+      d[l] -= pp;
+      e[l] = g;
+      e[mm] = 0.0L;
+    }
+  }
+  for (int i = 0; i < n; i++) {
+    t[i] = (double)d[i];
+    w[i] = (double)(z[i] * z[i]);
+  }
+}
 
 // ---- host side: constants per nu -------------------------------------------------------------
 // Coefficients c_k of 1/Gamma(z) = sum_{k>=1} c_k z^k (Abramowitz & Stegun 6.1.34); checked
@@ -126,6 +188,8 @@ inline void matern_prepare(double nu, MaternConsts *mc) {
       for (int k = 0; k < kMatExtTerms; k++) mc->ea[k] = mc->eb[k] = 0.0;
     }
   }
+  gauss_laguerre_rule(kGlNodes, (long double)nu - 0.5L, mc->gl_t, mc->gl_w);
+  mc->gl_c = 1.2533141373155002512 * mc->pref;  // sqrt(pi/2)
   double a = -mc->a1;
   for (int i = 1; i <= kCf2Tab; i++) {
     mc->r_i[i - 1] = 1.0 / (double)i;
@@ -262,7 +326,7 @@ inline void matern_series_params(const MaternConsts &mc, MaternSeriesParams *ms)
   ms->use_series = mc.use_series;
   // cancellation of the two sums grows like e^(2 phi D) / |sin(nu pi)|: keep ~1e-12 absolute
   const double snp = fabs(sin(3.14159265358979323846 * mc.nu));
-  ms->t_ext_max = !mc.use_series ? 0.0 : (snp > 0.1 ? 4.0 : 2.25);
+  ms->t_ext_max = !mc.use_series ? 1.0 : (snp > 0.1 ? 4.0 : 2.25);
   for (int k = 0; k < kMatSeriesTerms; k++) {
     ms->sa[k] = mc.sa[k];
     ms->sb[k] = mc.sb[k];

@@ -17,13 +17,17 @@
 // scheduler and two FP64-bound producers on each of the other three.
 //
 // Measured at n = 10^6, m = 15 (ms per launch; exponential / Matern): cooperative kernel 1.11 / 1.79,
-// single-role one-lane kernel 0.90 / 2.63, this kernel 0.72 / 1.63.  It is consumer-bound: the Cholesky
-// chain of one tile takes ~13k cycles against ~11k for its build.  Variants tried and rejected (all
-// ~0.91-1.01 ms): one 8-warp CTA with a consumer and a producer on every scheduler (the producer's DFMA
-// stream starves the consumer's dependent chain); 2-4 consumers packed on scheduler 0 with 6 producers on
-// schedulers 1-3 (the fully unrolled solve, 30 KB of code per consumer, thrashes the instruction cache:
-// ncu stall_no_instruction 40-49% in the solve).
+// single-role one-lane kernel 0.90 / 2.63, this kernel 0.62 / 1.11 (history: 0.72 / 1.63 with a static tile
+// split and gathers inside the producers' critical path; dynamic tiles + the Matern series/quadrature paths
+// -> 0.71 / 1.20; gathers software-pipelined one tile ahead -> 0.62 / 1.11).  The exponential kernel is
+// consumer-bound (the Cholesky chain of one tile takes ~9k cycles, B stores ~2k); Matern is bound by the
+// FP64 issue rate of the three producer schedulers (3, 4 or 5 producer warps measure the same).  Variants
+// tried and rejected (all ~0.91-1.01 ms): one 8-warp CTA with a consumer and a producer on every scheduler
+// (the producer's DFMA stream starves the consumer's dependent chain); 2-4 consumers packed on scheduler 0
+// with 6 producers on schedulers 1-3 (the fully unrolled solve, 30 KB of code per consumer, thrashes the
+// instruction cache: ncu stall_no_instruction 40-49% in the solve).
 #include <stdlib.h>
+
 
 #include "tpl_device.cuh"
 
@@ -35,7 +39,8 @@ struct WsGeo {
   static constexpr int OFF_RR = T::kWarpBytes;                   // double[MC+1][32]: residuals of neighbours, own
   static constexpr int kStageBytes = OFF_RR + (MC + 1) * 32 * 8;
   static constexpr int kStages = 2;
-  static constexpr int kSmemBytes = kStages * kStageBytes;
+  static constexpr int kRrBytes = (MC + 1) * 32 * 8;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kRrBytes;  // + third slot of the residual ring
   static constexpr int kProducerWarps = NP;
   static constexpr int kThreads = 32 * (1 + kProducerWarps);
 };
@@ -47,13 +52,21 @@ __device__ __forceinline__ void named_bar_arrive(int id, int count) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
+// residual ring, 3 deep: slots 0 and 1 live inside the two stages, slot 2 behind them
+template <int MC, int NP>
+__device__ __forceinline__ double *ws_rr(int slot) {
+  using Ws = WsGeo<MC, NP>;
+  return reinterpret_cast<double *>(tpl_smem + (slot < 2 ? slot * Ws::kStageBytes + Ws::OFF_RR : 2 * Ws::kStageBytes));
+}
+
 template <int MC, int COV, int NP>
 __global__ void __launch_bounds__(32 * (1 + NP), 2) bf_ws_kernel(const __grid_constant__ BfLaunch P) {
   using Geo = TplGeo<MC>;
   using Ws = WsGeo<MC, NP>;
   constexpr int kBatch = kTplBatch<COV>;
   __shared__ unsigned ent[kTplMaxEnt];
-  __shared__ long long next_tile[Ws::kStages];  // tile handed to each stage (>= ntiles: no more work)
+  __shared__ int ebeg[NP + 1];
+  __shared__ long long next_tile[8];  // ring of claimed tiles, slot j & 7 (>= ntiles: no more work)
   __shared__ double red[2][1 + NP];
   __shared__ int last_flag;
   const int tid = threadIdx.x;
@@ -68,7 +81,12 @@ __global__ void __launch_bounds__(32 * (1 + NP), 2) bf_ws_kernel(const __grid_co
 
   // ---- one-time setup: work list, zero padding of both stages --------------------------------------
   const int ne = m * (m - 1) / 2;
-  const int nent_pad = ((ne + m + NP * kBatch - 1) / (NP * kBatch)) * (NP * kBatch);
+  const int nent_pad = ((ne + m + kBatch - 1) / kBatch) * kBatch;
+  if (tid <= NP) {
+    // entry ranges of the producer warps, in whole batches
+    const int nb = nent_pad / kBatch;
+    ebeg[tid] = ((nb * tid) / NP) * kBatch;
+  }
   for (int e = tid; e < nent_pad; e += Ws::kThreads) {
     unsigned w;
     if (e < ne) {
@@ -93,6 +111,7 @@ __global__ void __launch_bounds__(32 * (1 + NP), 2) bf_ws_kernel(const __grid_co
     for (int x = tid; x < (MC - m) * 32; x += Ws::kThreads) cv[m * 32 + x] = 0.0;
     for (int x = tid; x < (MC + 1) * 32; x += Ws::kThreads) rr[x] = 0.0;
   }
+  for (int x = tid; x < (MC + 1) * 32; x += Ws::kThreads) ws_rr<MC, NP>(2)[x] = 0.0;
   __syncthreads();
 
   const long long ntiles = ((long long)P.loc_end - P.loc_begin + 31) / 32;
@@ -105,49 +124,84 @@ __global__ void __launch_bounds__(32 * (1 + NP), 2) bf_ws_kernel(const __grid_co
     // Tiles are handed out dynamically (one atomic per tile): the first tiles of an ordering have far-apart
     // neighbours (few predecessors), which sends Matern through its slow branches -- with a static split the
     // CTAs that drew them finished 0.3-0.5 ms after everybody else.
+    //
+    // Software pipeline, so that no producer ever waits for global memory: while tile j is being built, the
+    // sites/residuals of tile j+1 are in flight (cp.async into the other stage's site rows and the next slot
+    // of a 3-deep residual ring), the neighbour ids of tile j+2 are in flight into registers, and the atomic
+    // that claims tile j+3 is outstanding in thread 0.
+    constexpr int IDS = (MC + NP - 1) / NP;  // neighbour slots per producer thread: k = pw + q NP, location = lane
+    int ids[IDS];
+    auto load_ids = [&](long long tile) {
+      long long i = P.loc_begin + tile * 32 + lane;
+      if (i >= P.loc_end) i = (long long)P.loc_end - 1;  // tail lanes redo the last location
+      const int mi = site ? m : nn_count(i, m);
+      const long long off = site ? 0 : nn_offset(i, m);
+#pragma unroll
+      for (int q = 0; q < IDS; ++q) {
+        const int k = pw + q * NP;
+        ids[q] = -1;  // missing neighbour (ragged start of the ordering)
+        if (k < mi) ids[q] = site ? __ldg(&P.nn0[(size_t)k * P.q + i]) : __ldg(&P.nnIndx[off + k]);
+      }
+    };
+    auto issue_gathers = [&](long long tile, int stage, int ring) {
+      double2 *co = reinterpret_cast<double2 *>(tpl_smem + stage * Ws::kStageBytes + Geo::OFF_CO);
+      double *rr = ws_rr<MC, NP>(ring);
+      long long i = P.loc_begin + tile * 32 + lane;
+      if (i >= P.loc_end) i = (long long)P.loc_end - 1;
+#pragma unroll
+      for (int q = 0; q < IDS; ++q) {
+        const int k = pw + q * NP;
+        if (k < m) {
+          if (ids[q] >= 0) {
+            cp_async16(&co[k * 32 + lane], &P.coords[ids[q]]);
+            if (resid != nullptr) cp_async8(&rr[k * 32 + lane], &resid[ids[q]]);
+          } else {
+            // stand in the location's own site, so the masked entries stay on the straight-line correlation path
+            cp_async16(&co[k * 32 + lane], &P.coords[i]);
+            rr[k * 32 + lane] = 0.0;
+          }
+        }
+      }
+      if (pw == 0) {
+        cp_async16(&co[MC * 32 + lane], site ? &P.sites[i] : &P.coords[i]);
+        if (resid != nullptr && !site) cp_async8(&rr[MC * 32 + lane], &resid[i]);
+      }
+    };
+    if (pl == 0) {  // first three tiles: static round-robin (spreads the slow head of the ordering over the CTAs)
+      next_tile[0] = blockIdx.x;
+      next_tile[1] = (long long)blockIdx.x + gridDim.x;
+      next_tile[2] = (long long)blockIdx.x + 2ll * gridDim.x;
+    }
+    named_bar_sync(5, 32 * NP);
+    if (next_tile[0] < ntiles) {
+      load_ids(next_tile[0]);
+      issue_gathers(next_tile[0], 0, 0);
+    }
+    if (next_tile[1] < ntiles) load_ids(next_tile[1]);
+    int ring = 0;  // j % 3
     for (int j = 0;; ++j) {
       const int s = j & 1;
-      unsigned char *st = tpl_smem + s * Ws::kStageBytes;
-      double2 *co = reinterpret_cast<double2 *>(st + Geo::OFF_CO);
-      double *rr = reinterpret_cast<double *>(st + Ws::OFF_RR);
-      if (j >= Ws::kStages) named_bar_sync(3 + s, Ws::kThreads);  // stage released by the consumer
-      if (pl == 0) next_tile[s] = (long long)atomicAdd(th.tile_counter, 1u);
-      named_bar_sync(5, 32 * NP);
-      const long long tile = next_tile[s];
+      cp_async_wait_all();                                        // this thread's share of tile j has landed
+      named_bar_sync(5, 32 * NP);                                 // ... everybody's; build j-1 finished everywhere
+      if (j >= Ws::kStages) named_bar_sync(3 + s, Ws::kThreads);  // consumer done with tile j-2: stage s, ring slot j+1
+      const long long tile = next_tile[j & 7];
       if (tile >= ntiles) {
         named_bar_arrive(1 + s, Ws::kThreads);  // hands the consumer the end-of-work marker
         break;
       }
-      const long long base = P.loc_begin + tile * 32;
-      // ---- phase 0: ids -> asynchronous gathers of sites and residuals into the stage -------------------
-      for (int t = pl; t < m * 32; t += 32 * NP) {
-        const int k = t >> 5, loc = t & 31;
-        long long i = base + loc;
-        if (i >= P.loc_end) i = (long long)P.loc_end - 1;  // tail lanes redo the last location
-        const int mi = site ? m : nn_count(i, m);
-        if (k < mi) {
-          const int id = site ? __ldg(&P.nn0[(size_t)k * P.q + i]) : __ldg(&P.nnIndx[nn_offset(i, m) + k]);
-          cp_async16(&co[k * 32 + loc], &P.coords[id]);
-          if (resid != nullptr) cp_async8(&rr[k * 32 + loc], &resid[id]);
-        } else {
-          // missing neighbour (ragged start of the ordering): stand in the location's own site, so the masked
-          // entries stay on the straight-line correlation path
-          cp_async16(&co[k * 32 + loc], site ? &P.sites[i] : &P.coords[i]);
-          rr[k * 32 + loc] = 0.0;
-        }
-      }
-      if (pl < 32) {
-        long long i = base + pl;
-        if (i >= P.loc_end) i = (long long)P.loc_end - 1;
-        cp_async16(&co[MC * 32 + pl], site ? &P.sites[i] : &P.coords[i]);
-        if (resid != nullptr && !site) cp_async8(&rr[MC * 32 + pl], &resid[i]);
-      }
-      cp_async_wait_all();
-      named_bar_sync(5, 32 * NP);  // all sites of the tile visible to the three producer warps
-      // ---- phase A: this warp's third of the correlations (lane = location) --------------------------------
+      const int ring_next = (ring == 2) ? 0 : ring + 1;
+      const long long tile1 = next_tile[(j + 1) & 7], tile2 = next_tile[(j + 2) & 7];
+      if (tile1 < ntiles) issue_gathers(tile1, s ^ 1, ring_next);
+      if (tile2 < ntiles) load_ids(tile2);
+      unsigned claimed = 0u;
+      if (pl == 0) claimed = atomicAdd(th.tile_counter, 1u);  // tile 3 gridDim.x + claimed
+      // ---- this warp's share of tile j's correlations (lane = location) ---------------------------------
       tpl_build<COV, kBatch>(P, lane, s * Ws::kStageBytes + Geo::OFF_CO, s * Ws::kStageBytes + Geo::OFF_A, ent,
-                             pw * kBatch, NP * kBatch, nent_pad);
+                             ebeg[pw], kBatch, ebeg[pw + 1]);
+      asm volatile("" ::: "memory");
+      if (pl == 0) next_tile[(j + 3) & 7] = 3ll * gridDim.x + claimed;  // published by the rendezvous of the next trip
       named_bar_arrive(1 + s, Ws::kThreads);  // stage full
+      ring = ring_next;
     }
   } else {
     // ================================ consumer ==========================================================
@@ -157,9 +211,9 @@ __global__ void __launch_bounds__(32 * (1 + NP), 2) bf_ws_kernel(const __grid_co
       double *A = reinterpret_cast<double *>(st + Geo::OFF_A) + lane;
       double *cv = reinterpret_cast<double *>(st + Geo::OFF_CV);
       double *dv = reinterpret_cast<double *>(st + Geo::OFF_DV) + lane;
-      const double *rr = reinterpret_cast<const double *>(st + Ws::OFF_RR);
+      const double *rr = ws_rr<MC, NP>(j % 3);
       named_bar_sync(1 + s, Ws::kThreads);  // wait for the producers
-      const long long tile = next_tile[s];
+      const long long tile = next_tile[j & 7];
       if (tile >= ntiles) break;
       const long long base = P.loc_begin + tile * 32;
       const bool active = base + lane < P.loc_end;
@@ -293,23 +347,13 @@ static cudaError_t ws_launch_one(const BfLaunch &P, int grid_x, cudaStream_t str
   return cudaGetLastError();
 }
 
-static int ws_matern_producers() {
-  static int np = -1;
-  if (np < 0) {
-    const char *e = getenv("NNGP_WS_NP");
-    np = (e && atoi(e) == 3) ? 3 : 5;
-  }
-  return np;
-}
-
 template <int MC>
 static cudaError_t ws_launch_cov(const BfLaunch &P, int cov, int grid_x, cudaStream_t stream) {
   switch (cov) {
     case NNGP_COV_EXPONENTIAL: return ws_launch_one<MC, NNGP_COV_EXPONENTIAL, 3>(P, grid_x, stream);
     case NNGP_COV_SPHERICAL: return ws_launch_one<MC, NNGP_COV_SPHERICAL, 3>(P, grid_x, stream);
     case NNGP_COV_MATERN:
-      return ws_matern_producers() == 5 ? ws_launch_one<MC, NNGP_COV_MATERN, 5>(P, grid_x, stream)
-                                        : ws_launch_one<MC, NNGP_COV_MATERN, 3>(P, grid_x, stream);
+      return ws_launch_one<MC, NNGP_COV_MATERN, 3>(P, grid_x, stream);
     case NNGP_COV_GAUSSIAN: return ws_launch_one<MC, NNGP_COV_GAUSSIAN, 3>(P, grid_x, stream);
     default: return cudaErrorInvalidValue;
   }
@@ -321,7 +365,7 @@ static int ws_stage_bytes(int MC) {
 
 int ws_ctas_per_sm(int m) {
   const int MC = tpl_capacity_for_m(m);
-  int c = (227 * 1024) / (2 * ws_stage_bytes(MC) + 2048);
+  int c = (227 * 1024) / (2 * ws_stage_bytes(MC) + (MC + 1) * 32 * 8 + 2048);
   static int override_ctas = -1;
   if (override_ctas < 0) {
     const char *e = getenv("NNGP_WS_CTAS");

@@ -54,11 +54,12 @@ struct Cor<NNGP_COV_MATERN> {
   // power series in t for phi D <= 2 (clamped beyond: the caller re-evaluates those with slow())
   __device__ __forceinline__ double fast(double d2) const { return matern_series(fmin(q4 * d2, 1.0), ms); }
   __device__ __forceinline__ bool needs_slow(double d2) const { return !ms.use_series || q4 * d2 > 1.0; }
-  // phi D in (2, 4]: the extended series; otherwise Temme / Steed CF2 (data-dependent loops): phi D > 4, or nu
-  // within 1e-3 of an integer
+  // phi D in (2, 4]: the extended series; beyond: Gauss-Laguerre quadrature.  nu within 1e-3 of an integer
+  // (the series cancel): Temme's iteration for phi D <= 2, the quadrature beyond.
   __device__ __noinline__ double slow(double d2) const {
     const double t = q4 * d2;
-    if (t <= ms.t_ext_max) return matern_series_ext(t, *mc);
+    if (t > ms.t_ext_max) return matern_gl(nngp_sqrt(d2) * phi, *mc);
+    if (ms.use_series) return matern_series_ext(t, *mc);
     return matern_cor(nngp_sqrt(d2) * phi, *mc);
   }
   __device__ __forceinline__ double operator()(double d2) const { return needs_slow(d2) ? slow(d2) : fast(d2); }

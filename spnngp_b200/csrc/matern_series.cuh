@@ -42,4 +42,20 @@ NNGP_HD double matern_series_ext(double t, const MaternConsts &mc) {
   return fma(-pw, pb, pa);
 }
 
+// phi D = x > 2, any nu > 0 (integers included): the integral representation
+//   K_nu(x) = sqrt(pi/(2x)) e^-x / Gamma(nu+1/2)  int_0^inf e^-t t^(nu-1/2) (1 + t/(2x))^(nu-1/2) dt
+// by the kGlNodes-point Gauss-Laguerre rule for the weight t^(nu-1/2) e^-t (nodes prepared per nu on the host).
+// The integrand's only singularity sits at t = -2x, so the rule converges geometrically: 16 nodes give
+// 4e-13 relative at x = 2, 2e-15 at x = 3 and ~3e-16 beyond x = 4, for every nu (host test vs mpmath) -- with
+// no data-dependent loop, where Steed's continued fraction needs 10-90 iterations with a division each.
+//   rho(x) = gl_c x^(nu-1/2) e^-x  sum_i w_i (1 + t_i/(2x))^(nu-1/2)
+NNGP_FM double matern_gl(double x, const MaternConsts &mc) {
+  const double a = mc.nu - 0.5;
+  const double h = 0.5 * nngp_rcp_pos(x);
+  double S = 0.0;
+#pragma unroll 4
+  for (int i = 0; i < kGlNodes; ++i) S = fma(mc.gl_w[i], nngp_exp(a * nngp_log_pos(fma(mc.gl_t[i], h, 1.0))), S);
+  return mc.gl_c * nngp_exp(fma(a, nngp_log_pos(x), -x)) * S;
+}
+
 }  // namespace nngp

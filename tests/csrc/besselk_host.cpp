@@ -23,3 +23,12 @@ extern "C" double host_matern_series_ext(double x, double nu) {
   if (!mc.use_series) return -1.0;
   return nngp::matern_series_ext(0.25 * x * x, mc);
 }
+// large-argument path (phi D > 2): Gauss-Laguerre quadrature, any nu
+extern "C" double host_matern_gl(double x, double nu) {
+  nngp::MaternConsts mc; nngp::matern_prepare(nu, &mc);
+  return nngp::matern_gl(x, mc);
+}
+extern "C" void host_gl_rule(double nu, double *t, double *w) {
+  nngp::MaternConsts mc; nngp::matern_prepare(nu, &mc);
+  for (int i = 0; i < nngp::kGlNodes; i++) { t[i] = mc.gl_t[i]; w[i] = mc.gl_w[i]; }
+}

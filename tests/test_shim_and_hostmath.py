@@ -101,6 +101,34 @@ def test_device_besselk_on_host_vs_mpmath(tmp_path):
         assert abs(L.host_matern(x, 2.5) - (1 + x + x * x / 3) * np.exp(-x)) < 3e-15
 
 
+def test_matern_gauss_laguerre_on_host_vs_mpmath(tmp_path):
+    """Large-argument Matern path (spnngp_b200/csrc/matern_series.cuh: matern_gl), host build, vs mpmath; the
+    Gauss-Laguerre rule itself vs scipy."""
+    import mpmath as mp
+    from scipy.special import roots_genlaguerre, gamma
+    L = _build_host("besselk_host.cpp", str(tmp_path / "libbk.so"))
+    L.host_matern_gl.restype = C.c_double; L.host_matern_gl.argtypes = [C.c_double, C.c_double]
+    L.host_gl_rule.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    for nu in (0.1, 0.5, 1.0, 2.75):
+        t = (C.c_double * 16)(); w = (C.c_double * 16)()
+        L.host_gl_rule(nu, t, w)
+        ts, ws = roots_genlaguerre(16, nu - 0.5)
+        o = np.argsort(np.array(t[:]))
+        assert np.allclose(np.array(t[:])[o], ts, rtol=1e-12, atol=0)
+        assert np.allclose(np.array(w[:])[o], ws / gamma(nu + 0.5), rtol=1e-9, atol=1e-300)
+    mp.mp.dps = 40
+    worst2 = worst3 = worst4 = 0.0
+    for nu in (0.05, 0.25, 0.5, 0.75, 1.0, 1.0005, 1.5, 2.0, 2.3, 3.0, 3.7, 5.0):
+        for x in (2.0, 2.5, 3.0, 3.5, 4.0, 6.0, 9.0, 20.0, 55.0, 100.0, 400.0, 650.0):
+            rho = mp.mpf(x) ** nu * mp.besselk(nu, x) / (mp.mpf(2) ** (nu - 1) * mp.gamma(nu))
+            err = float(abs((mp.mpf(L.host_matern_gl(x, nu)) - rho) / rho))
+            worst2 = max(worst2, err)
+            if x >= 3.0: worst3 = max(worst3, err)
+            if x >= 4.0: worst4 = max(worst4, err)
+    assert worst2 < 1e-12 and worst3 < 1e-13 and worst4 < 5e-14, (worst2, worst3, worst4)
+    assert L.host_matern_gl(800.0, 0.75) == 0.0  # underflows like the reference's bessel_k
+
+
 def test_device_fastmath_on_host(tmp_path):
     """Branch-free sqrt / exp of spnngp_b200/csrc/fastmath.cuh (host build) vs libm."""
     L = _build_host("fastmath_host.cpp", str(tmp_path / "libfm.so"))
