@@ -366,9 +366,9 @@ static int kernel_for(int m, int cov) {
   const bool small = tpl_capacity_for_m(m) > 0;
   if (forced >= 0 && (forced == KERNEL_COOP || small)) return forced;
   if (!small) return KERNEL_COOP;
-  // tiles of m <= 10 are too small to amortise the producer/consumer hand-off (measured: m = 10 0.35 ms
-  // single-role vs 0.44-0.56 ms specialised; m = 5 0.11 vs 0.42 ms)
-  return tpl_capacity_for_m(m) >= 12 ? KERNEL_WS : KERNEL_TPL;
+  // small tiles do not amortise the producer/consumer hand-off (measured at n = 10^6, exponential: m = 5 0.112 ms
+  // single-role vs 0.133 ms specialised; m = 8 0.243 vs 0.223; m = 10 0.377 vs 0.313 ms)
+  return tpl_capacity_for_m(m) >= 8 ? KERNEL_WS : KERNEL_TPL;
 }
 
 int bf_grid_any(int m, int cov, long long nloc, int sms) {

@@ -52,6 +52,11 @@ __device__ __forceinline__ void named_bar_arrive(int id, int count) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
+// tile of 32 complete (m-neighbour) rows: its weights are one contiguous run of 32 m doubles in B
+__device__ __forceinline__ bool ws_full_tile(long long base, int m, long long loc_end) {
+  return base >= m && base + 32 <= loc_end;
+}
+
 // residual ring, 3 deep: slots 0 and 1 live inside the two stages, slot 2 behind them
 template <int MC, int NP>
 __device__ __forceinline__ double *ws_rr(int slot) {
@@ -64,6 +69,9 @@ __global__ void __launch_bounds__(32 * (1 + NP), 2) bf_ws_kernel(const __grid_co
   using Geo = TplGeo<MC>;
   using Ws = WsGeo<MC, NP>;
   constexpr int kBatch = kTplBatch<COV>;
+  // who stores a solved tile's weights: the producers where the consumer is the critical path (0.62 -> 0.59 ms,
+  // spherical), the consumer for Matern, whose producers are the critical path (1.11 vs 1.15 ms)
+  constexpr bool kProducersStoreB = (COV != NNGP_COV_MATERN);
   __shared__ unsigned ent[kTplMaxEnt];
   __shared__ int ebeg[NP + 1];
   __shared__ long long next_tile[8];  // ring of claimed tiles, slot j & 7 (>= ntiles: no more work)
@@ -179,13 +187,35 @@ __global__ void __launch_bounds__(32 * (1 + NP), 2) bf_ws_kernel(const __grid_co
     }
     if (next_tile[1] < ntiles) load_ids(next_tile[1]);
     int ring = 0;  // j % 3
+    // Weights of a solved tile go to global memory from here, not from the consumer (the CTA's critical path):
+    // 32 complete rows of B are contiguous, the producers copy them out of the stage before refilling it.
+    auto write_b = [&](long long tile, int stage) {
+      if (!kProducersStoreB || th.B == nullptr || site) return;
+      const long long base = P.loc_begin + tile * 32;
+      if (!ws_full_tile(base, m, P.loc_end)) return;  // ragged / partial tiles: the consumer stored them
+      const double *cv = reinterpret_cast<const double *>(tpl_smem + stage * Ws::kStageBytes + Geo::OFF_CV);
+      double *dst = th.B + nn_offset(base, m);
+      const float rm = 1.0f / (float)m;
+      for (int t = pl; t < 32 * m; t += 32 * NP) {
+        const int loc = (int)(((float)t + 0.5f) * rm);
+        const int k = t - loc * m;
+        dst[t] = cv[k * 32 + loc];
+      }
+    };
     for (int j = 0;; ++j) {
       const int s = j & 1;
-      cp_async_wait_all();                                        // this thread's share of tile j has landed
-      named_bar_sync(5, 32 * NP);                                 // ... everybody's; build j-1 finished everywhere
-      if (j >= Ws::kStages) named_bar_sync(3 + s, Ws::kThreads);  // consumer done with tile j-2: stage s, ring slot j+1
+      if (j >= Ws::kStages) {
+        named_bar_sync(3 + s, Ws::kThreads);  // consumer done with tile j-2: stage s, ring slot j+1
+        write_b(next_tile[(j - 2) & 7], s);
+      }
+      cp_async_wait_all();         // this thread's share of tile j has landed
+      named_bar_sync(5, 32 * NP);  // ... everybody's; build j-1 and the copy-out of tile j-2 finished everywhere
       const long long tile = next_tile[j & 7];
       if (tile >= ntiles) {
+        if (j >= 1) {
+          named_bar_sync(3 + (s ^ 1), Ws::kThreads);  // the CTA's last tile
+          write_b(next_tile[(j - 1) & 7], s ^ 1);
+        }
         named_bar_arrive(1 + s, Ws::kThreads);  // hands the consumer the end-of-work marker
         break;
       }
@@ -244,8 +274,9 @@ __global__ void __launch_bounds__(32 * (1 + NP), 2) bf_ws_kernel(const __grid_co
               if (k < m) th.B[(size_t)k * P.q + i] = cv[k * 32 + lane];
           }
         } else {
-          const bool full = (base >= m) && (base + 32 <= P.loc_end);  // 32 complete rows, contiguous in B
-          if (full) {
+          // 32 complete rows are contiguous in B: copied out by the producers (write_b) or, transposed, from here
+          const bool full = ws_full_tile(base, m, P.loc_end);
+          if (full && !kProducersStoreB) {
             __syncwarp();
             double *dst = th.B + nn_offset(base, m);
             const float rm = 1.0f / (float)m;
@@ -254,7 +285,7 @@ __global__ void __launch_bounds__(32 * (1 + NP), 2) bf_ws_kernel(const __grid_co
               const int k = t - loc * m;
               dst[t] = cv[k * 32 + loc];
             }
-          } else if (active) {
+          } else if (!full && active) {
 #pragma unroll
             for (int k = 0; k < MC; ++k)
               if (k < mi) th.B[off + k] = cv[k * 32 + lane];
