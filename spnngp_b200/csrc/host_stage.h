@@ -1,0 +1,121 @@
+// host_stage.h -- pageable host arrays -> device through a small ring of pinned buffers, filled by a few
+// host threads while earlier chunks are in flight (nngp_set_data's upload path).
+//
+// A plain cudaMemcpy from pageable memory stages through one driver thread (~6-8 GB/s here); the working
+// set of a fit (coords, neighbour ids, X, y: ~100 MB at n = 10^6, m = 15) then costs more wall time than
+// twenty sampler iterations.  Here T threads each own two pinned chunks and a stream: thread t takes chunks
+// t, t+T, ... of the job list, converts/copies one into pinned memory (fusing the (x, y) interleave and the
+// neighbour-id range check into that pass) and queues its DMA, so host copies and PCIe transfers overlap.
+#pragma once
+#include <cuda_runtime.h>
+#include <string.h>
+
+#include <atomic>
+#include <thread>
+#include <vector>
+
+namespace nngp {
+
+struct StageJob {
+  enum Kind { RAW, XY_INTERLEAVE, INT_RANGE };
+  Kind kind;
+  void *dst;        // device
+  const void *src;  // host (pageable)
+  size_t bytes;     // bytes written to dst
+  long long n;      // XY_INTERLEAVE: number of sites (src = x[n] then y[n]); INT_RANGE: valid ids are [0, n)
+};
+
+class HostStager {
+ public:
+  static constexpr size_t kChunk = (size_t)2 << 20;
+  static constexpr int kMaxThreads = 4;
+
+  ~HostStager() {
+    for (int t = 0; t < nthreads_; t++) {
+      for (int b = 0; b < 2; b++) {
+        if (ev_[t][b]) cudaEventDestroy(ev_[t][b]);
+        if (buf_[t][b]) cudaFreeHost(buf_[t][b]);
+      }
+      if (st_[t]) cudaStreamDestroy(st_[t]);
+    }
+  }
+
+  cudaError_t init(int device) {
+    device_ = device;
+    unsigned hc = std::thread::hardware_concurrency();
+    nthreads_ = hc >= 8 ? kMaxThreads : (hc >= 4 ? 2 : 1);
+    for (int t = 0; t < nthreads_; t++) {
+      cudaError_t e = cudaStreamCreateWithFlags(&st_[t], cudaStreamNonBlocking);
+      if (e != cudaSuccess) return e;
+      for (int b = 0; b < 2; b++) {
+        if ((e = cudaHostAlloc(&buf_[t][b], kChunk, cudaHostAllocDefault)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&ev_[t][b], cudaEventDisableTiming)) != cudaSuccess) return e;
+      }
+    }
+    return cudaSuccess;
+  }
+
+  // Runs all jobs; returns when every byte is on the device.  *bad_id is set if an INT_RANGE job saw an id
+  // outside [0, n) (the upload still completes).
+  cudaError_t run(const std::vector<StageJob> &jobs, bool *bad_id) {
+    struct Chunk { int job; size_t off, len; };
+    std::vector<Chunk> chunks;
+    for (size_t j = 0; j < jobs.size(); j++)
+      for (size_t off = 0; off < jobs[j].bytes; off += kChunk)
+        chunks.push_back({(int)j, off, jobs[j].bytes - off < kChunk ? jobs[j].bytes - off : kChunk});
+    std::atomic<int> err{(int)cudaSuccess};
+    std::atomic<bool> bad{false};
+    auto worker = [&](int t) {
+      cudaSetDevice(device_);
+      int b = 0;
+      for (size_t ci = (size_t)t; ci < chunks.size(); ci += (size_t)nthreads_, b ^= 1) {
+        const Chunk &ch = chunks[ci];
+        const StageJob &J = jobs[ch.job];
+        cudaError_t e = cudaEventSynchronize(ev_[t][b]);  // this buffer's previous DMA has finished
+        if (e != cudaSuccess) { err = (int)e; return; }
+        char *pin = (char *)buf_[t][b];
+        if (J.kind == StageJob::RAW) {
+          memcpy(pin, (const char *)J.src + ch.off, ch.len);
+        } else if (J.kind == StageJob::XY_INTERLEAVE) {
+          const double *x = (const double *)J.src, *y = x + J.n;
+          const size_t i0 = ch.off / 16, cnt = ch.len / 16;
+          double *o = (double *)pin;
+          for (size_t i = 0; i < cnt; i++) {
+            o[2 * i] = x[i0 + i];
+            o[2 * i + 1] = y[i0 + i];
+          }
+        } else {
+          const int *s = (const int *)((const char *)J.src + ch.off);
+          int *o = (int *)pin;
+          const size_t cnt = ch.len / 4;
+          unsigned worst = 0;  // as unsigned, a negative id is huge
+          for (size_t i = 0; i < cnt; i++) {
+            const int v = s[i];
+            o[i] = v;
+            worst = (unsigned)v > worst ? (unsigned)v : worst;
+          }
+          if ((long long)worst >= J.n) bad = true;
+        }
+        e = cudaMemcpyAsync((char *)J.dst + ch.off, pin, ch.len, cudaMemcpyHostToDevice, st_[t]);
+        if (e == cudaSuccess) e = cudaEventRecord(ev_[t][b], st_[t]);
+        if (e != cudaSuccess) { err = (int)e; return; }
+      }
+      cudaError_t e = cudaStreamSynchronize(st_[t]);
+      if (e != cudaSuccess) err = (int)e;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads_; t++) th.emplace_back(worker, t);
+    worker(0);
+    for (auto &x : th) x.join();
+    if (bad_id) *bad_id = bad.load();
+    return (cudaError_t)err.load();
+  }
+
+ private:
+  int device_ = 0, nthreads_ = 1;
+  cudaStream_t st_[kMaxThreads] = {};
+  void *buf_[kMaxThreads][2] = {};
+  cudaEvent_t ev_[kMaxThreads][2] = {};
+};
+
+}  // namespace nngp

@@ -12,6 +12,7 @@
 
 #include "host_linalg.h"
 #include "nngp_ctx.h"
+#include "host_stage.h"
 
 namespace nngp {
 
@@ -167,6 +168,7 @@ void nngp_destroy(nngp_ctx *c) {
   if (c->h_mat) cudaFreeHost(c->h_mat);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  delete c->stager;
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -201,9 +203,6 @@ int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const 
   c->has_nn = (nnIndx != nullptr);  // NULL: prediction-only use (sites, X, y), no B/F storage
   c->nIndx = c->has_nn ? nn_offset(n, m) : 0;  // == (1+m)/2*m + (n-m-1)*m for n > m
   const long long nI = c->nIndx > 0 ? c->nIndx : 1;
-  for (long long k = 0; k < c->nIndx; k++) {
-    if (nnIndx[k] < 0 || nnIndx[k] >= n) return ctx_fail(c, NNGP_EINVAL, "nngp_set_data: neighbour index out of range");
-  }
   int rc;
 #define NNGP_ENSURE(ptr, slot, count)                                     \
   do {                                                                    \
@@ -211,22 +210,33 @@ int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const 
     if (rc) return rc;                                                    \
   } while (0)
   NNGP_ENSURE(c->d_coords, 0, n);
-  {
-    // interleave (x, y) through pinned memory so the upload is a single DMA
-    double2 *xy = nullptr;
-    NNGP_CUDA(c, cudaMallocHost(&xy, (size_t)n * sizeof(double2)));
-    for (int i = 0; i < n; i++) xy[i] = make_double2(coords[i], coords[(size_t)n + i]);
-    cudaError_t e = cudaMemcpy(c->d_coords, xy, (size_t)n * sizeof(double2), cudaMemcpyHostToDevice);
-    cudaFreeHost(xy);
-    NNGP_CUDA(c, e);
-  }
   NNGP_ENSURE(c->d_nnIndx, 1, nI);
-  if (c->nIndx > 0) NNGP_CUDA(c, cudaMemcpy(c->d_nnIndx, nnIndx, (size_t)c->nIndx * sizeof(int), cudaMemcpyHostToDevice));
   if (p > 0) {
     NNGP_ENSURE(c->d_X, 2, (size_t)n * p);
-    NNGP_CUDA(c, cudaMemcpy(c->d_X, X, (size_t)n * p * sizeof(double), cudaMemcpyHostToDevice));
     NNGP_ENSURE(c->d_y, 3, n);
-    NNGP_CUDA(c, cudaMemcpy(c->d_y, y, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  {
+    // one threaded pass through pinned chunks (host_stage.h): coords interleaved to (x, y) pairs, neighbour ids
+    // range-checked on the way
+    if (!c->stager) {
+      c->stager = new HostStager();
+      NNGP_CUDA(c, c->stager->init(c->device));
+    }
+    std::vector<StageJob> jobs;
+    jobs.push_back({StageJob::XY_INTERLEAVE, c->d_coords, coords, (size_t)n * sizeof(double2), n});
+    if (c->nIndx > 0) jobs.push_back({StageJob::INT_RANGE, c->d_nnIndx, nnIndx, (size_t)c->nIndx * sizeof(int), n});
+    if (p > 0) {
+      jobs.push_back({StageJob::RAW, c->d_X, X, (size_t)n * p * sizeof(double), 0});
+      jobs.push_back({StageJob::RAW, c->d_y, y, (size_t)n * sizeof(double), 0});
+    }
+    bool bad_id = false;
+    NNGP_CUDA(c, c->stager->run(jobs, &bad_id));
+    if (bad_id) {
+      c->n = 0;
+      return ctx_fail(c, NNGP_EINVAL, "nngp_set_data: neighbour index out of range");
+    }
+  }
+  if (p > 0) {
     NNGP_ENSURE(c->d_beta, 4, (size_t)NNGP_MAX_BATCH * p);
     if (c->h_beta_cap < (size_t)NNGP_MAX_BATCH * p) {
       if (c->h_beta) cudaFreeHost(c->h_beta);

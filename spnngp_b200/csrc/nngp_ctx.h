@@ -7,6 +7,10 @@
 
 #include "nngp_common.cuh"
 
+namespace nngp {
+class HostStager;
+}
+
 struct nngp_ctx {
   int device = 0;
   int sms = 148;
@@ -42,6 +46,7 @@ struct nngp_ctx {
   int *h_fail = nullptr;
   double *h_beta = nullptr;
   size_t h_beta_cap = 0;
+  nngp::HostStager *stager = nullptr;  // pinned upload ring of nngp_set_data (host_stage.h)
   size_t cap[16] = {};  // capacities (bytes) of the grow-only model buffers, see nngp_set_data
   nngp::MaternConsts *h_mat = nullptr;
 
