@@ -144,10 +144,28 @@ typedef struct {
    * (NCCL allreduce); NULL for a single GPU. */
   void (*allreduce)(double *buf, int len, void *user);
   void *allreduce_user;
+  /* fit.rep (src/rNNGP.cpp:203-208,300-313): repIndx[s] != 0 marks the iterations that also draw a replicate
+   * y.rep = X beta + v (n extra rnorm calls each, between the beta draw and the proposals); column k of
+   * repSamples (n x nRep) receives the k-th marked iteration.  Both NULL: no replicates.  Needs the whole
+   * location range on this context (the recurrence is serial in the ordering). */
+  const int *repIndx;
+  double *repSamples;
 } nngp_rnngp_args;
 
 int nngp_rnngp(nngp_ctx *ctx, const nngp_rnngp_args *args, double *betaSamples, double *thetaSamples,
                int *accept_out);
+
+/* One replicated-data draw (updateRep, src/rNNGP.cpp:24-42): yrep = X beta + v with
+ * v_i = B_i . v_N(i) + sqrt(F_i) z_i, B and F taken from slot `slot` (as left by nngp_bf_loglik), z = n standard
+ * normals in location order.  yrep: n doubles. */
+int nngp_rep_draw(nngp_ctx *ctx, int slot, const double *beta, const double *z, double *yrep);
+
+/* `rNNGPReplicated` (src/rNNGPReplicated.cpp:76-222): one replicate per posterior sample.  betaSamples is
+ * nSamples x p column-major (R/generics.R:252-259), thetaSamples nTheta x nSamples, repSamples n x nSamples.
+ * rnorm is called n times per sample, in the reference's order. */
+int nngp_rnngp_replicated(nngp_ctx *ctx, int cov_model, const double *betaSamples, const double *thetaSamples,
+                          int nSamples, double (*rnorm)(double mu, double sd), void (*interrupt)(void),
+                          double *repSamples);
 
 /* `cNNGP` (src/cNNGP.cpp:73-357): conjugate model for g parameter sets.  thetaAlpha is nTheta x g
  * (phi, alpha[, nu]).  Outputs as the reference: betaHat p x g, ab (written with stride 2, reference

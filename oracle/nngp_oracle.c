@@ -465,13 +465,70 @@ static double log_post(double logDet, double Q, const double *theta, int cov_mod
   return lp;
 }
 
+/* updateRep, src/rNNGP.cpp:24-42 (same loop: src/rNNGPReplicated.cpp:187-197): v_i = B_i . v_N(i) + sqrt(F_i) z_i,
+ * one rnorm per location in index order. */
+void orc_update_rep(const double *B, const double *F, int n, const int *nnIndx, const int *nnIndxLU, orc_rnorm_fn rnorm,
+                    double *v) {
+  for (int i = 0; i < n; i++) {
+    double z = rnorm(0.0, 1.0);
+    if (i == 0) {
+      v[i] = sqrt(F[i]) * z;
+    } else {
+      double d = 0.0; /* ddot over the gathered neighbours, :35-38 */
+      for (int j = 0; j < nnIndxLU[n + i]; j++) d += B[nnIndxLU[i] + j] * v[nnIndx[nnIndxLU[i] + j]];
+      v[i] = d + sqrt(F[i]) * z;
+    }
+  }
+}
+
+/* rNNGPReplicated sample loop, src/rNNGPReplicated.cpp:183-201.  beta: nSamples x p column-major; theta: nTheta x
+ * nSamples; repSamples: n x nSamples. */
+int orc_rnngp_replicated(const double *X, int p, int n, int m, const double *coords, int cov_model, const int *nnIndx,
+                         const int *nnIndxLU, const double *beta, const double *theta, int nSamples,
+                         orc_rnorm_fn rnorm, double *repSamples) {
+  int nTheta = (cov_model == ORC_MATERN) ? 4 : 3, info = 0;
+  long nIndx = orc_n_indx(n, m);
+  double *B = (double *)malloc(sizeof(double) * (size_t)(nIndx > 0 ? nIndx : 1));
+  double *F = (double *)malloc(sizeof(double) * (size_t)n);
+  for (int s = 0; s < nSamples && !info; s++) {
+    double th[4] = {0, 0, 0, 0};
+    memcpy(th, &theta[(size_t)s * nTheta], sizeof(double) * nTheta);
+    orc_update_bf(B, F, coords, nnIndx, nnIndxLU, n, m, th, cov_model, &info);
+    if (info) break;
+    double *out = &repSamples[(size_t)s * n];
+    orc_update_rep(B, F, n, nnIndx, nnIndxLU, rnorm, out);
+    for (int j = 0; j < p; j++) { /* dgemv N, beta with stride nSamples, accumulating, :199-200 */
+      double t = beta[(size_t)j * nSamples + s];
+      const double *col = &X[(size_t)n * j];
+      for (int i = 0; i < n; i++) out[i] += t * col[i];
+    }
+  }
+  free(B); free(F);
+  return info ? -1 : 0;
+}
+
 int orc_rnngp(const double *y, const double *X, int p, int n, int m, const double *coords, int cov_model,
               const int *nnIndx, const int *nnIndxLU, const double *sigmaSqIG, const double *tauSqIG,
               const double *phiUnif, const double *nuUnif, const double *betaStarting, double sigmaSqStarting,
               double tauSqStarting, double phiStarting, double nuStarting, double sigmaSqTuning, double tauSqTuning,
               double phiTuning, double nuTuning, int nSamples, orc_rnorm_fn rnorm, orc_runif_fn runif,
               double *betaSamples, double *thetaSamples) {
+  return orc_rnngp_rep(y, X, p, n, m, coords, cov_model, nnIndx, nnIndxLU, sigmaSqIG, tauSqIG, phiUnif, nuUnif,
+                       betaStarting, sigmaSqStarting, tauSqStarting, phiStarting, nuStarting, sigmaSqTuning, tauSqTuning,
+                       phiTuning, nuTuning, nSamples, rnorm, runif, betaSamples, thetaSamples, NULL, NULL);
+}
+
+/* rNNGP with fit.rep: repIndx[s] != 0 marks iterations that draw a replicate (src/rNNGP.cpp:203-208,300-313);
+ * repSamples n x nRep.  Both NULL: plain sampler. */
+int orc_rnngp_rep(const double *y, const double *X, int p, int n, int m, const double *coords, int cov_model,
+                  const int *nnIndx, const int *nnIndxLU, const double *sigmaSqIG, const double *tauSqIG,
+                  const double *phiUnif, const double *nuUnif, const double *betaStarting, double sigmaSqStarting,
+                  double tauSqStarting, double phiStarting, double nuStarting, double sigmaSqTuning, double tauSqTuning,
+                  double phiTuning, double nuTuning, int nSamples, orc_rnorm_fn rnorm, orc_runif_fn runif,
+                  double *betaSamples, double *thetaSamples, const int *repIndx, double *repSamples) {
   int nTheta = (cov_model == ORC_MATERN) ? 4 : 3;
+  int repCnt = 0;
+  double *tmp_n2 = (double *)malloc(sizeof(double) * (size_t)n);
   long nIndx = orc_n_indx(n, m);
   double theta[4] = {sigmaSqStarting, tauSqStarting, phiStarting, nuStarting};
   double tuning[4] = {sigmaSqTuning, tauSqTuning, phiTuning, nuTuning};
@@ -520,10 +577,17 @@ int orc_rnngp(const double *y, const double *X, int p, int n, int m, const doubl
       const double *col = &X[(size_t)n * j];
       for (int i = 0; i < n; i++) tmp_n[i] += t * col[i];
     }
+    int rep = repIndx && repSamples && repIndx[s];
+    if (rep) memcpy(&repSamples[(size_t)repCnt * n], tmp_n, sizeof(double) * (size_t)n); /* X beta, :300-302 */
     for (int i = 0; i < n; i++) tmp_n[i] -= y[i];
 
     double logDetCur = orc_update_bf(B, F, coords, nnIndx, nnIndxLU, n, m, theta, cov_model, &info); /* :306 */
     if (info) { status = -1; break; }
+    if (rep) { /* :309-313 */
+      orc_update_rep(B, F, n, nnIndx, nnIndxLU, rnorm, tmp_n2);
+      for (int i = 0; i < n; i++) repSamples[(size_t)repCnt * n + i] += tmp_n2[i];
+      repCnt++;
+    }
     double QCur = orc_q(B, F, tmp_n, tmp_n, n, nnIndx, nnIndxLU);
     double lpCur = log_post(logDetCur, QCur, theta, cov_model, sigmaSqIG, tauSqIG, phiUnif, nuUnif);
 
@@ -547,7 +611,7 @@ int orc_rnngp(const double *y, const double *X, int p, int n, int m, const doubl
     memcpy(&betaSamples[(size_t)s * p], beta, sizeof(double) * p);
     memcpy(&thetaSamples[(size_t)s * nTheta], theta, sizeof(double) * nTheta);
   }
-  free(beta); free(B); free(F); free(tmp_pp); free(tmp_p); free(tmp_p2); free(tmp_n);
+  free(beta); free(B); free(F); free(tmp_pp); free(tmp_p); free(tmp_p2); free(tmp_n); free(tmp_n2);
   return status ? status : accept;
 }
 

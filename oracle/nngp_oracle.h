@@ -73,6 +73,22 @@ int orc_rnngp(const double *y, const double *X, int p, int n, int m, const doubl
               double tauSqTuning, double phiTuning, double nuTuning, int nSamples, orc_rnorm_fn rnorm,
               orc_runif_fn runif, double *betaSamples, double *thetaSamples);
 
+/* fit.rep / rNNGPReplicated.  orc_update_rep: src/rNNGP.cpp:24-42; orc_rnngp_rep: orc_rnngp plus the
+ * replicate draws of src/rNNGP.cpp:300-313 (repIndx per iteration, repSamples n x nRep; NULL, NULL = orc_rnngp);
+ * orc_rnngp_replicated: src/rNNGPReplicated.cpp:183-201 (beta nSamples x p column-major, theta nTheta x nSamples). */
+void orc_update_rep(const double *B, const double *F, int n, const int *nnIndx, const int *nnIndxLU, orc_rnorm_fn rnorm,
+                    double *v);
+int orc_rnngp_rep(const double *y, const double *X, int p, int n, int m, const double *coords, int cov_model,
+                  const int *nnIndx, const int *nnIndxLU, const double *sigmaSqIG, const double *tauSqIG,
+                  const double *phiUnif, const double *nuUnif, const double *betaStarting, double sigmaSqStarting,
+                  double tauSqStarting, double phiStarting, double nuStarting, double sigmaSqTuning,
+                  double tauSqTuning, double phiTuning, double nuTuning, int nSamples, orc_rnorm_fn rnorm,
+                  orc_runif_fn runif, double *betaSamples, double *thetaSamples, const int *repIndx,
+                  double *repSamples);
+int orc_rnngp_replicated(const double *X, int p, int n, int m, const double *coords, int cov_model, const int *nnIndx,
+                         const int *nnIndxLU, const double *beta, const double *theta, int nSamples,
+                         orc_rnorm_fn rnorm, double *repSamples);
+
 /* src/cNNGP.cpp:215-316 for g parameter sets; thetaAlpha is nTheta x g (phi, alpha[, nu]).
  * ab is written with stride 2 per set (reference quirk, :242-245).  y0Hat/y0HatVar may be NULL if n0 == 0. */
 int orc_cnngp(const double *y, const double *X, int p, int n, const double *coords, const double *thetaAlpha,

@@ -144,8 +144,9 @@ class Port:
         return out  # column-major q x m
 
     def rnngp(self, y, X, coords, cov, nnIndx, nnIndxLU, m, sigmaSqIG, tauSqIG, phiUnif, nuUnif, starting, tuning,
-              nSamples, rnorm, runif):
-        """starting/tuning: dict with beta (starting only), sigma.sq, tau.sq, phi, nu."""
+              nSamples, rnorm, runif, rep_indx=None):
+        """starting/tuning: dict with beta (starting only), sigma.sq, tau.sq, phi, nu.
+        rep_indx: 0/1 per iteration (fit.rep); then y.rep (n x nRep) is returned as a 4th item."""
         y = f64(y); n = len(y)
         X = np.asfortranarray(np.asarray(X, dtype=np.float64).reshape(n, -1)); p = X.shape[1]
         Xf = np.ascontiguousarray(X.T).ravel()
@@ -154,15 +155,38 @@ class Port:
         bs = np.zeros(p * nSamples); ts = np.zeros(nTheta * nSamples)
         beta0 = f64(starting["beta"])
         self._cb = (RNORM_FN(rnorm), RUNIF_FN(runif))
-        self.lib.orc_rnngp.restype = C.c_int
-        acc = self.lib.orc_rnngp(
+        self.lib.orc_rnngp_rep.restype = C.c_int
+        ri = rep = None
+        if rep_indx is not None:
+            ri = i32(rep_indx); k = int((ri != 0).sum()); rep = np.zeros(max(k * n, 1))
+        acc = self.lib.orc_rnngp_rep(
             dp(y), dp(Xf), C.c_int(p), C.c_int(n), C.c_int(m), dp(coords), C.c_int(cov), ip(nnIndx), ip(nnIndxLU),
             dp(f64(sigmaSqIG)), dp(f64(tauSqIG)), dp(f64(phiUnif)), dp(f64(nuUnif if nuUnif is not None else [0, 0])),
             dp(beta0), C.c_double(starting["sigma.sq"]), C.c_double(starting["tau.sq"]), C.c_double(starting["phi"]),
             C.c_double(starting.get("nu", 0.0)), C.c_double(tuning["sigma.sq"]), C.c_double(tuning["tau.sq"]),
             C.c_double(tuning["phi"]), C.c_double(tuning.get("nu", 0.0)), C.c_int(nSamples), self._cb[0], self._cb[1],
-            dp(bs), dp(ts))
-        return bs.reshape(nSamples, p).T.copy(), ts.reshape(nSamples, nTheta).T.copy(), int(acc)
+            dp(bs), dp(ts), ip(ri) if ri is not None else None, dp(rep) if rep is not None else None)
+        res = (bs.reshape(nSamples, p).T.copy(), ts.reshape(nSamples, nTheta).T.copy(), int(acc))
+        if rep is not None:
+            res = res + (rep[: k * n].reshape(k, n).T.copy(),)
+        return res
+
+    def rnngp_replicated(self, X, coords, cov, nnIndx, nnIndxLU, m, beta_samples, theta_samples, rnorm):
+        """src/rNNGPReplicated.cpp:183-201.  beta_samples S x p, theta_samples nTheta x S; returns n x S."""
+        bsm = np.asarray(beta_samples, dtype=np.float64); S, p = bsm.shape
+        coords = coords_flat(coords); n = coords.size // 2
+        X = np.asarray(X, dtype=np.float64).reshape(n, p)
+        Xf = np.ascontiguousarray(X.T).ravel(); bf = np.ascontiguousarray(bsm.T).ravel()
+        tf = np.ascontiguousarray(np.asarray(theta_samples, dtype=np.float64).T).ravel()
+        nnIndx = i32(nnIndx); nnIndxLU = i32(nnIndxLU)
+        out = np.zeros(max(n * S, 1))
+        self._cb = (RNORM_FN(rnorm),)
+        self.lib.orc_rnngp_replicated.restype = C.c_int
+        rc = self.lib.orc_rnngp_replicated(dp(Xf), C.c_int(p), C.c_int(n), C.c_int(m), dp(coords), C.c_int(cov), ip(nnIndx),
+                                           ip(nnIndxLU), dp(bf), dp(tf), C.c_int(S), self._cb[0], dp(out))
+        if rc:
+            raise RuntimeError("orc_rnngp_replicated: factorisation failed")
+        return out[: n * S].reshape(S, n).T.copy()
 
     def cnngp(self, y, X, coords, thetaAlpha, nnIndx, nnIndxLU, X0, coords0, nnIndx0, m, sigmaSqIG, cov):
         y = f64(y); n = len(y)
@@ -265,8 +289,9 @@ class _Sexp:
 
 
 def call_rnngp(sx: _Sexp, y, X, coords, cov, nnIndx, nnIndxLU, m, sigmaSqIG, tauSqIG, phiUnif, nuUnif, starting,
-               tuning, nSamples, nThreads=1, verbose=0, nReport=100, symbol="rNNGP"):
-    """Drive a 28-argument `rNNGP` .Call entry point (reference signature, src/spNNGP.h:9-13)."""
+               tuning, nSamples, nThreads=1, verbose=0, nReport=100, symbol="rNNGP", rep_indx=None):
+    """Drive a 28-argument `rNNGP` .Call entry point (reference signature, src/spNNGP.h:9-13).
+    rep_indx: 0/1 per iteration (R/spNNGP.R builds it from fit.rep / sub.sample); adds y_rep_samples (n x nRep)."""
     y = f64(y); n = len(y)
     X = np.asarray(X, dtype=np.float64).reshape(n, -1); p = X.shape[1]
     Xf = np.ascontiguousarray(X.T).ravel()
@@ -279,10 +304,30 @@ def call_rnngp(sx: _Sexp, y, X, coords, cov, nnIndx, nnIndxLU, m, sigmaSqIG, tau
             sx.scalar_real(tuning["sigma.sq"]), sx.scalar_real(tuning["tau.sq"]), sx.scalar_real(tuning["phi"]),
             sx.scalar_real(tuning.get("nu", 0.0)),
             sx.scalar_int(nSamples), sx.scalar_int(nThreads), sx.scalar_int(verbose), sx.scalar_int(nReport),
-            sx.scalar_int(0), sx.integer(np.zeros(max(nSamples, 1), dtype=np.int32))]
+            sx.scalar_int(0 if rep_indx is None else int((i32(rep_indx) != 0).sum())),
+            sx.integer(np.zeros(max(nSamples, 1), dtype=np.int32) if rep_indx is None else i32(rep_indx))]
     out = sx.call(symbol, args)
     res = dict(p_beta_samples=sx.get_real_matrix(out, "p.beta.samples"),
                p_theta_samples=sx.get_real_matrix(out, "p.theta.samples"))
+    if rep_indx is not None and int((i32(rep_indx) != 0).sum()) > 0:
+        res["y_rep_samples"] = sx.get_real_matrix(out, "y.rep.samples")
+    sx.reset()
+    return res
+
+
+def call_rnngp_replicated(sx: _Sexp, X, coords, cov, nnIndx, nnIndxLU, m, beta_samples, theta_samples, nThreads=1,
+                          verbose=0, nReport=100, symbol="rNNGPReplicated"):
+    """Drive the 14-argument `rNNGPReplicated` .Call entry point (src/spNNGP.h, src/rNNGPReplicated.cpp:76-78).
+    beta_samples S x p (R passes the coda matrix as is), theta_samples nTheta x S.  Returns y.rep.samples n x S."""
+    bsm = np.asarray(beta_samples, dtype=np.float64); S, p = bsm.shape
+    cf = coords_flat(coords); n = cf.size // 2
+    X = np.asarray(X, dtype=np.float64).reshape(n, p)
+    args = [sx.real(np.ascontiguousarray(X.T).ravel()), sx.scalar_int(p), sx.scalar_int(n), sx.scalar_int(m), sx.real(cf),
+            sx.scalar_int(cov), sx.integer(nnIndx), sx.integer(nnIndxLU), sx.real(np.ascontiguousarray(bsm.T).ravel()),
+            sx.real(np.ascontiguousarray(np.asarray(theta_samples, dtype=np.float64).T).ravel()), sx.scalar_int(S),
+            sx.scalar_int(nThreads), sx.scalar_int(verbose), sx.scalar_int(nReport)]
+    out = sx.call(symbol, args)
+    res = sx.get_real_matrix(out, "y.rep.samples")
     sx.reset()
     return res
 
@@ -413,6 +458,9 @@ class Ref:
 
     def rnngp(self, *a, **k):
         return call_rnngp(self.sx, *a, **k)
+
+    def rnngp_replicated(self, *a, **k):
+        return call_rnngp_replicated(self.sx, *a, **k)
 
     def cnngp(self, *a, **k):
         return call_cnngp(self.sx, *a, **k)

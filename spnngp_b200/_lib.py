@@ -35,6 +35,7 @@ class RnngpArgs(C.Structure):
         ("nSamples", C.c_int), ("mode", C.c_int), ("verbose", C.c_int), ("nReport", C.c_int),
         ("rnorm", RNORM_FN), ("runif", RUNIF_FN), ("print", PRINT_FN), ("interrupt", INTERRUPT_FN),
         ("allreduce", ALLREDUCE_FN), ("allreduce_user", C.c_void_p),
+        ("repIndx", C.POINTER(C.c_int)), ("repSamples", c_double_p),
     ]
 
 
@@ -42,7 +43,7 @@ class RnngpArgs(C.Structure):
 ABI_SYMBOLS = [
     "nngp_abi_version", "nngp_device_count", "nngp_create", "nngp_destroy", "nngp_last_error", "nngp_sync",
     "nngp_mk_nn_indx", "nngp_nn_query", "nngp_set_data", "nngp_bf_loglik", "nngp_q_resid", "nngp_q_forms",
-    "nngp_get_bf", "nngp_rnngp", "nngp_cnngp", "nngp_rnngp_predict", "nngp_time_bf_loglik", "nngp_launch_count",
+    "nngp_get_bf", "nngp_rnngp", "nngp_rep_draw", "nngp_rnngp_replicated", "nngp_cnngp", "nngp_rnngp_predict", "nngp_time_bf_loglik", "nngp_launch_count",
     "nngp_fp64_peak", "nngp_comm_unique_id", "nngp_comm_init", "nngp_comm_allreduce_sum", "nngp_comm_destroy",
 ]
 
@@ -77,6 +78,8 @@ def load():
     L.nngp_q_forms.argtypes = [vp, C.c_int, c_double_p]
     L.nngp_get_bf.argtypes = [vp, C.c_int, c_double_p, c_double_p]
     L.nngp_rnngp.argtypes = [vp, C.POINTER(RnngpArgs), c_double_p, c_double_p, c_int_p]
+    L.nngp_rep_draw.argtypes = [vp, C.c_int, c_double_p, c_double_p, c_double_p]
+    L.nngp_rnngp_replicated.argtypes = [vp, C.c_int, c_double_p, c_double_p, C.c_int, RNORM_FN, INTERRUPT_FN, c_double_p]
     L.nngp_time_bf_loglik.argtypes = [vp, C.c_int, C.c_int, c_double_p, c_double_p, C.c_int, C.c_int,
                                       C.POINTER(C.c_float)]
     L.nngp_fp64_peak.argtypes = [vp, c_double_p]

@@ -169,6 +169,9 @@ void nngp_destroy(nngp_ctx *c) {
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   delete c->stager;
+  if (c->d_rep_perm) cudaFree(c->d_rep_perm);
+  if (c->d_rep_levoff) cudaFree(c->d_rep_levoff);
+  if (c->h_z) cudaFreeHost(c->h_z);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -200,6 +203,7 @@ int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const 
   // device buffers are kept across calls and only grown (cudaMalloc/cudaFree of the ~0.5 GB working set
   // would otherwise dominate a short fit: the whole-call path is measured end to end by bench.py)
   c->n = n; c->m = m; c->p = p; c->loc_begin = loc_begin; c->loc_end = loc_end;
+  c->rep_ready = false;
   c->has_nn = (nnIndx != nullptr);  // NULL: prediction-only use (sites, X, y), no B/F storage
   c->nIndx = c->has_nn ? nn_offset(n, m) : 0;  // == (1+m)/2*m + (n-m-1)*m for n > m
   const long long nI = c->nIndx > 0 ? c->nIndx : 1;
@@ -542,7 +546,7 @@ int nngp_rnngp(nngp_ctx *c, const nngp_rnngp_args *a, double *betaSamples, doubl
   if (a->allreduce) a->allreduce(&logDetCur, 1, a->allreduce_user);
 
   bool thetaUpdate = true;
-  int accept = 0, batchAccept = 0, status = 0;
+  int accept = 0, batchAccept = 0, status = 0, repCnt = 0;
   for (int s = 0; s < a->nSamples; s++) {
     if (thetaUpdate) {  // src/rNNGP.cpp:274-292
       thetaUpdate = false;
@@ -562,6 +566,14 @@ int nngp_rnngp(nngp_ctx *c, const nngp_rnngp_args *a, double *betaSamples, doubl
     for (int i = 0; i < p; i++) beta[i] = a->rnorm(0.0, 1.0);
     hl::trmv_lower(tmp_pp.data(), p, beta.data());
     for (int i = 0; i < p; i++) beta[i] += mean[i];
+
+    // fit.rep: the n normals of updateRep come between the beta draw and the proposals (src/rNNGP.cpp:309-313)
+    const bool rep = a->repIndx && a->repSamples && a->repIndx[s];
+    if (rep) {
+      rc = rep_prepare(c);
+      if (rc) return rc;
+      for (int i = 0; i < c->n; i++) c->h_z[i] = a->rnorm(0.0, 1.0);
+    }
 
     // proposals, in the reference's draw order phi, sigma.sq, tau.sq[, nu] (src/rNNGP.cpp:327-333)
     cand[2] = logit_inv_(a->rnorm(logit_(theta[2], a->phiUnif[0], a->phiUnif[1]), tuning[2]), a->phiUnif[0], a->phiUnif[1]);
@@ -598,6 +610,11 @@ int nngp_rnngp(nngp_ctx *c, const nngp_rnngp_args *a, double *betaSamples, doubl
       if (a->allreduce) a->allreduce(red, 4, a->allreduce_user);
       QCur = red[1]; logDetCand = red[2]; QCand = red[3];
     }
+    if (rep) {  // B, F of the current theta are in slot `cur` in both modes
+      rc = rep_draw(c, cur, beta.data(), c->h_z, a->repSamples + (size_t)repCnt * c->n);
+      if (rc) return rc;
+      repCnt++;
+    }
     const double lpCur = log_post_(logDetCur, QCur, theta, a);
     const double lpCand = log_post_(logDetCand, QCand, cand, a);
     if (a->runif(0.0, 1.0) <= exp(lpCand - lpCur)) {  // src/rNNGP.cpp:349
@@ -631,6 +648,42 @@ int nngp_rnngp(nngp_ctx *c, const nngp_rnngp_args *a, double *betaSamples, doubl
     a->print("-------------------------------------------------\n");
   }
   if (accept_out) *accept_out = accept;
+  return NNGP_OK;
+}
+
+int nngp_rep_draw(nngp_ctx *c, int slot, const double *beta, const double *z, double *yrep) {
+  if (!c || !beta || !z || !yrep || slot < 0 || slot > 1) return NNGP_EINVAL;
+  NNGP_CUDA(c, cudaSetDevice(c->device));
+  return rep_draw(c, slot, beta, z, yrep);
+}
+
+int nngp_rnngp_replicated(nngp_ctx *c, int cov, const double *betaSamples, const double *thetaSamples, int nSamples,
+                          double (*rnorm)(double, double), void (*interrupt)(void), double *repSamples) {
+  if (!c || !betaSamples || !thetaSamples || !rnorm || !repSamples || nSamples < 0) return NNGP_EINVAL;
+  if (c->n == 0 || c->p == 0 || !c->has_nn) return ctx_fail(c, NNGP_ESTATE, "nngp_rnngp_replicated before nngp_set_data");
+  if (cov < 0 || cov > 3) return ctx_fail(c, NNGP_EINVAL, "cov.model is not correctly specified");
+  NNGP_CUDA(c, cudaSetDevice(c->device));
+  const int p = c->p, nTheta = (cov == NNGP_COV_MATERN) ? 4 : 3;
+  int rc = rep_prepare(c);
+  if (rc) return rc;
+  std::vector<double> beta(p);
+  double prev[4] = {-1, -1, -1, -1}, out[2];
+  int slot = 0;
+  for (int s = 0; s < nSamples; s++) {
+    // B, F at theta_s (src/rNNGPReplicated.cpp:185); rejected proposals repeat columns: solve once per run of equal theta
+    double th[4] = {0, 0, 0, 0};
+    memcpy(th, thetaSamples + (size_t)s * nTheta, nTheta * sizeof(double));
+    if (memcmp(th, prev, sizeof th) != 0) {
+      rc = nngp_bf_loglik(c, cov, 1, th, nullptr, &slot, out);  // asynchronous to the host draws below until its sync
+      if (rc) return rc;
+      memcpy(prev, th, sizeof th);
+    }
+    for (int i = 0; i < c->n; i++) c->h_z[i] = rnorm(0.0, 1.0);
+    for (int j = 0; j < p; j++) beta[j] = betaSamples[(size_t)j * nSamples + s];  // nSamples x p (R/generics.R:252)
+    rc = rep_draw(c, slot, beta.data(), c->h_z, repSamples + (size_t)s * c->n);
+    if (rc) return rc;
+    if (interrupt) interrupt();
+  }
   return NNGP_OK;
 }
 

@@ -46,6 +46,12 @@ struct nngp_ctx {
   int *h_fail = nullptr;
   double *h_beta = nullptr;
   size_t h_beta_cap = 0;
+  // replicated-data draws (rep_kernels.cu): level structure of the neighbour graph, built on first use
+  bool rep_ready = false;
+  int rep_levels = 0;
+  int *d_rep_perm = nullptr, *d_rep_levoff = nullptr;
+  double *h_z = nullptr;  // pinned, n doubles
+  size_t h_z_cap = 0;
   nngp::HostStager *stager = nullptr;  // pinned upload ring of nngp_set_data (host_stage.h)
   size_t cap[16] = {};  // capacities (bytes) of the grow-only model buffers, see nngp_set_data
   nngp::MaternConsts *h_mat = nullptr;
@@ -83,6 +89,10 @@ int q_forms_grid(long long nloc);
 cudaError_t q_forms_launch(const double *B, const double *F, const int *nnIndx, const double *X, const double *y,
                            int n, int p, int m, int loc_begin, int loc_end, double *partials, double *out,
                            cudaStream_t stream);
+
+// rep_kernels.cu
+int rep_prepare(nngp_ctx *c);  // levels + pinned z buffer (c->h_z), idempotent
+int rep_draw(nngp_ctx *c, int slot, const double *beta, const double *z, double *yrep);
 
 // shared helpers (nngp_abi.cu)
 int ctx_fail(nngp_ctx *ctx, int code, const std::string &msg);

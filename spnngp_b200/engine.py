@@ -182,9 +182,10 @@ class Engine:
 
     # ---- entry points ------------------------------------------------------------------------------
     def rnngp(self, cov, sigmaSqIG, tauSqIG, phiUnif, nuUnif, starting, tuning, n_samples, rnorm, runif, mode=0,
-              verbose=False, n_report=100, printer=None, allreduce=None):
+              verbose=False, n_report=100, printer=None, allreduce=None, rep_indx=None):
         """Response-model sampler on the data given to set_data (reference `rNNGP`, src/rNNGP.cpp:105).
-        rnorm/runif: ctypes function pointers or Python callables (mu, sd) / (a, b)."""
+        rnorm/runif: ctypes function pointers or Python callables (mu, sd) / (a, b).
+        rep_indx: 0/1 per iteration (fit.rep, src/rNNGP.cpp:203-208); then a 4th result, y.rep n x nRep, is returned."""
         a = RnngpArgs()
         a.cov_model = cov
         a.sigmaSqIG[:] = list(sigmaSqIG); a.tauSqIG[:] = list(tauSqIG); a.phiUnif[:] = list(phiUnif)
@@ -207,8 +208,36 @@ class Engine:
         nTheta = 4 if cov == COV_MODELS["matern"] else 3
         bs = np.zeros(self.p * n_samples); ts = np.zeros(nTheta * n_samples)
         acc = C.c_int(0)
+        rep = None
+        if rep_indx is not None:
+            ri = _i32(rep_indx)
+            if ri.size != n_samples:
+                raise ValueError("rep_indx needs one flag per iteration")
+            rep = np.zeros(max(int((ri != 0).sum()) * self.n, 1))
+            a.repIndx = _ip(ri); a.repSamples = _dp(rep)
         self._check(self.lib.nngp_rnngp(self.h, C.byref(a), _dp(bs), _dp(ts), C.byref(acc)))
-        return bs.reshape(n_samples, self.p).T.copy(), ts.reshape(n_samples, nTheta).T.copy(), int(acc.value)
+        res = (bs.reshape(n_samples, self.p).T.copy(), ts.reshape(n_samples, nTheta).T.copy(), int(acc.value))
+        if rep is not None:
+            k = int((ri != 0).sum())
+            res = res + (rep[: k * self.n].reshape(k, self.n).T.copy(),)
+        return res
+
+    def rep_draw(self, slot, beta, z):
+        """One replicate y.rep = X beta + v from the B, F of `slot` and n standard normals z (reference `updateRep`,
+        src/rNNGP.cpp:24-42)."""
+        b = _f64(beta); zf = _f64(z); out = np.zeros(self.n)
+        self._check(self.lib.nngp_rep_draw(self.h, slot, _dp(b), _dp(zf), _dp(out)))
+        return out
+
+    def rnngp_replicated(self, cov, beta_samples, theta_samples, rnorm):
+        """Replicates for given posterior samples (reference `rNNGPReplicated`, src/rNNGPReplicated.cpp:76).
+        beta_samples S x p (as R passes it, R/generics.R:252), theta_samples nTheta x S.  Returns n x S."""
+        bs = np.asarray(beta_samples, dtype=np.float64); S = bs.shape[0]
+        bsf = colmajor(bs); tsf = colmajor(np.asarray(theta_samples, dtype=np.float64))
+        out = np.zeros(max(self.n * S, 1))
+        self._check(self.lib.nngp_rnngp_replicated(self.h, cov, _dp(bsf), _dp(tsf), S, _as_cfunc(rnorm, _lib.RNORM_FN),
+                                                   _lib.INTERRUPT_FN(0), _dp(out)))
+        return out[: self.n * S].reshape(S, self.n).T.copy()
 
     def rnngp_predict(self, cov, X0, coords0, nnIndx0, beta_samples, theta_samples, z, site_range=None):
         """Posterior predictive draws (reference `rNNGPPredict`, src/rNNGPPredict.cpp:25).

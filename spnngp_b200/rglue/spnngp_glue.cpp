@@ -6,7 +6,7 @@
 //   rNNGPPredict(17 args)  src/spNNGP.h:36-37,  src/rNNGPPredict.cpp:25-222
 //   mkNNIndx(7 args)       src/nn.h:25,         src/nn.cpp:63-111
 //   mkNNIndxCB(7 args)     src/nn.h:38,         src/nn.cpp:214-257
-// The other seven symbols of the package (latent / logit / SLGP / replicate models) are outside the
+// The other six symbols of the package (latent / logit / SLGP models, mkUIndx) are outside the
 // hot path this engine accelerates; they are exported as stubs that raise an R error so that a package
 // built with this glue still loads.
 //
@@ -92,11 +92,10 @@ SEXP rNNGP(SEXP y_r, SEXP X_r, SEXP p_r, SEXP n_r, SEXP m_r, SEXP coords_r, SEXP
            SEXP tauSqTuning_r, SEXP phiTuning_r, SEXP nuTuning_r, SEXP nSamples_r, SEXP nThreads_r, SEXP verbose_r,
            SEXP nReport_r, SEXP nRep_r, SEXP repIndx_r) {
   (void)nThreads_r;
-  (void)repIndx_r;
   const int p = INTEGER(p_r)[0], n = INTEGER(n_r)[0], m = INTEGER(m_r)[0];
   const int covModel = INTEGER(covModel_r)[0];
   check_cov(covModel);
-  if (INTEGER(nRep_r)[0] > 0) Rf_error("fit.rep=TRUE (y.rep.samples) is not provided by the B200 engine yet");
+  const int nRep = INTEGER(nRep_r)[0];  // fit.rep: number of marked iterations (src/rNNGP.cpp:139-140)
   const int nSamples = INTEGER(nSamples_r)[0];
   const int nTheta = is_matern(covModel) ? 4 : 3;
 
@@ -132,13 +131,21 @@ SEXP rNNGP(SEXP y_r, SEXP X_r, SEXP p_r, SEXP n_r, SEXP m_r, SEXP coords_r, SEXP
 
   SEXP betaSamples_r = PROTECT(Rf_allocMatrix(REALSXP, p, nSamples));
   SEXP thetaSamples_r = PROTECT(Rf_allocMatrix(REALSXP, nTheta, nSamples));
+  SEXP repSamples_r = R_NilValue;
+  if (nRep > 0) {
+    repSamples_r = PROTECT(Rf_allocMatrix(REALSXP, n, nRep));  // src/rNNGP.cpp:203-208
+    a.repIndx = INTEGER(repIndx_r);
+    a.repSamples = REAL(repSamples_r);
+  }
   GetRNGstate();
   int accept = 0;
   const int rc = nngp_rnngp(c, &a, REAL(betaSamples_r), REAL(thetaSamples_r), &accept);
   PutRNGstate();
   check(rc);
-  SEXP out = named_list({"p.beta.samples", "p.theta.samples"}, {betaSamples_r, thetaSamples_r});
-  UNPROTECT(2);
+  SEXP out = nRep > 0 ? named_list({"p.beta.samples", "p.theta.samples", "y.rep.samples"},
+                                   {betaSamples_r, thetaSamples_r, repSamples_r})
+                      : named_list({"p.beta.samples", "p.theta.samples"}, {betaSamples_r, thetaSamples_r});
+  UNPROTECT(nRep > 0 ? 3 : 2);
   return out;
 }
 
@@ -234,8 +241,35 @@ SEXP cSLGP(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEX
 SEXP sNNGPPredict(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP,
                   SEXP, SEXP) { return not_provided("sNNGPPredict"); }
 SEXP PGLogit(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP) { return not_provided("PGLogit"); }
-SEXP rNNGPReplicated(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP) {
-  return not_provided("rNNGPReplicated");
+// src/rNNGPReplicated.cpp:76-222: one replicate of the data per posterior sample
+SEXP rNNGPReplicated(SEXP X_r, SEXP p_r, SEXP n_r, SEXP m_r, SEXP coords_r, SEXP covModel_r, SEXP nnIndx_r,
+                     SEXP nnIndxLU_r, SEXP beta_r, SEXP theta_r, SEXP nSamples_r, SEXP nThreads_r, SEXP verbose_r,
+                     SEXP nReport_r) {
+  (void)nThreads_r;
+  (void)nReport_r;
+  const int p = INTEGER(p_r)[0], n = INTEGER(n_r)[0], m = INTEGER(m_r)[0], nSamples = INTEGER(nSamples_r)[0];
+  const int covModel = INTEGER(covModel_r)[0];
+  check_cov(covModel);
+  if (INTEGER(verbose_r)[0]) {
+    Rprintf("----------------------------------------\n\tComputing replicates\n----------------------------------------\n");
+    Rprintf("NNGP Response model fit with %i observations.\n\n", n);
+    Rprintf("Number of covariates %i (including intercept if specified).\n\n", p);
+    Rprintf("Using %i nearest neighbors.\n\n", m);
+    Rprintf("Number of MCMC samples %i.\n\n", nSamples);
+  }
+  nngp_ctx *c = ctx();
+  double *y0 = (double *)R_alloc(n, sizeof(double));  // the response does not enter the replicates
+  for (int i = 0; i < n; i++) y0[i] = 0.0;
+  check(nngp_set_data(c, n, m, p, REAL(coords_r), INTEGER(nnIndx_r), INTEGER(nnIndxLU_r), REAL(X_r), y0, 0, n));
+  SEXP repSamples_r = PROTECT(Rf_allocMatrix(REALSXP, n, nSamples));
+  GetRNGstate();
+  const int rc = nngp_rnngp_replicated(c, covModel, REAL(beta_r), REAL(theta_r), nSamples, rnorm_hook, interrupt_hook,
+                                       REAL(repSamples_r));
+  PutRNGstate();
+  check(rc);
+  SEXP out = named_list({"y.rep.samples"}, {repSamples_r});
+  UNPROTECT(1);
+  return out;
 }
 SEXP mkUIndx(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP) { return not_provided("mkUIndx"); }
 

@@ -97,4 +97,27 @@ ref.set_seed(7)
 cp["pred_beta"] = beta; cp["pred_theta"] = theta
 cp["pred_y0_seed7"] = ref.predict(prob["X"], prob["y"], prob["coords"], m, X0, coords0, nn0, beta, theta, 0)
 np.savez_compressed(os.path.join(OUT, "conj_predict_n500_m10.npz"), **cp)
+# ---- 5. fit.rep / rNNGPReplicated: replicates from the reference, seeded ---------------
+rp = {}
+n, m = 300, 10
+prob = make_problem(n, m, seed=20246, domain=0.25)
+nnIndx, _, lu = ref.mk_nn_indx_cb(prob["coords"], m)
+rp.update(coords=prob["coords"], X=prob["X"], y=prob["y"], m=m, nnIndx=nnIndx, nnIndxLU=lu)
+starting = {"beta": [0.0, 0.0], "sigma.sq": 5.0, "tau.sq": 1.0, "phi": 6.0, "nu": 0.75}
+tuning = {"sigma.sq": 0.05, "tau.sq": 0.05, "phi": 0.05, "nu": 0.05}
+rep_indx = np.zeros(30, dtype=np.int32); rep_indx[10::4] = 1  # as R/spNNGP.R marks the sub.sample iterations
+rp["rep_indx"] = rep_indx
+for cov, name in ((0, "exp"), (2, "matern")):
+    ref.set_seed(3)
+    out = ref.rnngp(prob["y"], prob["X"], prob["coords"], cov, nnIndx, lu, m, pri["sigmaSqIG"], pri["tauSqIG"],
+                    pri["phiUnif"], [0.1, 2.0] if cov == 2 else None, starting, tuning, 30, rep_indx=rep_indx)
+    rp[f"{name}_beta"] = out["p_beta_samples"]; rp[f"{name}_theta"] = out["p_theta_samples"]
+    rp[f"{name}_yrep"] = out["y_rep_samples"]
+    ref.set_seed(4)
+    S = 6
+    bsm = out["p_beta_samples"][:, -S:].T.copy(); tsm = out["p_theta_samples"][:, -S:].copy()
+    rp[f"{name}_replicated_beta"] = bsm; rp[f"{name}_replicated_theta"] = tsm
+    rp[f"{name}_replicated_yrep_seed4"] = ref.rnngp_replicated(prob["X"], prob["coords"], cov, nnIndx, lu, m, bsm, tsm)
+np.savez_compressed(os.path.join(OUT, "rep_n300_m10.npz"), **rp)
+
 print("golden fixtures written to", OUT, [f for f in os.listdir(OUT) if f.endswith(".npz")])

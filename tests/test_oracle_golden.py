@@ -58,6 +58,26 @@ def test_chain_golden(port):
         assert np.allclose(b, d[f"{name}_beta"], rtol=1e-7, atol=1e-9)
 
 
+def test_replicates_golden(port):
+    """fit.rep draws and `rNNGPReplicated` of the port vs the reference's committed outputs (rep_n300_m10.npz)."""
+    from spnngp_b200 import _lib
+    R = _lib.load_rshim()
+    d = np.load(os.path.join(G, "rep_n300_m10.npz"))
+    starting = {"beta": [0.0, 0.0], "sigma.sq": 5.0, "tau.sq": 1.0, "phi": 6.0, "nu": 0.75}
+    tuning = {"sigma.sq": 0.05, "tau.sq": 0.05, "phi": 0.05, "nu": 0.05}
+    for cov, name in ((0, "exp"), (2, "matern")):
+        R.rshim_set_seed(3)
+        b, t, acc, yrep = port.rnngp(d["y"], d["X"], d["coords"], cov, d["nnIndx"], d["nnIndxLU"], int(d["m"]), [2.0, 5.0],
+                                     [2.0, 1.0], [3.0, 300.0], [0.1, 2.0] if cov == 2 else None, starting, tuning, 30,
+                                     lambda mu, sd: R.rnorm(mu, sd), lambda a, bb: R.runif(a, bb), rep_indx=d["rep_indx"])
+        assert np.allclose(t, d[f"{name}_theta"], rtol=1e-9)
+        assert np.allclose(yrep, d[f"{name}_yrep"], rtol=1e-8, atol=1e-8)
+        R.rshim_set_seed(4)
+        r = port.rnngp_replicated(d["X"], d["coords"], cov, d["nnIndx"], d["nnIndxLU"], int(d["m"]),
+                                  d[f"{name}_replicated_beta"], d[f"{name}_replicated_theta"], lambda mu, sd: R.rnorm(mu, sd))
+        assert np.allclose(r, d[f"{name}_replicated_yrep_seed4"], rtol=1e-9, atol=1e-10)
+
+
 def test_conj_and_predict_golden(port):
     from spnngp_b200 import _lib
     R = _lib.load_rshim()

@@ -53,6 +53,31 @@ def test_chain_port_equals_ref(port, ref):
     assert np.allclose(t, out["p_theta_samples"], rtol=1e-10) and np.allclose(b, out["p_beta_samples"], rtol=1e-8, atol=1e-10)
 
 
+def test_replicates_port_equals_ref(port, ref):
+    """fit.rep inside `rNNGP` and the `rNNGPReplicated` entry point: reference vs port, same seed."""
+    prob = make_problem(350, 8, seed=15, port=port, domain=0.27)
+    starting = {"beta": [0.0, 0.0], "sigma.sq": 5.0, "tau.sq": 1.0, "phi": 6.0}
+    tuning = {"sigma.sq": 0.05, "tau.sq": 0.05, "phi": 0.05}
+    rep_indx = np.zeros(24, dtype=np.int32); rep_indx[8::3] = 1
+    args = (prob["y"], prob["X"], prob["coords"], 0, prob["nnIndx"], prob["nnIndxLU"], 8, [2.0, 5.0], [2.0, 1.0],
+            [3.0, 300.0], None, starting, tuning, 24)
+    ref.set_seed(21)
+    out = ref.rnngp(*args, rep_indx=rep_indx)
+    assert out["y_rep_samples"].shape == (350, int(rep_indx.sum()))
+    ref.set_seed(21)
+    L = ref.lib
+    b, t, acc, yrep = port.rnngp(*args, lambda mu, sd: L.rnorm(mu, sd), lambda a, bb: L.runif(a, bb), rep_indx=rep_indx)
+    assert np.allclose(t, out["p_theta_samples"], rtol=1e-10)
+    assert np.allclose(yrep, out["y_rep_samples"], rtol=1e-9, atol=1e-9)
+    bsm = out["p_beta_samples"][:, -5:].T.copy(); tsm = out["p_theta_samples"][:, -5:].copy()
+    ref.set_seed(22)
+    r1 = ref.rnngp_replicated(prob["X"], prob["coords"], 0, prob["nnIndx"], prob["nnIndxLU"], 8, bsm, tsm)
+    ref.set_seed(22)
+    r2 = port.rnngp_replicated(prob["X"], prob["coords"], 0, prob["nnIndx"], prob["nnIndxLU"], 8, bsm, tsm,
+                               lambda mu, sd: L.rnorm(mu, sd))
+    assert r1.shape == (350, 5) and np.allclose(r1, r2, rtol=1e-10, atol=1e-11)
+
+
 def test_reference_error_path(ref, port):
     """The reference aborts with 'dpotrf failed' on a singular neighbour covariance (src/rNNGP.cpp:86)."""
     prob = make_problem(60, 5, seed=6, port=port)
