@@ -19,54 +19,58 @@ constexpr int kRepThreads = 1024;
 constexpr int kRepLanes = 4;  // lanes per location
 constexpr int kRepGroups = kRepThreads / kRepLanes;
 
+template <int KMAX>
+struct RepSlot {  // static data of one location's share held by one lane
+  int id[KMAX];
+  double w[KMAX];
+  double f, z;
+};
+
 template <int KMAX>  // neighbour slots per lane: ceil(m / 4)
 __global__ void __launch_bounds__(kRepThreads, 1)
 rep_solve_kernel(const int *__restrict__ perm, const int *__restrict__ levoff, int nlev, const int *__restrict__ nnIndx,
                  const double *__restrict__ B, const double *__restrict__ F, const double *__restrict__ z, double *v, int m) {
   const int tid = threadIdx.x, sub = tid & (kRepLanes - 1), g = tid / kRepLanes;
   const unsigned gmask = 0xFu << ((tid & 31) & ~3);
-  // prefetched state of this group's first location in the level about to be processed
-  int pi = -1, pid[KMAX];
-  double pb[KMAX], pfz = 0.0;
-  auto prefetch = [&](int L) {
-    pi = -1;
-    if (L >= nlev) return;
+  // Software pipeline over levels (everything here is independent of v):
+  //   location index of this group's slot in level L+2  <- perm        (one round trip ahead of ...)
+  //   ids, weights, F, z of its slot in level L+1       <- nnIndx, B, F, z   (loaded, not used, during level L)
+  // so that in level L only the v gathers (and the barrier) are exposed.  Missing neighbours gather v[0] with
+  // weight 0, so the gathers are unconditional and go out together.
+  auto slot_index = [&](int L) -> int {
+    if (L >= nlev) return -1;
     const int q = __ldg(&levoff[L]) + g;
-    if (q >= __ldg(&levoff[L + 1])) return;
-    pi = __ldg(&perm[q]);
-    const int mi = nn_count(pi, m);
-    const long long off = nn_offset(pi, m);
+    return (q < __ldg(&levoff[L + 1])) ? __ldg(&perm[q]) : -1;
+  };
+  auto load_static = [&](int i, RepSlot<KMAX> &S) {
+    const int mi = (i >= 0) ? nn_count(i, m) : 0;
+    const long long off = (i >= 0) ? nn_offset(i, m) : 0;
 #pragma unroll
     for (int t = 0; t < KMAX; ++t) {
       const int k = sub + t * kRepLanes;
-      pid[t] = -1;
-      pb[t] = 0.0;
-      if (k < mi) {
-        pid[t] = __ldg(&nnIndx[off + k]);
-        pb[t] = __ldg(&B[off + k]);
-      }
+      const bool ok = k < mi;
+      S.id[t] = ok ? __ldg(&nnIndx[off + k]) : 0;
+      S.w[t] = ok ? __ldg(&B[off + k]) : 0.0;
     }
-    if (sub == 0) pfz = sqrt(__ldg(&F[pi])) * __ldg(&z[pi]);
+    const int ii = i >= 0 ? i : 0;
+    S.f = __ldg(&F[ii]);
+    S.z = __ldg(&z[ii]);
   };
-  prefetch(0);
-  for (int L = 0; L < nlev; ++L) {
-    const int beg = __ldg(&levoff[L]), end = __ldg(&levoff[L + 1]);
-    // first pass: the prefetched location
-    const int i0 = pi;
-    double acc = 0.0;
-    if (i0 >= 0) {
+  // one level: `cur` holds its static data, `nxt` receives the next level's
+  auto level = [&](int L, int i_c, int i_n, int &i_nn, const RepSlot<KMAX> &cur, RepSlot<KMAX> &nxt) {
+    double vv[KMAX];
 #pragma unroll
-      for (int t = 0; t < KMAX; ++t)
-        if (pid[t] >= 0) acc = fma(pb[t], __ldcg(&v[pid[t]]), acc);
-    }
-    const double fz0 = pfz;
-    prefetch(L + 1);  // static data of the next level: in flight across the reduction and the barrier
-    if (i0 >= 0) {
-      acc += __shfl_xor_sync(gmask, acc, 1);
-      acc += __shfl_xor_sync(gmask, acc, 2);
-      if (sub == 0) v[i0] = acc + fz0;
-    }
+    for (int t = 0; t < KMAX; ++t) vv[t] = __ldcg(&v[cur.id[t]]);  // the only loads that depend on earlier levels
+    load_static(i_n, nxt);
+    i_nn = slot_index(L + 2);
+    double acc = 0.0;
+#pragma unroll
+    for (int t = 0; t < KMAX; ++t) acc = fma(cur.w[t], vv[t], acc);
+    acc += __shfl_xor_sync(gmask, acc, 1);
+    acc += __shfl_xor_sync(gmask, acc, 2);
+    if (i_c >= 0 && sub == 0) v[i_c] = acc + sqrt(cur.f) * cur.z;
     // levels wider than the CTA's 256 groups (not seen on x-sorted orderings): plain passes
+    const int beg = __ldg(&levoff[L]), end = __ldg(&levoff[L + 1]);
     for (int q = beg + g + kRepGroups; q < end; q += kRepGroups) {
       const int i = __ldg(&perm[q]);
       const int mi = nn_count(i, m);
@@ -78,6 +82,16 @@ rep_solve_kernel(const int *__restrict__ perm, const int *__restrict__ levoff, i
       if (sub == 0) v[i] = a + sqrt(__ldg(&F[i])) * __ldg(&z[i]);
     }
     __syncthreads();
+  };
+  RepSlot<KMAX> SA, SB;
+  int i0 = slot_index(0), i1 = slot_index(1), i2 = -1;
+  load_static(i0, SA);
+  for (int L = 0; L < nlev; L += 2) {  // two levels per trip: the slot sets swap roles without register moves
+    level(L, i0, i1, i2, SA, SB);
+    i0 = i1; i1 = i2;
+    if (L + 1 >= nlev) break;
+    level(L + 1, i0, i1, i2, SB, SA);
+    i0 = i1; i1 = i2;
   }
 }
 
