@@ -9,7 +9,8 @@
 
 namespace nngp {
 cudaError_t knn_brute_launch(const double2 *coords, int n, int m, int *nnIndx, double *nnDist, cudaStream_t stream);
-cudaError_t knn_cb_launch(const double2 *sxy, const int *sidx, int n, int m, int *nnIndx, double *nnDist,
+int knn_cb_head_count(int n, int m);
+cudaError_t knn_cb_launch(const double2 *sxy, const int *sidx, int n, int m, int *headpos, int *nnIndx, double *nnDist,
                           cudaStream_t stream);
 cudaError_t knn_keys_launch(const double2 *coords, int n, double *u, int *idx, cudaStream_t stream);
 cudaError_t knn_gather_launch(const double2 *coords, const int *sidx, int n, double2 *sxy, cudaStream_t stream);
@@ -117,13 +118,15 @@ int nngp_mk_nn_indx(nngp_ctx *c, int n, int m, const double *coords, int search_
     NNGP_CUDA(c, knn_brute_launch(d_coords.as<double2>(), n, m, d_idx.as<int>(), d_dist.as<double>(), c->stream));
     c->launches++;
   } else {
-    DevBuf d_sidx, d_u, d_sxy;
+    DevBuf d_sidx, d_u, d_sxy, d_head;
     rc = sort_by_u(c, d_coords.as<double2>(), n, d_sidx, d_u, &nties);
     if (rc) return rc;
     NNGP_CUDA(c, d_sxy.alloc((size_t)n * sizeof(double2)));
+    NNGP_CUDA(c, d_head.alloc((size_t)knn_cb_head_count(n, m) * sizeof(int)));
     NNGP_CUDA(c, knn_gather_launch(d_coords.as<double2>(), d_sidx.as<int>(), n, d_sxy.as<double2>(), c->stream));
-    NNGP_CUDA(c, knn_cb_launch(d_sxy.as<double2>(), d_sidx.as<int>(), n, m, d_idx.as<int>(), d_dist.as<double>(), c->stream));
-    c->launches += 2;
+    NNGP_CUDA(c, knn_cb_launch(d_sxy.as<double2>(), d_sidx.as<int>(), n, m, d_head.as<int>(), d_idx.as<int>(),
+                               d_dist.as<double>(), c->stream));
+    c->launches += 4;
     NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
   }
   NNGP_CUDA(c, cudaStreamSynchronize(c->stream));

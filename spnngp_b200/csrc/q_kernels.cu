@@ -26,27 +26,45 @@ __global__ void __launch_bounds__(256) resid_kernel(const double *__restrict__ X
 }
 
 // ---- Q(B,F,r,r) over a shard ----------------------------------------------------------------------
+// UN locations per lane group and trip: their id/weight loads, then their gathers, go out together (with one
+// location per trip the id -> gather chain leaves too few bytes in flight to fill HBM: 156 us vs 55 us at n = 10^6).
 template <int LP>
 __global__ void __launch_bounds__(256) q_resid_kernel(const double *__restrict__ B, const double *__restrict__ F,
                                                       const int *__restrict__ nnIndx,
                                                       const double *__restrict__ resid, int m, int loc_begin,
                                                       int loc_end, double *__restrict__ partials) {
   constexpr int G = 256 / LP;
+  constexpr int UN = 4;
   __shared__ double red[8];
   const int tid = threadIdx.x, lane = tid % LP, g = tid / LP;
   double qsum = 0.0;
-  for (long long base = loc_begin + (long long)blockIdx.x * G; base < loc_end; base += (long long)gridDim.x * G) {
-    const long long i = base + g;
-    const bool active = i < loc_end;
-    const int mi = active ? nn_count(i, m) : 0;
-    const long long off = active ? nn_offset(i, m) : 0;
-    double a = 0.0;
-    if (lane < mi) a = __ldg(&B[off + lane]) * __ldg(&resid[__ldg(&nnIndx[off + lane])]);
+  for (long long base = loc_begin + (long long)blockIdx.x * (G * UN); base < loc_end; base += (long long)gridDim.x * (G * UN)) {
+    double b[UN], ri[UN], fi[UN];
+    int id[UN];
+    bool act[UN];
 #pragma unroll
-    for (int s = LP / 2; s >= 1; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s, LP);
-    if (lane == 0 && active) {
-      const double e = __ldg(&resid[i]) - a;
-      qsum += e * e / __ldg(&F[i]);
+    for (int u = 0; u < UN; ++u) {
+      const long long i = base + u * G + g;  // consecutive groups take consecutive locations: coalesced B, nnIndx
+      act[u] = i < loc_end;
+      const int mi = act[u] ? nn_count(i, m) : 0;
+      const long long off = act[u] ? nn_offset(i, m) : 0;
+      const bool ok = lane < mi;
+      b[u] = ok ? __ldg(&B[off + lane]) : 0.0;
+      id[u] = ok ? __ldg(&nnIndx[off + lane]) : 0;
+      ri[u] = (act[u] && lane == 0) ? __ldg(&resid[i]) : 0.0;
+      fi[u] = (act[u] && lane == 0) ? __ldg(&F[i]) : 1.0;
+    }
+    double a[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) a[u] = b[u] * __ldg(&resid[id[u]]);  // weight 0 for missing neighbours
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+#pragma unroll
+      for (int s = LP / 2; s >= 1; s >>= 1) a[u] += __shfl_xor_sync(0xffffffffu, a[u], s, LP);
+      if (lane == 0 && act[u]) {
+        const double e = ri[u] - a[u];
+        qsum += e * e / fi[u];
+      }
     }
   }
 #pragma unroll
@@ -95,25 +113,40 @@ __global__ void __launch_bounds__(256) q_forms_kernel(const double *__restrict__
   const int tid = threadIdx.x, lane = tid % LP, g = tid / LP;
   const long long chunk0 = loc_begin + (long long)blockIdx.x * CH;
 
-  for (int s0 = 0; s0 < CH; s0 += G) {
-    const int s = s0 + g;
-    const long long i = chunk0 + s;
-    const bool active = (s < CH) && (i < loc_end);
-    const int mi = active ? nn_count(i, m) : 0;
-    const long long off = active ? nn_offset(i, m) : 0;
-    double b = 0.0;
-    int idx = 0;
-    if (lane < mi) {
-      b = __ldg(&B[off + lane]);
-      idx = __ldg(&nnIndx[off + lane]);
-    }
-    const double rs = active ? rsqrt(__ldg(&F[i])) : 0.0;
-    for (int c = 0; c < K; ++c) {
-      const double *__restrict__ u = (c < p) ? (X + (size_t)c * n) : y;
-      double a = (lane < mi) ? b * __ldg(&u[idx]) : 0.0;
+  constexpr int UN = 4;  // locations per lane group and trip: ids/weights first, then all gathers (bytes in flight)
+  static_assert(CH % (G * UN) == 0, "chunk must be a whole number of trips");
+  for (int s0 = 0; s0 < CH; s0 += G * UN) {
+    double b[UN], rs[UN];
+    int idx[UN];
+    bool active[UN];
+    long long ii[UN];
 #pragma unroll
-      for (int sh = LP / 2; sh >= 1; sh >>= 1) a += __shfl_xor_sync(0xffffffffu, a, sh, LP);
-      if (lane == 0 && s < CH) W[c * CH + s] = active ? (__ldg(&u[i]) - a) * rs : 0.0;
+    for (int u = 0; u < UN; ++u) {
+      const int s = s0 + u * G + g;
+      const long long i = chunk0 + s;
+      ii[u] = i;
+      active[u] = i < loc_end;
+      const int mi = active[u] ? nn_count(i, m) : 0;
+      const long long off = active[u] ? nn_offset(i, m) : 0;
+      const bool ok = lane < mi;
+      b[u] = ok ? __ldg(&B[off + lane]) : 0.0;
+      idx[u] = ok ? __ldg(&nnIndx[off + lane]) : 0;
+      rs[u] = (active[u] && lane == 0) ? __ldg(&F[i]) : 1.0;
+    }
+    for (int c = 0; c < K; ++c) {
+      const double *__restrict__ uc = (c < p) ? (X + (size_t)c * n) : y;
+      double a[UN], own[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        a[u] = b[u] * __ldg(&uc[idx[u]]);  // weight 0 for missing neighbours
+        own[u] = (active[u] && lane == 0) ? __ldg(&uc[ii[u]]) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+#pragma unroll
+        for (int sh = LP / 2; sh >= 1; sh >>= 1) a[u] += __shfl_xor_sync(0xffffffffu, a[u], sh, LP);
+        if (lane == 0) W[c * CH + s0 + u * G + g] = active[u] ? (own[u] - a[u]) * rsqrt(rs[u]) : 0.0;
+      }
     }
   }
   __syncthreads();
@@ -151,7 +184,7 @@ cudaError_t resid_launch(const double *X, const double *y, const double *beta, i
 }
 
 int q_resid_grid(int m, long long nloc, int sms) {
-  const int G = 256 / lanes_for_m(m);
+  const int G = 4 * (256 / lanes_for_m(m));  // locations per CTA and trip (UN = 4)
   long long need = (nloc + G - 1) / G;
   long long g = (long long)sms * 8;
   if (need < g) g = need;
