@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(32 * (1 + NP), 2) bf_ws_kernel(const __grid_co
   __shared__ long long next_tile[8];  // ring of claimed tiles, slot j & 7 (>= ntiles: no more work)
   __shared__ double red[2][1 + NP];
   __shared__ int last_flag;
+  __shared__ __align__(16) double s_tab[COV == NNGP_COV_MATERN ? 160 : 2];  // exp / log tables (fasttab.cuh)
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
 
@@ -87,6 +88,9 @@ __global__ void __launch_bounds__(32 * (1 + NP), 2) bf_ws_kernel(const __grid_co
   const double diag = sigmaSq + tauSq;
   const double *__restrict__ resid = th.resid;
 
+  if (COV == NNGP_COV_MATERN) {
+    for (int x = tid; x < 160; x += Ws::kThreads) s_tab[x] = (x < 32) ? kExpTab32[x] : kLogTab64[x - 32];
+  }
   // ---- one-time setup: work list, zero padding of both stages --------------------------------------
   const int ne = m * (m - 1) / 2;
   const int nent_pad = ((ne + m + kBatch - 1) / kBatch) * kBatch;
@@ -226,8 +230,8 @@ __global__ void __launch_bounds__(32 * (1 + NP), 2) bf_ws_kernel(const __grid_co
       unsigned claimed = 0u;
       if (pl == 0) claimed = atomicAdd(th.tile_counter, 1u);  // tile 3 gridDim.x + claimed
       // ---- this warp's share of tile j's correlations (lane = location) ---------------------------------
-      tpl_build<COV, kBatch>(P, lane, s * Ws::kStageBytes + Geo::OFF_CO, s * Ws::kStageBytes + Geo::OFF_A, ent,
-                             ebeg[pw], kBatch, ebeg[pw + 1]);
+      tpl_build<COV, kBatch, true>(P, lane, s * Ws::kStageBytes + Geo::OFF_CO, s * Ws::kStageBytes + Geo::OFF_A, ent,
+                                   ebeg[pw], kBatch, ebeg[pw + 1], s_tab);
       asm volatile("" ::: "memory");
       if (pl == 0) next_tile[(j + 3) & 7] = 3ll * gridDim.x + claimed;  // published by the rendezvous of the next trip
       named_bar_arrive(1 + s, Ws::kThreads);  // stage full

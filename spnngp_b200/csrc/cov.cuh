@@ -50,7 +50,10 @@ struct Cor<NNGP_COV_MATERN> {
   double phi, q4;  // q4 = phi^2 / 4: t = q4 d2 = (phi D / 2)^2
   const MaternSeriesParams &ms;
   const MaternConsts *mc;  // global memory: Temme / CF2 tables for the slow path
-  __device__ __forceinline__ Cor(const BfTheta &t) : phi(t.phi), q4(0.25 * t.phi * t.phi), ms(t.ms), mc(t.mat) {}
+  const double *tab;       // shared memory: exp / log tables (fasttab.cuh) when the kernel staged them, else NULL
+  __device__ __forceinline__ Cor(const BfTheta &t, const double *tab_ = nullptr)
+      : phi(t.phi), q4(0.25 * t.phi * t.phi), ms(t.ms), mc(t.mat), tab(tab_) {}
+  __device__ __forceinline__ double fast_tab(double d2) const { return matern_series_tab(fmin(q4 * d2, 1.0), ms, tab); }
   // power series in t for phi D <= 2 (clamped beyond: the caller re-evaluates those with slow())
   __device__ __forceinline__ double fast(double d2) const { return matern_series(fmin(q4 * d2, 1.0), ms); }
   __device__ __forceinline__ bool needs_slow(double d2) const { return !ms.use_series || q4 * d2 > 1.0; }

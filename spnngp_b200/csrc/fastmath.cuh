@@ -14,6 +14,8 @@
 #include <stdint.h>
 #include <string.h>
 
+#include "fasttab.cuh"
+
 #if defined(__CUDACC__)
 #define NNGP_FM __device__ __forceinline__
 #else
@@ -182,6 +184,83 @@ NNGP_FM double nngp_log_pos(double x) {
   const double R = t2 + t1;
   const double hfsq = 0.5 * f * f;
   return dk * ln2_hi - ((hfsq - (sv * (hfsq + R) + dk * ln2_lo)) - f);
+}
+
+// ---- table-driven variants (tables of fasttab.cuh, staged in shared memory by the caller) --------------------
+// Same contracts as nngp_exp / nngp_log_pos with ~40% fewer FP64 instructions (12 vs 19, 11 vs 28): the Matern
+// producers are bound by the FP64 issue rate, each correlation needs one log and one exp (t^nu).
+//   exp: x = (32 k + j) ln2/32 + r, |r| <= ln2/64:  2^k * T[j] * (1 + r + ... + r^6/720)       (truncation 5e-20)
+//   log: x = 2^k m, m in [1,2), i = top 6 mantissa bits: r = m * rc_i - 1, |r| <= 2^-7,
+//        log x = k ln2 + (-log rc_i) + log1p(r), log1p by its degree-8 Taylor polynomial        (truncation 2e-18)
+// Absolute error ~1e-16 (max of the result's ulp and 1e-16); the log is NOT relatively accurate next to x = 1,
+// which the callers (t^nu = exp(nu log t), log F summed over locations) do not need.
+NNGP_FM double nngp_exp_tab(double x, const double *etab) {
+  const double L2E32 = 46.166241308446828384;  // 32 / ln 2
+  const double LN2_32_HI = 6.93147180369123816490e-01 / 32.0, LN2_32_LO = 1.90821492927058770002e-10 / 32.0;
+  const double SHIFTER = 6755399441055744.0;
+  const double t = fma(x, L2E32, SHIFTER);
+  const double n = t - SHIFTER;
+  double r = fma(n, -LN2_32_HI, x);
+  r = fma(n, -LN2_32_LO, r);
+  double q = fma(r, 1.0 / 720.0, 1.0 / 120.0);
+  q = fma(q, r, 1.0 / 24.0);
+  q = fma(q, r, 1.0 / 6.0);
+  q = fma(q, r, 0.5);
+  q = fma(q * r, r, r);  // r + r^2 (1/2 + ...)
+#if defined(__CUDA_ARCH__)
+  const int ni = __double2loint(t);
+#else
+  const int ni = (int)n;
+#endif
+  const double T = etab[ni & 31];
+  const double v = fma(T, q, T);
+  const int k = ni >> 5;
+#if defined(__CUDA_ARCH__)
+  const double res = __hiloint2double(__double2hiint(v) + (k << 20), __double2loint(v));
+#else
+  uint64_t bits;
+  memcpy(&bits, &v, sizeof bits);
+  bits += (uint64_t)((int64_t)k << 52);
+  double res;
+  memcpy(&res, &bits, sizeof res);
+#endif
+  return (x < -708.0) ? 0.0 : res;
+}
+
+NNGP_FM double nngp_log_tab(double x, const double *ltab /* 64 pairs {rc, -log rc} */) {
+  const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
+#if defined(__CUDA_ARCH__)
+  const int hx = __double2hiint(x);
+  const int lx = __double2loint(x);
+#else
+  uint64_t bits;
+  memcpy(&bits, &x, sizeof bits);
+  const int hx = (int)(bits >> 32);
+  const int lx = (int)(bits & 0xffffffffu);
+#endif
+  const int k = (hx >> 20) - 1023;
+  const int idx = (hx >> 14) & 63;
+  const int hm = (hx & 0x000fffff) | 0x3ff00000;
+#if defined(__CUDA_ARCH__)
+  const double m = __hiloint2double(hm, lx);
+  const double2 tb = reinterpret_cast<const double2 *>(ltab)[idx];
+  const double rc = tb.x, lc = tb.y;
+#else
+  const uint64_t mb = ((uint64_t)(uint32_t)hm << 32) | (uint32_t)lx;
+  double m;
+  memcpy(&m, &mb, sizeof m);
+  const double rc = ltab[2 * idx], lc = ltab[2 * idx + 1];
+#endif
+  const double r = fma(m, rc, -1.0);
+  double p = fma(r, -1.0 / 8.0, 1.0 / 7.0);
+  p = fma(p, r, -1.0 / 6.0);
+  p = fma(p, r, 1.0 / 5.0);
+  p = fma(p, r, -1.0 / 4.0);
+  p = fma(p, r, 1.0 / 3.0);
+  p = fma(p, r, -0.5);
+  const double dk = (double)k;
+  p = fma(p * r, r, r);  // log1p(r)
+  return fma(dk, ln2_hi, lc) + fma(dk, ln2_lo, p);
 }
 
 // exp for any x <= 700 (no overflow handling), flushing to 0 below -708: same kernel as nngp_exp_nonpos

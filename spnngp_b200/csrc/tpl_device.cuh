@@ -33,7 +33,7 @@ constexpr int kTplBatch = (COV == NNGP_COV_MATERN) ? 4 : 8;  // entries evaluate
 // Batches of UNR entries: all loads, then UNR independent evaluation chains, then all stores.
 // (A plain unrolled loop is serialised by ptxas: it cannot prove that the store of entry e does not
 // alias the site loads of entry e+1, so the chains never overlap -- seen in SASS.)
-template <int COV, int UNR, typename CorT>
+template <int COV, int UNR, bool TAB, typename CorT>
 __device__ __forceinline__ void tpl_build_body(const CorT &cor, int lane, int off_co, int off_a, const unsigned *ent,
                                                int e_begin, int e_step, int nent_pad, double sigmaSq) {
   const unsigned char *cob = tpl_smem + off_co + lane * 16;
@@ -51,7 +51,10 @@ __device__ __forceinline__ void tpl_build_body(const CorT &cor, int lane, int of
       d2[u] = dx * dx + dy * dy;
     }
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) v[u] = sigmaSq * cor.fast(d2[u]);
+    for (int u = 0; u < UNR; ++u) {
+      if constexpr (TAB && COV == NNGP_COV_MATERN) v[u] = sigmaSq * cor.fast_tab(d2[u]);
+      else v[u] = sigmaSq * cor.fast(d2[u]);
+    }
     if (COV == NNGP_COV_MATERN) {  // rare arguments outside the straight-line path (phi D > 2, integer nu)
       bool any = false;
 #pragma unroll
@@ -69,19 +72,20 @@ __device__ __forceinline__ void tpl_build_body(const CorT &cor, int lane, int of
 
 // The parameter set of this CTA is P.th[blockIdx.y]; Matern specialises on the index so that its series
 // coefficients become constant-bank operands with static addresses (see Cor<NNGP_COV_MATERN>).
-template <int COV, int UNR>
+// tab: exp / log tables in shared memory (Matern only; NULL: straight-line log / exp)
+template <int COV, int UNR, bool TAB = false>
 __device__ __forceinline__ void tpl_build(const BfLaunch &P, int lane, int off_co, int off_a, const unsigned *ent,
-                                          int e_begin, int e_step, int nent_pad) {
+                                          int e_begin, int e_step, int nent_pad, const double *tab = nullptr) {
   if constexpr (COV == NNGP_COV_MATERN) {
     switch (blockIdx.y) {  // uniform over the CTA
-      case 0: tpl_build_body<COV, UNR>(Cor<COV>(P.th[0]), lane, off_co, off_a, ent, e_begin, e_step, nent_pad, P.th[0].sigmaSq); break;
-      case 1: tpl_build_body<COV, UNR>(Cor<COV>(P.th[1]), lane, off_co, off_a, ent, e_begin, e_step, nent_pad, P.th[1].sigmaSq); break;
-      case 2: tpl_build_body<COV, UNR>(Cor<COV>(P.th[2]), lane, off_co, off_a, ent, e_begin, e_step, nent_pad, P.th[2].sigmaSq); break;
-      default: tpl_build_body<COV, UNR>(Cor<COV>(P.th[3]), lane, off_co, off_a, ent, e_begin, e_step, nent_pad, P.th[3].sigmaSq); break;
+      case 0: tpl_build_body<COV, UNR, TAB>(Cor<COV>(P.th[0], tab), lane, off_co, off_a, ent, e_begin, e_step, nent_pad, P.th[0].sigmaSq); break;
+      case 1: tpl_build_body<COV, UNR, TAB>(Cor<COV>(P.th[1], tab), lane, off_co, off_a, ent, e_begin, e_step, nent_pad, P.th[1].sigmaSq); break;
+      case 2: tpl_build_body<COV, UNR, TAB>(Cor<COV>(P.th[2], tab), lane, off_co, off_a, ent, e_begin, e_step, nent_pad, P.th[2].sigmaSq); break;
+      default: tpl_build_body<COV, UNR, TAB>(Cor<COV>(P.th[3], tab), lane, off_co, off_a, ent, e_begin, e_step, nent_pad, P.th[3].sigmaSq); break;
     }
   } else {
     const BfTheta &th = P.th[blockIdx.y];
-    tpl_build_body<COV, UNR>(Cor<COV>(th), lane, off_co, off_a, ent, e_begin, e_step, nent_pad, th.sigmaSq);
+    tpl_build_body<COV, UNR, false>(Cor<COV>(th), lane, off_co, off_a, ent, e_begin, e_step, nent_pad, th.sigmaSq);
   }
 }
 

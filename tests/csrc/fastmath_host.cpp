@@ -7,3 +7,6 @@ double host_nngp_exp_nonpos(double x) { return nngp::nngp_exp_nonpos(x); }
 extern "C" double host_nngp_sqrt_eps(double x) { return nngp::nngp_sqrt_eps(x); }
 extern "C" double host_nngp_rsqrt_pos(double x) { return nngp::nngp_rsqrt_pos(x); }
 extern "C" double host_nngp_rcp_pos(double x) { return nngp::nngp_rcp_pos(x); }
+
+extern "C" double host_nngp_exp_tab(double x) { return nngp::nngp_exp_tab(x, nngp::kExpTab32); }
+extern "C" double host_nngp_log_tab(double x) { return nngp::nngp_log_tab(x, nngp::kLogTab64); }

@@ -146,6 +146,31 @@ def test_device_fastmath_on_host(tmp_path):
     assert L.host_nngp_exp_nonpos(0.0) == 1.0 and L.host_nngp_exp_nonpos(-800.0) == 0.0
 
 
+def test_table_driven_exp_log_on_host(tmp_path):
+    """Table-driven exp / log of fastmath.cuh + fasttab.cuh (host build) vs mpmath: absolute error ~1e-16."""
+    import mpmath as mp
+    L = _build_host("fastmath_host.cpp", str(tmp_path / "libfm2.so"))
+    for f in (L.host_nngp_exp_tab, L.host_nngp_log_tab):
+        f.restype = C.c_double; f.argtypes = [C.c_double]
+    mp.mp.dps = 40
+    rng = np.random.default_rng(3)
+    xs = np.concatenate([-10 ** rng.uniform(-12, 2.85, 3000), 10 ** rng.uniform(-12, 2.8, 1500), rng.uniform(-2, 2, 1500)])
+    worst = 0.0
+    for x in xs:
+        r = mp.exp(mp.mpf(float(x)))
+        worst = max(worst, float(abs((mp.mpf(L.host_nngp_exp_tab(float(x))) - r) / r)))
+    assert worst < 4e-16, worst
+    assert L.host_nngp_exp_tab(0.0) == 1.0 and L.host_nngp_exp_tab(-800.0) == 0.0
+    ts = np.concatenate([10 ** rng.uniform(-300, 300, 3000), 1 + rng.uniform(-0.5, 1.0, 2000), 10 ** rng.uniform(-6, 0, 2000)])
+    worst_abs = 0.0
+    for t in ts:
+        r = mp.log(mp.mpf(float(t)))
+        err = float(abs(mp.mpf(L.host_nngp_log_tab(float(t))) - r))
+        worst_abs = max(worst_abs, err / max(1.0, float(abs(r))))
+    assert worst_abs < 3e-16, worst_abs
+    assert abs(L.host_nngp_log_tab(1.0)) < 2e-17
+
+
 def test_kats_on_the_oracle(port):
     """Analytic known answers on the CPU oracle itself."""
     s2, t2, phi = 5.0, 1.0, 6.0
