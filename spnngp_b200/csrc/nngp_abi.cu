@@ -158,6 +158,7 @@ void nngp_destroy(nngp_ctx *c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   free_model(c);
   free_dev(c->d_ticket);
+  free_dev(c->d_Xy);
   free_dev(c->d_fail);
   free_dev(c->d_mat);
   if (c->d_flush) cudaFree(c->d_flush);
@@ -249,6 +250,8 @@ int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const 
       c->h_beta_cap = (size_t)NNGP_MAX_BATCH * p;
     }
     for (int b = 0; b < NNGP_MAX_BATCH; b++) NNGP_ENSURE(c->d_resid[b], 5 + b, n);
+    NNGP_ENSURE(c->d_Xy, 15, xy_rows_count(n, p));
+    NNGP_CUDA(c, xy_rows_launch(c->d_X, c->d_y, n, p, c->d_Xy, c->sms, c->stream));
   }
   for (int s = 0; s < 2 && c->has_nn; s++) {
     NNGP_ENSURE(c->d_B[s], 9 + s, nI);
@@ -454,7 +457,7 @@ int nngp_q_forms(nngp_ctx *c, int slot, double *S) {
   if (c->n == 0 || c->p == 0 || !c->has_nn) return ctx_fail(c, NNGP_ESTATE, "nngp_q_forms before nngp_set_data");
   NNGP_CUDA(c, cudaSetDevice(c->device));
   const int K = c->p + 1, npairs = K * (K + 1) / 2;
-  NNGP_CUDA(c, q_forms_launch(c->d_B[slot], c->d_F[slot], c->d_nnIndx, c->d_X, c->d_y, c->n, c->p, c->m, c->loc_begin,
+  NNGP_CUDA(c, q_forms_launch(c->d_B[slot], c->d_F[slot], c->d_nnIndx, c->d_Xy, c->n, c->p, c->m, c->loc_begin,
                               c->loc_end, c->d_partials, c->d_out, c->stream));
   c->launches += 2;
   if (c->comm) {

@@ -28,6 +28,7 @@ struct nngp_ctx {
   int *d_nnIndx = nullptr;      // reference CSR
   double *d_X = nullptr;        // n x p column-major
   double *d_y = nullptr;
+  double *d_Xy = nullptr;       // [X y] as rows, n x roundup4(p+1) row-major, zero padded (q_forms gathers)
   double *d_B[2] = {nullptr, nullptr};  // two slots: current / candidate
   double *d_F[2] = {nullptr, nullptr};
   double *d_resid[NNGP_MAX_BATCH] = {};
@@ -86,9 +87,10 @@ int q_resid_grid(int m, long long nloc, int sms);
 cudaError_t q_resid_launch(const double *B, const double *F, const int *nnIndx, const double *resid, int m,
                            int loc_begin, int loc_end, double *partials, double *out, int sms, cudaStream_t stream);
 int q_forms_grid(long long nloc);
-cudaError_t q_forms_launch(const double *B, const double *F, const int *nnIndx, const double *X, const double *y,
-                           int n, int p, int m, int loc_begin, int loc_end, double *partials, double *out,
-                           cudaStream_t stream);
+cudaError_t q_forms_launch(const double *B, const double *F, const int *nnIndx, const double *Xy, int n, int p, int m,
+                           int loc_begin, int loc_end, double *partials, double *out, cudaStream_t stream);
+size_t xy_rows_count(int n, int p);
+cudaError_t xy_rows_launch(const double *X, const double *y, int n, int p, double *Xy, int sms, cudaStream_t stream);
 
 // rep_kernels.cu
 int rep_prepare(nngp_ctx *c);  // levels + pinned z buffer (c->h_z), idempotent

@@ -39,32 +39,36 @@ __global__ void __launch_bounds__(256) q_resid_kernel(const double *__restrict__
   const int tid = threadIdx.x, lane = tid % LP, g = tid / LP;
   double qsum = 0.0;
   for (long long base = loc_begin + (long long)blockIdx.x * (G * UN); base < loc_end; base += (long long)gridDim.x * (G * UN)) {
-    double b[UN], ri[UN], fi[UN];
+    double b[UN];
     int id[UN];
-    bool act[UN];
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
       const long long i = base + u * G + g;  // consecutive groups take consecutive locations: coalesced B, nnIndx
-      act[u] = i < loc_end;
-      const int mi = act[u] ? nn_count(i, m) : 0;
-      const long long off = act[u] ? nn_offset(i, m) : 0;
+      const bool act = i < loc_end;
+      const int mi = act ? nn_count(i, m) : 0;
+      const long long off = act ? nn_offset(i, m) : 0;
       const bool ok = lane < mi;
       b[u] = ok ? __ldg(&B[off + lane]) : 0.0;
       id[u] = ok ? __ldg(&nnIndx[off + lane]) : 0;
-      ri[u] = (act[u] && lane == 0) ? __ldg(&resid[i]) : 0.0;
-      fi[u] = (act[u] && lane == 0) ? __ldg(&F[i]) : 1.0;
     }
+    // lane u of the group finishes row u (one division per trip instead of UN predicated ones)
+    const long long imine = base + (long long)lane * G + g;
+    const bool mine = lane < UN && imine < loc_end;
+    const double ri = mine ? __ldg(&resid[imine]) : 0.0;
+    const double fi = mine ? __ldg(&F[imine]) : 1.0;
     double a[UN];
 #pragma unroll
     for (int u = 0; u < UN; ++u) a[u] = b[u] * __ldg(&resid[id[u]]);  // weight 0 for missing neighbours
+    double am = 0.0;
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
 #pragma unroll
-      for (int s = LP / 2; s >= 1; s >>= 1) a[u] += __shfl_xor_sync(0xffffffffu, a[u], s, LP);
-      if (lane == 0 && act[u]) {
-        const double e = ri[u] - a[u];
-        qsum += e * e / fi[u];
-      }
+      for (int s = LP / 2; s >= 1; s >>= 1) a[u] += __shfl_xor_sync(0xffffffffu, a[u], s, LP);  // every lane: the row's sum
+      am = (lane == u) ? a[u] : am;
+    }
+    if (mine) {
+      const double e = ri - am;
+      qsum += e * e / fi;
     }
   }
 #pragma unroll
@@ -100,11 +104,42 @@ __global__ void __launch_bounds__(256) sum_partials_kernel(const double *__restr
 // CTA = 256 threads handles CH = 128 consecutive locations: phase 1 writes the whitened columns
 // e_c(i) = (u_c[i] - B_i . u_c[N(i)]) / sqrt(F_i) of its chunk to shared memory; phase 2 forms the
 // K(K+1)/2 cross products of the chunk; per-CTA partials are summed by sum_partials_kernel.
+// Xy: the columns [X y] as ROWS (n x KS row-major, KS = K rounded up to 4, zero padded; xy_rows_kernel), so that the
+// cross-form pass fetches four columns of a neighbour with ONE 32-byte load.  ncu on the column-wise version: the
+// pass is bound by L1 wavefronts (l1tex data pipe 85%: every 8-byte gather of a warp is its own wavefront), not by
+// HBM or L2 -- a quarter of the gather instructions is a quarter of the wavefronts.
+__host__ __device__ inline int xy_row_stride(int p) { return ((p + 1) + 3) & ~3; }
+
+__global__ void __launch_bounds__(256) xy_rows_kernel(const double *__restrict__ X, const double *__restrict__ y, int n,
+                                                      int p, double *__restrict__ Xy) {
+  const int KS = xy_row_stride(p);
+  const long long total = (long long)n * KS, stride = (long long)gridDim.x * blockDim.x;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const long long i = t / KS;
+    const int c = (int)(t - i * KS);
+    Xy[t] = (c < p) ? __ldg(&X[(size_t)c * n + i]) : (c == p ? __ldg(&y[i]) : 0.0);
+  }
+}
+
+// 32-byte read-only load (sm_100: 256-bit vector loads)
+__device__ __forceinline__ void ldg256(const double *p, double (&v)[4]) {
+  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+
+size_t xy_rows_count(int n, int p) { return (size_t)n * xy_row_stride(p); }
+
+cudaError_t xy_rows_launch(const double *X, const double *y, int n, int p, double *Xy, int sms, cudaStream_t stream) {
+  long long g = ((long long)n * xy_row_stride(p) + 255) / 256;
+  if (g > (long long)sms * 16) g = (long long)sms * 16;
+  xy_rows_kernel<<<(int)(g < 1 ? 1 : g), 256, 0, stream>>>(X, y, n, p, Xy);
+  return cudaGetLastError();
+}
+
 template <int LP>
 __global__ void __launch_bounds__(256) q_forms_kernel(const double *__restrict__ B, const double *__restrict__ F,
-                                                      const int *__restrict__ nnIndx, const double *__restrict__ X,
-                                                      const double *__restrict__ y, int n, int p, int m,
-                                                      int loc_begin, int loc_end, double *__restrict__ partials) {
+                                                      const int *__restrict__ nnIndx, const double *__restrict__ Xy,
+                                                      int n, int p, int m, int loc_begin, int loc_end,
+                                                      double *__restrict__ partials) {
   constexpr int CH = 128;
   constexpr int G = 256 / LP;
   extern __shared__ double W[];  // CH x K, column c at W[c*CH ...]
@@ -116,36 +151,44 @@ __global__ void __launch_bounds__(256) q_forms_kernel(const double *__restrict__
   constexpr int UN = 4;  // locations per lane group and trip: ids/weights first, then all gathers (bytes in flight)
   static_assert(CH % (G * UN) == 0, "chunk must be a whole number of trips");
   for (int s0 = 0; s0 < CH; s0 += G * UN) {
-    double b[UN], rs[UN];
+    double b[UN];
     int idx[UN];
-    bool active[UN];
-    long long ii[UN];
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
-      const int s = s0 + u * G + g;
-      const long long i = chunk0 + s;
-      ii[u] = i;
-      active[u] = i < loc_end;
-      const int mi = active[u] ? nn_count(i, m) : 0;
-      const long long off = active[u] ? nn_offset(i, m) : 0;
+      const long long i = chunk0 + s0 + u * G + g;
+      const bool act = i < loc_end;
+      const int mi = act ? nn_count(i, m) : 0;
+      const long long off = act ? nn_offset(i, m) : 0;
       const bool ok = lane < mi;
       b[u] = ok ? __ldg(&B[off + lane]) : 0.0;
       idx[u] = ok ? __ldg(&nnIndx[off + lane]) : 0;
-      rs[u] = (active[u] && lane == 0) ? __ldg(&F[i]) : 1.0;
     }
-    for (int c = 0; c < K; ++c) {
-      const double *__restrict__ uc = (c < p) ? (X + (size_t)c * n) : y;
-      double a[UN], own[UN];
+    // lane u of the group finishes row u: one rsqrt per row and trip
+    const int smine = s0 + lane * G + g;
+    const long long imine = chunk0 + smine;
+    const bool own_row = lane < UN;
+    const bool mine = own_row && imine < loc_end;
+    const double rsq = mine ? rsqrt(__ldg(&F[imine])) : 0.0;
+    // KC columns at a time: all their gathers (KC x UN per lane) are issued before the first reduction -- with one
+    // column per trip the pass waited one L2 round trip per column (ncu: 75% of the samples on long scoreboard)
+    constexpr int KC = 4;
+    const int KS = xy_row_stride(p);
+    for (int c0 = 0; c0 < K; c0 += KC) {
+      double a[UN][KC], own[KC] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        a[u] = b[u] * __ldg(&uc[idx[u]]);  // weight 0 for missing neighbours
-        own[u] = (active[u] && lane == 0) ? __ldg(&uc[ii[u]]) : 0.0;
-      }
+      for (int u = 0; u < UN; ++u) ldg256(&Xy[(size_t)idx[u] * KS + c0], a[u]);  // row 0 with weight 0: missing neighbour
+      if (mine) ldg256(&Xy[(size_t)imine * KS + c0], own);
 #pragma unroll
-      for (int u = 0; u < UN; ++u) {
+      for (int cc = 0; cc < KC; ++cc) {
+        double am = 0.0;
 #pragma unroll
-        for (int sh = LP / 2; sh >= 1; sh >>= 1) a[u] += __shfl_xor_sync(0xffffffffu, a[u], sh, LP);
-        if (lane == 0) W[c * CH + s0 + u * G + g] = active[u] ? (own[u] - a[u]) * rsqrt(rs[u]) : 0.0;
+        for (int u = 0; u < UN; ++u) {
+          double t = b[u] * a[u][cc];
+#pragma unroll
+          for (int sh = LP / 2; sh >= 1; sh >>= 1) t += __shfl_xor_sync(0xffffffffu, t, sh, LP);
+          am = (lane == u) ? t : am;
+        }
+        if (own_row && c0 + cc < K) W[(c0 + cc) * CH + smine] = (own[cc] - am) * rsq;  // 0 beyond the shard's end
       }
     }
   }
@@ -210,9 +253,8 @@ int q_forms_grid(long long nloc) { return (int)((nloc + 127) / 128 < 1 ? 1 : (nl
 
 // partials must hold q_forms_grid() * (p+1)(p+2)/2 doubles; out receives the packed lower triangle
 // (column-major: (0,0),(1,0),..,(K-1,0),(1,1),...).
-cudaError_t q_forms_launch(const double *B, const double *F, const int *nnIndx, const double *X, const double *y,
-                           int n, int p, int m, int loc_begin, int loc_end, double *partials, double *out,
-                           cudaStream_t stream) {
+cudaError_t q_forms_launch(const double *B, const double *F, const int *nnIndx, const double *Xy, int n, int p, int m,
+                           int loc_begin, int loc_end, double *partials, double *out, cudaStream_t stream) {
   const int K = p + 1, npairs = K * (K + 1) / 2;
   const int grid = q_forms_grid((long long)loc_end - loc_begin);
   const size_t smem = (size_t)128 * K * sizeof(double);
@@ -224,7 +266,7 @@ cudaError_t q_forms_launch(const double *B, const double *F, const int *nnIndx, 
       e = cudaFuncSetAttribute(q_forms_kernel<LPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
       if (e != cudaSuccess) return e;                                                                        \
     }                                                                                                        \
-    q_forms_kernel<LPV><<<grid, 256, smem, stream>>>(B, F, nnIndx, X, y, n, p, m, loc_begin, loc_end, partials); \
+    q_forms_kernel<LPV><<<grid, 256, smem, stream>>>(B, F, nnIndx, Xy, n, p, m, loc_begin, loc_end, partials); \
   } while (0)
   if (lp == 8) NNGP_QF(8);
   else if (lp == 16) NNGP_QF(16);
