@@ -1,0 +1,103 @@
+"""GPU, BASELINE.json's full size (n = 10^6, m = 15; configs[2]): the CUDA path against the CPU oracle where the oracle
+finishes in seconds (exponential: every B, F, logDet, Q), and through size-independent properties of the path
+(scaling of (sigma.sq, tau.sq), quadratic scaling of Q, determinism, shard additivity, neighbour-list invariants)."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.util import relerr, relerr_norm
+
+pytestmark = pytest.mark.gpu
+N, M = 1000000, 15
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def full(engine, port):
+    rng = np.random.default_rng(20250)
+    W = np.sqrt(N / 5000.0)
+    coords = rng.random((N, 2)) * W
+    coords = coords[np.argsort(coords[:, 0], kind="stable")]
+    X = np.column_stack([np.ones(N), rng.standard_normal(N)])
+    beta = np.array([1.0, 5.0])
+    y = X @ beta + rng.standard_normal(N) * 2.0
+    idx, dist, lu = engine.mk_nn_indx(coords, M, "cb")
+    port.set_threads(os.cpu_count())
+    return dict(coords=coords, X=X, y=y, beta=beta, idx=idx, dist=dist, lu=lu)
+
+
+def test_neighbour_lists_full_size(engine, port, full):
+    """Invariants of mkNNIndxCB's output at n = 10^6, and bit-equality with the CPU oracle's search."""
+    idx, dist, lu, coords = full["idx"], full["dist"], full["lu"], full["coords"]
+    rows = idx[lu[M]:].reshape(-1, M); drows = dist[lu[M]:].reshape(-1, M)
+    i = np.arange(M, N)[:, None]
+    assert (rows < i).all() and (rows >= 0).all()                      # predecessors only
+    assert (np.diff(drows, axis=1) >= 0).all()                         # ascending distance
+    d = np.sqrt(((coords[rows] - coords[M:, None, :]) ** 2).sum(axis=2))
+    assert np.allclose(d, drows, rtol=1e-15, atol=0)                   # nnDist is the distance to nnIndx
+    rng = np.random.default_rng(1)
+    for s in rng.integers(M, N, 40):                                    # exhaustive check of sampled locations
+        dd = np.sqrt(((coords[:s] - coords[s]) ** 2).sum(axis=1))
+        assert np.array_equal(np.sort(dd)[:M], drows[s - M])
+    o_idx, o_dist, o_lu = port.mk_nn_indx_cb(coords, M)                 # the whole search on the host cores
+    assert np.array_equal(o_idx, idx) and np.array_equal(o_dist.view(np.int64), dist.view(np.int64))
+    assert np.array_equal(o_lu, lu)
+
+
+def test_bf_loglik_full_size_against_oracle(engine, port, full):
+    """Exponential model: all 15*10^6 weights, 10^6 variances, logDet and Q against the oracle (<= 1e-10)."""
+    theta = [5.0, 1.0, 6.0]
+    engine.set_data(full["coords"], full["idx"], full["lu"], full["X"], full["y"], M)
+    out = engine.bf_loglik(0, [theta], [full["beta"]], slots=[0])
+    B, F = engine.get_bf(0)
+    Bo, Fo, ld, info = port.update_bf(full["coords"], full["idx"], full["lu"], N, M, theta, 0)
+    assert info == 0
+    r = full["X"] @ full["beta"] - full["y"]
+    Qo = port.q(Bo, Fo, r, r, N, full["idx"], full["lu"])
+    assert relerr(F, Fo) < TOL and relerr_norm(B[: len(full["idx"])], Bo[: len(full["idx"])]) < TOL
+    assert abs(out[0, 0] - ld) <= TOL * abs(ld) and abs(out[0, 1] - Qo) <= TOL * abs(Qo)
+    S = engine.q_forms(0)
+    assert abs(S[2, 2] - port.q(Bo, Fo, full["y"], full["y"], N, full["idx"], full["lu"])) <= TOL * abs(S[2, 2])
+    assert abs(engine.q_resid(0, full["beta"]) - Qo) <= TOL * abs(Qo)
+
+
+@pytest.mark.parametrize("cov,theta", [(0, [5.0, 1.0, 6.0]), (2, [5.0, 1.0, 6.0, 0.75]), (3, [5.0, 1.0, 6.0]), (1, [5.0, 1.0, 6.0])])
+def test_bf_properties_full_size(engine, full, cov, theta):
+    """(sigma.sq, tau.sq) -> c (sigma.sq, tau.sq) leaves B unchanged, scales F by c, shifts logDet by n log c and
+    divides Q by c; Q is quadratic in the residual; a launch is reproducible bit for bit; shards add up."""
+    engine.set_data(full["coords"], full["idx"], full["lu"], full["X"], full["y"], M)
+    beta = full["beta"]
+    a = engine.bf_loglik(cov, [theta], [beta], slots=[0])
+    B0, F0 = engine.get_bf(0)
+    a2 = engine.bf_loglik(cov, [theta], [beta], slots=[1])
+    B1, F1 = engine.get_bf(1)
+    assert np.array_equal(a, a2) and np.array_equal(B0, B1) and np.array_equal(F0, F1)      # deterministic
+    c = 4.0                                                                                    # power of two: exact scaling
+    th2 = list(theta); th2[0] *= c; th2[1] *= c
+    b = engine.bf_loglik(cov, [th2], [beta], slots=[1])
+    B2, F2 = engine.get_bf(1)
+    assert np.array_equal(B2, B0) and np.array_equal(F2, c * F0)
+    assert abs(b[0, 0] - (a[0, 0] + N * np.log(c))) <= 1e-12 * abs(b[0, 0])
+    assert abs(b[0, 1] - a[0, 1] / c) <= 1e-12 * abs(b[0, 1])
+    # Q is quadratic in r = X beta - y: beta' = beta + t e_0 moves r by t -> Q(t) is a parabola; check second difference
+    q = [engine.bf_loglik(cov, [theta], [beta + np.array([t, 0.0])], slots=[1])[0, 1] for t in (-1.0, 0.0, 1.0, 2.0)]
+    d2a = q[0] - 2 * q[1] + q[2]; d2b = q[1] - 2 * q[2] + q[3]
+    assert abs(d2a - d2b) <= 1e-9 * abs(d2a)
+    assert all(np.isfinite(F0)) and (F0 > 0).all() and (F0 <= theta[0] + theta[1] + 1e-12).all()   # 0 < F_i <= sigma.sq + tau.sq
+
+
+def test_shards_add_up_full_size(full):
+    from spnngp_b200 import Engine
+    from spnngp_b200.dist import shard_range
+    theta = [5.0, 1.0, 6.0]
+    e = Engine(0)
+    e.set_data(full["coords"], full["idx"], full["lu"], full["X"], full["y"], M)
+    whole = e.bf_loglik(0, [theta], [full["beta"]], slots=[0])
+    acc = np.zeros(2)
+    for r in range(4):
+        lo, hi = shard_range(N, M, r, 4)
+        e.set_data(full["coords"], full["idx"], full["lu"], full["X"], full["y"], M, loc_range=(lo, hi))
+        acc += e.bf_loglik(0, [theta], [full["beta"]], slots=[0])[0]
+    e.close()
+    assert np.allclose(acc, whole[0], rtol=1e-12)
