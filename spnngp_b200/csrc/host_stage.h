@@ -19,8 +19,8 @@ namespace nngp {
 struct StageJob {
   enum Kind { RAW, XY_INTERLEAVE, INT_RANGE };
   Kind kind;
-  void *dst;        // device
-  const void *src;  // host (pageable)
+  void *dst;        // device (run) / host, pageable (run_d2h)
+  const void *src;  // host, pageable (run) / device (run_d2h)
   size_t bytes;     // bytes written to dst
   long long n;      // XY_INTERLEAVE: number of sites (src = x[n] then y[n]); INT_RANGE: valid ids are [0, n)
 };
@@ -108,6 +108,43 @@ class HostStager {
     worker(0);
     for (auto &x : th) x.join();
     if (bad_id) *bad_id = bad.load();
+    return (cudaError_t)err.load();
+  }
+
+  // The other direction: device -> pageable host arrays (RAW jobs; dst = host, src = device).  Each thread drains
+  // its chunks through its two pinned buffers: the DMA of chunk k+1 runs while chunk k is copied out (first touch of
+  // a fresh result array page-faults, which is why the threads matter more here than on the way in).
+  cudaError_t run_d2h(const std::vector<StageJob> &jobs) {
+    struct Chunk { int job; size_t off, len; };
+    std::vector<Chunk> chunks;
+    for (size_t j = 0; j < jobs.size(); j++)
+      for (size_t off = 0; off < jobs[j].bytes; off += kChunk)
+        chunks.push_back({(int)j, off, jobs[j].bytes - off < kChunk ? jobs[j].bytes - off : kChunk});
+    std::atomic<int> err{(int)cudaSuccess};
+    auto worker = [&](int t) {
+      cudaSetDevice(device_);
+      std::vector<size_t> mine;
+      for (size_t ci = (size_t)t; ci < chunks.size(); ci += (size_t)nthreads_) mine.push_back(ci);
+      auto issue = [&](size_t k) {
+        const Chunk &ch = chunks[mine[k]];
+        cudaError_t e = cudaMemcpyAsync(buf_[t][k & 1], (const char *)jobs[ch.job].src + ch.off, ch.len,
+                                        cudaMemcpyDeviceToHost, st_[t]);
+        if (e == cudaSuccess) e = cudaEventRecord(ev_[t][k & 1], st_[t]);
+        if (e != cudaSuccess) err = (int)e;
+      };
+      if (!mine.empty()) issue(0);
+      for (size_t k = 0; k < mine.size(); k++) {
+        if (k + 1 < mine.size()) issue(k + 1);
+        cudaError_t e = cudaEventSynchronize(ev_[t][k & 1]);
+        if (e != cudaSuccess) { err = (int)e; return; }
+        const Chunk &ch = chunks[mine[k]];
+        memcpy((char *)jobs[ch.job].dst + ch.off, buf_[t][k & 1], ch.len);
+      }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads_; t++) th.emplace_back(worker, t);
+    worker(0);
+    for (auto &x : th) x.join();
     return (cudaError_t)err.load();
   }
 

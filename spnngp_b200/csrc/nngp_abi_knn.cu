@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "nngp_ctx.h"
+#include "host_stage.h"
 
 namespace nngp {
 cudaError_t knn_brute_launch(const double2 *coords, int n, int m, int *nnIndx, double *nnDist, cudaStream_t stream);
@@ -86,11 +87,21 @@ static int sort_by_u(nngp_ctx *c, const double2 *d_coords, int n, DevBuf &d_sidx
   return NNGP_OK;
 }
 
+static int ensure_stager(nngp_ctx *c) {
+  if (!c->stager) {
+    c->stager = new HostStager();
+    NNGP_CUDA(c, c->stager->init(c->device));
+  }
+  return NNGP_OK;
+}
+
+// column-major (x[n], y[n]) host sites -> interleaved double2 on the device, through the pinned ring
 static int upload_sites(nngp_ctx *c, const double *coords, int n, DevBuf &d) {
-  std::vector<double2> xy((size_t)n);
-  for (int i = 0; i < n; i++) xy[i] = make_double2(coords[i], coords[(size_t)n + i]);
   NNGP_CUDA(c, d.alloc((size_t)n * sizeof(double2)));
-  NNGP_CUDA(c, cudaMemcpy(d.p, xy.data(), (size_t)n * sizeof(double2), cudaMemcpyHostToDevice));
+  int rc = ensure_stager(c);
+  if (rc) return rc;
+  std::vector<StageJob> up{{StageJob::XY_INTERLEAVE, d.p, coords, (size_t)n * sizeof(double2), n}};
+  NNGP_CUDA(c, c->stager->run(up, nullptr));
   return NNGP_OK;
 }
 
@@ -130,9 +141,12 @@ int nngp_mk_nn_indx(nngp_ctx *c, int n, int m, const double *coords, int search_
     NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
   }
   NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (nIndx > 0) {
-    NNGP_CUDA(c, cudaMemcpy(nnIndx, d_idx.p, (size_t)nIndx * sizeof(int), cudaMemcpyDeviceToHost));
-    NNGP_CUDA(c, cudaMemcpy(nnDist, d_dist.p, (size_t)nIndx * sizeof(double), cudaMemcpyDeviceToHost));
+  if (nIndx > 0) {  // 12 bytes per neighbour slot back to pageable arrays: threaded pinned ring (host_stage.h)
+    rc = ensure_stager(c);
+    if (rc) return rc;
+    std::vector<StageJob> down{{StageJob::RAW, nnIndx, d_idx.p, (size_t)nIndx * sizeof(int), 0},
+                               {StageJob::RAW, nnDist, d_dist.p, (size_t)nIndx * sizeof(double), 0}};
+    NNGP_CUDA(c, c->stager->run_d2h(down));
   }
   for (int i = 0; i < n; i++) {  // src/util.cpp:55-70 via src/nn.cpp:95-97
     nnIndxLU[i] = (i == 0) ? 0 : (int)nn_offset(i, m);

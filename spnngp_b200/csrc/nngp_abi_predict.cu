@@ -12,6 +12,7 @@
 
 #include "host_linalg.h"
 #include "nngp_ctx.h"
+#include "host_stage.h"
 
 namespace nngp {
 cudaError_t site_reduce_launch(const double *W, const int *nn0, const double *X, const double *y, const double *X0,
@@ -185,7 +186,16 @@ int nngp_rnngp_predict(nngp_ctx *c, int cov, int q, const double *X0, const doub
     if (rc) return rc;
     NNGP_CUDA(c, d_z.alloc((size_t)cs * S * sizeof(double)));
     NNGP_CUDA(c, d_y0.alloc((size_t)cs * S * sizeof(double)));
-    NNGP_CUDA(c, cudaMemcpy(d_z.p, z + (size_t)i0 * S, (size_t)cs * S * sizeof(double), cudaMemcpyHostToDevice));
+    // the normals in and the draws out go through the threaded pinned ring (host_stage.h): a q x S job is
+    // dominated by these two transfers, not by the solves
+    if (!c->stager) {
+      c->stager = new HostStager();
+      NNGP_CUDA(c, c->stager->init(c->device));
+    }
+    {
+      std::vector<StageJob> up{{StageJob::RAW, d_z.p, z + (size_t)i0 * S, (size_t)cs * S * sizeof(double), 0}};
+      NNGP_CUDA(c, c->stager->run(up, nullptr));
+    }
     for (size_t g = 0; g < groups.size(); g++) {
       rc = site_solve(c, cov, thetas[g].data(), ch);
       if (rc) return rc;
@@ -195,9 +205,13 @@ int nngp_rnngp_predict(nngp_ctx *c, int cov, int q, const double *X0, const doub
       c->launches++;
     }
     NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
-    // y0 is q x S column-major on the host: one strided copy per chunk
-    NNGP_CUDA(c, cudaMemcpy2D(y0 + i0, (size_t)q * sizeof(double), d_y0.p, (size_t)cs * sizeof(double),
-                              (size_t)cs * sizeof(double), (size_t)S, cudaMemcpyDeviceToHost));
+    // y0 is q x S column-major on the host: column s of the chunk is contiguous on both sides
+    {
+      std::vector<StageJob> down((size_t)S);
+      for (int s = 0; s < S; s++)
+        down[s] = {StageJob::RAW, y0 + (size_t)s * q + i0, d_y0.as<double>() + (size_t)s * cs, (size_t)cs * sizeof(double), 0};
+      NNGP_CUDA(c, c->stager->run_d2h(down));
+    }
   }
   return NNGP_OK;
 }
