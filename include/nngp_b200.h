@@ -81,6 +81,13 @@ int nngp_sync(nngp_ctx *ctx);
 int nngp_mk_nn_indx(nngp_ctx *ctx, int n, int m, const double *coords, int search_type, int *nnIndx,
                     double *nnDist, int *nnIndxLU, int *n_tie_replayed);
 
+/* `mkUIndx` (src/nn.cpp:25-56): the transposed neighbour graph the latent model walks.  uIndx (nIndx): for each
+ * location i, ascending, the locations that have i as a neighbour; uIndxLU (2n): [0,n) offset of i's list, [n,2n) its
+ * length; uiIndx (nIndx): the slot i occupies in each of those neighbour lists.  search_type as `u.search.type`
+ * (R/spNNGP.R:99): 0 and 2 give ascending lists, 1 the same lists descending. */
+int nngp_mk_u_indx(nngp_ctx *ctx, int n, int m, const int *nnIndx, int search_type, int *uIndx, int *uIndxLU,
+                   int *uiIndx);
+
 /* unordered query kNN (all n sites are candidates), ascending (d^2, index): the stand-in for
  * RANN::nn2(coords, coords.0, k=m)$nn.idx - 1 (R/generics.R:642, R/spConjNNGP.R:311).
  * nnIndx0 is q x m column-major, 0-based. */

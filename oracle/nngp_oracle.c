@@ -465,6 +465,39 @@ static double log_post(double logDet, double Q, const double *theta, int cov_mod
   return lp;
 }
 
+/* mkUIndx, src/nn.cpp:25-56 with mkUIndx2 / crs_csc (src/util.cpp:115-185): transpose of the neighbour graph.
+ * uIndx: per location i the locations having i as a neighbour, ascending; uIndxLU: offsets then counts;
+ * uiIndx: slot of i in each of those lists (which(), src/util.cpp:248-258).  search_type 0, 2: ascending; 1: descending. */
+void orc_mk_u_indx(int n, int m, const int *nnIndx, const int *nnIndxLU, int search_type, int *uIndx, int *uIndxLU,
+                   int *uiIndx) {
+  long nIndx = orc_n_indx(n, m);
+  int *start = (int *)calloc((size_t)n + 1, sizeof(int));
+  for (long e = 0; e < nIndx; e++) start[nnIndx[e] + 1]++;          /* count per column */
+  for (int i = 0; i < n; i++) start[i + 1] += start[i];             /* cumulative sum */
+  for (int i = 0; i < n; i++) {
+    uIndxLU[i] = start[i];
+    uIndxLU[n + i] = start[i + 1] - start[i];
+  }
+  int *fill = (int *)malloc(sizeof(int) * (size_t)n);
+  for (int i = 0; i < n; i++) fill[i] = start[i];
+  for (int row = 0; row < n; row++) {                               /* rows ascending: each list ends up ascending */
+    for (int k = 0; k < nnIndxLU[n + row]; k++) {
+      int col = nnIndx[nnIndxLU[row] + k];
+      uIndx[fill[col]] = row;
+      uiIndx[fill[col]] = k;                                        /* == which(col, nn list of row) */
+      fill[col]++;
+    }
+  }
+  if (search_type == 1) { /* mkUIndx1 (src/util.cpp:93-111) scans j downwards: descending lists */
+    for (int i = 0; i < n; i++)
+      for (int a = start[i], b = start[i + 1] - 1; a < b; a++, b--) {
+        int t = uIndx[a]; uIndx[a] = uIndx[b]; uIndx[b] = t;
+        t = uiIndx[a]; uiIndx[a] = uiIndx[b]; uiIndx[b] = t;
+      }
+  }
+  free(start); free(fill);
+}
+
 /* updateRep, src/rNNGP.cpp:24-42 (same loop: src/rNNGPReplicated.cpp:187-197): v_i = B_i . v_N(i) + sqrt(F_i) z_i,
  * one rnorm per location in index order. */
 void orc_update_rep(const double *B, const double *F, int n, const int *nnIndx, const int *nnIndxLU, orc_rnorm_fn rnorm,

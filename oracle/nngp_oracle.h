@@ -73,6 +73,10 @@ int orc_rnngp(const double *y, const double *X, int p, int n, int m, const doubl
               double tauSqTuning, double phiTuning, double nuTuning, int nSamples, orc_rnorm_fn rnorm,
               orc_runif_fn runif, double *betaSamples, double *thetaSamples);
 
+/* mkUIndx (src/nn.cpp:25-56): transposed neighbour graph. */
+void orc_mk_u_indx(int n, int m, const int *nnIndx, const int *nnIndxLU, int search_type, int *uIndx, int *uIndxLU,
+                   int *uiIndx);
+
 /* fit.rep / rNNGPReplicated.  orc_update_rep: src/rNNGP.cpp:24-42; orc_rnngp_rep: orc_rnngp plus the
  * replicate draws of src/rNNGP.cpp:300-313 (repIndx per iteration, repSamples n x nRep; NULL, NULL = orc_rnngp);
  * orc_rnngp_replicated: src/rNNGPReplicated.cpp:183-201 (beta nSamples x p column-major, theta nTheta x nSamples). */

@@ -133,6 +133,12 @@ class Port:
     def mk_nn_indx(self, coords, m):
         return self._mk(self.lib.orc_mk_nn_indx, coords, m)
 
+    def mk_u_indx(self, n, m, nnIndx, nnIndxLU, search_type=2):
+        nnIndx = i32(nnIndx); nnIndxLU = i32(nnIndxLU); nI = max(n_indx(n, m), 1)
+        u = np.zeros(nI, dtype=np.int32); ui = np.zeros(nI, dtype=np.int32); lu = np.zeros(2 * n, dtype=np.int32)
+        self.lib.orc_mk_u_indx(C.c_int(n), C.c_int(m), ip(nnIndx), ip(nnIndxLU), C.c_int(search_type), ip(u), ip(lu), ip(ui))
+        return u, lu, ui
+
     def mk_nn_indx_cb(self, coords, m):
         return self._mk(self.lib.orc_mk_nn_indx_cb, coords, m)
 
@@ -385,6 +391,18 @@ def call_mk_nn(sx: _Sexp, coords, m, nThreads=1, symbol="mkNNIndxCB"):
     return nnIndx, nnDist, lu
 
 
+def call_mk_u_indx(sx: _Sexp, n, m, nnIndx, nnIndxLU, search_type=2, symbol="mkUIndx"):
+    """Drive the 8-argument `mkUIndx` .Call entry point (src/nn.cpp:25; R/nn.R:19): outputs written into the arguments."""
+    nnIndx = i32(nnIndx); nnIndxLU = i32(nnIndxLU); nI = max(n_indx(n, m), 1)
+    u = np.zeros(nI, dtype=np.int32); ui = np.zeros(nI, dtype=np.int32); lu = np.zeros(2 * n, dtype=np.int32)
+    args = [sx.scalar_int(n), sx.scalar_int(m), sx.integer(nnIndx), sx.lib.rshim_wrap_int(ip(u), u.size),
+            sx.lib.rshim_wrap_int(ip(lu), lu.size), sx.lib.rshim_wrap_int(ip(ui), ui.size), sx.integer(nnIndxLU),
+            sx.scalar_int(search_type)]
+    sx.call(symbol, args)
+    sx.reset()
+    return u, lu, ui
+
+
 class Ref:
     """The reference's own C++ (unmodified), compiled against rshim. None of this is product code."""
 
@@ -461,6 +479,9 @@ class Ref:
 
     def rnngp_replicated(self, *a, **k):
         return call_rnngp_replicated(self.sx, *a, **k)
+
+    def mk_u_indx(self, *a, **k):
+        return call_mk_u_indx(self.sx, *a, **k)
 
     def cnngp(self, *a, **k):
         return call_cnngp(self.sx, *a, **k)

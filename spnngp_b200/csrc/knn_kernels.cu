@@ -437,6 +437,52 @@ __global__ void __launch_bounds__(128) knn_query_kernel(const double2 *__restric
   for (int k = 0; k < m; ++k) out[(size_t)k * nq + qi] = (k < mm) ? li[k] : -1;
 }
 
+// ---- mkUIndx: the transposed neighbour graph (src/nn.cpp:25-56, crs_csc src/util.cpp:151-185) ------------
+// uIndx lists, for every location i, the locations that have i as a neighbour (ascending), uiIndx the slot i
+// occupies in each of those neighbour lists.  The reference builds it serially; here the nIndx (neighbour id,
+// entry number) pairs are sorted by id with a STABLE radix sort -- entries are numbered row by row, so equal
+// ids stay in ascending row order, which is the reference's order -- and the row / slot of an entry come from
+// the closed form of the ragged layout (src/util.cpp:55-70).
+__global__ void uindx_keys_kernel(const int *__restrict__ nnIndx, long long nIndx, int *__restrict__ keys,
+                                  int *__restrict__ vals, int *__restrict__ counts) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nIndx) return;
+  const int j = nnIndx[e];
+  keys[e] = j;
+  vals[e] = (int)e;
+  atomicAdd(&counts[j], 1);
+}
+
+__global__ void uindx_scatter_kernel(const int *__restrict__ sorted_entry, long long nIndx, int m, int *__restrict__ uIndx,
+                                     int *__restrict__ uiIndx) {
+  const long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= nIndx) return;
+  const long long e = sorted_entry[pos];
+  const long long head = (long long)m * (m - 1) / 2;  // entries of the ragged rows 1 .. m-1
+  long long i, k;
+  if (e >= head) {
+    i = m + (e - head) / m;
+    k = (e - head) % m;
+  } else {  // row i holds entries i(i-1)/2 .. i(i+1)/2 - 1
+    i = (long long)((1.0 + sqrt(1.0 + 8.0 * (double)e)) * 0.5);
+    while (i * (i - 1) / 2 > e) --i;
+    while (i * (i + 1) / 2 <= e) ++i;
+    k = e - i * (i - 1) / 2;
+  }
+  uIndx[pos] = (int)i;
+  uiIndx[pos] = (int)k;
+}
+
+cudaError_t uindx_keys_launch(const int *nnIndx, long long nIndx, int *keys, int *vals, int *counts, cudaStream_t stream) {
+  uindx_keys_kernel<<<(unsigned)((nIndx + 255) / 256), 256, 0, stream>>>(nnIndx, nIndx, keys, vals, counts);
+  return cudaGetLastError();
+}
+
+cudaError_t uindx_scatter_launch(const int *sorted_entry, long long nIndx, int m, int *uIndx, int *uiIndx, cudaStream_t stream) {
+  uindx_scatter_kernel<<<(unsigned)((nIndx + 255) / 256), 256, 0, stream>>>(sorted_entry, nIndx, m, uIndx, uiIndx);
+  return cudaGetLastError();
+}
+
 // ---- launchers ------------------------------------------------------------------------------------
 cudaError_t knn_brute_launch(const double2 *coords, int n, int m, int *nnIndx, double *nnDist, cudaStream_t stream) {
   const int nchunks = (n + kBruteThreads - 1) / kBruteThreads;

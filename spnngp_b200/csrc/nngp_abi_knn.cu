@@ -3,6 +3,7 @@
 // nngp_nn_query stands in for RANN::nn2 (R/generics.R:642).
 #include <cub/cub.cuh>
 
+#include <algorithm>
 #include <vector>
 
 #include "nngp_ctx.h"
@@ -13,6 +14,8 @@ cudaError_t knn_brute_launch(const double2 *coords, int n, int m, int *nnIndx, d
 int knn_cb_head_count(int n, int m);
 cudaError_t knn_cb_launch(const double2 *sxy, const int *sidx, int n, int m, int *headpos, int *nnIndx, double *nnDist,
                           cudaStream_t stream);
+cudaError_t uindx_keys_launch(const int *nnIndx, long long nIndx, int *keys, int *vals, int *counts, cudaStream_t stream);
+cudaError_t uindx_scatter_launch(const int *sorted_entry, long long nIndx, int m, int *uIndx, int *uiIndx, cudaStream_t stream);
 cudaError_t knn_keys_launch(const double2 *coords, int n, double *u, int *idx, cudaStream_t stream);
 cudaError_t knn_gather_launch(const double2 *coords, const int *sidx, int n, double2 *sxy, cudaStream_t stream);
 cudaError_t knn_count_ties_launch(const double *u_sorted, int n, int *count, cudaStream_t stream);
@@ -153,6 +156,60 @@ int nngp_mk_nn_indx(nngp_ctx *c, int n, int m, const double *coords, int search_
     nnIndxLU[n + i] = nn_count(i, m);
   }
   if (n_tie_replayed) *n_tie_replayed = nties;
+  return NNGP_OK;
+}
+
+int nngp_mk_u_indx(nngp_ctx *c, int n, int m, const int *nnIndx, int search_type, int *uIndx, int *uIndxLU, int *uiIndx) {
+  if (!c) return NNGP_EINVAL;
+  if (n < 1 || m < 1 || !nnIndx || !uIndx || !uIndxLU || !uiIndx) return ctx_fail(c, NNGP_EINVAL, "nngp_mk_u_indx: bad arguments");
+  NNGP_CUDA(c, cudaSetDevice(c->device));
+  const long long nIndx = nn_offset(n, m);
+  if (nIndx > 0x7fffffffLL) return ctx_fail(c, NNGP_EINVAL, "nngp_mk_u_indx: more than 2^31 neighbour slots");
+  for (long long e = 0; e < nIndx; e++)
+    if (nnIndx[e] < 0 || nnIndx[e] >= n) return ctx_fail(c, NNGP_EINVAL, "nngp_mk_u_indx: neighbour index out of range");
+  int rc = ensure_stager(c);
+  if (rc) return rc;
+  std::vector<int> counts((size_t)n);
+  if (nIndx > 0) {
+    DevBuf d_nn, d_keys, d_vals, d_keys2, d_vals2, d_counts, d_u, d_ui, tmp;
+    const size_t ib = (size_t)nIndx * sizeof(int);
+    NNGP_CUDA(c, d_nn.alloc(ib)); NNGP_CUDA(c, d_keys.alloc(ib)); NNGP_CUDA(c, d_vals.alloc(ib));
+    NNGP_CUDA(c, d_keys2.alloc(ib)); NNGP_CUDA(c, d_vals2.alloc(ib)); NNGP_CUDA(c, d_u.alloc(ib)); NNGP_CUDA(c, d_ui.alloc(ib));
+    NNGP_CUDA(c, d_counts.alloc((size_t)n * sizeof(int)));
+    std::vector<StageJob> up{{StageJob::RAW, d_nn.p, nnIndx, ib, 0}};
+    NNGP_CUDA(c, c->stager->run(up, nullptr));
+    NNGP_CUDA(c, cudaMemsetAsync(d_counts.p, 0, (size_t)n * sizeof(int), c->stream));
+    NNGP_CUDA(c, uindx_keys_launch(d_nn.as<int>(), nIndx, d_keys.as<int>(), d_vals.as<int>(), d_counts.as<int>(), c->stream));
+    int bits = 1;
+    while ((1LL << bits) < n) ++bits;
+    size_t tmp_bytes = 0;
+    NNGP_CUDA(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys.as<int>(), d_keys2.as<int>(), d_vals.as<int>(),
+                                                 d_vals2.as<int>(), (int)nIndx, 0, bits, c->stream));
+    NNGP_CUDA(c, tmp.alloc(tmp_bytes));
+    NNGP_CUDA(c, cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, d_keys.as<int>(), d_keys2.as<int>(), d_vals.as<int>(),
+                                                 d_vals2.as<int>(), (int)nIndx, 0, bits, c->stream));
+    NNGP_CUDA(c, uindx_scatter_launch(d_vals2.as<int>(), nIndx, m, d_u.as<int>(), d_ui.as<int>(), c->stream));
+    c->launches += 3;
+    NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::vector<StageJob> down{{StageJob::RAW, uIndx, d_u.p, ib, 0}, {StageJob::RAW, uiIndx, d_ui.p, ib, 0},
+                               {StageJob::RAW, counts.data(), d_counts.p, (size_t)n * sizeof(int), 0}};
+    NNGP_CUDA(c, c->stager->run_d2h(down));
+  }
+  long long run = 0;  // offsets: running sum of the per-location counts (crs_csc, src/util.cpp:163-168)
+  for (int i = 0; i < n; i++) {
+    uIndxLU[i] = (int)run;
+    uIndxLU[n + i] = counts[i];
+    run += counts[i];
+  }
+  if (search_type == 1) {  // mkUIndx1 walks j = n-1 .. i+1: the same lists, descending (src/util.cpp:93-111)
+    for (int i = 0; i < n; i++) {
+      int a = uIndxLU[i], b = a + uIndxLU[n + i] - 1;
+      for (; a < b; a++, b--) {
+        std::swap(uIndx[a], uIndx[b]);
+        std::swap(uiIndx[a], uiIndx[b]);
+      }
+    }
+  }
   return NNGP_OK;
 }
 

@@ -282,6 +282,13 @@ class Engine:
         self._check(self.lib.nngp_mk_nn_indx(self.h, n, m, _dp(cf), st, _ip(nnIndx), _dp(nnDist), _ip(lu), C.byref(ties)))
         return nnIndx, nnDist, lu
 
+    def mk_u_indx(self, n, m, nnIndx, search_type=2):
+        """Transposed neighbour graph (reference `mkUIndx`, src/nn.cpp:25): returns uIndx, uIndxLU, uiIndx."""
+        nn = _i32(nnIndx); nI = max(n_indx(n, m), 1)
+        u = np.zeros(nI, dtype=np.int32); ui = np.zeros(nI, dtype=np.int32); lu = np.zeros(2 * n, dtype=np.int32)
+        self._check(self.lib.nngp_mk_u_indx(self.h, n, m, _ip(nn), int(search_type), _ip(u), _ip(lu), _ip(ui)))
+        return u, lu, ui
+
     def nn_query(self, coords, coords0, m):
         """Unordered query kNN, q x m column-major flat (stand-in for RANN::nn2(...)$nn.idx - 1)."""
         cf = colmajor(coords); c0 = colmajor(coords0); n = cf.size // 2; q = c0.size // 2

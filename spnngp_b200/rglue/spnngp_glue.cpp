@@ -6,7 +6,7 @@
 //   rNNGPPredict(17 args)  src/spNNGP.h:36-37,  src/rNNGPPredict.cpp:25-222
 //   mkNNIndx(7 args)       src/nn.h:25,         src/nn.cpp:63-111
 //   mkNNIndxCB(7 args)     src/nn.h:38,         src/nn.cpp:214-257
-// The other six symbols of the package (latent / logit / SLGP models, mkUIndx) are outside the
+// The other five symbols of the package (latent / logit / SLGP models) are outside the
 // hot path this engine accelerates; they are exported as stubs that raise an R error so that a package
 // built with this glue still loads.
 //
@@ -271,7 +271,14 @@ SEXP rNNGPReplicated(SEXP X_r, SEXP p_r, SEXP n_r, SEXP m_r, SEXP coords_r, SEXP
   UNPROTECT(1);
   return out;
 }
-SEXP mkUIndx(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP) { return not_provided("mkUIndx"); }
+// src/nn.cpp:25-56: writes uIndx, uIndxLU, uiIndx in place (R/nn.R:19-23)
+SEXP mkUIndx(SEXP n_r, SEXP m_r, SEXP nnIndx_r, SEXP uIndx_r, SEXP uIndxLU_r, SEXP uiIndx_r, SEXP nnIndxLU_r,
+             SEXP searchType_r) {
+  (void)nnIndxLU_r;
+  check(nngp_mk_u_indx(ctx(), INTEGER(n_r)[0], INTEGER(m_r)[0], INTEGER(nnIndx_r), INTEGER(searchType_r)[0],
+                       INTEGER(uIndx_r), INTEGER(uIndxLU_r), INTEGER(uiIndx_r)));
+  return R_NilValue;
+}
 
 // registration of all 12 symbols (the reference's init.cpp registers 9 and is never run)
 static const R_CallMethodDef CallEntries[] = {

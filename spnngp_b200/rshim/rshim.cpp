@@ -231,6 +231,7 @@ int rshim_call(void *fn, int nargs, SEXP *a, SEXP *out) {
   switch (nargs) {
     case 7: r = ((F7)fn)(A(0), A(1), A(2), A(3), A(4), A(5), A(6)); break;
     case 8: r = ((SEXP(*)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP))fn)(A(0), A(1), A(2), A(3), A(4), A(5), A(6), A(7)); break;
+    case 9: r = ((SEXP(*)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP))fn)(A(0), A(1), A(2), A(3), A(4), A(5), A(6), A(7), A(8)); break;
     case 14: r = ((SEXP(*)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP))fn)(
                  A(0), A(1), A(2), A(3), A(4), A(5), A(6), A(7), A(8), A(9), A(10), A(11), A(12), A(13)); break;
     case 17: r = ((SEXP(*)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP))fn)(

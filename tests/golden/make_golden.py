@@ -120,4 +120,15 @@ for cov, name in ((0, "exp"), (2, "matern")):
     rp[f"{name}_replicated_yrep_seed4"] = ref.rnngp_replicated(prob["X"], prob["coords"], cov, nnIndx, lu, m, bsm, tsm)
 np.savez_compressed(os.path.join(OUT, "rep_n300_m10.npz"), **rp)
 
+# ---- 6. mkUIndx: transposed neighbour graph from the reference, all three search types ----
+ui = {}
+n, m = 600, 10
+prob = make_problem(n, m, seed=20247, domain=0.3)
+nnIndx, _, lu = ref.mk_nn_indx_cb(prob["coords"], m)
+ui.update(n=n, m=m, nnIndx=nnIndx, nnIndxLU=lu)
+for st in (0, 1, 2):
+    u, ulu, uii = ref.mk_u_indx(n, m, nnIndx, lu, search_type=st)
+    ui[f"st{st}_uIndx"] = u; ui[f"st{st}_uIndxLU"] = ulu; ui[f"st{st}_uiIndx"] = uii
+np.savez_compressed(os.path.join(OUT, "uindx_n600_m10.npz"), **ui)
+
 print("golden fixtures written to", OUT, [f for f in os.listdir(OUT) if f.endswith(".npz")])

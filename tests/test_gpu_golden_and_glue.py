@@ -87,6 +87,15 @@ def test_glue_mk_nn_in_place(glue, port):
         assert all(np.array_equal(a, b) for a, b in zip(got, ref))
 
 
+def test_glue_mk_u_indx_against_golden(glue):
+    """`mkUIndx` .Call symbol: in-place outputs equal the reference's (uindx_n600_m10.npz)."""
+    d = np.load(os.path.join(G, "uindx_n600_m10.npz"))
+    for st in (0, 1, 2):
+        u, lu, ui = po.call_mk_u_indx(glue, int(d["n"]), int(d["m"]), d["nnIndx"], d["nnIndxLU"], search_type=st)
+        assert np.array_equal(u, d[f"st{st}_uIndx"]) and np.array_equal(lu, d[f"st{st}_uIndxLU"])
+        assert np.array_equal(ui, d[f"st{st}_uiIndx"])
+
+
 def test_glue_error_text_matches_reference(glue, port):
     prob = make_problem(60, 5, seed=6, port=port)
     coords = prob["coords"].copy(); coords[30] = coords[29]; coords[31] = coords[29]
@@ -97,7 +106,7 @@ def test_glue_error_text_matches_reference(glue, port):
         po.call_rnngp(glue, prob["y"], prob["X"], coords, 0, nnIndx, lu, 5, [2.0, 5.0], [2.0, 1.0], [3.0, 300.0], None,
                       starting, tuning, 3)
     with pytest.raises(RuntimeError, match="outside the hot path"):
-        glue.call("mkUIndx", [glue.scalar_int(1)] * 8)
+        glue.call("PGLogit", [glue.scalar_int(1)] * 9)
 
 
 def test_glue_vs_live_reference_when_built(glue, ref, port):

@@ -104,3 +104,21 @@ def test_nn_query_matches_exhaustive(engine, port, n, q, m):
                                   out.ctypes.data_as(c_int_p))
     assert st == 0
     assert np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("n,m", [(5000, 15), (600, 10), (40, 32), (300, 1), (200000, 15)])
+def test_u_indx_bit_exact(engine, port, n, m):
+    """nngp_mk_u_indx (reference `mkUIndx`, src/nn.cpp:25-56) vs the oracle, all three `u.search.type` values."""
+    rng = np.random.default_rng(n + m)
+    c = rng.random((n, 2)); c = c[np.argsort(c[:, 0], kind="stable")]
+    idx, _, lu = engine.mk_nn_indx(c, m, "cb")
+    for st in ((0, 1, 2) if n <= 5000 else (2,)):
+        u, ulu, ui = engine.mk_u_indx(n, m, idx, search_type=st)
+        uo, uluo, uio = port.mk_u_indx(n, m, idx, lu, search_type=st)
+        nI = len(idx) if n > 1 else 0
+        assert np.array_equal(u[:nI], uo[:nI]) and np.array_equal(ulu, uluo) and np.array_equal(ui[:nI], uio[:nI])
+    # definition: location u[k] has i as its ui[k]-th neighbour
+    u, ulu, ui = engine.mk_u_indx(n, m, idx)
+    for i in rng.integers(0, n, 50):
+        for k in range(ulu[i], ulu[i] + ulu[n + i]):
+            assert idx[lu[u[k]] + ui[k]] == i

@@ -97,3 +97,13 @@ def test_conj_and_predict_golden(port):
     y0, st = port.predict(d["X"], d["y"], d["coords"], m, d["X0"], d["coords0"], d["nn0"], d["pred_beta"],
                           d["pred_theta"], 0, z)
     assert st == 0 and np.allclose(y0, d["pred_y0_seed7"], rtol=1e-11, atol=1e-12)
+
+
+def test_u_indx_golden(port):
+    """`mkUIndx` of the port vs the reference's committed output (uindx_n600_m10.npz), all three search types."""
+    d = np.load(os.path.join(G, "uindx_n600_m10.npz"))
+    n, m = int(d["n"]), int(d["m"])
+    for st in (0, 1, 2):
+        u, lu, ui = port.mk_u_indx(n, m, d["nnIndx"], d["nnIndxLU"], search_type=st)
+        assert np.array_equal(u, d[f"st{st}_uIndx"]) and np.array_equal(lu, d[f"st{st}_uIndxLU"])
+        assert np.array_equal(ui, d[f"st{st}_uiIndx"])

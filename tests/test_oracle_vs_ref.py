@@ -53,6 +53,18 @@ def test_chain_port_equals_ref(port, ref):
     assert np.allclose(t, out["p_theta_samples"], rtol=1e-10) and np.allclose(b, out["p_beta_samples"], rtol=1e-8, atol=1e-10)
 
 
+@pytest.mark.parametrize("n,m", [(700, 10), (40, 15), (300, 1), (9, 3)])
+def test_u_indx_port_equals_ref(port, ref, n, m):
+    """`mkUIndx` (transposed neighbour graph), the reference's three search types (1 lists descending) vs the port."""
+    prob = make_problem(n, m, seed=40 + m, port=port)
+    for st in (0, 1, 2):
+        want = port.mk_u_indx(n, m, prob["nnIndx"], prob["nnIndxLU"], search_type=st)
+        got = ref.mk_u_indx(n, m, prob["nnIndx"], prob["nnIndxLU"], search_type=st)
+        nI = len(prob["nnIndx"])
+        assert np.array_equal(got[0][:nI], want[0][:nI]) and np.array_equal(got[1], want[1])
+        assert np.array_equal(got[2][:nI], want[2][:nI])
+
+
 def test_replicates_port_equals_ref(port, ref):
     """fit.rep inside `rNNGP` and the `rNNGPReplicated` entry point: reference vs port, same seed."""
     prob = make_problem(350, 8, seed=15, port=port, domain=0.27)
