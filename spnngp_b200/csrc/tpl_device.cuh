@@ -117,7 +117,7 @@ __device__ __forceinline__ void tpl_chol_pair(double *A, double *cv, double *dv,
       else a1[i] = cv[J1 * 32];
     }
   }
-#pragma unroll
+#pragma unroll  // (a rolled k loop, unroll 2 or 4, shrinks the code 3x but measured 3-8% slower: less load hoisting)
   for (int k = 0; k < J0; ++k) {
     const double v0 = V_(J0, k);
     a0[J0] = fma(-v0, v0, a0[J0]);
