@@ -172,6 +172,8 @@ void nngp_destroy(nngp_ctx *c) {
   delete c->stager;
   if (c->d_rep_perm) cudaFree(c->d_rep_perm);
   if (c->d_rep_levoff) cudaFree(c->d_rep_levoff);
+  if (c->d_rep_z) cudaFree(c->d_rep_z);
+  if (c->d_rep_v) cudaFree(c->d_rep_v);
   if (c->h_z) cudaFreeHost(c->h_z);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;

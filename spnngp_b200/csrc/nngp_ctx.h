@@ -51,6 +51,7 @@ struct nngp_ctx {
   bool rep_ready = false;
   int rep_levels = 0;
   int *d_rep_perm = nullptr, *d_rep_levoff = nullptr;
+  double *d_rep_z = nullptr, *d_rep_v = nullptr;  // n doubles each: the normals, the solved v / y.rep
   double *h_z = nullptr;  // pinned, n doubles
   size_t h_z_cap = 0;
   nngp::HostStager *stager = nullptr;  // pinned upload ring of nngp_set_data (host_stage.h)

@@ -142,6 +142,11 @@ int rep_prepare(nngp_ctx *c) {
   NNGP_CUDA(c, cudaMemcpy(c->d_rep_perm, perm.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
   NNGP_CUDA(c, cudaMemcpy(c->d_rep_levoff, off.data(), ((size_t)depth + 1) * sizeof(int), cudaMemcpyHostToDevice));
   c->rep_levels = depth;
+  if (c->d_rep_z) cudaFree(c->d_rep_z);
+  if (c->d_rep_v) cudaFree(c->d_rep_v);
+  c->d_rep_z = c->d_rep_v = nullptr;
+  NNGP_CUDA(c, cudaMalloc(&c->d_rep_z, (size_t)n * sizeof(double)));
+  NNGP_CUDA(c, cudaMalloc(&c->d_rep_v, (size_t)n * sizeof(double)));
   if (c->h_z_cap < (size_t)n) {
     if (c->h_z) cudaFreeHost(c->h_z);
     c->h_z = nullptr;
@@ -161,8 +166,8 @@ int rep_draw(nngp_ctx *c, int slot, const double *beta, const double *z, double 
   int rc = rep_prepare(c);
   if (rc) return rc;
   const int n = c->n;
-  double *d_z = c->d_resid[2], *d_v = c->d_resid[3];  // batch entries 2, 3 are idle outside 4-set launches
-  if (c->p == 0 || !d_z || !d_v) return ctx_fail(c, NNGP_ESTATE, "replicates need a model with covariates");
+  double *d_z = c->d_rep_z, *d_v = c->d_rep_v;
+  if (c->p == 0) return ctx_fail(c, NNGP_ESTATE, "replicates need a model with covariates");
   if (z != c->h_z) memcpy(c->h_z, z, (size_t)n * sizeof(double));
   NNGP_CUDA(c, cudaMemcpyAsync(d_z, c->h_z, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   if (c->m <= 16)
