@@ -113,6 +113,12 @@ int nngp_set_data(nngp_ctx *ctx, int n, int m, int p, const double *coords, cons
 int nngp_bf_loglik(nngp_ctx *ctx, int cov_model, int nbatch, const double *theta, const double *beta,
                    const int *slots, double *out);
 
+/* The same launch with the vector to whiten given directly (n doubles) instead of r = X beta - y: Q = u' C~^-1 u.
+ * With tau.sq = 0 and u = w this is the latent model's likelihood piece -- its tau.sq-free updateBF plus the
+ * OpenMP reductions over b_i^2 / F_i and log F_i (src/sNNGP.cpp:24-65, 323-400). */
+int nngp_bf_loglik_vec(nngp_ctx *ctx, int cov_model, int nbatch, const double *theta, const double *u,
+                       const int *slots, double *out);
+
 /* Q(B,F,r,r) only, from the B,F already stored in `slot` (the double-buffered sampler uses this for
  * the unchanged current theta instead of re-solving, SURVEY §3.1 note).  out[0] = Q over the shard. */
 int nngp_q_resid(nngp_ctx *ctx, int slot, const double *beta, double *out);

@@ -360,6 +360,29 @@ static void share_resid(nngp_ctx *c, BfLaunch *P) {
       }
 }
 
+// after the launch: sum over ranks if sharded, one stream sync, unpack (logDet, Q) per set, report failures
+static int finish_bf(nngp_ctx *c, int nbatch, bool have_q, double *out) {
+  const double *res = c->h_out;
+  if (c->comm) {  // sum (logDet, Q, fail flag) over the ranks on the device, then one small copy back
+    int rc = comm_allreduce_dev(c, c->d_red, 3 * nbatch);
+    if (rc) return rc;
+    NNGP_CUDA(c, cudaMemcpyAsync(c->h_red, c->d_red, 3 * nbatch * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    res = c->h_red;
+  }
+  NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
+  int status = 0;
+  bool any_rank_failed = false;
+  for (int b = 0; b < nbatch; b++) {
+    out[2 * b] = res[3 * b];
+    out[2 * b + 1] = have_q ? res[3 * b + 1] : 0.0;
+    if (res[3 * b + 2] > 0.0) any_rank_failed = true;
+    if (c->h_fail[b] != INT_MAX && (status == 0 || c->h_fail[b] < status)) status = c->h_fail[b];
+  }
+  if (status == 0 && any_rank_failed) status = INT_MAX;  // the failing location lives on another rank
+  if (status > 0) return ctx_fail(c, status, "c++ error: dpotrf failed (neighbour covariance not positive definite)");
+  return NNGP_OK;
+}
+
 int nngp_bf_loglik(nngp_ctx *c, int cov, int nbatch, const double *theta, const double *beta, const int *slots,
                    double *out) {
   if (!c || !theta || !out) return NNGP_EINVAL;
@@ -371,25 +394,31 @@ int nngp_bf_loglik(nngp_ctx *c, int cov, int nbatch, const double *theta, const 
   share_resid(c, &P);
   rc = enqueue_bf(c, cov, P, grid, beta != nullptr);
   if (rc) return rc;
-  const double *res = c->h_out;
-  if (c->comm) {  // sum (logDet, Q, fail flag) over the ranks on the device, then one small copy back
-    rc = comm_allreduce_dev(c, c->d_red, 3 * nbatch);
-    if (rc) return rc;
-    NNGP_CUDA(c, cudaMemcpyAsync(c->h_red, c->d_red, 3 * nbatch * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    res = c->h_red;
+  return finish_bf(c, nbatch, beta != nullptr, out);
+}
+
+int nngp_bf_loglik_vec(nngp_ctx *c, int cov, int nbatch, const double *theta, const double *u, const int *slots,
+                       double *out) {
+  if (!c || !theta || !u || !out) return NNGP_EINVAL;
+  NNGP_CUDA(c, cudaSetDevice(c->device));
+  if (c->n == 0 || !c->has_nn) return ctx_fail(c, NNGP_ESTATE, "likelihood requested before nngp_set_data (with neighbours)");
+  int rc = ensure_dev(c, c->d_resid[0], c->cap[5], (size_t)c->n);
+  if (rc) return rc;
+  if (!c->stager) {
+    c->stager = new HostStager();
+    NNGP_CUDA(c, c->stager->init(c->device));
   }
   NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
-  int status = 0;
-  bool any_rank_failed = false;
-  for (int b = 0; b < nbatch; b++) {
-    out[2 * b] = res[3 * b];
-    out[2 * b + 1] = beta ? res[3 * b + 1] : 0.0;
-    if (res[3 * b + 2] > 0.0) any_rank_failed = true;
-    if (c->h_fail[b] != INT_MAX && (status == 0 || c->h_fail[b] < status)) status = c->h_fail[b];
-  }
-  if (status == 0 && any_rank_failed) status = INT_MAX;  // the failing location lives on another rank
-  if (status > 0) return ctx_fail(c, status, "c++ error: dpotrf failed (neighbour covariance not positive definite)");
-  return NNGP_OK;
+  std::vector<StageJob> up{{StageJob::RAW, c->d_resid[0], u, (size_t)c->n * sizeof(double), 0}};
+  NNGP_CUDA(c, c->stager->run(up, nullptr));
+  BfLaunch P;
+  int grid = 0;
+  rc = prepare_bf(c, cov, nbatch, theta, nullptr, slots, true, &P, &grid);
+  if (rc) return rc;
+  for (int b = 0; b < nbatch; b++) P.th[b].resid = c->d_resid[0];  // every set whitens the same vector
+  rc = enqueue_bf(c, cov, P, grid, false);
+  if (rc) return rc;
+  return finish_bf(c, nbatch, true, out);
 }
 
 int nngp_time_bf_loglik(nngp_ctx *c, int cov, int nbatch, const double *theta, const double *beta, int iters,

@@ -123,6 +123,19 @@ class Engine:
         self._check(self.lib.nngp_bf_loglik(self.h, cov, nb, _dp(th), bp, _ip(sl) if sl is not None else None, _dp(out)))
         return out
 
+    def bf_loglik_vec(self, cov, thetas, u, slots=None):
+        """As bf_loglik with the vector to whiten given directly: returns (nb, 2) = (sum log F, u' C~^-1 u).
+        tau.sq = 0 and u = w is the latent model's likelihood piece (src/sNNGP.cpp:24-65, 323-400)."""
+        t2 = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
+        th = np.zeros((t2.shape[0], 4)); th[:, : t2.shape[1]] = t2
+        nb = th.shape[0]
+        uf = _f64(u)
+        assert uf.size == self.n
+        sl = _i32(slots) if slots is not None else None
+        out = np.zeros((nb, 2))
+        self._check(self.lib.nngp_bf_loglik_vec(self.h, cov, nb, _dp(th), _dp(uf), _ip(sl) if sl is not None else None, _dp(out)))
+        return out
+
     def time_bf_loglik(self, cov, thetas, betas=None, iters=10, flush_l2=False):
         th = np.zeros((np.atleast_2d(thetas).shape[0], 4))
         t2 = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
