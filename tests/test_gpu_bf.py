@@ -219,3 +219,30 @@ def test_latent_likelihood_piece(engine, port, cov, theta):
     assert relerr(F, Fo) < tol and relerr_norm(B[: len(prob["nnIndx"])], Bo[: len(prob["nnIndx"])]) < tol
     assert abs(out[0, 0] - ld) <= tol * max(abs(ld), 1.0) and abs(out[0, 1] - a) <= tol * abs(a)
     assert np.array_equal(out[0], out[1])
+
+
+@pytest.mark.parametrize("p,m", [(1, 8), (4, 15), (7, 10), (12, 20)])
+def test_cross_forms_other_widths(engine, port, p, m):
+    """All cross forms for p + 1 = 2, 5, 8, 13 columns (one to four 256-bit row loads per neighbour) and the sampler's
+    beta update built on them, against the oracle's Q on every pair of columns."""
+    n = 2500
+    rng = np.random.default_rng(100 + p)
+    prob = make_problem(n, m, seed=60 + p, port=port, p=min(p, 4), domain=0.7)
+    X = np.column_stack([prob["X"]] + [rng.standard_normal(n) for _ in range(p - prob["X"].shape[1])])[:, :p]
+    engine.set_data(prob["coords"], prob["nnIndx"], prob["nnIndxLU"], X, prob["y"], m)
+    theta = [5.0, 1.0, 6.0]
+    engine.bf_loglik(0, [theta], None, slots=[0])
+    Bo, Fo, _, _ = port.update_bf(prob["coords"], prob["nnIndx"], prob["nnIndxLU"], n, m, theta, 0)
+    S = engine.q_forms(0)
+    cols = [X[:, j].copy() for j in range(p)] + [prob["y"]]
+    scale = abs(S[p, p])
+    for a in range(p + 1):
+        for b in range(a, p + 1):
+            q = port.q(Bo, Fo, cols[a], cols[b], n, prob["nnIndx"], prob["nnIndxLU"])
+            assert abs(S[a, b] - q) <= 1e-10 * max(abs(q), 1e-6 * scale) and S[a, b] == S[b, a]
+    beta = rng.standard_normal(p)
+    r = X @ beta - prob["y"]
+    q = port.q(Bo, Fo, r, r, n, prob["nnIndx"], prob["nnIndxLU"])
+    assert abs(engine.q_resid(0, beta) - q) <= 1e-10 * abs(q)
+    out = engine.bf_loglik(0, [theta], [beta], slots=[1])
+    assert abs(out[0, 1] - q) <= 1e-10 * abs(q)
