@@ -87,14 +87,14 @@ inline void gauss_laguerre_rule(int n, long double a, double *t, double *w) {
       }
       if (mm == l) break;
       long double g = (d[l + 1] - d[l]) / (2.0L * e[l]);
-      long double r = hypotl(g, 1.0L);
+      long double r = sqrtl(g * g + 1.0L);
       g = d[mm] - d[l] + e[l] / (g + copysignl(r, g));
       long double sn = 1.0L, cs = 1.0L, pp = 0.0L;
       int i = mm - 1;
       for (; i >= l; i--) {
         long double f = sn * e[i];
         const long double b = cs * e[i];
-        r = hypotl(f, g);
+        r = sqrtl(f * f + g * g);  // entries are O(n): no overflow guard needed (hypotl is 5x slower)
         e[i + 1] = r;
         if (r == 0.0L) {
           d[i + 1] -= pp;

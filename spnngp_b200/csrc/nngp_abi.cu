@@ -307,7 +307,16 @@ static int prepare_bf(nngp_ctx *c, int cov, int nbatch, const double *theta, con
     th.mat = nullptr;
     if (cov == NNGP_COV_MATERN) {
       if (!(t[3] > 0.0)) return ctx_fail(c, NNGP_EINVAL, "matern nu must be > 0");
-      matern_prepare(t[3], &c->h_mat[b]);
+      int hit = -1;
+      for (int k = 0; k < 4; k++)
+        if (c->mat_cache[k].nu == t[3]) hit = k;
+      if (hit < 0) {  // 10 us of host time (the Gauss-Laguerre rule): skipped for a smoothness seen recently
+        hit = c->mat_cache_next;
+        c->mat_cache_next = (c->mat_cache_next + 1) & 3;
+        matern_prepare(t[3], &c->mat_cache[hit].mc);
+        c->mat_cache[hit].nu = t[3];
+      }
+      c->h_mat[b] = c->mat_cache[hit].mc;
       matern_series_params(c->h_mat[b], &th.ms);
       th.mat = c->d_mat + b;
     }

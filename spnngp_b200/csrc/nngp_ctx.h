@@ -57,6 +57,12 @@ struct nngp_ctx {
   nngp::HostStager *stager = nullptr;  // pinned upload ring of nngp_set_data (host_stage.h)
   size_t cap[16] = {};  // capacities (bytes) of the grow-only model buffers, see nngp_set_data
   nngp::MaternConsts *h_mat = nullptr;
+  // last few prepared smoothness values (the sampler re-evaluates its current theta every iteration)
+  struct MatCache {
+    double nu = -1.0;
+    nngp::MaternConsts mc;
+  } mat_cache[4];
+  int mat_cache_next = 0;
 
   // multi-GPU: NCCL communicator over the ranks of a sharded fit (nngp_comm_init); when set, the
   // results of nngp_bf_loglik / nngp_q_resid / nngp_q_forms are summed over the ranks on the device

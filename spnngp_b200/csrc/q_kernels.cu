@@ -25,6 +25,48 @@ __global__ void __launch_bounds__(256) resid_kernel(const double *__restrict__ X
   }
 }
 
+// ---- sums of V values per lane over groups of LP lanes, by a butterfly that HALVES the value count at each step ----
+// Step with mask M: a lane keeps the upper half of its values if (lane & M), the lower half otherwise, and adds the
+// partner's copy of the same half: V/2 shuffles instead of V.  After log2(LP) steps the V sums are spread over the
+// lanes: V - 1 (+ a few) 64-bit shuffles in place of V log2(LP) -- shuffles run through the LSU data pipe, which is
+// what bounded these passes (ncu: l1tex data-pipe wavefronts 81%, SHFL on short scoreboard / mio).
+// On return lane l holds, in v[0 .. max(1, V/LP)), the sums with original indices
+//   reduce_index<V, LP>(l) + j,  j < max(1, V/LP)       (replicated over lanes that agree in their low log2(V) bits).
+template <int V, int LP>
+__device__ __forceinline__ int reduce_index(int lane) {
+  int idx = 0, c = V, s = 0;
+#pragma unroll
+  for (int M = 1; M < LP; M <<= 1, ++s) {
+    if (c > 1) {
+      c >>= 1;
+      idx |= ((lane >> s) & 1) * c;
+    }
+  }
+  return idx;
+}
+
+template <int V, int LP>
+__device__ __forceinline__ void lanes_reduce(double (&v)[V], int lane) {
+  int c = V;  // compile-time after unrolling
+#pragma unroll
+  for (int M = 1; M < LP; M <<= 1) {
+    if (c > 1) {
+      c >>= 1;
+      const bool upper = (lane & M) != 0;
+#pragma unroll
+      for (int j = 0; j < V / 2; ++j) {
+        if (j < c) {
+          const double send = upper ? v[j] : v[j + c];
+          const double keep = upper ? v[j + c] : v[j];
+          v[j] = keep + __shfl_xor_sync(0xffffffffu, send, M, LP);
+        }
+      }
+    } else {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], M, LP);
+    }
+  }
+}
+
 // ---- Q(B,F,r,r) over a shard ----------------------------------------------------------------------
 // UN locations per lane group and trip: their id/weight loads, then their gathers, go out together (with one
 // location per trip the id -> gather chain leaves too few bytes in flight to fill HBM: 156 us vs 55 us at n = 10^6).
@@ -51,23 +93,18 @@ __global__ void __launch_bounds__(256) q_resid_kernel(const double *__restrict__
       b[u] = ok ? __ldg(&B[off + lane]) : 0.0;
       id[u] = ok ? __ldg(&nnIndx[off + lane]) : 0;
     }
-    // lane u of the group finishes row u (one division per trip instead of UN predicated ones)
-    const long long imine = base + (long long)lane * G + g;
+    // lanes 0..UN-1 of the group each finish one row: the one whose sum the butterfly leaves with them
+    const int umine = reduce_index<UN, LP>(lane);
+    const long long imine = base + (long long)umine * G + g;
     const bool mine = lane < UN && imine < loc_end;
     const double ri = mine ? __ldg(&resid[imine]) : 0.0;
     const double fi = mine ? __ldg(&F[imine]) : 1.0;
     double a[UN];
 #pragma unroll
     for (int u = 0; u < UN; ++u) a[u] = b[u] * __ldg(&resid[id[u]]);  // weight 0 for missing neighbours
-    double am = 0.0;
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-#pragma unroll
-      for (int s = LP / 2; s >= 1; s >>= 1) a[u] += __shfl_xor_sync(0xffffffffu, a[u], s, LP);  // every lane: the row's sum
-      am = (lane == u) ? a[u] : am;
-    }
+    lanes_reduce<UN, LP>(a, lane);
     if (mine) {
-      const double e = ri - am;
+      const double e = ri - a[0];
       qsum += e * e / fi;
     }
   }
@@ -163,33 +200,31 @@ __global__ void __launch_bounds__(256) q_forms_kernel(const double *__restrict__
       b[u] = ok ? __ldg(&B[off + lane]) : 0.0;
       idx[u] = ok ? __ldg(&nnIndx[off + lane]) : 0;
     }
-    // lane u of the group finishes row u: one rsqrt per row and trip
-    const int smine = s0 + lane * G + g;
-    const long long imine = chunk0 + smine;
-    const bool own_row = lane < UN;
-    const bool mine = own_row && imine < loc_end;
-    const double rsq = mine ? rsqrt(__ldg(&F[imine])) : 0.0;
-    // KC columns at a time: all their gathers (KC x UN per lane) are issued before the first reduction -- with one
-    // column per trip the pass waited one L2 round trip per column (ncu: 75% of the samples on long scoreboard)
-    constexpr int KC = 4;
+    // KC columns at a time: their UN x KC products per lane are summed over the group by one halving butterfly,
+    // which leaves sum (row u, column cc) with lane reduce_index(lane) = u KC + cc; that lane finishes the entry.
+    constexpr int KC = 4, V = UN * KC, HELD = (V / LP > 1) ? V / LP : 1;
     const int KS = xy_row_stride(p);
+    const int vidx = reduce_index<V, LP>(lane);
+    const int umine = vidx / KC, ccmine = vidx % KC;  // HELD consecutive columns of row umine, starting at ccmine
+    const int smine = s0 + umine * G + g;
+    const long long imine = chunk0 + smine;
+    const bool fin = lane < V;  // lanes V.. of a 32-lane group hold replicas
+    const bool mine = fin && imine < loc_end;
+    const double rsq = mine ? rsqrt(__ldg(&F[imine])) : 0.0;
     for (int c0 = 0; c0 < K; c0 += KC) {
-      double a[UN][KC], own[KC] = {0.0, 0.0, 0.0, 0.0};
+      double prod[V], row[KC], own[HELD];
 #pragma unroll
-      for (int u = 0; u < UN; ++u) ldg256(&Xy[(size_t)idx[u] * KS + c0], a[u]);  // row 0 with weight 0: missing neighbour
-      if (mine) ldg256(&Xy[(size_t)imine * KS + c0], own);
+      for (int h = 0; h < HELD; ++h) own[h] = (mine && c0 + ccmine + h < K) ? __ldg(&Xy[(size_t)imine * KS + c0 + ccmine + h]) : 0.0;
 #pragma unroll
-      for (int cc = 0; cc < KC; ++cc) {
-        double am = 0.0;
+      for (int u = 0; u < UN; ++u) {
+        ldg256(&Xy[(size_t)idx[u] * KS + c0], row);  // row 0 with weight 0: missing neighbour
 #pragma unroll
-        for (int u = 0; u < UN; ++u) {
-          double t = b[u] * a[u][cc];
-#pragma unroll
-          for (int sh = LP / 2; sh >= 1; sh >>= 1) t += __shfl_xor_sync(0xffffffffu, t, sh, LP);
-          am = (lane == u) ? t : am;
-        }
-        if (own_row && c0 + cc < K) W[(c0 + cc) * CH + smine] = (own[cc] - am) * rsq;  // 0 beyond the shard's end
+        for (int cc = 0; cc < KC; ++cc) prod[u * KC + cc] = b[u] * row[cc];
       }
+      lanes_reduce<V, LP>(prod, lane);
+#pragma unroll
+      for (int h = 0; h < HELD; ++h)
+        if (fin && c0 + ccmine + h < K) W[(c0 + ccmine + h) * CH + smine] = (own[h] - prod[h]) * rsq;  // 0 beyond the shard
     }
   }
   __syncthreads();
