@@ -338,7 +338,7 @@ def run_b200(args, rank, world, local_rank):
         roofline = {
             "bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
             "traffic": traffic_from_profile(n, m, args.cov),
-            "kernel": "bf_ws_kernel" if 6 <= m <= 16 else ("bf_tpl_kernel" if m <= 5 else "bf_kernel"),
+            "kernel": "bf_ws_kernel" if 6 <= m <= 24 else ("bf_tpl_kernel" if m <= 5 else "bf_kernel"),
             "kernel_ms": k_ms, "locations_per_launch": nloc, "updateBF_loc_per_s": loc_s,
             "flops_per_location": fl, "bytes_per_location": bytes_per_location(m),
             "peak_source": "FP64 FMA peak measured live by nngp_fp64_peak (DFMA micro-benchmark; MEASURED_PEAKS.json has no "

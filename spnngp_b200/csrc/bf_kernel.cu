@@ -343,6 +343,7 @@ cudaError_t coop_launch(const BfLaunch &P, int cov, int grid_x, cudaStream_t str
 int tpl_capacity_for_m(int m);
 int tpl_grid_for(int m, long long nloc, int sms);
 cudaError_t tpl_launch(const BfLaunch &P, int cov, int grid_x, cudaStream_t stream);
+int ws_capacity_for_m(int m);
 int ws_grid_for(int m, long long nloc, int sms);
 cudaError_t ws_launch(const BfLaunch &P, int cov, int grid_x, cudaStream_t stream);
 
@@ -363,12 +364,15 @@ static int kernel_for(int m, int cov) {
     }
   }
   (void)cov;
-  const bool small = tpl_capacity_for_m(m) > 0;
-  if (forced >= 0 && (forced == KERNEL_COOP || small)) return forced;
-  if (!small) return KERNEL_COOP;
+  const bool tpl_ok = tpl_capacity_for_m(m) > 0, ws_ok = ws_capacity_for_m(m) > 0;
+  if (forced == KERNEL_COOP) return forced;
+  if (forced == KERNEL_TPL && tpl_ok) return forced;
+  if (forced == KERNEL_WS && ws_ok) return forced;
   // small tiles do not amortise the producer/consumer hand-off (measured at n = 10^6, exponential: m = 5 0.112 ms
-  // single-role vs 0.133 ms specialised; m = 8 0.243 vs 0.223; m = 10 0.377 vs 0.313 ms)
-  return tpl_capacity_for_m(m) >= 8 ? KERNEL_WS : KERNEL_TPL;
+  // single-role vs 0.133 ms specialised; m = 8 0.243 vs 0.223; m = 10 0.377 vs 0.313 ms); beyond m = 24 two stages of
+  // the specialised kernel no longer fit an SM's shared memory
+  if (m <= 5) return KERNEL_TPL;
+  return ws_ok ? KERNEL_WS : KERNEL_COOP;
 }
 
 int bf_grid_any(int m, int cov, long long nloc, int sms) {

@@ -26,7 +26,7 @@ extern __shared__ __align__(16) unsigned char tpl_smem[];
 // strict lower triangle (dst = packed index), the m entries of c (l = MC: the location's own site,
 // dst = a row of cv) and is padded to a multiple of the batch width with harmless duplicates that
 // write into dv (overwritten by the factorisation afterwards).
-constexpr int kTplMaxEnt = 160;
+constexpr int kTplMaxEnt = 320;  // m(m-1)/2 + m entries at m = 24, padded to a batch
 template <int COV>
 constexpr int kTplBatch = (COV == NNGP_COV_MATERN) ? 4 : 8;  // entries evaluated together (independent chains)
 
