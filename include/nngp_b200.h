@@ -188,6 +188,25 @@ int nngp_cnngp(nngp_ctx *ctx, int cov_model, int g, const double *thetaAlpha, co
                int n0, const double *X0, const double *coords0, const int *nnIndx0, double *betaHat,
                double *ab, double *bBInv, double *bb, double *y0Hat, double *y0HatVar);
 
+/* `cNNGP` on held-out sites, scored on the device (the k-fold body of R/spConjNNGP.R:322-334 with crps / rmspe of
+ * R/util.R:247-255): the n0 x g predictions never leave the GPU.  y0: the n0 held-out responses.
+ * crps[k] = mean(-sd (1/sqrt(pi) - 2 dnorm(z) - z (2 pnorm(z) - 1))), rmspe[k] = sqrt(mean((y0 - y0.hat)^2)), k < g. */
+int nngp_cnngp_score(nngp_ctx *ctx, int cov_model, int g, const double *thetaAlpha, const double sigmaSqIG[2],
+                     int n0, const double *X0, const double *coords0, const int *nnIndx0, const double *y0,
+                     double *crps, double *rmspe);
+
+/* The whole k-fold loop of spConjNNGP (R/spConjNNGP.R:286-349) in one call, for the parameter sets
+ * [set_begin, set_end) of thetaAlpha (nTheta x g): per fold, drop the hold-out rows, rebuild the ordered neighbour
+ * search on the rest (mkNNIndx / mkNNIndxCB, search_type), find the m nearest fitted sites of every held-out site
+ * (RANN::nn2 -> nngp_nn_query), fit and score.  y, X (n x p), coords (n x 2) are in NNGP order (R/spConjNNGP.R:116-118).
+ * hoIdx: k_fold x n_ho hold-out row ids, 0-based, ascending within a fold (R: sort(sample(1:n, floor(n/k.fold))) - 1,
+ * drawn by the caller so R's RNG stream is the reference's).  scores: g x 2 column-major like `k.fold.scores`
+ * (column 0 rmspe, column 1 crps), each the mean over the folds; rows outside [set_begin, set_end) are zero, so the
+ * shards of a multi-GPU run (one context per GPU, disjoint set ranges) simply add.  Replaces the data of nngp_set_data. */
+int nngp_conj_kfold(nngp_ctx *ctx, int n, int p, int m, const double *y, const double *X, const double *coords,
+                    int cov_model, int g, const double *thetaAlpha, const double sigmaSqIG[2], int search_type,
+                    int k_fold, int n_ho, const int *hoIdx, int set_begin, int set_end, double *scores);
+
 /* `rNNGPPredict` (src/rNNGPPredict.cpp:25-222): posterior predictive draws at q sites.
  * betaSamples p x nSamples, thetaSamples nTheta x nSamples, nnIndx0 q x m column-major,
  * z: q*nSamples standard normals in the reference's single-thread order z[i*nSamples+s]

@@ -488,3 +488,48 @@ class Ref:
 
     def predict(self, *a, **k):
         return call_predict(self.sx, *a, **k)
+
+
+# ---- k-fold scoring of the conjugate model: a restatement of the reference's R layer --------------------
+def crps(y, y_hat, y_var):
+    """R/util.R:247-251.  dnorm / pnorm are R nmath in the reference; scipy's ndtr stands in (unpinned, ~1e-16)."""
+    from scipy.special import ndtr
+    y = np.asarray(y, dtype=np.float64); sd = np.sqrt(np.asarray(y_var, dtype=np.float64))
+    z = (y - np.asarray(y_hat, dtype=np.float64)) / sd
+    dn = np.exp(-0.5 * z * z) / np.sqrt(2.0 * np.pi)
+    return float(np.mean(-sd * (1.0 / np.sqrt(np.pi) - 2.0 * dn - z * (2.0 * ndtr(z) - 1.0))))
+
+
+def rmspe(y, y_hat):
+    """R/util.R:253-255."""
+    d = np.asarray(y, dtype=np.float64) - np.asarray(y_hat, dtype=np.float64)
+    return float(np.sqrt(np.mean(d * d)))
+
+
+def conj_kfold(backend, port, y, X, coords, m, cov, theta_alpha, sigmaSqIG, ho_idx, search_type="cb"):
+    """The k-fold loop of spConjNNGP, R/spConjNNGP.R:286-349, with `backend` (Port or Ref) supplying mkNNIndx[CB] and
+    cNNGP and `port.nn_query` standing in for RANN::nn2 (:311).  ho_idx: k_fold x n_ho, 0-based, ascending per fold
+    (R: sort(sample(1:n, floor(n/k.fold))), :289).  Returns k.fold.scores/k.fold, g x 2 (columns rmspe, crps)."""
+    y = f64(y); n = len(y)
+    X = np.asarray(X, dtype=np.float64).reshape(n, -1)
+    coords = np.asarray(coords, dtype=np.float64).reshape(n, 2)
+    ta = np.asarray(theta_alpha, dtype=np.float64); g = ta.shape[1]
+    ho_idx = np.asarray(ho_idx); k_fold = ho_idx.shape[0]
+    scores = np.zeros((g, 2))
+    for f in range(k_fold):
+        ho = ho_idx[f]
+        keep = np.ones(n, dtype=bool); keep[ho] = False
+        X_mod, y_mod, c_mod = X[keep], y[keep], coords[keep]          # :291-294
+        X_ho, y_ho, c_ho = X[ho], y[ho], coords[ho]                   # :296-299
+        mk = backend.mk_nn_indx if search_type in (0, "brute") else backend.mk_nn_indx_cb   # :302-306
+        nnIndx, _, lu = mk(c_mod, m)
+        nn0 = port.nn_query(c_mod, c_ho, m)                           # :311
+        out = backend.cnngp(y_mod, X_mod, c_mod, ta, nnIndx, lu, X_ho, c_ho, nn0, m, sigmaSqIG, cov)  # :322-328
+        yh = out["y0_hat"] if "y0_hat" in out else out["y.0.hat"]
+        yv = out["y0_hat_var"] if "y0_hat_var" in out else out["y.0.hat.var"]
+        yh = np.asarray(yh).reshape(len(ho), g, order="F") if np.asarray(yh).ndim == 1 else np.asarray(yh)
+        yv = np.asarray(yv).reshape(len(ho), g, order="F") if np.asarray(yv).ndim == 1 else np.asarray(yv)
+        for j in range(g):                                            # :330-334
+            scores[j, 1] += crps(y_ho, yh[:, j], yv[:, j])
+            scores[j, 0] += rmspe(y_ho, yh[:, j])
+    return scores / k_fold                                             # :345

@@ -43,7 +43,7 @@ class RnngpArgs(C.Structure):
 ABI_SYMBOLS = [
     "nngp_abi_version", "nngp_device_count", "nngp_create", "nngp_destroy", "nngp_last_error", "nngp_sync",
     "nngp_mk_nn_indx", "nngp_mk_u_indx", "nngp_nn_query", "nngp_set_data", "nngp_bf_loglik", "nngp_bf_loglik_vec", "nngp_q_resid", "nngp_q_forms",
-    "nngp_get_bf", "nngp_rnngp", "nngp_rep_draw", "nngp_rnngp_replicated", "nngp_cnngp", "nngp_rnngp_predict", "nngp_time_bf_loglik", "nngp_launch_count",
+    "nngp_get_bf", "nngp_rnngp", "nngp_rep_draw", "nngp_rnngp_replicated", "nngp_cnngp", "nngp_cnngp_score", "nngp_conj_kfold", "nngp_rnngp_predict", "nngp_time_bf_loglik", "nngp_launch_count",
     "nngp_fp64_peak", "nngp_comm_unique_id", "nngp_comm_init", "nngp_comm_allreduce_sum", "nngp_comm_destroy",
 ]
 
@@ -99,6 +99,10 @@ def load():
     if hasattr(L, "nngp_cnngp"):
         L.nngp_cnngp.argtypes = [vp, C.c_int, C.c_int, c_double_p, c_double_p, C.c_int, c_double_p, c_double_p,
                                  c_int_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]
+    L.nngp_cnngp_score.argtypes = [vp, C.c_int, C.c_int, c_double_p, c_double_p, C.c_int, c_double_p, c_double_p, c_int_p,
+                                   c_double_p, c_double_p, c_double_p]
+    L.nngp_conj_kfold.argtypes = [vp, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, C.c_int, C.c_int,
+                                  c_double_p, c_double_p, C.c_int, C.c_int, C.c_int, c_int_p, C.c_int, C.c_int, c_double_p]
     if hasattr(L, "nngp_rnngp_predict"):
         L.nngp_rnngp_predict.argtypes = [vp, C.c_int, C.c_int, c_double_p, c_double_p, c_int_p, C.c_int, c_double_p,
                                          c_double_p, c_double_p, c_double_p, C.c_int, C.c_int]

@@ -4,6 +4,7 @@
 // The m x m solves run in the B/F kernels' site mode; sites are processed in chunks so that the
 // q x nSamples normals and predictions never have to be resident at once.
 #include <limits.h>
+#include <math.h>
 #include <string.h>
 
 #include <algorithm>
@@ -22,6 +23,9 @@ cudaError_t predict_emit_launch(const double *a, const double *U, const double *
 cudaError_t conj_emit_launch(const double *a, const double *U, const double *F, const double *betaHat, const double *V,
                              int p, int cs, double bIG, double aIG, double *y0Hat, double *y0HatVar,
                              cudaStream_t stream);
+size_t conj_score_scratch_bytes();
+cudaError_t conj_score_launch(const double *y0, const double *y0Hat, const double *y0HatVar, int cs, void *scratch,
+                              double *out, cudaStream_t stream);
 
 namespace {
 
@@ -216,21 +220,38 @@ int nngp_rnngp_predict(nngp_ctx *c, int cov, int q, const double *X0, const doub
   return NNGP_OK;
 }
 
-int nngp_cnngp(nngp_ctx *c, int cov, int g, const double *thetaAlpha, const double sigmaSqIG[2], int n0,
-               const double *X0, const double *coords0, const int *nnIndx0, double *betaHat, double *ab, double *bBInv,
-               double *bb, double *y0Hat, double *y0HatVar) {
+// Shared body of nngp_cnngp and nngp_cnngp_score.  Score mode (y0Obs != NULL): the predictions stay on the device,
+// scoreSums gets 2 doubles per parameter set -- sum of the CRPS terms, sum of squared errors -- and betaHat / ab /
+// bBInv / bb / y0Hat / y0HatVar may be NULL.
+static int cnngp_impl(nngp_ctx *c, int cov, int g, const double *thetaAlpha, const double sigmaSqIG[2], int n0,
+                      const double *X0, const double *coords0, const int *nnIndx0, double *betaHat, double *ab,
+                      double *bBInv, double *bb, double *y0Hat, double *y0HatVar, const double *y0Obs,
+                      double *scoreSums) {
   if (!c) return NNGP_EINVAL;
   if (c->n == 0 || c->p == 0) return ctx_fail(c, NNGP_ESTATE, "nngp_cnngp before nngp_set_data");
-  if (g < 1 || !thetaAlpha || !sigmaSqIG || !betaHat || !ab || !bBInv || !bb) return ctx_fail(c, NNGP_EINVAL, "nngp_cnngp: bad arguments");
-  if (n0 > 0 && (!X0 || !coords0 || !nnIndx0 || !y0Hat || !y0HatVar)) return ctx_fail(c, NNGP_EINVAL, "nngp_cnngp: prediction inputs missing");
+  const bool score = (y0Obs != nullptr);
+  if (g < 1 || !thetaAlpha || !sigmaSqIG) return ctx_fail(c, NNGP_EINVAL, "nngp_cnngp: bad arguments");
+  if (!score && (!betaHat || !ab || !bBInv || !bb)) return ctx_fail(c, NNGP_EINVAL, "nngp_cnngp: bad arguments");
+  if (score && (n0 < 1 || !scoreSums)) return ctx_fail(c, NNGP_EINVAL, "nngp_cnngp_score: bad arguments");
+  if (n0 > 0 && (!X0 || !coords0 || !nnIndx0 || (!score && (!y0Hat || !y0HatVar))))
+    return ctx_fail(c, NNGP_EINVAL, "nngp_cnngp: prediction inputs missing");
   if (cov < 0 || cov > 3) return ctx_fail(c, NNGP_EINVAL, "cov.model is not correctly specified");
   NNGP_CUDA(c, cudaSetDevice(c->device));
   const int p = c->p, K = p + 1, n = c->n;
   const int nTheta = (cov == NNGP_COV_MATERN) ? 3 : 2;
   std::vector<double> S((size_t)K * K), V((size_t)p * p), tmp_p(p);
-  Dev d_bh, d_V, d_y0, d_y0v;
+  Dev d_bh, d_V, d_y0, d_y0v, d_obs, d_sc, d_scratch;
   NNGP_CUDA(c, d_bh.alloc(p * sizeof(double)));
   NNGP_CUDA(c, d_V.alloc((size_t)p * p * sizeof(double)));
+  std::vector<double> bh_local(p);
+  if (score) {
+    NNGP_CUDA(c, d_obs.alloc((size_t)n0 * sizeof(double)));
+    NNGP_CUDA(c, cudaMemcpy(d_obs.p, y0Obs, (size_t)n0 * sizeof(double), cudaMemcpyHostToDevice));
+    NNGP_CUDA(c, d_sc.alloc((size_t)2 * g * sizeof(double)));
+    NNGP_CUDA(c, cudaMemsetAsync(d_sc.p, 0, (size_t)2 * g * sizeof(double), c->stream));
+    NNGP_CUDA(c, d_scratch.alloc(conj_score_scratch_bytes()));
+    NNGP_CUDA(c, cudaMemsetAsync(d_scratch.p, 0, conj_score_scratch_bytes(), c->stream));
+  }
 
   const int cs_max = 1 << 20;
   std::vector<SiteChunk> chunks;  // the query sites do not change across parameter sets: upload once
@@ -264,14 +285,16 @@ int nngp_cnngp(nngp_ctx *c, int cov, int g, const double *thetaAlpha, const doub
     hl::chol_inverse(V.data(), p);
     for (int i = 0; i < p; i++)
       for (int j = 0; j < i; j++) V[(size_t)i * p + j] = V[(size_t)j * p + i];  // full symmetric
-    double *bh = betaHat + (size_t)k * p;
+    double *bh = betaHat ? betaHat + (size_t)k * p : bh_local.data();
     hl::symv(V.data(), p, tmp_p.data(), bh);                               // :239
     const double aIG = sigmaSqIG[0] + 1.0 * n / 2.0;                       // :242
     const double bIG = sigmaSqIG[1] + 0.5 * (S[(size_t)p * K + p] - hl::dot(bh, tmp_p.data(), p));  // :245
-    ab[(size_t)k * 2] = aIG;  // stride 2 even for Matern (reference quirk, :242-245)
-    ab[(size_t)k * 2 + 1] = bIG;
-    memcpy(bBInv + (size_t)k * p * p, V.data(), (size_t)p * p * sizeof(double));
-    memcpy(bb + (size_t)k * p, tmp_p.data(), p * sizeof(double));
+    if (ab) {
+      ab[(size_t)k * 2] = aIG;  // stride 2 even for Matern (reference quirk, :242-245)
+      ab[(size_t)k * 2 + 1] = bIG;
+    }
+    if (bBInv) memcpy(bBInv + (size_t)k * p * p, V.data(), (size_t)p * p * sizeof(double));
+    if (bb) memcpy(bb + (size_t)k * p, tmp_p.data(), p * sizeof(double));
 
     if (n0 > 0) {  // :252-300
       NNGP_CUDA(c, cudaMemcpyAsync(d_bh.p, bh, p * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -285,14 +308,112 @@ int nngp_cnngp(nngp_ctx *c, int cov, int g, const double *thetaAlpha, const doub
                                       c->stream));
         c->launches++;
         const size_t i0 = ck * (size_t)cs_max;
-        NNGP_CUDA(c, cudaMemcpyAsync(y0Hat + (size_t)k * n0 + i0, d_y0.p, (size_t)ch.cs * sizeof(double),
-                                     cudaMemcpyDeviceToHost, c->stream));
-        NNGP_CUDA(c, cudaMemcpyAsync(y0HatVar + (size_t)k * n0 + i0, d_y0v.p, (size_t)ch.cs * sizeof(double),
-                                     cudaMemcpyDeviceToHost, c->stream));
+        if (score) {  // R/spConjNNGP.R:330-334: the scores are all that leaves the device
+          NNGP_CUDA(c, conj_score_launch(d_obs.as<double>() + i0, d_y0.as<double>(), d_y0v.as<double>(), ch.cs,
+                                         d_scratch.p, d_sc.as<double>() + (size_t)2 * k, c->stream));
+          c->launches++;
+        }
+        if (y0Hat)
+          NNGP_CUDA(c, cudaMemcpyAsync(y0Hat + (size_t)k * n0 + i0, d_y0.p, (size_t)ch.cs * sizeof(double),
+                                       cudaMemcpyDeviceToHost, c->stream));
+        if (y0HatVar)
+          NNGP_CUDA(c, cudaMemcpyAsync(y0HatVar + (size_t)k * n0 + i0, d_y0v.p, (size_t)ch.cs * sizeof(double),
+                                       cudaMemcpyDeviceToHost, c->stream));
         NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
       }
     }
   }
+  if (score) NNGP_CUDA(c, cudaMemcpy(scoreSums, d_sc.p, (size_t)2 * g * sizeof(double), cudaMemcpyDeviceToHost));
+  return NNGP_OK;
+}
+
+int nngp_cnngp(nngp_ctx *c, int cov, int g, const double *thetaAlpha, const double sigmaSqIG[2], int n0,
+               const double *X0, const double *coords0, const int *nnIndx0, double *betaHat, double *ab, double *bBInv,
+               double *bb, double *y0Hat, double *y0HatVar) {
+  return cnngp_impl(c, cov, g, thetaAlpha, sigmaSqIG, n0, X0, coords0, nnIndx0, betaHat, ab, bBInv, bb, y0Hat, y0HatVar,
+                    nullptr, nullptr);
+}
+
+int nngp_cnngp_score(nngp_ctx *c, int cov, int g, const double *thetaAlpha, const double sigmaSqIG[2], int n0,
+                     const double *X0, const double *coords0, const int *nnIndx0, const double *y0, double *crps,
+                     double *rmspe) {
+  if (!c) return NNGP_EINVAL;
+  if (!y0 || !crps || !rmspe || g < 1) return ctx_fail(c, NNGP_EINVAL, "nngp_cnngp_score: bad arguments");
+  std::vector<double> sums((size_t)2 * g);
+  const int rc = cnngp_impl(c, cov, g, thetaAlpha, sigmaSqIG, n0, X0, coords0, nnIndx0, nullptr, nullptr, nullptr,
+                            nullptr, nullptr, nullptr, y0, sums.data());
+  if (rc) return rc;
+  for (int k = 0; k < g; k++) {
+    crps[k] = sums[(size_t)2 * k] / n0;               // mean(...)          R/util.R:250
+    rmspe[k] = sqrt(sums[(size_t)2 * k + 1] / n0);    // sqrt(mean(e^2))    R/util.R:254
+  }
+  return NNGP_OK;
+}
+
+// The k-fold loop of spConjNNGP (R/spConjNNGP.R:286-349) as one call: per fold the hold-out rows are removed, the
+// ordered neighbour search is rebuilt on the remaining sites (mkNNIndx / mkNNIndxCB), the held-out sites get their
+// m nearest fitted sites (nn2), the conjugate model is fitted and scored for every parameter set.  The hold-out ids
+// come from the caller (R draws them with sample(), :289), so the R RNG stream is untouched.
+int nngp_conj_kfold(nngp_ctx *c, int n, int p, int m, const double *y, const double *X, const double *coords, int cov,
+                    int g, const double *thetaAlpha, const double sigmaSqIG[2], int search_type, int k_fold, int n_ho,
+                    const int *hoIdx, int set_begin, int set_end, double *scores) {
+  if (!c) return NNGP_EINVAL;
+  if (n < 2 || p < 1 || m < 1 || g < 1 || k_fold < 1 || n_ho < 1 || n_ho >= n || !y || !X || !coords || !thetaAlpha ||
+      !sigmaSqIG || !hoIdx || !scores || set_begin < 0 || set_end > g || set_begin > set_end)
+    return ctx_fail(c, NNGP_EINVAL, "nngp_conj_kfold: bad arguments");
+  if (cov < 0 || cov > 3) return ctx_fail(c, NNGP_EINVAL, "cov.model is not correctly specified");
+  const int nTheta = (cov == NNGP_COV_MATERN) ? 3 : 2;
+  const int n_mod = n - n_ho, gs = set_end - set_begin;
+  if (m >= n_mod) return ctx_fail(c, NNGP_EINVAL, "nngp_conj_kfold: n.neighbors must be smaller than the fold's fit set");
+  for (int k = 0; k < 2 * g; k++) scores[k] = 0.0;
+  if (gs == 0) return NNGP_OK;
+  const long long nIndx = (long long)(1 + m) * m / 2 + (long long)(n_mod - m - 1) * m;
+  std::vector<double> y_mod(n_mod), X_mod((size_t)n_mod * p), co_mod((size_t)2 * n_mod);
+  std::vector<double> y_ho(n_ho), X_ho((size_t)n_ho * p), co_ho((size_t)2 * n_ho);
+  std::vector<int> nnIndx((size_t)nIndx), nnIndxLU((size_t)2 * n_mod), nn0((size_t)n_ho * m);
+  std::vector<double> nnDist((size_t)nIndx), crps(gs), rmspe(gs);
+  std::vector<char> held(n);
+  for (int f = 0; f < k_fold; f++) {
+    const int *ho = hoIdx + (size_t)f * n_ho;
+    std::fill(held.begin(), held.end(), 0);
+    for (int j = 0; j < n_ho; j++) {
+      if (ho[j] < 0 || ho[j] >= n || held[ho[j]] || (j > 0 && ho[j] <= ho[j - 1]))
+        return ctx_fail(c, NNGP_EINVAL, "nngp_conj_kfold: hold-out ids must be ascending, distinct, in [0, n)");
+      held[ho[j]] = 1;
+    }
+    int a = 0, b = 0;  // X[-ho.id,], X[ho.id,] (:291-299): both keep the row order
+    for (int i = 0; i < n; i++) {
+      if (held[i]) {
+        y_ho[b] = y[i];
+        co_ho[b] = coords[i];
+        co_ho[(size_t)n_ho + b] = coords[(size_t)n + i];
+        for (int cc = 0; cc < p; cc++) X_ho[(size_t)cc * n_ho + b] = X[(size_t)cc * n + i];
+        b++;
+      } else {
+        y_mod[a] = y[i];
+        co_mod[a] = coords[i];
+        co_mod[(size_t)n_mod + a] = coords[(size_t)n + i];
+        for (int cc = 0; cc < p; cc++) X_mod[(size_t)cc * n_mod + a] = X[(size_t)cc * n + i];
+        a++;
+      }
+    }
+    int rc = nngp_mk_nn_indx(c, n_mod, m, co_mod.data(), search_type, nnIndx.data(), nnDist.data(), nnIndxLU.data(),
+                             nullptr);
+    if (rc) return rc;
+    rc = nngp_nn_query(c, n_mod, co_mod.data(), n_ho, co_ho.data(), m, nn0.data());
+    if (rc) return rc;
+    rc = nngp_set_data(c, n_mod, m, p, co_mod.data(), nnIndx.data(), nnIndxLU.data(), X_mod.data(), y_mod.data(), 0,
+                       n_mod);
+    if (rc) return rc;
+    rc = nngp_cnngp_score(c, cov, gs, thetaAlpha + (size_t)set_begin * nTheta, sigmaSqIG, n_ho, X_ho.data(),
+                          co_ho.data(), nn0.data(), y_ho.data(), crps.data(), rmspe.data());
+    if (rc) return rc;
+    for (int k = 0; k < gs; k++) {  // column order of k.fold.scores: rmspe, crps (:271-274)
+      scores[set_begin + k] += rmspe[k];
+      scores[(size_t)g + set_begin + k] += crps[k];
+    }
+  }
+  for (int k = 0; k < 2 * g; k++) scores[k] /= k_fold;  // :345
   return NNGP_OK;
 }
 

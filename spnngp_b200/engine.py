@@ -285,6 +285,35 @@ class Engine:
                     bb=bb.reshape(g, p).T.copy(), y0_hat=y0[: n0 * g].reshape(g, n0).T.copy(),
                     y0_hat_var=y0v[: n0 * g].reshape(g, n0).T.copy())
 
+    def cnngp_score(self, cov, theta_alpha, sigmaSqIG, X0, coords0, nnIndx0, y0):
+        """Hold-out scores of the conjugate model, computed on the device (R/spConjNNGP.R:322-334, R/util.R:247-255).
+        Returns (crps[g], rmspe[g])."""
+        ta = np.asarray(theta_alpha, dtype=np.float64); nTheta, g = ta.shape
+        taf = colmajor(ta); ig = _f64(sigmaSqIG); p = self.p
+        X0 = np.asarray(X0, dtype=np.float64).reshape(-1, p); n0 = X0.shape[0]
+        x0f = colmajor(X0); c0 = colmajor(coords0); nn0 = _i32(nnIndx0); yo = _f64(y0)
+        crps = np.zeros(g); rmspe = np.zeros(g)
+        self._check(self.lib.nngp_cnngp_score(self.h, cov, g, _dp(taf), _dp(ig), n0, _dp(x0f), _dp(c0), _ip(nn0), _dp(yo),
+                                              _dp(crps), _dp(rmspe)))
+        return crps, rmspe
+
+    def conj_kfold(self, y, X, coords, m, cov, theta_alpha, sigmaSqIG, ho_idx, search_type="cb", set_range=None):
+        """The k-fold loop of spConjNNGP (R/spConjNNGP.R:286-349) in one call.  ho_idx: k_fold x n_ho hold-out rows
+        (0-based, ascending per fold).  Returns g x 2 scores (columns rmspe, crps; means over folds); with
+        set_range=(lo, hi) only those parameter sets are evaluated and the other rows are zero."""
+        ta = np.asarray(theta_alpha, dtype=np.float64); nTheta, g = ta.shape
+        taf = colmajor(ta); ig = _f64(sigmaSqIG)
+        X = np.asarray(X, dtype=np.float64); n, p = X.shape
+        xf = colmajor(X); cf = colmajor(coords); yf = _f64(y)
+        ho = np.ascontiguousarray(np.asarray(ho_idx, dtype=np.int32)); k_fold, n_ho = ho.shape
+        lo, hi = set_range if set_range is not None else (0, g)
+        st = 0 if search_type in (0, "brute") else 1
+        scores = np.zeros(2 * g)
+        self._check(self.lib.nngp_conj_kfold(self.h, n, p, m, _dp(yf), _dp(xf), _dp(cf), cov, g, _dp(taf), _dp(ig), st,
+                                             k_fold, n_ho, _ip(ho), lo, hi, _dp(scores)))
+        self.n, self.m, self.p = n - n_ho, m, p
+        return scores.reshape(2, g).T.copy()
+
     def mk_nn_indx(self, coords, m, search_type="cb"):
         """Ordered neighbour search (reference `mkNNIndx` / `mkNNIndxCB`, src/nn.cpp:63,214)."""
         cf = colmajor(coords); n = cf.size // 2

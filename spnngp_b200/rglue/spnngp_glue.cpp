@@ -185,6 +185,25 @@ SEXP cNNGP(SEXP y_r, SEXP X_r, SEXP p_r, SEXP n_r, SEXP coords_r, SEXP thetaAlph
   return out;
 }
 
+// NEW symbol (not in the reference): the k-fold loop of R/spConjNNGP.R:286-349 in one call, scores formed on the GPU.
+// INTEGRATION.md shows the three-line change in spConjNNGP() that uses it; without that change the reference's R loop
+// keeps calling cNNGP per fold and everything still works.  hoIdx_r: n.ho x k.fold integer matrix, 1-based, each
+// column sort(sample(1:n, floor(n/k.fold))) drawn in R; searchType_r: 0 brute, 1 cb.
+// Returns the g x 2 matrix k.fold.scores/k.fold (columns rmspe, crps).
+SEXP cNNGPKFold(SEXP y_r, SEXP X_r, SEXP p_r, SEXP n_r, SEXP coords_r, SEXP thetaAlpha_r, SEXP g_r, SEXP m_r,
+                SEXP sigmaSqIG_r, SEXP covModel_r, SEXP searchType_r, SEXP hoIdx_r, SEXP nHo_r, SEXP kFold_r) {
+  const int p = INTEGER(p_r)[0], n = INTEGER(n_r)[0], m = INTEGER(m_r)[0], g = INTEGER(g_r)[0];
+  const int covModel = INTEGER(covModel_r)[0], nHo = INTEGER(nHo_r)[0], kFold = INTEGER(kFold_r)[0];
+  check_cov(covModel);
+  std::vector<int> ho((size_t)nHo * kFold);
+  for (size_t i = 0; i < ho.size(); i++) ho[i] = INTEGER(hoIdx_r)[i] - 1;
+  SEXP scores_r = PROTECT(Rf_allocMatrix(REALSXP, g, 2));
+  check(nngp_conj_kfold(ctx(), n, p, m, REAL(y_r), REAL(X_r), REAL(coords_r), covModel, g, REAL(thetaAlpha_r),
+                        REAL(sigmaSqIG_r), INTEGER(searchType_r)[0], kFold, nHo, ho.data(), 0, g, REAL(scores_r)));
+  UNPROTECT(1);
+  return scores_r;
+}
+
 SEXP rNNGPPredict(SEXP X_r, SEXP y_r, SEXP coords_r, SEXP n_r, SEXP p_r, SEXP m_r, SEXP X0_r, SEXP coords0_r, SEXP q_r,
                   SEXP nnIndx0_r, SEXP betaSamples_r, SEXP thetaSamples_r, SEXP nSamples_r, SEXP covModel_r,
                   SEXP nThreads_r, SEXP verbose_r, SEXP nReport_r) {
@@ -280,7 +299,7 @@ SEXP mkUIndx(SEXP n_r, SEXP m_r, SEXP nnIndx_r, SEXP uIndx_r, SEXP uIndxLU_r, SE
   return R_NilValue;
 }
 
-// registration of all 12 symbols (the reference's init.cpp registers 9 and is never run)
+// registration of all 12 reference symbols (+ cNNGPKFold) (the reference's init.cpp registers 9 and is never run)
 static const R_CallMethodDef CallEntries[] = {
     {"rNNGP", (DL_FUNC)&rNNGP, 28},          {"sNNGP", (DL_FUNC)&sNNGP, 29},
     {"sNNGPLogit", (DL_FUNC)&sNNGPLogit, 27}, {"cNNGP", (DL_FUNC)&cNNGP, 18},
@@ -288,6 +307,7 @@ static const R_CallMethodDef CallEntries[] = {
     {"sNNGPPredict", (DL_FUNC)&sNNGPPredict, 19}, {"PGLogit", (DL_FUNC)&PGLogit, 9},
     {"rNNGPReplicated", (DL_FUNC)&rNNGPReplicated, 14}, {"mkNNIndx", (DL_FUNC)&mkNNIndx, 7},
     {"mkNNIndxCB", (DL_FUNC)&mkNNIndxCB, 7}, {"mkUIndx", (DL_FUNC)&mkUIndx, 8},
+    {"cNNGPKFold", (DL_FUNC)&cNNGPKFold, 14},  // addition, see above
     {NULL, NULL, 0}};
 
 void R_init_spNNGP(DllInfo *dll) {

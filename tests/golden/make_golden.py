@@ -27,6 +27,28 @@ def grid_sites(k):
     return np.column_stack([xx.ravel(), yy.ravel()])
 
 
+# ---- 7. k-fold scores of the conjugate model: the reference's mkNNIndxCB + cNNGP per fold, the
+#         R-layer loop and crps / rmspe restated in oracle/pyoracle.py (R/spConjNNGP.R:286-349, R/util.R:247-255)
+def kfold_fixture():
+    port = po.Port()
+    n, m, k_fold = 600, 10, 3
+    prob = make_problem(n, m, seed=20248, domain=0.35)
+    rng = np.random.default_rng(20249)
+    n_ho = n // k_fold
+    ho = np.stack([np.sort(rng.choice(n, n_ho, replace=False)) for _ in range(k_fold)]).astype(np.int32)
+    kf = dict(coords=prob["coords"], X=prob["X"], y=prob["y"], m=m, ho_idx=ho, sigmaSqIG=np.array([2.0, float(np.var(prob["y"]))]))
+    for cov, name in ((0, "exp"), (2, "matern")):
+        rows = [[ph, al] + ([0.8] if cov == 2 else []) for ph in (3.0, 9.0) for al in (0.1, 0.4)]
+        ta = np.array(rows).T
+        kf[f"{name}_theta_alpha"] = ta
+        kf[f"{name}_scores"] = po.conj_kfold(ref, port, prob["y"], prob["X"], prob["coords"], m, cov, ta, kf["sigmaSqIG"], ho, "cb")
+    np.savez_compressed(os.path.join(OUT, "kfold_n600_m10.npz"), **kf)
+
+
+if "--kfold-only" in sys.argv:
+    kfold_fixture()
+    sys.exit(0)
+
 # ---- 1. B, F, logDet, Q for the four covariance models -----------------------------------------------
 n, m = 400, 10
 prob = make_problem(n, m, seed=20241, domain=0.3)
@@ -130,5 +152,7 @@ for st in (0, 1, 2):
     u, ulu, uii = ref.mk_u_indx(n, m, nnIndx, lu, search_type=st)
     ui[f"st{st}_uIndx"] = u; ui[f"st{st}_uIndxLU"] = ulu; ui[f"st{st}_uiIndx"] = uii
 np.savez_compressed(os.path.join(OUT, "uindx_n600_m10.npz"), **ui)
+
+kfold_fixture()
 
 print("golden fixtures written to", OUT, [f for f in os.listdir(OUT) if f.endswith(".npz")])

@@ -47,6 +47,7 @@ def test_r_glue_exports_the_reference_call_symbols():
     glue = C.CDLL(path)
     for s in ("rNNGP", "cNNGP", "rNNGPPredict", "mkNNIndx", "mkNNIndxCB",  # accelerated (src/spNNGP.h, src/nn.h)
               "sNNGP", "sNNGPLogit", "cSLGP", "sNNGPPredict", "PGLogit", "rNNGPReplicated", "mkUIndx",  # stubs
+              "cNNGPKFold",  # added: the k-fold loop of R/spConjNNGP.R in one call
               "R_init_spNNGP"):
         assert hasattr(glue, s)
 

@@ -120,3 +120,18 @@ def test_glue_vs_live_reference_when_built(glue, ref, port):
     glue.lib.rshim_set_seed(5); b = po.call_rnngp(glue, *args)
     assert np.allclose(a["p_theta_samples"], b["p_theta_samples"], rtol=1e-9)
     assert np.allclose(a["p_beta_samples"], b["p_beta_samples"], rtol=1e-7, atol=1e-9)
+
+
+def test_glue_kfold_symbol_against_golden(glue):
+    """`cNNGPKFold` (the one added .Call symbol): 1-based n.ho x k.fold hold-out matrix in, k.fold.scores/k.fold out."""
+    d = np.load(os.path.join(G, "kfold_n600_m10.npz"))
+    ho = d["ho_idx"]; k_fold, n_ho = ho.shape
+    y = d["y"]; n = len(y); X = d["X"]; p = X.shape[1]; ta = d["exp_theta_alpha"]; g = ta.shape[1]
+    args = [glue.real(y), glue.real(np.ascontiguousarray(X.T).ravel()), glue.scalar_int(p), glue.scalar_int(n),
+            glue.real(po.coords_flat(d["coords"])), glue.real(np.ascontiguousarray(ta.T).ravel()), glue.scalar_int(g),
+            glue.scalar_int(int(d["m"])), glue.real(d["sigmaSqIG"]), glue.scalar_int(0), glue.scalar_int(1),
+            glue.integer((ho + 1).ravel()), glue.scalar_int(n_ho), glue.scalar_int(k_fold)]
+    out = glue.call("cNNGPKFold", args)
+    got = np.ctypeslib.as_array(glue.lib.REAL(out), shape=(2 * g,)).copy().reshape(2, g).T
+    glue.reset()
+    assert np.max(np.abs(got - d["exp_scores"]) / np.abs(d["exp_scores"])) < 1e-10

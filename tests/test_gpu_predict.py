@@ -80,3 +80,43 @@ def test_cnngp_without_prediction(engine, port):
     got = engine.cnngp(0, ta, [2.0, 1.0])
     assert np.allclose(got["beta_hat"], ref["beta_hat"], rtol=1e-9)
     assert np.allclose(got["ab"][:4], ref["ab"][:4], rtol=1e-10)
+
+
+@pytest.mark.parametrize("cov,m", [(0, 15), (2, 10)])
+def test_cnngp_score_on_device(engine, port, cov, m):
+    """crps / rmspe formed on the GPU (nngp_cnngp_score) vs the R-layer restatement applied to the oracle's cNNGP."""
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(17 + cov)
+    prob = make_problem(2000, m, seed=37, port=port, domain=0.63)
+    n0 = 700
+    coords0 = rng.random((n0, 2)) * 0.63
+    X0 = np.column_stack([np.ones(n0), rng.standard_normal(n0)])
+    y0 = X0 @ prob["beta"] + np.sqrt(5.0) * (np.sin(3 * coords0[:, 0]) + np.cos(2 * coords0[:, 1])) + rng.standard_normal(n0)
+    nn0 = port.nn_query(prob["coords"], coords0, m)
+    rows = [[ph, al] + ([0.8] if cov == 2 else []) for ph in (3.0, 12.0) for al in (0.1, 0.5)]
+    ta = np.array(rows).T
+    ig = [2.0, float(np.var(prob["y"]))]
+    ref = port.cnngp(prob["y"], prob["X"], prob["coords"], ta, prob["nnIndx"], prob["nnIndxLU"], X0, coords0, nn0, m, ig, cov)
+    engine.set_data(prob["coords"], prob["nnIndx"], prob["nnIndxLU"], prob["X"], prob["y"], m)
+    crps, rmspe = engine.cnngp_score(cov, ta, ig, X0, coords0, nn0, y0)
+    for k in range(ta.shape[1]):
+        assert abs(crps[k] - po.crps(y0, ref["y0_hat"][:, k], ref["y0_hat_var"][:, k])) < 1e-10 * abs(crps[k])
+        assert abs(rmspe[k] - po.rmspe(y0, ref["y0_hat"][:, k])) < 1e-10 * rmspe[k]
+    again = engine.cnngp_score(cov, ta, ig, X0, coords0, nn0, y0)
+    assert np.array_equal(again[0], crps) and np.array_equal(again[1], rmspe)  # deterministic reduction
+
+
+def test_conj_kfold_golden(engine):
+    """The whole k-fold loop in one call (nngp_conj_kfold) vs scores obtained with the reference's own mkNNIndxCB and
+    cNNGP (tests/golden/kfold_n600_m10.npz); parameter-set shards add up to the whole."""
+    import os
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kfold_n600_m10.npz"))
+    for cov, name in ((0, "exp"), (2, "matern")):
+        ta = d[f"{name}_theta_alpha"]
+        got = engine.conj_kfold(d["y"], d["X"], d["coords"], int(d["m"]), cov, ta, d["sigmaSqIG"], d["ho_idx"], "cb")
+        assert np.max(np.abs(got - d[f"{name}_scores"]) / np.abs(d[f"{name}_scores"])) < 1e-10
+        a = engine.conj_kfold(d["y"], d["X"], d["coords"], int(d["m"]), cov, ta, d["sigmaSqIG"], d["ho_idx"], "cb", set_range=(0, 1))
+        b = engine.conj_kfold(d["y"], d["X"], d["coords"], int(d["m"]), cov, ta, d["sigmaSqIG"], d["ho_idx"], "cb", set_range=(1, 4))
+        assert np.array_equal(a + b, got)
+    brute = engine.conj_kfold(d["y"], d["X"], d["coords"], int(d["m"]), 0, d["exp_theta_alpha"], d["sigmaSqIG"], d["ho_idx"], "brute")
+    assert np.max(np.abs(brute - d["exp_scores"]) / np.abs(d["exp_scores"])) < 1e-10  # tie-free sites: brute == cb

@@ -107,3 +107,21 @@ def test_u_indx_golden(port):
         u, lu, ui = port.mk_u_indx(n, m, d["nnIndx"], d["nnIndxLU"], search_type=st)
         assert np.array_equal(u, d[f"st{st}_uIndx"]) and np.array_equal(lu, d[f"st{st}_uIndxLU"])
         assert np.array_equal(ui, d[f"st{st}_uiIndx"])
+
+
+def test_kfold_scores_golden(port):
+    """k-fold loop of spConjNNGP + crps / rmspe (R/spConjNNGP.R:286-349): port-backed restatement vs the scores
+    obtained with the reference's own mkNNIndxCB and cNNGP (fixture 7 of make_golden.py)."""
+    from oracle import pyoracle as po
+    d = np.load(os.path.join(G, "kfold_n600_m10.npz"))
+    for cov, name in ((0, "exp"), (2, "matern")):
+        got = po.conj_kfold(port, port, d["y"], d["X"], d["coords"], int(d["m"]), cov, d[f"{name}_theta_alpha"],
+                            d["sigmaSqIG"], d["ho_idx"], "cb")
+        assert relerr(got, d[f"{name}_scores"]) < (1e-10 if cov == 2 else 1e-12)
+
+
+def test_score_rules_known_answers():
+    """crps of a perfect forecast with unit variance: -(1/sqrt(pi) - 2 dnorm(0)) = (sqrt(2) - 1)/sqrt(pi)."""
+    from oracle import pyoracle as po
+    assert abs(po.crps([0.0, 3.0], [0.0, 3.0], [1.0, 1.0]) - (np.sqrt(2.0) - 1.0) / np.sqrt(np.pi)) < 1e-15
+    assert abs(po.rmspe([1.0, 2.0, 3.0], [1.0, 2.0, 5.0]) - np.sqrt(4.0 / 3.0)) < 1e-15
