@@ -330,6 +330,13 @@ def run_b200(args, rank, world, local_rank):
         k_ms = eng.time_bf_loglik(cov, [theta], [wl["beta"]], iters=20)
         nloc = hi - lo
         loc_s = nloc / (k_ms * 1e-3)
+        ab = {}
+        if cov == 2:  # A/B of the launch-level series choice (csrc/matern_series.cuh): same launch with the 14-term series
+            ab["matern_short_series_used"] = bool(eng.get_option("matern_short_used"))
+            eng.set_option("matern_short", 0)
+            eng.time_bf_loglik(cov, [theta], [wl["beta"]], iters=3)
+            ab["kernel_ms_full_series"] = eng.time_bf_loglik(cov, [theta], [wl["beta"]], iters=20)
+            eng.set_option("matern_short", 1)
         fp64_peak = eng.fp64_peak_tflops()
         peaks, peak_src = measured_peaks()
         fl = flops_per_location(m)
@@ -380,7 +387,7 @@ def run_b200(args, rank, world, local_rank):
                 "alt_sampler_iter_per_s": args.steps / (ms_alt * 1e-3),
                 "alt_sampler": "double-buffered" if args.mode == 0 else "reference-faithful",
                 f"updateBF_loc_per_s_{other}": (hi - lo) / (k_ms_o * 1e-3),
-                "knn_cb_setup_s": t_knn,
+                "knn_cb_setup_s": t_knn, **ab,
             },
         }
         print(json.dumps(line), flush=True)

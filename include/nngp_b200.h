@@ -238,6 +238,12 @@ int nngp_time_bf_loglik(nngp_ctx *ctx, int cov_model, int nbatch, const double *
 /* FP64 FMA throughput of this device measured with a DFMA micro-benchmark (TFLOP/s, FMA = 2 flops):
  * the roofline denominator for the B/F kernels (MEASURED_PEAKS.json has no FP64 figure). */
 int nngp_fp64_peak(nngp_ctx *ctx, double *tflops);
+/* Tuning switches (tests and A/B measurements; defaults are the fast settings).
+ *   "matern_short" (default 1): let Matern launches use the 9-term series when the data set's neighbourhoods are
+ *   dense enough for it (dropped terms < 1e-16, see csrc/matern_series.cuh); 0 forces the 14-term series. */
+int nngp_set_option(nngp_ctx *ctx, const char *name, int value);
+/* reads an option back; "matern_short_used": how many parameter sets of the last likelihood launch ran the short series */
+int nngp_get_option(nngp_ctx *ctx, const char *name, int *value);
 /* number of kernel launches issued by this context so far (bench.py `gpu_launches`) */
 long long nngp_launch_count(const nngp_ctx *ctx);
 

@@ -43,7 +43,7 @@ class RnngpArgs(C.Structure):
 ABI_SYMBOLS = [
     "nngp_abi_version", "nngp_device_count", "nngp_create", "nngp_destroy", "nngp_last_error", "nngp_sync",
     "nngp_mk_nn_indx", "nngp_mk_u_indx", "nngp_nn_query", "nngp_set_data", "nngp_bf_loglik", "nngp_bf_loglik_vec", "nngp_q_resid", "nngp_q_forms",
-    "nngp_get_bf", "nngp_rnngp", "nngp_rep_draw", "nngp_rnngp_replicated", "nngp_cnngp", "nngp_cnngp_score", "nngp_conj_kfold", "nngp_rnngp_predict", "nngp_time_bf_loglik", "nngp_launch_count",
+    "nngp_get_bf", "nngp_rnngp", "nngp_rep_draw", "nngp_rnngp_replicated", "nngp_cnngp", "nngp_cnngp_score", "nngp_conj_kfold", "nngp_rnngp_predict", "nngp_time_bf_loglik", "nngp_launch_count", "nngp_set_option", "nngp_get_option",
     "nngp_fp64_peak", "nngp_comm_unique_id", "nngp_comm_init", "nngp_comm_allreduce_sum", "nngp_comm_destroy",
 ]
 
@@ -90,6 +90,8 @@ def load():
     L.nngp_comm_allreduce_sum.argtypes = [vp, c_double_p, C.c_int]
     L.nngp_comm_destroy.restype = None
     L.nngp_comm_destroy.argtypes = [vp]
+    L.nngp_set_option.argtypes = [vp, C.c_char_p, C.c_int]
+    L.nngp_get_option.argtypes = [vp, C.c_char_p, c_int_p]
     L.nngp_launch_count.restype = C.c_longlong
     L.nngp_launch_count.argtypes = [vp]
     if hasattr(L, "nngp_mk_nn_indx"):

@@ -19,6 +19,7 @@
 namespace nngp {
 
 constexpr int kMatSeriesTerms = 14;  // t^k/(k!)^2-like decay: 1e-17 relative at t = 1 by k = 13
+constexpr int kMatShortTerms = 9;    // truncated series for small arguments (dense neighbourhoods), see t_short_max
 constexpr int kMatExtTerms = 32;     // 6.25^k / (k!)^2 < 1e-19 by k = 31
 constexpr int kTemmeTerms = 24;  // (x^2/4)^i / i! < 1e-18 well before i = 24 for x <= 2
 constexpr int kCf2Tab = 64;      // tabulated reciprocals for the first CF2 iterations
@@ -29,6 +30,7 @@ constexpr int kGlNodes = 16;     // generalised Gauss-Laguerre rule for phi D > 
 struct MaternSeriesParams {
   double nu;
   double t_ext_max;  // largest t = (phi D / 2)^2 served by the extended series (beyond: Gauss-Laguerre, matern_gl)
+  double t_fast_max; // largest t the straight-line path serves: 1 for the full series, t_short_max for the short one
   int use_series;
   double sa[kMatSeriesTerms];
   double sb[kMatSeriesTerms];
@@ -61,6 +63,9 @@ struct MaternConsts {
   // cancellation against K's decay still leaves ~1e-12; evaluated by a short loop (matern_series_ext)
   double ea[kMatExtTerms];
   double eb[kMatExtTerms];
+  // largest t for which the first kMatShortTerms terms of both sums are enough: the dropped terms
+  // sum_{k >= kMatShortTerms} (|ea_k| + t^nu |eb_k|) t^k stay below 1e-16 (absolute; rho is O(1) there)
+  double t_short_max;
   // Gauss-Laguerre rule for the weight t^(nu-1/2) e^-t (nodes, weights normalised to sum 1) and
   // gl_c = sqrt(pi/2) / (2^(nu-1) Gamma(nu)): the large-argument path, see matern_gl()
   double gl_t[kGlNodes];
@@ -186,6 +191,26 @@ inline void matern_prepare(double nu, MaternConsts *mc) {
     } else {
       for (int k = 0; k < kMatSeriesTerms; k++) mc->sa[k] = mc->sb[k] = 0.0;
       for (int k = 0; k < kMatExtTerms; k++) mc->ea[k] = mc->eb[k] = 0.0;
+    }
+    mc->t_short_max = 0.0;
+    if (mc->use_series) {
+      auto tail = [&](double t) {
+        double sa_t = 0.0, sb_t = 0.0, pw = pow(t, (double)kMatShortTerms);
+        for (int k = kMatShortTerms; k < kMatExtTerms; k++) {
+          sa_t += fabs(mc->ea[k]) * pw;
+          sb_t += fabs(mc->eb[k]) * pw;
+          pw *= t;
+        }
+        return sa_t + pow(t, nu) * sb_t;
+      };
+      double lo = 0.0, hi = 1.0;
+      if (tail(hi) <= 1e-16) lo = hi;
+      for (int it = 0; it < 50 && lo < hi; it++) {
+        const double mid = 0.5 * (lo + hi);
+        if (tail(mid) <= 1e-16) lo = mid;
+        else hi = mid;
+      }
+      mc->t_short_max = lo;
     }
   }
   gauss_laguerre_rule(kGlNodes, (long double)nu - 0.5L, mc->gl_t, mc->gl_w);
@@ -327,6 +352,7 @@ inline void matern_series_params(const MaternConsts &mc, MaternSeriesParams *ms)
   // cancellation of the two sums grows like e^(2 phi D) / |sin(nu pi)|: keep ~1e-12 absolute
   const double snp = fabs(sin(3.14159265358979323846 * mc.nu));
   ms->t_ext_max = !mc.use_series ? 1.0 : (snp > 0.1 ? 4.0 : 2.25);
+  ms->t_fast_max = 1.0;
   for (int k = 0; k < kMatSeriesTerms; k++) {
     ms->sa[k] = mc.sa[k];
     ms->sb[k] = mc.sb[k];

@@ -383,6 +383,8 @@ int bf_grid_any(int m, int cov, long long nloc, int sms) {
   }
 }
 
+bool bf_has_matern_short(int m) { return kernel_for(m, NNGP_COV_MATERN) == KERNEL_WS; }
+
 // upper bound of bf_grid_any over all kernels (for sizing the partial-sum scratch)
 int bf_grid_max(int m, long long nloc, int sms) {
   int a = bf_grid_for(m, nloc, sms);

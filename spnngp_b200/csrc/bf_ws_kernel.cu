@@ -71,13 +71,13 @@ __global__ void __launch_bounds__(32 * (1 + NP), 2) bf_ws_kernel(const __grid_co
   constexpr int kBatch = kTplBatch<COV>;
   // who stores a solved tile's weights: the producers where the consumer is the critical path (0.62 -> 0.59 ms,
   // spherical), the consumer for Matern, whose producers are the critical path (1.11 vs 1.15 ms)
-  constexpr bool kProducersStoreB = (COV != NNGP_COV_MATERN);
+  constexpr bool kProducersStoreB = !kIsMatern<COV>;
   __shared__ unsigned ent[kTplMaxEnt];
   __shared__ int ebeg[NP + 1];
   __shared__ long long next_tile[8];  // ring of claimed tiles, slot j & 7 (>= ntiles: no more work)
   __shared__ double red[2][1 + NP];
   __shared__ int last_flag;
-  __shared__ __align__(16) double s_tab[COV == NNGP_COV_MATERN ? 160 : 2];  // exp / log tables (fasttab.cuh)
+  __shared__ __align__(16) double s_tab[kIsMatern<COV> ? 160 : 2];  // exp / log tables (fasttab.cuh)
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
 
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(32 * (1 + NP), 2) bf_ws_kernel(const __grid_co
   const double diag = sigmaSq + tauSq;
   const double *__restrict__ resid = th.resid;
 
-  if (COV == NNGP_COV_MATERN) {
+  if (kIsMatern<COV>) {
     for (int x = tid; x < 160; x += Ws::kThreads) s_tab[x] = (x < 32) ? kExpTab32[x] : kLogTab64[x - 32];
   }
   // ---- one-time setup: work list, zero padding of both stages --------------------------------------
@@ -388,6 +388,7 @@ static cudaError_t ws_launch_cov(const BfLaunch &P, int cov, int grid_x, cudaStr
     case NNGP_COV_EXPONENTIAL: return ws_launch_one<MC, NNGP_COV_EXPONENTIAL, 3>(P, grid_x, stream);
     case NNGP_COV_SPHERICAL: return ws_launch_one<MC, NNGP_COV_SPHERICAL, 3>(P, grid_x, stream);
     case NNGP_COV_MATERN:
+      if (P.matern_short) return ws_launch_one<MC, NNGP_COV_MATERN_SHORT, 3>(P, grid_x, stream);
       return ws_launch_one<MC, NNGP_COV_MATERN, 3>(P, grid_x, stream);
     case NNGP_COV_GAUSSIAN: return ws_launch_one<MC, NNGP_COV_GAUSSIAN, 3>(P, grid_x, stream);
     default: return cudaErrorInvalidValue;

@@ -8,6 +8,11 @@
 
 namespace nngp {
 
+// Kernel-template code of the short-series Matern variant (not an ABI value: the C ABI's cov_model stays 0..3).
+constexpr int NNGP_COV_MATERN_SHORT = 4;
+template <int COV>
+constexpr bool kIsMatern = (COV == NNGP_COV_MATERN || COV == NNGP_COV_MATERN_SHORT);
+
 // Every functor maps the SQUARED distance to the correlation.  fast() is straight-line code valid for
 // most arguments; needs_slow() flags the rare arguments that must be re-evaluated with slow().
 template <int COV>
@@ -65,6 +70,19 @@ struct Cor<NNGP_COV_MATERN> {
     if (ms.use_series) return matern_series_ext(t, *mc);
     return matern_cor(nngp_sqrt(d2) * phi, *mc);
   }
+  __device__ __forceinline__ double operator()(double d2) const { return needs_slow(d2) ? slow(d2) : fast(d2); }
+};
+
+// Matern with the series cut to kMatShortTerms terms: exact (dropped terms < 1e-16) for t <= ms.t_fast_max, which the
+// host sets to MaternConsts::t_short_max; larger arguments take slow() (extended series / quadrature) as before.
+template <>
+struct Cor<NNGP_COV_MATERN_SHORT> : Cor<NNGP_COV_MATERN> {
+  __device__ __forceinline__ Cor(const BfTheta &t, const double *tab_ = nullptr) : Cor<NNGP_COV_MATERN>(t, tab_) {}
+  __device__ __forceinline__ double fast_tab(double d2) const {
+    return matern_series_tab<kMatShortTerms>(fmin(q4 * d2, 1.0), ms, tab);
+  }
+  __device__ __forceinline__ double fast(double d2) const { return fast_tab(d2); }
+  __device__ __forceinline__ bool needs_slow(double d2) const { return q4 * d2 > ms.t_fast_max; }
   __device__ __forceinline__ double operator()(double d2) const { return needs_slow(d2) ? slow(d2) : fast(d2); }
 };
 

@@ -17,12 +17,13 @@
 namespace nngp {
 
 // t = (phi^2/4) d2 in (0, 1]; returns rho.  t == 0 gives exactly sa[0] = 1.
+template <int NT = kMatSeriesTerms>
 NNGP_FM double matern_series(double t, const MaternSeriesParams &mc) {
   const double L = nngp_log_pos(t + 1e-300);
   const double pw = nngp_exp(mc.nu * L);  // t^nu
-  double pa = mc.sa[kMatSeriesTerms - 1], pb = mc.sb[kMatSeriesTerms - 1];
+  double pa = mc.sa[NT - 1], pb = mc.sb[NT - 1];
 #pragma unroll
-  for (int k = kMatSeriesTerms - 2; k >= 0; --k) {
+  for (int k = NT - 2; k >= 0; --k) {
     pa = fma(pa, t, mc.sa[k]);
     pb = fma(pb, t, mc.sb[k]);
   }
@@ -31,12 +32,13 @@ NNGP_FM double matern_series(double t, const MaternSeriesParams &mc) {
 
 // matern_series with the table-driven log / exp (tab: 32 doubles of kExpTab32, then the 64 pairs of kLogTab64, in
 // shared memory): 26 fewer FP64 instructions of ~95 per correlation.
+template <int NT = kMatSeriesTerms>
 NNGP_FM double matern_series_tab(double t, const MaternSeriesParams &mc, const double *tab) {
   const double L = nngp_log_tab(t + 1e-300, tab + 32);
   const double pw = nngp_exp_tab(mc.nu * L, tab);  // t^nu
-  double pa = mc.sa[kMatSeriesTerms - 1], pb = mc.sb[kMatSeriesTerms - 1];
+  double pa = mc.sa[NT - 1], pb = mc.sb[NT - 1];
 #pragma unroll
-  for (int k = kMatSeriesTerms - 2; k >= 0; --k) {
+  for (int k = NT - 2; k >= 0; --k) {
     pa = fma(pa, t, mc.sa[k]);
     pb = fma(pb, t, mc.sb[k]);
   }
@@ -44,7 +46,9 @@ NNGP_FM double matern_series_tab(double t, const MaternSeriesParams &mc, const d
 }
 
 // (A truncated 9-term variant for t <= 1/16 behind a warp-uniform branch was measured and dropped: 0.99 -> 1.33 ms,
-// the branch breaks the batch's load / chain / store interleaving.)
+// the branch breaks the batch's load / chain / store interleaving.  The short series is therefore a LAUNCH-level
+// choice: Cor<NNGP_COV_MATERN_SHORT> (cov.cuh) evaluates kMatShortTerms terms and sends t > t_fast_max to slow(); the
+// host picks it when 99 % of the locations keep every pair of their neighbourhood under that bound.)
 
 // The same series with kMatExtTerms terms from the global-memory tables, for 1 < t <= 4 (2 < phi D <= 4; 3 when nu is within ~0.03 of an integer):
 // a 32-trip loop instead of the 40-90 divisions-in-the-loop iterations Steed's CF2 needs in that range.

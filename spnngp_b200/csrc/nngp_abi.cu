@@ -158,6 +158,7 @@ void nngp_destroy(nngp_ctx *c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   free_model(c);
   free_dev(c->d_ticket);
+  free_dev(c->d_hist);
   free_dev(c->d_Xy);
   free_dev(c->d_fail);
   free_dev(c->d_mat);
@@ -187,6 +188,29 @@ int nngp_sync(nngp_ctx *c) {
 }
 
 long long nngp_launch_count(const nngp_ctx *c) { return c ? c->launches : 0; }
+
+int nngp_set_option(nngp_ctx *c, const char *name, int value) {
+  if (!c || !name) return NNGP_EINVAL;
+  if (!strcmp(name, "matern_short")) {
+    c->opt_matern_short = value ? 1 : 0;
+    return NNGP_OK;
+  }
+  return ctx_fail(c, NNGP_EINVAL, std::string("nngp_set_option: unknown option ") + name);
+}
+
+int nngp_get_option(nngp_ctx *c, const char *name, int *value) {
+  if (!c || !name || !value) return NNGP_EINVAL;
+  if (!strcmp(name, "matern_short")) {
+    *value = c->opt_matern_short;
+    return NNGP_OK;
+  }
+  if (!strcmp(name, "matern_short_used")) {  // parameter sets of the last likelihood launch that ran the short series
+    *value = 0;
+    for (int b = 0; b < NNGP_MAX_BATCH; b++) *value += c->bf_short[b];
+    return NNGP_OK;
+  }
+  return ctx_fail(c, NNGP_EINVAL, std::string("nngp_get_option: unknown option ") + name);
+}
 
 int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const int *nnIndx, const int *nnIndxLU,
                   const double *X, const double *y, int loc_begin, int loc_end) {
@@ -259,6 +283,28 @@ int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const 
     NNGP_ENSURE(c->d_B[s], 9 + s, nI);
     NNGP_ENSURE(c->d_F[s], 11 + s, n);
   }
+  c->pair_d2_q99 = 1e300;
+  if (c->has_nn && (long long)loc_end > m && loc_end > loc_begin) {
+    // 99 % quantile of the largest squared pair distance inside a neighbourhood (stat_kernels.cu)
+    const int nb = pair_d2_hist_bins();
+    if (!c->d_hist) NNGP_CUDA(c, cudaMalloc(&c->d_hist, nb * sizeof(unsigned int)));
+    NNGP_CUDA(c, pair_d2_hist_launch(c->d_coords, c->d_nnIndx, m, loc_begin, loc_end, c->d_hist, c->stream));
+    c->launches++;
+    std::vector<unsigned int> hist((size_t)nb);
+    NNGP_CUDA(c, cudaMemcpyAsync(hist.data(), c->d_hist, nb * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
+    unsigned long long total = 0, above = 0;
+    for (int b = 0; b < nb; b++) total += hist[b];
+    int b = nb - 1;
+    for (; b > 0; b--) {
+      if ((above + hist[b]) * 100ull > total) break;  // more than 1 % of the locations at or above this bin
+      above += hist[b];
+    }
+    const unsigned long long edge = (unsigned long long)(b + 1) << 48;  // upper edge of bin b
+    double v;
+    memcpy(&v, &edge, sizeof v);
+    if (total > 0 && b + 1 < 0x7ff0) c->pair_d2_q99 = v;
+  }
   const long long nloc = (long long)loc_end - loc_begin;
   const int K = p + 1, npairs = K * (K + 1) / 2;
   // per parameter set: 2 doubles per CTA or per 32-location tile, whichever is more (site-mode chunks are <= 2^20)
@@ -286,6 +332,7 @@ static int prepare_bf(nngp_ctx *c, int cov, int nbatch, const double *theta, con
   if (beta && c->p == 0) return ctx_fail(c, NNGP_EINVAL, "beta given but the model has no covariates");
   const int grid = bf_grid_any(c->m, cov, (long long)c->loc_end - c->loc_begin, c->sms);
   memset(P, 0, sizeof *P);
+  memset(c->bf_short, 0, sizeof c->bf_short);
   P->coords = c->d_coords;
   P->nnIndx = c->d_nnIndx;
   P->n = c->n;
@@ -319,6 +366,11 @@ static int prepare_bf(nngp_ctx *c, int cov, int nbatch, const double *theta, con
       c->h_mat[b] = c->mat_cache[hit].mc;
       matern_series_params(c->h_mat[b], &th.ms);
       th.mat = c->d_mat + b;
+      // short series: 99 % of the locations keep t = phi^2 d^2 / 4 of every pair inside its range
+      const double t99 = 0.25 * t[2] * t[2] * c->pair_d2_q99;
+      c->bf_short[b] = (c->opt_matern_short && th.ms.use_series && bf_has_matern_short(c->m) &&
+                        t99 <= c->h_mat[b].t_short_max) ? 1 : 0;
+      if (c->bf_short[b]) th.ms.t_fast_max = c->h_mat[b].t_short_max;
     }
     const int slot = slots ? slots[b] : (b & 1);
     if (slot < 0 || slot > 1) return ctx_fail(c, NNGP_EINVAL, "slot must be 0 or 1");
@@ -354,8 +406,31 @@ static int enqueue_bf(nngp_ctx *c, int cov, const BfLaunch &P, int grid, bool wi
       c->launches++;
     }
   }
-  NNGP_CUDA(c, bf_launch(P, cov, grid, c->stream));
-  c->launches++;
+  int nshort = 0;
+  if (cov == NNGP_COV_MATERN)
+    for (int b = 0; b < P.nbatch; b++) nshort += c->bf_short[b];
+  if (nshort == 0 || nshort == P.nbatch) {
+    if (nshort == 0) {
+      NNGP_CUDA(c, bf_launch(P, cov, grid, c->stream));
+    } else {
+      BfLaunch Ps = P;
+      Ps.matern_short = 1;
+      NNGP_CUDA(c, bf_launch(Ps, cov, grid, c->stream));
+    }
+    c->launches++;
+    return NNGP_OK;
+  }
+  // mixed batch (the sampler's current and candidate phi straddle the short series' range): one launch per
+  // variant, so that the result of a parameter set never depends on what it was batched with
+  for (int v = 0; v < 2; v++) {
+    BfLaunch Pv = P;
+    Pv.nbatch = 0;
+    for (int b = 0; b < P.nbatch; b++)
+      if (c->bf_short[b] == v) Pv.th[Pv.nbatch++] = P.th[b];
+    Pv.matern_short = v;
+    NNGP_CUDA(c, bf_launch(Pv, cov, grid, c->stream));
+    c->launches++;
+  }
   return NNGP_OK;
 }
 

@@ -43,6 +43,9 @@ struct BfLaunch {
   const double2 *sites;  // q interleaved query sites
   const int *nn0;        // q x m column-major neighbour ids (R/generics.R:642 layout)
   int q;
+  // Matern: every parameter set of this launch may use the short series (th.ms.t_fast_max set accordingly);
+  // only bf_ws_kernel has that variant, the other kernels ignore the flag (their t_fast_max is 1)
+  int matern_short;
   BfTheta th[NNGP_MAX_BATCH];
 };
 

@@ -64,6 +64,12 @@ struct nngp_ctx {
   } mat_cache[4];
   int mat_cache_next = 0;
 
+  // Matern short series (matern_series.cuh): chosen per parameter set when phi^2/4 * pair_d2_q99 <= t_short_max(nu)
+  int opt_matern_short = 1;      // nngp_set_option("matern_short", 0/1)
+  double pair_d2_q99 = 1e300;    // 99 % quantile over this shard's locations of the largest squared pair distance
+  unsigned int *d_hist = nullptr;
+  unsigned char bf_short[NNGP_MAX_BATCH] = {};  // decision of the last prepare_bf, per parameter set
+
   // multi-GPU: NCCL communicator over the ranks of a sharded fit (nngp_comm_init); when set, the
   // results of nngp_bf_loglik / nngp_q_resid / nngp_q_forms are summed over the ranks on the device
   void *comm = nullptr;
@@ -98,6 +104,13 @@ cudaError_t q_forms_launch(const double *B, const double *F, const int *nnIndx, 
                            int loc_begin, int loc_end, double *partials, double *out, cudaStream_t stream);
 size_t xy_rows_count(int n, int p);
 cudaError_t xy_rows_launch(const double *X, const double *y, int n, int p, double *Xy, int sms, cudaStream_t stream);
+
+// bf_kernel.cu: true when the kernel that serves m neighbours has the short-series Matern variant
+bool bf_has_matern_short(int m);
+// stat_kernels.cu
+int pair_d2_hist_bins();
+cudaError_t pair_d2_hist_launch(const double2 *coords, const int *nnIndx, int m, int loc_begin, int loc_end,
+                                unsigned int *hist, cudaStream_t stream);
 
 // rep_kernels.cu
 int rep_prepare(nngp_ctx *c);  // levels + pinned z buffer (c->h_z), idempotent

@@ -28,7 +28,7 @@ extern __shared__ __align__(16) unsigned char tpl_smem[];
 // write into dv (overwritten by the factorisation afterwards).
 constexpr int kTplMaxEnt = 320;  // m(m-1)/2 + m entries at m = 24, padded to a batch
 template <int COV>
-constexpr int kTplBatch = (COV == NNGP_COV_MATERN) ? 4 : 8;  // entries evaluated together (independent chains)
+constexpr int kTplBatch = kIsMatern<COV> ? 4 : 8;  // entries evaluated together (independent chains)
 
 // Batches of UNR entries: all loads, then UNR independent evaluation chains, then all stores.
 // (A plain unrolled loop is serialised by ptxas: it cannot prove that the store of entry e does not
@@ -52,10 +52,10 @@ __device__ __forceinline__ void tpl_build_body(const CorT &cor, int lane, int of
     }
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
-      if constexpr (TAB && COV == NNGP_COV_MATERN) v[u] = sigmaSq * cor.fast_tab(d2[u]);
+      if constexpr (TAB && kIsMatern<COV>) v[u] = sigmaSq * cor.fast_tab(d2[u]);
       else v[u] = sigmaSq * cor.fast(d2[u]);
     }
-    if (COV == NNGP_COV_MATERN) {  // rare arguments outside the straight-line path (phi D > 2, integer nu)
+    if (kIsMatern<COV>) {  // rare arguments outside the straight-line path (phi D > 2, integer nu)
       bool any = false;
 #pragma unroll
       for (int u = 0; u < UNR; ++u) any |= cor.needs_slow(d2[u]);
@@ -76,7 +76,7 @@ __device__ __forceinline__ void tpl_build_body(const CorT &cor, int lane, int of
 template <int COV, int UNR, bool TAB = false>
 __device__ __forceinline__ void tpl_build(const BfLaunch &P, int lane, int off_co, int off_a, const unsigned *ent,
                                           int e_begin, int e_step, int nent_pad, const double *tab = nullptr) {
-  if constexpr (COV == NNGP_COV_MATERN) {
+  if constexpr (kIsMatern<COV>) {
     switch (blockIdx.y) {  // uniform over the CTA
       case 0: tpl_build_body<COV, UNR, TAB>(Cor<COV>(P.th[0], tab), lane, off_co, off_a, ent, e_begin, e_step, nent_pad, P.th[0].sigmaSq); break;
       case 1: tpl_build_body<COV, UNR, TAB>(Cor<COV>(P.th[1], tab), lane, off_co, off_a, ent, e_begin, e_step, nent_pad, P.th[1].sigmaSq); break;

@@ -190,6 +190,15 @@ class Engine:
         self._check(self.lib.nngp_fp64_peak(self.h, _dp(out)))
         return float(out[0])
 
+    def set_option(self, name, value):
+        """Tuning switch of the engine (include/nngp_b200.h: nngp_set_option), e.g. ("matern_short", 0)."""
+        self._check(self.lib.nngp_set_option(self.h, name.encode(), int(value)))
+
+    def get_option(self, name):
+        v = C.c_int(0)
+        self._check(self.lib.nngp_get_option(self.h, name.encode(), C.byref(v)))
+        return v.value
+
     def launch_count(self):
         return int(self.lib.nngp_launch_count(self.h))
 

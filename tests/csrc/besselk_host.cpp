@@ -32,3 +32,14 @@ extern "C" void host_gl_rule(double nu, double *t, double *w) {
   nngp::MaternConsts mc; nngp::matern_prepare(nu, &mc);
   for (int i = 0; i < nngp::kGlNodes; i++) { t[i] = mc.gl_t[i]; w[i] = mc.gl_w[i]; }
 }
+// short series (kMatShortTerms terms) and the largest t it is used for
+extern "C" double host_matern_series_short(double t, double nu) {
+  nngp::MaternConsts mc; nngp::matern_prepare(nu, &mc);
+  if (!mc.use_series) return -1.0;
+  nngp::MaternSeriesParams ms; nngp::matern_series_params(mc, &ms);
+  return nngp::matern_series<nngp::kMatShortTerms>(t, ms);
+}
+extern "C" double host_t_short_max(double nu) {
+  nngp::MaternConsts mc; nngp::matern_prepare(nu, &mc);
+  return mc.t_short_max;
+}

@@ -246,3 +246,34 @@ def test_cross_forms_other_widths(engine, port, p, m):
     assert abs(engine.q_resid(0, beta) - q) <= 1e-10 * abs(q)
     out = engine.bf_loglik(0, [theta], [beta], slots=[1])
     assert abs(out[0, 1] - q) <= 1e-10 * abs(q)
+
+
+@pytest.mark.parametrize("nu", [0.3, 0.75, 1.5, 2.5])
+@pytest.mark.parametrize("m", [10, 15, 20])
+def test_matern_short_series_variant(engine, port, nu, m):
+    """Dense neighbourhoods (phi D well under 1): the launch picks the 9-term series (Cor<NNGP_COV_MATERN_SHORT>).
+    Both variants meet the oracle tolerance, agree to ~1e-14, and a batch whose phi values straddle the short
+    series' range is split into one launch per variant without changing any parameter set's result."""
+    n = 4000
+    prob = make_problem(n, m, seed=41 + m, port=port, domain=np.sqrt(n / 5000.0))
+    theta = [5.0, 1.0, 6.0, nu]
+    try:
+        engine.set_option("matern_short", 1)
+        Bs, Fs, outs = _check(engine, port, prob, 2, theta)
+        assert engine.get_option("matern_short_used") == 1
+        engine.set_option("matern_short", 0)
+        Bf, Ff, outf = _check(engine, port, prob, 2, theta)
+        assert engine.get_option("matern_short_used") == 0
+        assert relerr(Fs, Ff) < 1e-13 and relerr_norm(Bs, Bf) < 1e-13
+        assert abs(outs[0, 0] - outf[0, 0]) < 1e-13 * abs(outf[0, 0])
+        engine.set_option("matern_short", 1)
+        far = [5.0, 1.0, 60.0, nu]  # phi D ~ 5: outside the short range -> full series / quadrature
+        beta = prob["beta"]
+        mixed = engine.bf_loglik(2, [theta, far], [beta, beta], slots=[0, 1])
+        assert engine.get_option("matern_short_used") == 1
+        a = engine.bf_loglik(2, [theta], [beta], slots=[0])
+        b = engine.bf_loglik(2, [far], [beta], slots=[0])
+        assert engine.get_option("matern_short_used") == 0
+        assert np.array_equal(mixed[0], a[0]) and np.array_equal(mixed[1], b[0])
+    finally:
+        engine.set_option("matern_short", 1)

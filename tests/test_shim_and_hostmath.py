@@ -129,6 +129,27 @@ def test_matern_gauss_laguerre_on_host_vs_mpmath(tmp_path):
     assert L.host_matern_gl(800.0, 0.75) == 0.0  # underflows like the reference's bessel_k
 
 
+def test_matern_short_series_on_host_vs_mpmath(tmp_path):
+    """The 9-term series (matern_series.cuh, Cor<NNGP_COV_MATERN_SHORT>) over its whole range t <= t_short_max(nu):
+    as accurate as the 14-term one (vs mpmath), and the range is wide enough to be useful."""
+    import mpmath as mp
+    L = _build_host("besselk_host.cpp", str(tmp_path / "libbk.so"))
+    L.host_matern_series_short.restype = C.c_double; L.host_matern_series_short.argtypes = [C.c_double, C.c_double]
+    L.host_t_short_max.restype = C.c_double; L.host_t_short_max.argtypes = [C.c_double]
+    mp.mp.dps = 40
+    worst = 0.0
+    for nu in (0.1, 0.3, 0.5, 0.75, 0.9, 1.2, 1.5, 1.9, 2.5, 3.3):
+        T = L.host_t_short_max(nu)
+        assert 0.05 < T <= 1.0, (nu, T)
+        for f in (1e-12, 1e-6, 1e-3, 0.1, 0.5, 0.9, 1.0):
+            t = T * f
+            x = 2.0 * np.sqrt(t)
+            rho = mp.mpf(x) ** nu * mp.besselk(nu, x) / (mp.mpf(2) ** (nu - 1) * mp.gamma(nu))
+            worst = max(worst, float(abs((mp.mpf(L.host_matern_series_short(t, nu)) - rho) / rho)))
+    assert worst < 5e-14, worst
+    assert L.host_t_short_max(1.0) == 0.0 and L.host_t_short_max(2.0005) == 0.0  # integer nu: no series at all
+
+
 def test_device_fastmath_on_host(tmp_path):
     """Branch-free sqrt / exp of spnngp_b200/csrc/fastmath.cuh (host build) vs libm."""
     L = _build_host("fastmath_host.cpp", str(tmp_path / "libfm.so"))
