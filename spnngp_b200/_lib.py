@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnngp_b200.so")
+# NNGP_B200_LIB: an alternative build of the same library (kernel A/B experiments, tools/ab_bench.py)
+LIB_PATH = os.environ.get("NNGP_B200_LIB") or os.path.join(_HERE, "libnngp_b200.so")
 RSHIM_PATH = os.path.join(_HERE, "librshim.so")
 
 c_double_p = C.POINTER(C.c_double)

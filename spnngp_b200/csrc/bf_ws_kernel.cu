@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(32 * (1 + NP), 2) bf_ws_kernel(const __grid_co
   __shared__ long long next_tile[8];  // ring of claimed tiles, slot j & 7 (>= ntiles: no more work)
   __shared__ double red[2][1 + NP];
   __shared__ int last_flag;
-  __shared__ __align__(16) double s_tab[kIsMatern<COV> ? 160 : 2];  // exp / log tables (fasttab.cuh)
+  constexpr int kTabLen = 32 + 128 * kLogTabStride;  // exp table, then the log table (x8 interleaved copies when replicated)
+  __shared__ __align__(16) double s_tab[kIsMatern<COV> ? kTabLen : 2];  // exp / log tables (fasttab.cuh)
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
 
@@ -89,7 +90,11 @@ __global__ void __launch_bounds__(32 * (1 + NP), 2) bf_ws_kernel(const __grid_co
   const double *__restrict__ resid = th.resid;
 
   if (kIsMatern<COV>) {
-    for (int x = tid; x < 160; x += Ws::kThreads) s_tab[x] = (x < 32) ? kExpTab32[x] : kLogTab64[x - 32];
+    for (int x = tid; x < 32; x += Ws::kThreads) s_tab[x] = kExpTab32[x];
+    for (int x = tid; x < 128 * kLogTabStride; x += Ws::kThreads) {  // pair idx, copy c -> slot idx * stride + c
+      const int pr = x >> 1, idx = pr / kLogTabStride;
+      s_tab[32 + x] = kLogTab64[2 * idx + (x & 1)];
+    }
   }
   // ---- one-time setup: work list, zero padding of both stages --------------------------------------
   const int ne = m * (m - 1) / 2;
@@ -430,6 +435,10 @@ int ws_grid_for(int m, long long nloc, int sms) {
 
 cudaError_t ws_launch(const BfLaunch &P, int cov, int grid_x, cudaStream_t stream) {
   switch (ws_capacity_for_m(P.m)) {
+#ifdef NNGP_WS_ONLY15  // experiment builds (tools/ab_bench.py): only the m = 13..15 capacity, for short compile times
+    case 15: return ws_launch_cov<15>(P, cov, grid_x, stream);
+    default: return cudaErrorInvalidValue;
+#else
     case 8: return ws_launch_cov<8>(P, cov, grid_x, stream);
     case 10: return ws_launch_cov<10>(P, cov, grid_x, stream);
     case 12: return ws_launch_cov<12>(P, cov, grid_x, stream);
@@ -438,6 +447,7 @@ cudaError_t ws_launch(const BfLaunch &P, int cov, int grid_x, cudaStream_t strea
     case 20: return ws_launch_cov<20>(P, cov, grid_x, stream);
     case 24: return ws_launch_cov<24>(P, cov, grid_x, stream);
     default: return cudaErrorInvalidValue;
+#endif
   }
 }
 

@@ -55,10 +55,12 @@ struct Cor<NNGP_COV_MATERN> {
   double phi, q4;  // q4 = phi^2 / 4: t = q4 d2 = (phi D / 2)^2
   const MaternSeriesParams &ms;
   const MaternConsts *mc;  // global memory: Temme / CF2 tables for the slow path
-  const double *tab;       // shared memory: exp / log tables (fasttab.cuh) when the kernel staged them, else NULL
+  const double *tab;       // shared memory: exp table (fasttab.cuh) when the kernel staged the tables, else NULL
+  const double *ltab;      // shared memory: log table, this lane's copy when replicated (kLogTabStride)
   __device__ __forceinline__ Cor(const BfTheta &t, const double *tab_ = nullptr)
-      : phi(t.phi), q4(0.25 * t.phi * t.phi), ms(t.ms), mc(t.mat), tab(tab_) {}
-  __device__ __forceinline__ double fast_tab(double d2) const { return matern_series_tab(fmin(q4 * d2, 1.0), ms, tab); }
+      : phi(t.phi), q4(0.25 * t.phi * t.phi), ms(t.ms), mc(t.mat), tab(tab_),
+        ltab(tab_ ? tab_ + 32 + (kLogTabStride > 1 ? 2 * (threadIdx.x & 7) : 0) : nullptr) {}
+  __device__ __forceinline__ double fast_tab(double d2) const { return matern_series_tab(fmin(q4 * d2, 1.0), ms, tab, ltab); }
   // power series in t for phi D <= 2 (clamped beyond: the caller re-evaluates those with slow())
   __device__ __forceinline__ double fast(double d2) const { return matern_series(fmin(q4 * d2, 1.0), ms); }
   __device__ __forceinline__ bool needs_slow(double d2) const { return !ms.use_series || q4 * d2 > 1.0; }
@@ -79,7 +81,7 @@ template <>
 struct Cor<NNGP_COV_MATERN_SHORT> : Cor<NNGP_COV_MATERN> {
   __device__ __forceinline__ Cor(const BfTheta &t, const double *tab_ = nullptr) : Cor<NNGP_COV_MATERN>(t, tab_) {}
   __device__ __forceinline__ double fast_tab(double d2) const {
-    return matern_series_tab<kMatShortTerms>(fmin(q4 * d2, 1.0), ms, tab);
+    return matern_series_tab<kMatShortTerms>(fmin(q4 * d2, 1.0), ms, tab, ltab);
   }
   __device__ __forceinline__ double fast(double d2) const { return fast_tab(d2); }
   __device__ __forceinline__ bool needs_slow(double d2) const { return q4 * d2 > ms.t_fast_max; }

@@ -227,6 +227,9 @@ NNGP_FM double nngp_exp_tab(double x, const double *etab) {
   return (x < -708.0) ? 0.0 : res;
 }
 
+// LSTRIDE: distance, in pairs, between consecutive table entries (8 when the table is replicated per quarter-warp lane
+// so that the 8 lanes of one 128-bit shared-memory wavefront never share a bank group; ltab then points at the lane's copy)
+template <int LSTRIDE = 1>
 NNGP_FM double nngp_log_tab(double x, const double *ltab /* 64 pairs {rc, -log rc} */) {
   const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
 #if defined(__CUDA_ARCH__)
@@ -243,13 +246,13 @@ NNGP_FM double nngp_log_tab(double x, const double *ltab /* 64 pairs {rc, -log r
   const int hm = (hx & 0x000fffff) | 0x3ff00000;
 #if defined(__CUDA_ARCH__)
   const double m = __hiloint2double(hm, lx);
-  const double2 tb = reinterpret_cast<const double2 *>(ltab)[idx];
+  const double2 tb = reinterpret_cast<const double2 *>(ltab)[idx * LSTRIDE];
   const double rc = tb.x, lc = tb.y;
 #else
   const uint64_t mb = ((uint64_t)(uint32_t)hm << 32) | (uint32_t)lx;
   double m;
   memcpy(&m, &mb, sizeof m);
-  const double rc = ltab[2 * idx], lc = ltab[2 * idx + 1];
+  const double rc = ltab[2 * idx * LSTRIDE], lc = ltab[2 * idx * LSTRIDE + 1];
 #endif
   const double r = fma(m, rc, -1.0);
   double p = fma(r, -1.0 / 8.0, 1.0 / 7.0);

@@ -28,7 +28,7 @@ struct StageJob {
 class HostStager {
  public:
   static constexpr size_t kChunk = (size_t)2 << 20;
-  static constexpr int kMaxThreads = 4;
+  static constexpr int kMaxThreads = 8;
 
   ~HostStager() {
     for (int t = 0; t < nthreads_; t++) {
@@ -43,7 +43,7 @@ class HostStager {
   cudaError_t init(int device) {
     device_ = device;
     unsigned hc = std::thread::hardware_concurrency();
-    nthreads_ = hc >= 8 ? kMaxThreads : (hc >= 4 ? 2 : 1);
+    nthreads_ = hc >= 16 ? kMaxThreads : (hc >= 8 ? 4 : (hc >= 4 ? 2 : 1));  // multi-GPU boxes run one stager per rank
     for (int t = 0; t < nthreads_; t++) {
       cudaError_t e = cudaStreamCreateWithFlags(&st_[t], cudaStreamNonBlocking);
       if (e != cudaSuccess) return e;

@@ -32,9 +32,15 @@ NNGP_FM double matern_series(double t, const MaternSeriesParams &mc) {
 
 // matern_series with the table-driven log / exp (tab: 32 doubles of kExpTab32, then the 64 pairs of kLogTab64, in
 // shared memory): 26 fewer FP64 instructions of ~95 per correlation.
+#ifndef NNGP_LOGTAB_REP
+#define NNGP_LOGTAB_REP 0  // 1: the kernel staged 8 interleaved copies of the log table (one per quarter-warp lane)
+#endif
+constexpr int kLogTabStride = NNGP_LOGTAB_REP ? 8 : 1;
+
+// tab: kExpTab32; ltab: the log table (this lane's copy when replicated)
 template <int NT = kMatSeriesTerms>
-NNGP_FM double matern_series_tab(double t, const MaternSeriesParams &mc, const double *tab) {
-  const double L = nngp_log_tab(t + 1e-300, tab + 32);
+NNGP_FM double matern_series_tab(double t, const MaternSeriesParams &mc, const double *tab, const double *ltab) {
+  const double L = nngp_log_tab<kLogTabStride>(t + 1e-300, ltab);
   const double pw = nngp_exp_tab(mc.nu * L, tab);  // t^nu
   double pa = mc.sa[NT - 1], pb = mc.sb[NT - 1];
 #pragma unroll

@@ -27,8 +27,11 @@ extern __shared__ __align__(16) unsigned char tpl_smem[];
 // dst = a row of cv) and is padded to a multiple of the batch width with harmless duplicates that
 // write into dv (overwritten by the factorisation afterwards).
 constexpr int kTplMaxEnt = 320;  // m(m-1)/2 + m entries at m = 24, padded to a batch
+#ifndef NNGP_MATERN_BATCH
+#define NNGP_MATERN_BATCH 4
+#endif
 template <int COV>
-constexpr int kTplBatch = kIsMatern<COV> ? 4 : 8;  // entries evaluated together (independent chains)
+constexpr int kTplBatch = kIsMatern<COV> ? NNGP_MATERN_BATCH : 8;  // entries evaluated together (independent chains)
 
 // Batches of UNR entries: all loads, then UNR independent evaluation chains, then all stores.
 // (A plain unrolled loop is serialised by ptxas: it cannot prove that the store of entry e does not

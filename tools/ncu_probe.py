@@ -6,7 +6,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import pyoracle  # noqa: E402 (neighbour lists for the probe only)
 from spnngp_b200 import Engine  # noqa: E402
 from tests.util import make_problem  # noqa: E402
 
@@ -14,9 +13,9 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
 m = int(sys.argv[2]) if len(sys.argv) > 2 else 15
 cov = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
-port = pyoracle.Port(); port.set_threads(os.cpu_count())
-prob = make_problem(n, m, seed=1, port=port, domain=np.sqrt(n / 5000.0))
+prob = make_problem(n, m, seed=1, domain=np.sqrt(n / 5000.0))
 eng = Engine(0)
+prob["nnIndx"], _, prob["nnIndxLU"] = eng.mk_nn_indx(prob["coords"], m, "cb")
 eng.set_data(prob["coords"], prob["nnIndx"], prob["nnIndxLU"], prob["X"], prob["y"], m)
 theta = [5, 1, 6, 0.75][: 4 if cov == 2 else 3]
 for _ in range(reps):

@@ -8,18 +8,15 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import pyoracle  # noqa: E402  (only to get neighbour lists for the probe)
 from spnngp_b200 import Engine  # noqa: E402
 from tests.util import make_problem  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
 m = int(sys.argv[2]) if len(sys.argv) > 2 else 15
-port = pyoracle.Port()
-port.set_threads(os.cpu_count())
 t = time.time()
-prob = make_problem(n, m, seed=1, port=port, domain=np.sqrt(n / 5000.0))
-print(f"n={n} m={m} cpu cb search {time.time()-t:.2f}s on {os.cpu_count()} threads", flush=True)
+prob = make_problem(n, m, seed=1, domain=np.sqrt(n / 5000.0))
 eng = Engine(0)
+prob["nnIndx"], _, prob["nnIndxLU"] = eng.mk_nn_indx(prob["coords"], m, "cb")
 t = time.time()
 eng.set_data(prob["coords"], prob["nnIndx"], prob["nnIndxLU"], prob["X"], prob["y"], m)
 print(f"set_data {time.time()-t:.3f}s", flush=True)

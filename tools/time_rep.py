@@ -16,9 +16,6 @@ z = np.random.default_rng(1).standard_normal(n)
 for k in range(4):
     t = time.perf_counter(); y = eng.rep_draw(0, wl["beta"], z); print(f"rep_draw {k}: {(time.perf_counter()-t)*1e3:.2f} ms", flush=True)
 B, F = eng.get_bf(0)
-from oracle import pyoracle
-import ctypes as C
-port = pyoracle.Port()
 R = __import__("spnngp_b200")._lib.load_rshim()
 t = time.perf_counter()
 zz = np.array([R.rnorm(0.0, 1.0) for _ in range(100000)])
