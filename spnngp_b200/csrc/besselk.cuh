@@ -9,6 +9,7 @@
 // contain no divisions except the one CF2 needs.
 #pragma once
 #include <math.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define NNGP_HD __host__ __device__ __forceinline__
@@ -32,8 +33,11 @@ struct MaternSeriesParams {
   double t_ext_max;  // largest t = (phi D / 2)^2 served by the extended series (beyond: Gauss-Laguerre, matern_gl)
   double t_fast_max; // largest t the straight-line path serves: 1 for the full series, t_short_max for the short one
   int use_series;
+  // high word of the squared distance d2 = t_fast_max / (phi^2/4) from which on an entry MAY need slow(): positive
+  // doubles order like their bit patterns, so the producers' per-batch test is one integer compare (matern_set_phi)
+  int d2_slow_hi;
   double sa[kMatSeriesTerms];
-  double sb[kMatSeriesTerms];
+  double sb[kMatSeriesTerms];  // NEGATED coefficients of the second sum
 };
 
 struct MaternConsts {
@@ -353,10 +357,22 @@ inline void matern_series_params(const MaternConsts &mc, MaternSeriesParams *ms)
   const double snp = fabs(sin(3.14159265358979323846 * mc.nu));
   ms->t_ext_max = !mc.use_series ? 1.0 : (snp > 0.1 ? 4.0 : 2.25);
   ms->t_fast_max = 1.0;
+  ms->d2_slow_hi = 0;  // every entry is checked until matern_set_phi is called
   for (int k = 0; k < kMatSeriesTerms; k++) {
     ms->sa[k] = mc.sa[k];
-    ms->sb[k] = mc.sb[k];
+    ms->sb[k] = -mc.sb[k];  // negated: rho = pa + t^nu * pb
   }
+}
+
+// after t_fast_max is final: the integer threshold of the producers' "may need slow()" test for this phi
+inline void matern_set_phi(MaternSeriesParams *ms, double phi) {
+  ms->d2_slow_hi = 0;
+  if (!ms->use_series) return;  // integer nu: every entry takes slow()
+  const double d2 = ms->t_fast_max / (0.25 * phi * phi);
+  if (!(d2 > 0.0) || d2 > 1e300) return;
+  long long bits;
+  memcpy(&bits, &d2, sizeof bits);
+  ms->d2_slow_hi = (int)(bits >> 32);
 }
 
 }  // namespace nngp

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(32) bf_tpl_kernel(const __grid_constant__ BfLa
     for (int k = m; k < MC; ++k) cv[k * 32 + lane] = 0.0;
   }
   // work list of phase A (see tpl_build)
-  __shared__ unsigned ent[kTplMaxEnt];
+  __shared__ TplEnt<COV> ent[kTplMaxEnt];
   const int ne = m * (m - 1) / 2;
   constexpr int kBatch = kTplBatch<COV>;
   const int nent_pad = ((ne + m + kBatch - 1) / kBatch) * kBatch;
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(32) bf_tpl_kernel(const __grid_constant__ BfLa
     } else {
       w = 0u | ((unsigned)MC << 8) | ((unsigned)((Geo::OFF_DV - Geo::OFF_A) / 256) << 16);  // padding
     }
-    ent[e] = w;
+    tpl_pack_ent(w, &ent[e]);
   }
   __syncwarp();
 

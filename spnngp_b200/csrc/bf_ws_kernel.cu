@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(32 * (1 + NP), 2) bf_ws_kernel(const __grid_co
   // who stores a solved tile's weights: the producers where the consumer is the critical path (0.62 -> 0.59 ms,
   // spherical), the consumer for Matern, whose producers are the critical path (1.11 vs 1.15 ms)
   constexpr bool kProducersStoreB = !kIsMatern<COV>;
-  __shared__ unsigned ent[kTplMaxEnt];
+  __shared__ TplEnt<COV> ent[kTplMaxEnt];
   __shared__ int ebeg[NP + 1];
   __shared__ long long next_tile[8];  // ring of claimed tiles, slot j & 7 (>= ntiles: no more work)
   __shared__ double red[2][1 + NP];
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(32 * (1 + NP), 2) bf_ws_kernel(const __grid_co
     } else {
       w = 0u | ((unsigned)MC << 8) | ((unsigned)((Geo::OFF_DV - Geo::OFF_A) / 256) << 16);  // padding -> dv row 0
     }
-    ent[e] = w;
+    tpl_pack_ent(w, &ent[e]);
   }
   for (int s = 0; s < Ws::kStages; ++s) {
     unsigned char *st = tpl_smem + s * Ws::kStageBytes;

@@ -60,10 +60,14 @@ struct Cor<NNGP_COV_MATERN> {
   __device__ __forceinline__ Cor(const BfTheta &t, const double *tab_ = nullptr)
       : phi(t.phi), q4(0.25 * t.phi * t.phi), ms(t.ms), mc(t.mat), tab(tab_),
         ltab(tab_ ? tab_ + 32 + (kLogTabStride > 1 ? 2 * (threadIdx.x & 7) : 0) : nullptr) {}
-  __device__ __forceinline__ double fast_tab(double d2) const { return matern_series_tab(fmin(q4 * d2, 1.0), ms, tab, ltab); }
-  // power series in t for phi D <= 2 (clamped beyond: the caller re-evaluates those with slow())
-  __device__ __forceinline__ double fast(double d2) const { return matern_series(fmin(q4 * d2, 1.0), ms); }
+  // power series in t for phi D <= 2.  Beyond, the value is garbage (possibly inf / NaN, never a trap: the table
+  // indices are masked) and the caller re-evaluates the entry with slow(); no clamp, it cost 7 instructions per entry.
+  __device__ __forceinline__ double fast_tab(double d2) const { return matern_series_tab(q4 * d2, ms, tab, ltab); }
+  __device__ __forceinline__ double fast(double d2) const { return matern_series(q4 * d2, ms); }
   __device__ __forceinline__ bool needs_slow(double d2) const { return !ms.use_series || q4 * d2 > 1.0; }
+  // conservative integer form of needs_slow for the per-batch test (true for every entry that needs slow(), and for
+  // the few whose d2 shares the threshold's high word): keeps the test off the FP64 pipe
+  __device__ __forceinline__ bool maybe_slow(double d2) const { return __double2hiint(d2) >= ms.d2_slow_hi; }
   // phi D in (2, 4]: the extended series; beyond: Gauss-Laguerre quadrature.  nu within 1e-3 of an integer
   // (the series cancel): Temme's iteration for phi D <= 2, the quadrature beyond.
   __device__ __noinline__ double slow(double d2) const {
@@ -81,7 +85,7 @@ template <>
 struct Cor<NNGP_COV_MATERN_SHORT> : Cor<NNGP_COV_MATERN> {
   __device__ __forceinline__ Cor(const BfTheta &t, const double *tab_ = nullptr) : Cor<NNGP_COV_MATERN>(t, tab_) {}
   __device__ __forceinline__ double fast_tab(double d2) const {
-    return matern_series_tab<kMatShortTerms>(fmin(q4 * d2, 1.0), ms, tab, ltab);
+    return matern_series_tab<kMatShortTerms>(q4 * d2, ms, tab, ltab);
   }
   __device__ __forceinline__ double fast(double d2) const { return fast_tab(d2); }
   __device__ __forceinline__ bool needs_slow(double d2) const { return q4 * d2 > ms.t_fast_max; }

@@ -215,16 +215,19 @@ NNGP_FM double nngp_exp_tab(double x, const double *etab) {
   const double T = etab[ni & 31];
   const double v = fma(T, q, T);
   const int k = ni >> 5;
+  // results below 2^-1000 are flushed to zero; decided on the integer side (k), not with an FP64 compare of x
 #if defined(__CUDA_ARCH__)
-  const double res = __hiloint2double(__double2hiint(v) + (k << 20), __double2loint(v));
+  const bool tiny = k < -1000;
+  return __hiloint2double(tiny ? 0 : __double2hiint(v) + (k << 20), tiny ? 0 : __double2loint(v));
 #else
+  if (k < -1000) return 0.0;
   uint64_t bits;
   memcpy(&bits, &v, sizeof bits);
   bits += (uint64_t)((int64_t)k << 52);
   double res;
   memcpy(&res, &bits, sizeof res);
+  return res;
 #endif
-  return (x < -708.0) ? 0.0 : res;
 }
 
 // LSTRIDE: distance, in pairs, between consecutive table entries (8 when the table is replicated per quarter-warp lane

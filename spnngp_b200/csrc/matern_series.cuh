@@ -3,6 +3,7 @@
 //
 //   K_nu(x) = pi/2 (I_-nu(x) - I_nu(x)) / sin(nu pi),  I_+-nu(x) = (x/2)^(+-nu) sum_k t^k / (k! Gamma(k+1+-nu))
 //   rho(x)  = x^nu K_nu(x) / (2^(nu-1) Gamma(nu)) = sum_k sa[k] t^k  -  t^nu sum_k sb[k] t^k
+// (the kernel-parameter copy MaternSeriesParams stores -sb[k], so the last step is one fma without a negation)
 //
 // with the nu-only coefficients sa, sb prepared on the host (besselk.cuh, matern_prepare).  No square
 // root (t comes straight from the squared distance), no data-dependent loop, no Gamma functions on the
@@ -27,7 +28,7 @@ NNGP_FM double matern_series(double t, const MaternSeriesParams &mc) {
     pa = fma(pa, t, mc.sa[k]);
     pb = fma(pb, t, mc.sb[k]);
   }
-  return fma(-pw, pb, pa);
+  return fma(pw, pb, pa);  // MaternSeriesParams::sb holds the NEGATED coefficients
 }
 
 // matern_series with the table-driven log / exp (tab: 32 doubles of kExpTab32, then the 64 pairs of kLogTab64, in
@@ -40,7 +41,8 @@ constexpr int kLogTabStride = NNGP_LOGTAB_REP ? 8 : 1;
 // tab: kExpTab32; ltab: the log table (this lane's copy when replicated)
 template <int NT = kMatSeriesTerms>
 NNGP_FM double matern_series_tab(double t, const MaternSeriesParams &mc, const double *tab, const double *ltab) {
-  const double L = nngp_log_tab<kLogTabStride>(t + 1e-300, ltab);
+  // t = 0 (coincident sites) needs no guard here: the table log reads it as 2^-1023, so t^nu ~ 0 and rho = sa[0] = 1
+  const double L = nngp_log_tab<kLogTabStride>(t, ltab);
   const double pw = nngp_exp_tab(mc.nu * L, tab);  // t^nu
   double pa = mc.sa[NT - 1], pb = mc.sb[NT - 1];
 #pragma unroll
@@ -48,7 +50,7 @@ NNGP_FM double matern_series_tab(double t, const MaternSeriesParams &mc, const d
     pa = fma(pa, t, mc.sa[k]);
     pb = fma(pb, t, mc.sb[k]);
   }
-  return fma(-pw, pb, pa);
+  return fma(pw, pb, pa);  // MaternSeriesParams::sb holds the NEGATED coefficients
 }
 
 // (A truncated 9-term variant for t <= 1/16 behind a warp-uniform branch was measured and dropped: 0.99 -> 1.33 ms,

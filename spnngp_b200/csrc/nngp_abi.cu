@@ -371,6 +371,7 @@ static int prepare_bf(nngp_ctx *c, int cov, int nbatch, const double *theta, con
       c->bf_short[b] = (c->opt_matern_short && th.ms.use_series && bf_has_matern_short(c->m) &&
                         t99 <= c->h_mat[b].t_short_max) ? 1 : 0;
       if (c->bf_short[b]) th.ms.t_fast_max = c->h_mat[b].t_short_max;
+      matern_set_phi(&th.ms, t[2]);
     }
     const int slot = slots ? slots[b] : (b & 1);
     if (slot < 0 || slot > 1) return ctx_fail(c, NNGP_EINVAL, "slot must be 0 or 1");

