@@ -31,6 +31,13 @@
 
 #include "tpl_device.cuh"
 
+#ifndef NNGP_WS_MATERN_NP
+#define NNGP_WS_MATERN_NP 5  // producer warps of the Matern kernels: 3 / 4 / 5 / 6 -> 0.879 / 0.927 / 0.859 / 0.957 ms (n = 1e6, m = 15)
+#endif
+#ifndef NNGP_WS_SHARES  // relative shares of the Matern producer warps, one decimal digit each, warp 1 first
+#define NNGP_WS_SHARES 11111  // (NNGP_WS_MATERN_NP digits) equal; 58855 / 59935 / 67756 / 68836 measured 0.900 / 0.887 / 0.877 / 0.864 ms
+#endif
+
 namespace nngp {
 
 template <int MC, int NP>
@@ -65,7 +72,7 @@ __device__ __forceinline__ double *ws_rr(int slot) {
 }
 
 template <int MC, int COV, int NP>
-__global__ void __launch_bounds__(32 * (1 + NP), 2) bf_ws_kernel(const __grid_constant__ BfLaunch P) {
+__global__ void __launch_bounds__(32 * (1 + NP), (MC <= 16) ? 2 : 1) bf_ws_kernel(const __grid_constant__ BfLaunch P) {  // 20, 24: one CTA per SM
   using Geo = TplGeo<MC>;
   using Ws = WsGeo<MC, NP>;
   constexpr int kBatch = kTplBatch<COV>;
@@ -102,7 +109,15 @@ __global__ void __launch_bounds__(32 * (1 + NP), 2) bf_ws_kernel(const __grid_co
   if (tid <= NP) {
     // entry ranges of the producer warps, in whole batches
     const int nb = nent_pad / kBatch;
-    ebeg[tid] = ((nb * tid) / NP) * kBatch;
+    int shares[8] = {1, 1, 1, 1, 1, 1, 1, 1};
+    if (kIsMatern<COV>) {
+      long long d = NNGP_WS_SHARES;
+      for (int i = NP - 1; i >= 0; --i, d /= 10) shares[i] = (int)(d % 10);
+    }
+    int tot = 0, cum = 0;
+    for (int i = 0; i < NP; ++i) tot += shares[i];
+    for (int i = 0; i < tid; ++i) cum += shares[i];
+    ebeg[tid] = ((2 * nb * cum + tot) / (2 * tot)) * kBatch;  // rounded cumulative share, in whole batches
   }
   for (int e = tid; e < nent_pad; e += Ws::kThreads) {
     unsigned w;
@@ -393,8 +408,8 @@ static cudaError_t ws_launch_cov(const BfLaunch &P, int cov, int grid_x, cudaStr
     case NNGP_COV_EXPONENTIAL: return ws_launch_one<MC, NNGP_COV_EXPONENTIAL, 3>(P, grid_x, stream);
     case NNGP_COV_SPHERICAL: return ws_launch_one<MC, NNGP_COV_SPHERICAL, 3>(P, grid_x, stream);
     case NNGP_COV_MATERN:
-      if (P.matern_short) return ws_launch_one<MC, NNGP_COV_MATERN_SHORT, 3>(P, grid_x, stream);
-      return ws_launch_one<MC, NNGP_COV_MATERN, 3>(P, grid_x, stream);
+      if (P.matern_short) return ws_launch_one<MC, NNGP_COV_MATERN_SHORT, NNGP_WS_MATERN_NP>(P, grid_x, stream);
+      return ws_launch_one<MC, NNGP_COV_MATERN, NNGP_WS_MATERN_NP>(P, grid_x, stream);
     case NNGP_COV_GAUSSIAN: return ws_launch_one<MC, NNGP_COV_GAUSSIAN, 3>(P, grid_x, stream);
     default: return cudaErrorInvalidValue;
   }

@@ -273,7 +273,7 @@ class Engine:
         lo, hi = site_range if site_range is not None else (0, q)
         self._check(self.lib.nngp_rnngp_predict(self.h, cov, q, _dp(x0f), _dp(c0), _ip(nn0), S, _dp(bsf), _dp(tsf),
                                                 _dp(zf), _dp(y0), lo, hi))
-        return y0.reshape(S, q).T.copy()
+        return y0.reshape(S, q).T  # q x S, column-major like the reference's p.y.0 (a view: no 8 GB transpose at C4 sizes)
 
     def cnngp(self, cov, theta_alpha, sigmaSqIG, X0=None, coords0=None, nnIndx0=None):
         """Conjugate model for g parameter sets (reference `cNNGP`, src/cNNGP.cpp:73).
