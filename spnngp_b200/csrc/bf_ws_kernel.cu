@@ -281,7 +281,11 @@ __global__ void __launch_bounds__(32 * (1 + NP), (MC <= 16) ? 2 : 1) bf_ws_kerne
         }
       }
       double Fsum;
-      const bool ok = tpl_solve<MC>(A, cv + lane, dv, mi, diag, &Fsum);
+      // Cholesky block width: 4 columns where the consumer is the critical path and registers allow (exponential at
+      // m = 15: W = 2 / 3 / 4 -> 0.642 / 0.629 / 0.620 ms; gaussian 0.600 -> 0.571).  Matern (168 registers with five
+      // producers) keeps 2, and so do the small capacities, where W = 4 measured slower (m = 10: 0.307 -> 0.343 ms).
+      constexpr int kCholW = (!kIsMatern<COV> && MC >= 12 && MC <= 16) ? 4 : 2;
+      const bool ok = tpl_solve<MC, kCholW>(A, cv + lane, dv, mi, diag, &Fsum);
       if (!ok && active) failed = min(failed, (int)min(i + 1, (long long)INT_MAX - 1));
       const double Fv = diag - Fsum;
       double part = 0.0;

@@ -121,86 +121,77 @@ __device__ __forceinline__ void tpl_build(const BfLaunch &P, int lane, int off_c
 }
 
 // ---- phase B: Cholesky + solves, fully unrolled -----------------------------------------------------
-// Left-looking C = V V' two columns at a time; V(i,j) overwrites A, the right-hand side rides along
+// Left-looking C = V V' W columns at a time; V(i,j) overwrites A, the right-hand side rides along
 // as row MC (cv[j] becomes y_j = (V^-1 c)_j), 1/V(j,j) goes to dv[j].  Then V' B = y.
 // On return: Bout[0..MC) kriging weights, *Fsum = c' C^-1 c = |y|^2; false if a pivot is not positive.
 #define V_(i, j) A[((i) * ((i)-1) / 2 + (j)) * 32]
 
-// columns J0 and J0+1 (compile-time), then recurse; the memory clobber between pairs keeps ptxas from
-// hoisting the next pair's loads across this pair's stores (which would blow up register pressure).
-template <int MC, int J0>
-__device__ __forceinline__ void tpl_chol_pair(double *A, double *cv, double *dv, int mi, double diag, double &Fsum,
-                                              bool &ok) {
-  constexpr bool two = (J0 + 1 < MC);
-  constexpr int J1 = J0 + 1;
-  double a0[MC + 1], a1[MC + 1];  // rows J0..MC of columns J0 and J1 (row MC: right-hand side)
+// columns J0 .. J0+W-1 (compile-time), then recurse; the memory clobber between blocks keeps ptxas from
+// hoisting the next block's loads across this block's stores (which would blow up register pressure).
+// One load of V(i,k) feeds W FMAs: W = 2 needs 336 loads per location at MC = 15, W = 3 needs 210.
+template <int MC, int J0, int W>
+__device__ __forceinline__ void tpl_chol_block(double *A, double *cv, double *dv, int mi, double diag, double &Fsum,
+                                               bool &ok) {
+  constexpr int NW = (J0 + W <= MC) ? W : (MC - J0);  // columns in this block
+  double a[NW][MC + 1];  // a[c][i]: rows i = J0+c .. MC of column J0+c (row MC: right-hand side)
 #pragma unroll
-  for (int i = J0; i <= MC; ++i) {
-    if (i == J0) a0[i] = (J0 < mi) ? diag : 1.0;
-    else if (i < MC) a0[i] = V_(i, J0);
-    else a0[i] = cv[J0 * 32];
-  }
-  if (two) {
+  for (int c = 0; c < NW; ++c) {
 #pragma unroll
-    for (int i = J1; i <= MC; ++i) {
-      if (i == J1) a1[i] = (J1 < mi) ? diag : 1.0;
-      else if (i < MC) a1[i] = V_(i, J1);
-      else a1[i] = cv[J1 * 32];
+    for (int i = J0 + c; i <= MC; ++i) {
+      if (i == J0 + c) a[c][i] = (J0 + c < mi) ? diag : 1.0;
+      else if (i < MC) a[c][i] = V_(i, J0 + c);
+      else a[c][i] = cv[(J0 + c) * 32];
     }
   }
 #pragma unroll  // (a rolled k loop, unroll 2 or 4, shrinks the code 3x but measured 3-8% slower: less load hoisting)
   for (int k = 0; k < J0; ++k) {
-    const double v0 = V_(J0, k);
-    a0[J0] = fma(-v0, v0, a0[J0]);
-    double v1 = 0.0;
-    if (two) {
-      v1 = V_(J1, k);
-      a0[J1] = fma(-v1, v0, a0[J1]);
-      a1[J1] = fma(-v1, v1, a1[J1]);
+    double vc[NW];
+#pragma unroll
+    for (int c = 0; c < NW; ++c) vc[c] = V_(J0 + c, k);
+#pragma unroll
+    for (int r = 0; r < NW; ++r) {  // the triangle inside the block
+#pragma unroll
+      for (int c = 0; c <= r; ++c) a[c][J0 + r] = fma(-vc[r], vc[c], a[c][J0 + r]);
     }
 #pragma unroll
-    for (int i = J0 + (two ? 2 : 1); i <= MC; ++i) {  // remaining rows; row MC = right-hand side
+    for (int i = J0 + NW; i <= MC; ++i) {  // remaining rows; row MC = right-hand side
       const double v = (i < MC) ? V_(i, k) : cv[k * 32];
-      a0[i] = fma(-v, v0, a0[i]);
-      if (two) a1[i] = fma(-v, v1, a1[i]);
+#pragma unroll
+      for (int c = 0; c < NW; ++c) a[c][i] = fma(-v, vc[c], a[c][i]);
     }
   }
-  // finalise column J0
-  const double d0 = a0[J0];
-  if (J0 < mi && !(d0 > 0.0)) ok = false;
-  const double r0 = nngp_rsqrt_pos(d0);
-  dv[J0 * 32] = r0;
 #pragma unroll
-  for (int i = J0 + 1; i <= MC; ++i) a0[i] *= r0;
-  Fsum = fma(a0[MC], a0[MC], Fsum);
-  cv[J0 * 32] = a0[MC];
+  for (int c = 0; c < NW; ++c) {
 #pragma unroll
-  for (int i = J0 + 1; i < MC; ++i) V_(i, J0) = a0[i];
-  if (two) {
-    const double v = a0[J1];  // V(J1, J0), still in registers
+    for (int cc = 0; cc < c; ++cc) {  // columns of this block already finished, still in registers
+      const double v = a[cc][J0 + c];
 #pragma unroll
-    for (int i = J1; i <= MC; ++i) a1[i] = fma(-a0[i], v, a1[i]);
-    const double d1 = a1[J1];
-    if (J1 < mi && !(d1 > 0.0)) ok = false;
-    const double r1 = nngp_rsqrt_pos(d1);
-    dv[J1 * 32] = r1;
+      for (int i = J0 + c; i <= MC; ++i) a[c][i] = fma(-a[cc][i], v, a[c][i]);
+    }
+    const double d = a[c][J0 + c];
+    if (J0 + c < mi && !(d > 0.0)) ok = false;
+    const double r = nngp_rsqrt_pos(d);
+    dv[(J0 + c) * 32] = r;
 #pragma unroll
-    for (int i = J1 + 1; i <= MC; ++i) a1[i] *= r1;
-    Fsum = fma(a1[MC], a1[MC], Fsum);
-    cv[J1 * 32] = a1[MC];
+    for (int i = J0 + c + 1; i <= MC; ++i) a[c][i] *= r;
+    Fsum = fma(a[c][MC], a[c][MC], Fsum);
+    cv[(J0 + c) * 32] = a[c][MC];
 #pragma unroll
-    for (int i = J1 + 1; i < MC; ++i) V_(i, J1) = a1[i];
+    for (int i = J0 + c + 1; i < MC; ++i) V_(i, J0 + c) = a[c][i];
   }
   asm volatile("" ::: "memory");
-  if constexpr (J0 + 2 < MC) tpl_chol_pair<MC, J0 + 2>(A, cv, dv, mi, diag, Fsum, ok);
+  if constexpr (J0 + NW < MC) tpl_chol_block<MC, J0 + NW, W>(A, cv, dv, mi, diag, Fsum, ok);
 }
 
 // On return cv[k] holds the kriging weight B_k (k < MC), *Fsum_out = c' C^-1 c; false if a pivot <= 0.
-template <int MC>
+#ifndef NNGP_CHOL_W
+#define NNGP_CHOL_W 2
+#endif
+template <int MC, int W = NNGP_CHOL_W>
 __device__ __forceinline__ bool tpl_solve(double *A, double *cv, double *dv, int mi, double diag, double *Fsum_out) {
   double Fsum = 0.0;
   bool ok = true;
-  tpl_chol_pair<MC, 0>(A, cv, dv, mi, diag, Fsum, ok);
+  tpl_chol_block<MC, 0, W>(A, cv, dv, mi, diag, Fsum, ok);
   // back substitution V' B = y: B_k = (y_k - sum_{i>k} V(i,k) B_i) / V(k,k)
   double w[MC];
 #pragma unroll
