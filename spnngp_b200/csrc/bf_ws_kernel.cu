@@ -31,6 +31,10 @@
 
 #include "tpl_device.cuh"
 
+#ifndef NNGP_WS_EXP_TAB
+#define NNGP_WS_EXP_TAB 0  // 1: exponential / gaussian producers use the table-driven exp -- measured SLOWER (0.619 -> 0.665 ms,
+                           // gaussian 0.569 -> 0.646): the lookups' shared-memory latency outweighs the 8 FP64 instructions saved
+#endif
 #ifndef NNGP_WS_MATERN_NP
 #define NNGP_WS_MATERN_NP 5  // producer warps of the Matern kernels: 3 / 4 / 5 / 6 -> 0.879 / 0.927 / 0.859 / 0.957 ms (n = 1e6, m = 15)
 #endif
@@ -85,7 +89,8 @@ __global__ void __launch_bounds__(32 * (1 + NP), (MC <= 16) ? 2 : 1) bf_ws_kerne
   __shared__ double red[2][1 + NP];
   __shared__ int last_flag;
   constexpr int kTabLen = 32 + 128 * kLogTabStride;  // exp table, then the log table (x8 interleaved copies when replicated)
-  __shared__ __align__(16) double s_tab[kIsMatern<COV> ? kTabLen : 2];  // exp / log tables (fasttab.cuh)
+  constexpr bool kExpTab = NNGP_WS_EXP_TAB && (COV == NNGP_COV_EXPONENTIAL || COV == NNGP_COV_GAUSSIAN);  // exp table only
+  __shared__ __align__(16) double s_tab[kIsMatern<COV> ? kTabLen : (kExpTab ? 32 : 2)];  // exp / log tables (fasttab.cuh)
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
 
@@ -96,6 +101,9 @@ __global__ void __launch_bounds__(32 * (1 + NP), (MC <= 16) ? 2 : 1) bf_ws_kerne
   const double diag = sigmaSq + tauSq;
   const double *__restrict__ resid = th.resid;
 
+  if (kExpTab) {
+    for (int x = tid; x < 32; x += Ws::kThreads) s_tab[x] = kExpTab32[x];
+  }
   if (kIsMatern<COV>) {
     for (int x = tid; x < 32; x += Ws::kThreads) s_tab[x] = kExpTab32[x];
     for (int x = tid; x < 128 * kLogTabStride; x += Ws::kThreads) {  // pair idx, copy c -> slot idx * stride + c
@@ -250,8 +258,9 @@ __global__ void __launch_bounds__(32 * (1 + NP), (MC <= 16) ? 2 : 1) bf_ws_kerne
       unsigned claimed = 0u;
       if (pl == 0) claimed = atomicAdd(th.tile_counter, 1u);  // tile 3 gridDim.x + claimed
       // ---- this warp's share of tile j's correlations (lane = location) ---------------------------------
-      tpl_build<COV, kBatch, true>(P, lane, s * Ws::kStageBytes + Geo::OFF_CO, s * Ws::kStageBytes + Geo::OFF_A, ent,
-                                   ebeg[pw], kBatch, ebeg[pw + 1], s_tab);
+      tpl_build<COV, kBatch, kIsMatern<COV> || kExpTab>(P, lane, s * Ws::kStageBytes + Geo::OFF_CO,
+                                                        s * Ws::kStageBytes + Geo::OFF_A, ent, ebeg[pw], kBatch,
+                                                        ebeg[pw + 1], s_tab);
       asm volatile("" ::: "memory");
       if (pl == 0) next_tile[(j + 3) & 7] = 3ll * gridDim.x + claimed;  // published by the rendezvous of the next trip
       named_bar_arrive(1 + s, Ws::kThreads);  // stage full

@@ -83,7 +83,7 @@ __device__ __forceinline__ void tpl_build_body(const CorT &cor, int lane, int of
     }
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
-      if constexpr (TAB && kIsMatern<COV>) v[u] = sigmaSq * cor.fast_tab(d2[u]);
+      if constexpr (TAB) v[u] = sigmaSq * cor.fast_tab(d2[u]);
       else v[u] = sigmaSq * cor.fast(d2[u]);
     }
     if constexpr (kIsMatern<COV>) {  // rare arguments outside the straight-line path (phi D > 2, integer nu)
@@ -116,7 +116,7 @@ __device__ __forceinline__ void tpl_build(const BfLaunch &P, int lane, int off_c
     }
   } else {
     const BfTheta &th = P.th[blockIdx.y];
-    tpl_build_body<COV, UNR, false>(Cor<COV>(th), lane, off_co, off_a, ent, e_begin, e_step, nent_pad, th.sigmaSq);
+    tpl_build_body<COV, UNR, TAB>(Cor<COV>(th, tab), lane, off_co, off_a, ent, e_begin, e_step, nent_pad, th.sigmaSq);
   }
 }
 

@@ -26,7 +26,7 @@ def child(n, m):
     eng.set_data(c, idx, lu, X, y, m)
     res = {}
     for name, cov, theta, short in (("matern", 2, [5, 1, 6, 0.75], 1), ("matern_full", 2, [5, 1, 6, 0.75], 0),
-                                    ("exponential", 0, [5, 1, 6], 1)):
+                                    ("exponential", 0, [5, 1, 6], 1), ("gaussian", 3, [5, 1, 6], 1)):
         eng.set_option("matern_short", short)
         out = eng.bf_loglik(cov, [theta], [beta], slots=[0])
         for nb in (1, 2):
