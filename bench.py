@@ -367,7 +367,9 @@ def run_b200(args, rank, world, local_rank):
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": f"rNNGP response model n={n} m={m} p=2 cov={args.cov} (BASELINE.json configs[2])",
+                "workload": f"rNNGP response model n={n} m={m} p=2 cov={args.cov}"
+                + (" (BASELINE.json configs[2])" if (n, m, args.cov) == (1000000, 15, "matern") else
+                   " (BASELINE.json configs[0])" if (n, m, args.cov) == (5000, 15, "exponential") else ""),
                 "n": n, "m": m, "cov_model": args.cov, "p": 2,
                 "sampler": "reference-faithful: 2 B/F solves + 2 Q per iteration, one batched launch" if args.mode == 0
                 else "double-buffered: 1 B/F solve + 1 Q-only pass per iteration",
