@@ -437,6 +437,136 @@ __global__ void __launch_bounds__(128) knn_query_kernel(const double2 *__restric
   for (int k = 0; k < m; ++k) out[(size_t)k * nq + qi] = (k < mm) ? li[k] : -1;
 }
 
+// ---- unordered query kNN on a uniform grid (the default nn2 stand-in) ---------------------------------------------
+// The strip walk above inspects every site whose x + y lies within sqrt(2) of the current radius -- a band across the
+// whole domain, ~6,000 candidates per query at n = 10^6 -- and its threads walk unrelated strips (queries arrive in user
+// order).  Here the sites are binned into square cells of ~4 sites, the queries are processed in cell order (one warp =
+// neighbouring queries = the same cells: broadcast loads), and a query visits its own cell, then ring after ring of
+// cells until the m-th best distance is below the distance to everything not yet visited.  Exact; ties resolve by
+// ascending (d^2, site index) exactly as in knn_query_kernel and the oracle's exhaustive search.
+struct GridGeo {
+  double x0, y0, inv_h, h;
+  int gx, gy;
+};
+
+__device__ __forceinline__ int grid_cell_1d(double v, double v0, double inv_h, int g) {
+  const int c = (int)floor((v - v0) * inv_h);
+  return c < 0 ? 0 : (c >= g ? g - 1 : c);
+}
+
+__global__ void __launch_bounds__(256) grid_cell_kernel(const double2 *__restrict__ pts, int n, GridGeo G,
+                                                        int *__restrict__ cell, int *__restrict__ idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double2 p = pts[i];
+  cell[i] = grid_cell_1d(p.y, G.y0, G.inv_h, G.gy) * G.gx + grid_cell_1d(p.x, G.x0, G.inv_h, G.gx);
+  idx[i] = i;
+}
+
+// start[c] = first sorted position whose cell id is >= c, c = 0 .. ncells (binary search per cell)
+__global__ void __launch_bounds__(256) grid_start_kernel(const int *__restrict__ sorted_cell, int n, int ncells,
+                                                         int *__restrict__ start) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > ncells) return;
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (sorted_cell[mid] < c) lo = mid + 1;
+    else hi = mid;
+  }
+  start[c] = lo;
+}
+
+__global__ void __launch_bounds__(128) knn_grid_query_kernel(const double2 *__restrict__ sxy /* sites in cell order */,
+                                                             const int *__restrict__ sidx /* their site ids */,
+                                                             const int *__restrict__ start, GridGeo G, int n,
+                                                             const double2 *__restrict__ q,
+                                                             const int *__restrict__ qorder /* queries in cell order */,
+                                                             int nq, int m, int *__restrict__ out /* nq x m col-major */) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nq) return;
+  const int qi = qorder[t];
+  const double2 me = q[qi];
+  const int cx = grid_cell_1d(me.x, G.x0, G.inv_h, G.gx), cy = grid_cell_1d(me.y, G.y0, G.inv_h, G.gy);
+  double ld[NNGP_MAX_M];
+  int li[NNGP_MAX_M];
+  const int mm = min(m, n);
+  for (int k = 0; k < NNGP_MAX_M; ++k) {
+    ld[k] = INFINITY;
+    li[k] = 0x7fffffff;
+  }
+  double worst = INFINITY;
+  int worst_id = 0x7fffffff;
+  // (a query outside the sites' bounding box is clamped into a border cell; every unvisited cell then lies on the far
+  // side of the visited block, so the bound ring * h below still holds)
+  const int rmax = max(max(cx, G.gx - 1 - cx), max(cy, G.gy - 1 - cy));
+  for (int ring = 0; ring <= rmax; ++ring) {
+    const int y_lo = cy - ring, y_hi = cy + ring;
+    for (int yy = max(y_lo, 0); yy <= min(y_hi, G.gy - 1); ++yy) {
+      const bool edge_row = (yy == y_lo || yy == y_hi);
+      // edge rows: the whole span of the ring; inner rows: only its two end cells
+      const int x_lo = cx - ring, x_hi = cx + ring;
+      for (int pass = 0; pass < 2; ++pass) {
+        int xa, xb;
+        if (edge_row) {
+          if (pass == 1) break;
+          xa = max(x_lo, 0);
+          xb = min(x_hi, G.gx - 1);
+        } else {
+          const int xc = pass == 0 ? x_lo : x_hi;
+          if (xc < 0 || xc >= G.gx || (pass == 1 && ring == 0)) continue;
+          xa = xb = xc;
+        }
+        if (xa > xb) continue;
+        const int p0 = start[yy * G.gx + xa], p1 = start[yy * G.gx + xb + 1];  // cells of one row are contiguous
+        for (int pos = p0; pos < p1; ++pos) {
+          const double2 pc = sxy[pos];
+          const double dx = me.x - pc.x, dy = me.y - pc.y;
+          const double de = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+          if (de > worst) continue;
+          const int cid = sidx[pos];
+          if (de < worst || cid < worst_id) {
+            int k = mm - 1;  // insertion keeping (d2, id) ascending
+            while (k > 0 && (ld[k - 1] > de || (ld[k - 1] == de && li[k - 1] > cid))) {
+              ld[k] = ld[k - 1];
+              li[k] = li[k - 1];
+              --k;
+            }
+            ld[k] = de;
+            li[k] = cid;
+            worst = ld[mm - 1];
+            worst_id = li[mm - 1];
+          }
+        }
+      }
+    }
+    // everything not yet visited is farther than reach: stop once the m-th best is strictly inside it
+    const double reach = (double)ring * G.h;
+    if (worst < reach * reach * (1.0 - 1e-9)) break;
+  }
+  for (int k = 0; k < m; ++k) out[(size_t)k * nq + qi] = (k < mm) ? li[k] : -1;
+}
+
+cudaError_t grid_cell_launch(const double2 *pts, int n, double x0, double y0, double h, int gx, int gy, int *cell, int *idx,
+                             cudaStream_t stream) {
+  GridGeo G{x0, y0, 1.0 / h, h, gx, gy};
+  grid_cell_kernel<<<(n + 255) / 256, 256, 0, stream>>>(pts, n, G, cell, idx);
+  return cudaGetLastError();
+}
+
+cudaError_t grid_start_launch(const int *sorted_cell, int n, int ncells, int *start, cudaStream_t stream) {
+  grid_start_kernel<<<(ncells + 1 + 255) / 256, 256, 0, stream>>>(sorted_cell, n, ncells, start);
+  return cudaGetLastError();
+}
+
+cudaError_t knn_grid_query_launch(const double2 *sxy, const int *sidx, const int *start, double x0, double y0, double h,
+                                  int gx, int gy, int n, const double2 *q, const int *qorder, int nq, int m, int *out,
+                                  cudaStream_t stream) {
+  GridGeo G{x0, y0, 1.0 / h, h, gx, gy};
+  knn_grid_query_kernel<<<(nq + 127) / 128, 128, 0, stream>>>(sxy, sidx, start, G, n, q, qorder, nq, m, out);
+  return cudaGetLastError();
+}
+
 // ---- mkUIndx: the transposed neighbour graph (src/nn.cpp:25-56, crs_csc src/util.cpp:151-185) ------------
 // uIndx lists, for every location i, the locations that have i as a neighbour (ascending), uiIndx the slot i
 // occupies in each of those neighbour lists.  The reference builds it serially; here the nIndx (neighbour id,

@@ -3,7 +3,12 @@
 // nngp_nn_query stands in for RANN::nn2 (R/generics.R:642).
 #include <cub/cub.cuh>
 
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include <algorithm>
+#include <cmath>
 #include <vector>
 
 #include "nngp_ctx.h"
@@ -21,6 +26,12 @@ cudaError_t knn_gather_launch(const double2 *coords, const int *sidx, int n, dou
 cudaError_t knn_count_ties_launch(const double *u_sorted, int n, int *count, cudaStream_t stream);
 cudaError_t knn_query_launch(const double2 *sxy, const int *sidx, const double *u_sorted, int n, const double2 *q,
                              int nq, int m, int *out, cudaStream_t stream);
+cudaError_t grid_cell_launch(const double2 *pts, int n, double x0, double y0, double h, int gx, int gy, int *cell, int *idx,
+                             cudaStream_t stream);
+cudaError_t grid_start_launch(const int *sorted_cell, int n, int ncells, int *start, cudaStream_t stream);
+cudaError_t knn_grid_query_launch(const double2 *sxy, const int *sidx, const int *start, double x0, double y0, double h,
+                                  int gx, int gy, int n, const double2 *q, const int *qorder, int nq, int m, int *out,
+                                  cudaStream_t stream);
 
 // R's rsort_with_index on the host (src/main/sort.c; third-party algorithm restated): only used
 // when u = x + y has exact ties, where the reference's Shell-sort order decides the scan order.
@@ -213,6 +224,27 @@ int nngp_mk_u_indx(nngp_ctx *c, int n, int m, const int *nnIndx, int search_type
   return NNGP_OK;
 }
 
+// cell ids of `cnt` points -> (sorted cell ids, point ids in cell order)
+static int grid_sort(nngp_ctx *c, const double2 *d_pts, int cnt, double x0, double y0, double h, int gx, int gy,
+                     DevBuf &d_cell_sorted, DevBuf &d_order) {
+  DevBuf d_cell, d_idx, tmp;
+  const size_t ib = (size_t)cnt * sizeof(int);
+  NNGP_CUDA(c, d_cell.alloc(ib)); NNGP_CUDA(c, d_idx.alloc(ib));
+  NNGP_CUDA(c, d_cell_sorted.alloc(ib)); NNGP_CUDA(c, d_order.alloc(ib));
+  NNGP_CUDA(c, grid_cell_launch(d_pts, cnt, x0, y0, h, gx, gy, d_cell.as<int>(), d_idx.as<int>(), c->stream));
+  int bits = 1;
+  while ((1LL << bits) < (long long)gx * gy) ++bits;
+  size_t tmp_bytes = 0;
+  NNGP_CUDA(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_cell.as<int>(), d_cell_sorted.as<int>(), d_idx.as<int>(),
+                                               d_order.as<int>(), cnt, 0, bits, c->stream));
+  NNGP_CUDA(c, tmp.alloc(tmp_bytes));
+  NNGP_CUDA(c, cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, d_cell.as<int>(), d_cell_sorted.as<int>(), d_idx.as<int>(),
+                                               d_order.as<int>(), cnt, 0, bits, c->stream));
+  c->launches += 2;
+  NNGP_CUDA(c, cudaStreamSynchronize(c->stream));  // tmp and the unsorted buffers are freed on return
+  return NNGP_OK;
+}
+
 int nngp_nn_query(nngp_ctx *c, int n, const double *coords, int q, const double *coords0, int m, int *nnIndx0) {
   if (!c) return NNGP_EINVAL;
   if (n < 1 || q < 0 || m < 1 || !coords || (q > 0 && (!coords0 || !nnIndx0))) return ctx_fail(c, NNGP_EINVAL, "nngp_nn_query: bad arguments");
@@ -224,15 +256,55 @@ int nngp_nn_query(nngp_ctx *c, int n, const double *coords, int q, const double 
   if (rc) return rc;
   rc = upload_sites(c, coords0, q, d_q);
   if (rc) return rc;
-  int nties = 0;
-  rc = sort_by_u(c, d_coords.as<double2>(), n, d_sidx, d_u, &nties);
-  if (rc) return rc;
   NNGP_CUDA(c, d_sxy.alloc((size_t)n * sizeof(double2)));
   NNGP_CUDA(c, d_out.alloc((size_t)q * m * sizeof(int)));
-  NNGP_CUDA(c, knn_gather_launch(d_coords.as<double2>(), d_sidx.as<int>(), n, d_sxy.as<double2>(), c->stream));
-  NNGP_CUDA(c, knn_query_launch(d_sxy.as<double2>(), d_sidx.as<int>(), d_u.as<double>(), n, d_q.as<double2>(), q, m,
-                                d_out.as<int>(), c->stream));
-  c->launches += 2;
+  static int use_strip = -1;  // NNGP_NN_QUERY=strip: the (x+y)-strip walk (kept for cross-checks)
+  if (use_strip < 0) {
+    const char *e = getenv("NNGP_NN_QUERY");
+    use_strip = (e && !strcmp(e, "strip")) ? 1 : 0;
+  }
+  if (use_strip) {
+    int nties = 0;
+    rc = sort_by_u(c, d_coords.as<double2>(), n, d_sidx, d_u, &nties);
+    if (rc) return rc;
+    NNGP_CUDA(c, knn_gather_launch(d_coords.as<double2>(), d_sidx.as<int>(), n, d_sxy.as<double2>(), c->stream));
+    NNGP_CUDA(c, knn_query_launch(d_sxy.as<double2>(), d_sidx.as<int>(), d_u.as<double>(), n, d_q.as<double2>(), q, m,
+                                  d_out.as<int>(), c->stream));
+    c->launches += 2;
+  } else {
+    // uniform grid over the sites' bounding box, ~4 sites per cell (knn_kernels.cu: knn_grid_query_kernel)
+    double x0 = coords[0], x1 = coords[0], y0 = coords[n], y1 = coords[n];
+    for (int i = 1; i < n; i++) {
+      x0 = std::min(x0, coords[i]); x1 = std::max(x1, coords[i]);
+      y0 = std::min(y0, coords[(size_t)n + i]); y1 = std::max(y1, coords[(size_t)n + i]);
+    }
+    if (!(x1 - x0 >= 0.0) || !(y1 - y0 >= 0.0) || !std::isfinite(x1 - x0) || !std::isfinite(y1 - y0))
+      return ctx_fail(c, NNGP_EINVAL, "nngp_nn_query: coordinates must be finite");
+    const double wx = x1 - x0, wy = y1 - y0;
+    double h;
+    if (wx > 0.0 && wy > 0.0) h = sqrt(wx * wy * 4.0 / n);
+    else h = std::max(wx, wy) * 4.0 / n;  // collinear sites: a 1-D grid
+    if (!(h > 0.0)) h = 1.0;              // all sites coincide: one cell
+    long long gx, gy;
+    for (;;) {
+      gx = (long long)floor(wx / h) + 1;
+      gy = (long long)floor(wy / h) + 1;
+      if (gx * gy <= (1LL << 26) && gx < (1LL << 20) && gy < (1LL << 20)) break;
+      h *= 1.5;  // very elongated boxes: coarser cells keep the table small
+    }
+    DevBuf d_cell_sorted, d_qcell_sorted, d_qorder, d_start;
+    rc = grid_sort(c, d_coords.as<double2>(), n, x0, y0, h, (int)gx, (int)gy, d_cell_sorted, d_sidx);
+    if (rc) return rc;
+    rc = grid_sort(c, d_q.as<double2>(), q, x0, y0, h, (int)gx, (int)gy, d_qcell_sorted, d_qorder);
+    if (rc) return rc;
+    const int ncells = (int)(gx * gy);
+    NNGP_CUDA(c, d_start.alloc(((size_t)ncells + 1) * sizeof(int)));
+    NNGP_CUDA(c, grid_start_launch(d_cell_sorted.as<int>(), n, ncells, d_start.as<int>(), c->stream));
+    NNGP_CUDA(c, knn_gather_launch(d_coords.as<double2>(), d_sidx.as<int>(), n, d_sxy.as<double2>(), c->stream));
+    NNGP_CUDA(c, knn_grid_query_launch(d_sxy.as<double2>(), d_sidx.as<int>(), d_start.as<int>(), x0, y0, h, (int)gx, (int)gy,
+                                       n, d_q.as<double2>(), d_qorder.as<int>(), q, m, d_out.as<int>(), c->stream));
+    c->launches += 3;
+  }
   NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
   NNGP_CUDA(c, cudaMemcpy(nnIndx0, d_out.p, (size_t)q * m * sizeof(int), cudaMemcpyDeviceToHost));
   return NNGP_OK;

@@ -56,3 +56,18 @@ def make_allreduce(device=None, group=None):
         buf[:] = t.cpu().numpy()
 
     return allreduce
+
+
+def conj_kfold_sharded(engine, y, X, coords, m, cov, theta_alpha, sigmaSqIG, ho_idx, search_type="cb", rank=0, world=1,
+                       allreduce=None):
+    """k-fold scores of spConjNNGP with the parameter sets split over the ranks (zero communication
+    until the end).  Each rank runs every fold for its sets (`Engine.conj_kfold`, set_range); the g x 2 score
+    matrices have disjoint non-zero rows, so one sum over ranks assembles the result on every rank."""
+    g = np.asarray(theta_alpha).shape[1]
+    lo, hi = split_even(g, rank, world)
+    scores = engine.conj_kfold(y, X, coords, m, cov, theta_alpha, sigmaSqIG, ho_idx, search_type, set_range=(lo, hi))
+    if allreduce is not None and world > 1:
+        flat = np.ascontiguousarray(scores.T).ravel()
+        allreduce(flat)
+        scores = flat.reshape(2, g).T.copy()
+    return scores

@@ -62,3 +62,51 @@ def test_sharded_partials_allreduce_gloo(tmp_path):
         assert p.exitcode == 0
     for _, e1, e2 in res:
         assert e1 < 1e-13 and e2 < 1e-13
+
+
+class _OracleKfoldEngine:
+    """Stands in for spnngp_b200.Engine in the CPU test of the sharding logic: same conj_kfold signature, computed by
+    the oracle's restatement of the R loop on the selected parameter sets."""
+
+    def __init__(self, port):
+        self.port = port
+
+    def conj_kfold(self, y, X, coords, m, cov, theta_alpha, sigmaSqIG, ho_idx, search_type="cb", set_range=None):
+        from oracle import pyoracle as po
+        ta = np.asarray(theta_alpha); g = ta.shape[1]
+        lo, hi = set_range if set_range is not None else (0, g)
+        out = np.zeros((g, 2))
+        if hi > lo:
+            out[lo:hi] = po.conj_kfold(self.port, self.port, y, X, coords, m, cov, ta[:, lo:hi], sigmaSqIG, ho_idx, search_type)
+        return out
+
+
+def _kfold_worker(rank, world, port_file, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from oracle import pyoracle as po
+    from spnngp_b200.dist import conj_kfold_sharded, make_allreduce
+    dist.init_process_group("gloo", init_method=f"file://{port_file}", rank=rank, world_size=world)
+    port = po.Port(); port.set_threads(1)
+    d = np.load(os.path.join(ROOT, "tests", "golden", "kfold_n600_m10.npz"))
+    ta = d["exp_theta_alpha"]
+    got = conj_kfold_sharded(_OracleKfoldEngine(port), d["y"], d["X"], d["coords"], int(d["m"]), 0, ta, d["sigmaSqIG"],
+                             d["ho_idx"], "cb", rank=rank, world=world, allreduce=make_allreduce(device=None))
+    q.put((rank, float(np.max(np.abs(got - d["exp_scores"]) / np.abs(d["exp_scores"])))))
+    dist.destroy_process_group()
+
+
+def test_kfold_parameter_sets_shard_over_ranks_gloo(tmp_path):
+    """world_size 2: each rank scores half of the theta.alpha grid; the summed matrices equal the golden scores."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    f = str(tmp_path / "rdzv_kfold")
+    procs = [ctx.Process(target=_kfold_worker, args=(k, 2, f, q)) for k in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(e < 1e-12 for _, e in res), res

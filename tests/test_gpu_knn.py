@@ -106,6 +106,49 @@ def test_nn_query_matches_exhaustive(engine, port, n, q, m):
     assert np.array_equal(out, ref)
 
 
+def _nn_query(engine, coords, coords0, m):
+    cf, c0 = coords_flat(coords), coords_flat(coords0)
+    n, q = len(coords), len(coords0)
+    out = np.zeros(q * m, dtype=np.int32)
+    st = engine.lib.nngp_nn_query(engine.h, n, cf.ctypes.data_as(c_double_p), q, c0.ctypes.data_as(c_double_p), m,
+                                  out.ctypes.data_as(c_int_p))
+    assert st == 0
+    return out
+
+
+@pytest.mark.parametrize("case", ["tied_grid", "outside_box", "clustered", "collinear", "coincident", "few_sites", "big"])
+def test_nn_query_grid_edge_cases(engine, port, case):
+    """The grid search (knn_grid_query_kernel) against the exhaustive oracle where its geometry is stressed: exact
+    distance ties (lower site index wins), queries far outside the sites' bounding box, empty cells between clusters,
+    degenerate boxes (all sites on a line / in one point), fewer sites than neighbours asked for."""
+    rng = np.random.default_rng(11)
+    m = 10
+    if case == "tied_grid":
+        g = np.arange(30) / 30.0
+        xx, yy = np.meshgrid(g, g, indexing="ij")
+        coords = np.column_stack([xx.ravel(), yy.ravel()])
+        coords0 = np.vstack([coords[::7] + 0.0, coords[5::11] + np.array([0.5 / 30, 0.5 / 30]), rng.random((200, 2))])
+    elif case == "outside_box":
+        coords = rng.random((3000, 2))
+        coords0 = np.vstack([rng.random((100, 2)) * 5.0 - 2.0, np.array([[-50.0, 0.5], [0.5, 80.0], [1e3, -1e3]])])
+    elif case == "clustered":
+        coords = np.vstack([rng.normal(0.0, 0.01, (1500, 2)), rng.normal(5.0, 0.02, (1500, 2)), [[2.5, 2.5]]])
+        coords0 = np.vstack([rng.normal(0.0, 0.05, (200, 2)), rng.random((200, 2)) * 5.0])
+    elif case == "collinear":
+        coords = np.column_stack([rng.random(800), np.full(800, 0.25)])
+        coords0 = rng.random((150, 2))
+    elif case == "coincident":
+        coords = np.tile(np.array([[0.3, 0.7]]), (40, 1))
+        coords0 = rng.random((20, 2))
+    elif case == "few_sites":
+        coords = rng.random((6, 2)); coords0 = rng.random((30, 2)); m = 6
+    else:
+        coords = rng.random((200000, 2)) * 6.0
+        coords0 = rng.random((20000, 2)) * 6.0
+        m = 15
+    assert np.array_equal(_nn_query(engine, coords, coords0, m), port.nn_query(coords, coords0, m))
+
+
 @pytest.mark.parametrize("n,m", [(5000, 15), (600, 10), (40, 32), (300, 1), (200000, 15)])
 def test_u_indx_bit_exact(engine, port, n, m):
     """nngp_mk_u_indx (reference `mkUIndx`, src/nn.cpp:25-56) vs the oracle, all three `u.search.type` values."""

@@ -1,13 +1,16 @@
-"""Developer probe for ncu: one code-book search at size n, m."""
+"""Developer probe: wall time of repeated nngp_nn_query calls (grid search; NNGP_NN_QUERY=strip for the strip walk)."""
 import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from spnngp_b200 import Engine
-n = int(sys.argv[1]); m = int(sys.argv[2]); kind = sys.argv[3] if len(sys.argv) > 3 else "cb"
-rng = np.random.default_rng(7)
-c = rng.random((n, 2)) * np.sqrt(n / 5000.0)
-c = c[np.argsort(c[:, 0], kind="stable")]
 eng = Engine(0)
-for _ in range(2):
-    t = time.perf_counter(); eng.mk_nn_indx(c, m, kind); print(kind, n, m, time.perf_counter() - t, flush=True)
+rng = np.random.default_rng(5)
+for n, q in ((151000, 37700), (1000000, 250000), (1000000, 1000000)):
+    W = np.sqrt(n / 5000.0)
+    c = rng.random((n, 2)) * W
+    c0 = rng.random((q, 2)) * W
+    ts = []
+    for r in range(5):
+        t = time.perf_counter(); out = eng.nn_query(c, c0, 15); ts.append(time.perf_counter() - t)
+    print(f"n={n} q={q}: " + " ".join(f"{x*1e3:.1f}" for x in ts) + " ms", flush=True)
