@@ -132,6 +132,13 @@ int nngp_create(int device, void *stream_handle, nngp_ctx **out) {
     NNGP_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
   }
+  {  // keep freed scratch blocks cached in the stream-ordered pool (DevBuf, nngp_ctx.h)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) {
+      unsigned long long thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  }
   NNGP_CUDA(c, cudaMalloc(&c->d_ticket, 2 * NNGP_MAX_BATCH * sizeof(unsigned int)));  // tickets, tile counters
   NNGP_CUDA(c, cudaMemset(c->d_ticket, 0, 2 * NNGP_MAX_BATCH * sizeof(unsigned int)));
   NNGP_CUDA(c, cudaMalloc(&c->d_fail, NNGP_MAX_BATCH * sizeof(int)));

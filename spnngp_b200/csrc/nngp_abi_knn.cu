@@ -4,8 +4,10 @@
 #include <cub/cub.cuh>
 
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <cmath>
@@ -54,15 +56,30 @@ static void host_rsort_with_index(double *x, int *indx, int n) {
     }
 }
 
-struct DevBuf {
-  void *p = nullptr;
-  ~DevBuf() {
-    if (p) cudaFree(p);
+// NNGP_TRACE=1: phase timings of the search entry points on stderr
+struct PhaseTrace {
+  bool on;
+  double t0;
+  const char *what;
+  static double now() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
   }
-  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
-  template <typename Tp>
-  Tp *as() {
-    return reinterpret_cast<Tp *>(p);
+  explicit PhaseTrace(const char *w) : what(w) {
+    static int flag = -1;
+    if (flag < 0) {
+      const char *e = getenv("NNGP_TRACE");
+      flag = (e && e[0] == '1') ? 1 : 0;
+    }
+    on = flag == 1;
+    t0 = on ? now() : 0.0;
+  }
+  void mark(const char *phase) {
+    if (!on) return;
+    const double t = now();
+    fprintf(stderr, "[nngp trace] %s: %s %.3f ms\n", what, phase, (t - t0) * 1e3);
+    t0 = t;
   }
 };
 
@@ -112,7 +129,8 @@ static int ensure_stager(nngp_ctx *c) {
 // column-major (x[n], y[n]) host sites -> interleaved double2 on the device, through the pinned ring
 static int upload_sites(nngp_ctx *c, const double *coords, int n, DevBuf &d) {
   NNGP_CUDA(c, d.alloc((size_t)n * sizeof(double2)));
-  int rc = ensure_stager(c);
+  NNGP_CUDA(c, cudaStreamSynchronize(c->stream));  // the block may be recycled: earlier work on it has to be over before
+  int rc = ensure_stager(c);                        // the stager's own streams write into it
   if (rc) return rc;
   std::vector<StageJob> up{{StageJob::XY_INTERLEAVE, d.p, coords, (size_t)n * sizeof(double2), n}};
   NNGP_CUDA(c, c->stager->run(up, nullptr));
@@ -132,6 +150,7 @@ int nngp_mk_nn_indx(nngp_ctx *c, int n, int m, const double *coords, int search_
   if (m > NNGP_MAX_M) return ctx_fail(c, NNGP_EINVAL, "nngp_mk_nn_indx: n.neighbors > 32 is not supported");
   if (search_type != NNGP_SEARCH_BRUTE && search_type != NNGP_SEARCH_CB) return ctx_fail(c, NNGP_EINVAL, "search.type must be brute (0) or cb (1)");
   NNGP_CUDA(c, cudaSetDevice(c->device));
+  ScratchScope scratch(c->stream);
   const long long nIndx = nn_offset(n, m);
   DevBuf d_coords, d_idx, d_dist;
   int rc = upload_sites(c, coords, n, d_coords);
@@ -174,6 +193,7 @@ int nngp_mk_u_indx(nngp_ctx *c, int n, int m, const int *nnIndx, int search_type
   if (!c) return NNGP_EINVAL;
   if (n < 1 || m < 1 || !nnIndx || !uIndx || !uIndxLU || !uiIndx) return ctx_fail(c, NNGP_EINVAL, "nngp_mk_u_indx: bad arguments");
   NNGP_CUDA(c, cudaSetDevice(c->device));
+  ScratchScope scratch(c->stream);
   const long long nIndx = nn_offset(n, m);
   if (nIndx > 0x7fffffffLL) return ctx_fail(c, NNGP_EINVAL, "nngp_mk_u_indx: more than 2^31 neighbour slots");
   for (long long e = 0; e < nIndx; e++)
@@ -251,13 +271,17 @@ int nngp_nn_query(nngp_ctx *c, int n, const double *coords, int q, const double 
   if (m > NNGP_MAX_M) return ctx_fail(c, NNGP_EINVAL, "nngp_nn_query: k > 32 is not supported");
   if (q == 0) return NNGP_OK;
   NNGP_CUDA(c, cudaSetDevice(c->device));
+  ScratchScope scratch(c->stream);
+  PhaseTrace tr("nngp_nn_query");
   DevBuf d_coords, d_q, d_sidx, d_u, d_sxy, d_out;
   int rc = upload_sites(c, coords, n, d_coords);
   if (rc) return rc;
   rc = upload_sites(c, coords0, q, d_q);
   if (rc) return rc;
+  tr.mark("upload");
   NNGP_CUDA(c, d_sxy.alloc((size_t)n * sizeof(double2)));
   NNGP_CUDA(c, d_out.alloc((size_t)q * m * sizeof(int)));
+  tr.mark("alloc");
   static int use_strip = -1;  // NNGP_NN_QUERY=strip: the (x+y)-strip walk (kept for cross-checks)
   if (use_strip < 0) {
     const char *e = getenv("NNGP_NN_QUERY");
@@ -292,11 +316,13 @@ int nngp_nn_query(nngp_ctx *c, int n, const double *coords, int q, const double 
       if (gx * gy <= (1LL << 26) && gx < (1LL << 20) && gy < (1LL << 20)) break;
       h *= 1.5;  // very elongated boxes: coarser cells keep the table small
     }
+    tr.mark("bounding box");
     DevBuf d_cell_sorted, d_qcell_sorted, d_qorder, d_start;
     rc = grid_sort(c, d_coords.as<double2>(), n, x0, y0, h, (int)gx, (int)gy, d_cell_sorted, d_sidx);
     if (rc) return rc;
     rc = grid_sort(c, d_q.as<double2>(), q, x0, y0, h, (int)gx, (int)gy, d_qcell_sorted, d_qorder);
     if (rc) return rc;
+    tr.mark("cell sorts");
     const int ncells = (int)(gx * gy);
     NNGP_CUDA(c, d_start.alloc(((size_t)ncells + 1) * sizeof(int)));
     NNGP_CUDA(c, grid_start_launch(d_cell_sorted.as<int>(), n, ncells, d_start.as<int>(), c->stream));
@@ -306,7 +332,9 @@ int nngp_nn_query(nngp_ctx *c, int n, const double *coords, int q, const double 
     c->launches += 3;
   }
   NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
+  tr.mark("search kernels");
   NNGP_CUDA(c, cudaMemcpy(nnIndx0, d_out.p, (size_t)q * m * sizeof(int), cudaMemcpyDeviceToHost));
+  tr.mark("result copy");
   return NNGP_OK;
 }
 

@@ -29,21 +29,7 @@ cudaError_t conj_score_launch(const double *y0, const double *y0Hat, const doubl
 
 namespace {
 
-struct Dev {
-  void *p = nullptr;
-  ~Dev() {
-    if (p) cudaFree(p);
-  }
-  cudaError_t alloc(size_t bytes) {
-    if (p) cudaFree(p);
-    p = nullptr;
-    return cudaMalloc(&p, bytes ? bytes : 1);
-  }
-  template <typename Tp>
-  Tp *as() const {
-    return reinterpret_cast<Tp *>(p);
-  }
-};
+typedef DevBuf Dev;
 
 // device-side description of one chunk of query sites
 struct SiteChunk {
@@ -74,6 +60,7 @@ int upload_chunk(nngp_ctx *c, SiteChunk &ch, int q, int i0, int i1, const double
   NNGP_CUDA(c, ch.F.alloc((size_t)cs * sizeof(double)));
   NNGP_CUDA(c, ch.a.alloc((size_t)cs * sizeof(double)));
   NNGP_CUDA(c, ch.U.alloc((size_t)cs * (p > 0 ? p : 1) * sizeof(double)));
+  NNGP_CUDA(c, cudaStreamSynchronize(c->stream));  // recycled pool blocks: nothing earlier may still be using them
   NNGP_CUDA(c, cudaMemcpy(ch.sites.p, xy.data(), (size_t)cs * sizeof(double2), cudaMemcpyHostToDevice));
   NNGP_CUDA(c, cudaMemcpy(ch.nn0.p, nn.data(), (size_t)cs * m * sizeof(int), cudaMemcpyHostToDevice));
   if (p > 0) NNGP_CUDA(c, cudaMemcpy(ch.X0.p, x0.data(), (size_t)cs * p * sizeof(double), cudaMemcpyHostToDevice));
@@ -147,6 +134,7 @@ int nngp_rnngp_predict(nngp_ctx *c, int cov, int q, const double *X0, const doub
   if (cov < 0 || cov > 3) return ctx_fail(c, NNGP_EINVAL, "cov.model is not correctly specified");
   if (site_begin < 0 || site_end > q || site_begin > site_end) return ctx_fail(c, NNGP_EINVAL, "bad site range");
   NNGP_CUDA(c, cudaSetDevice(c->device));
+  ScratchScope scratch(c->stream);
   const int p = c->p, S = nSamples;
   const int nTheta = (cov == NNGP_COV_MATERN) ? 4 : 3;
 
@@ -191,6 +179,7 @@ int nngp_rnngp_predict(nngp_ctx *c, int cov, int q, const double *X0, const doub
     if (rc) return rc;
     NNGP_CUDA(c, d_z.alloc((size_t)cs * S * sizeof(double)));
     NNGP_CUDA(c, d_y0.alloc((size_t)cs * S * sizeof(double)));
+    NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
     // the normals in and the draws out go through the threaded pinned ring (host_stage.h): a q x S job is
     // dominated by these two transfers, not by the solves
     if (!c->stager) {
@@ -238,6 +227,7 @@ static int cnngp_impl(nngp_ctx *c, int cov, int g, const double *thetaAlpha, con
     return ctx_fail(c, NNGP_EINVAL, "nngp_cnngp: prediction inputs missing");
   if (cov < 0 || cov > 3) return ctx_fail(c, NNGP_EINVAL, "cov.model is not correctly specified");
   NNGP_CUDA(c, cudaSetDevice(c->device));
+  ScratchScope scratch(c->stream);
   const int p = c->p, K = p + 1, n = c->n;
   const int nTheta = (cov == NNGP_COV_MATERN) ? 3 : 2;
   std::vector<double> S((size_t)K * K), V((size_t)p * p), tmp_p(p);

@@ -85,6 +85,43 @@ struct nngp_ctx {
 
 namespace nngp {
 
+// Transient device buffers of the search / prediction entry points.  They come from the device's stream-ordered pool
+// (cudaMallocAsync on the context stream; nngp_create raises the pool's release threshold so freed blocks stay cached):
+// plain cudaMalloc / cudaFree cost 50-650 ms per call once a few GB had been allocated and released by an earlier
+// prediction (traced at n = 10^6: 16 ms of work inside a 340 ms nngp_nn_query).  ScratchScope names the stream for the
+// buffers declared below it; every entry point that declares a DevBuf opens one.
+inline cudaStream_t &scratch_stream() {
+  static thread_local cudaStream_t s = nullptr;
+  return s;
+}
+struct ScratchScope {
+  cudaStream_t prev;
+  explicit ScratchScope(cudaStream_t s) : prev(scratch_stream()) { scratch_stream() = s; }
+  ~ScratchScope() { scratch_stream() = prev; }
+};
+struct DevBuf {
+  void *p = nullptr;
+  cudaStream_t s = nullptr;
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  DevBuf(DevBuf &&o) noexcept : p(o.p), s(o.s) { o.p = nullptr; }
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFreeAsync(p, s);
+    p = nullptr;
+  }
+  cudaError_t alloc(size_t bytes) {
+    release();
+    s = scratch_stream();
+    return cudaMallocAsync(&p, bytes ? bytes : 1, s);
+  }
+  template <typename Tp>
+  Tp *as() const {
+    return reinterpret_cast<Tp *>(p);
+  }
+};
+
 // bf_kernel.cu
 int bf_tile_for_m(int m);
 int bf_locations_per_cta(int m);
