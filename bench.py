@@ -57,7 +57,9 @@ def make_workload(n: int, m: int, seed: int = 1):
     beta = np.array([1.0, 5.0])
     w = np.sin(3.0 * coords[:, 0]) + np.cos(2.0 * coords[:, 1])
     y = X @ beta + np.sqrt(5.0) * w + rng.standard_normal(n)
-    return dict(n=n, m=m, p=2, coords=coords, X=X, y=y, beta=beta)
+    # column-major like the R matrices the reference receives (REAL(coords_r), REAL(X_r)): the engine's wrapper then
+    # passes the buffers through without a layout copy
+    return dict(n=n, m=m, p=2, coords=np.asfortranarray(coords), X=np.asfortranarray(X), y=y, beta=beta)
 
 
 def sampler_settings(cov: int):

@@ -226,14 +226,19 @@ int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const 
   if (m > NNGP_MAX_M) return ctx_fail(c, NNGP_EINVAL, "nngp_set_data: n.neighbors > 32 is not supported by the warp-group solver");
   if (p > 0 && (!X || !y)) return ctx_fail(c, NNGP_EINVAL, "nngp_set_data: X / y missing");
   if (loc_begin < 0 || loc_end > n || loc_begin > loc_end) return ctx_fail(c, NNGP_EINVAL, "nngp_set_data: bad shard range");
-  if (nnIndxLU) {  // must be the closed form of src/util.cpp:55-70
-    for (int i = 0; i < n; i++) {
-      if (i > 0 && (nnIndxLU[i] != (int)nn_offset(i, m) || nnIndxLU[n + i] != nn_count(i, m)))
-        return ctx_fail(c, NNGP_EINVAL, "nngp_set_data: nnIndxLU is not the reference's closed-form layout");
+  PhaseTrace tr("nngp_set_data");
+  if (nnIndxLU) {  // must be the closed form of src/util.cpp:55-70 (offset = running sum of the counts min(i, m))
+    long long run = 0;
+    int bad = 0;
+    for (int i = 1; i < n; i++) {
+      run += (i - 1 < m) ? i - 1 : m;
+      bad |= (nnIndxLU[i] != (int)run) | (nnIndxLU[n + i] != ((i < m) ? i : m));
     }
+    if (bad) return ctx_fail(c, NNGP_EINVAL, "nngp_set_data: nnIndxLU is not the reference's closed-form layout");
   }
   NNGP_CUDA(c, cudaSetDevice(c->device));
   NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
+  tr.mark("validate + sync");
   // device buffers are kept across calls and only grown (cudaMalloc/cudaFree of the ~0.5 GB working set
   // would otherwise dominate a short fit: the whole-call path is measured end to end by bench.py)
   c->n = n; c->m = m; c->p = p; c->loc_begin = loc_begin; c->loc_end = loc_end;
@@ -268,7 +273,9 @@ int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const 
       jobs.push_back({StageJob::RAW, c->d_y, y, (size_t)n * sizeof(double), 0});
     }
     bool bad_id = false;
+    tr.mark("buffers");
     NNGP_CUDA(c, c->stager->run(jobs, &bad_id));
+    tr.mark("staged upload");
     if (bad_id) {
       c->n = 0;
       return ctx_fail(c, NNGP_EINVAL, "nngp_set_data: neighbour index out of range");
@@ -311,6 +318,7 @@ int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const 
     double v;
     memcpy(&v, &edge, sizeof v);
     if (total > 0 && b + 1 < 0x7ff0) c->pair_d2_q99 = v;
+    tr.mark("row layout + pair-distance histogram");
   }
   const long long nloc = (long long)loc_end - loc_begin;
   const int K = p + 1, npairs = K * (K + 1) / 2;

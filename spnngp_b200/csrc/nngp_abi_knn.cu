@@ -56,33 +56,6 @@ static void host_rsort_with_index(double *x, int *indx, int n) {
     }
 }
 
-// NNGP_TRACE=1: phase timings of the search entry points on stderr
-struct PhaseTrace {
-  bool on;
-  double t0;
-  const char *what;
-  static double now() {
-    timespec ts;
-    clock_gettime(CLOCK_MONOTONIC, &ts);
-    return ts.tv_sec + 1e-9 * ts.tv_nsec;
-  }
-  explicit PhaseTrace(const char *w) : what(w) {
-    static int flag = -1;
-    if (flag < 0) {
-      const char *e = getenv("NNGP_TRACE");
-      flag = (e && e[0] == '1') ? 1 : 0;
-    }
-    on = flag == 1;
-    t0 = on ? now() : 0.0;
-  }
-  void mark(const char *phase) {
-    if (!on) return;
-    const double t = now();
-    fprintf(stderr, "[nngp trace] %s: %s %.3f ms\n", what, phase, (t - t0) * 1e3);
-    t0 = t;
-  }
-};
-
 // sort the sites by u = x + y on the device; falls back to the reference's exact Shell sort on the
 // host when u has ties.  Outputs: d_sidx (NNGP index per sorted position), d_u (sorted keys).
 static int sort_by_u(nngp_ctx *c, const double2 *d_coords, int n, DevBuf &d_sidx, DevBuf &d_u, int *n_ties) {

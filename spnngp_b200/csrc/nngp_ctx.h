@@ -1,6 +1,9 @@
 // nngp_ctx.h -- the engine context behind the C ABI (one context drives one GPU).
 #pragma once
 #include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <time.h>
 
 #include <string>
 #include <vector>
@@ -119,6 +122,33 @@ struct DevBuf {
   template <typename Tp>
   Tp *as() const {
     return reinterpret_cast<Tp *>(p);
+  }
+};
+
+// NNGP_TRACE=1: phase timings of the host-side entry points on stderr
+struct PhaseTrace {
+  bool on;
+  double t0;
+  const char *what;
+  static double now() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+  }
+  explicit PhaseTrace(const char *w) : what(w) {
+    static int flag = -1;
+    if (flag < 0) {
+      const char *e = getenv("NNGP_TRACE");
+      flag = (e && e[0] == '1') ? 1 : 0;
+    }
+    on = flag == 1;
+    t0 = on ? now() : 0.0;
+  }
+  void mark(const char *phase) {
+    if (!on) return;
+    const double t = now();
+    fprintf(stderr, "[nngp trace] %s: %s %.3f ms\n", what, phase, (t - t0) * 1e3);
+    t0 = t;
   }
 };
 

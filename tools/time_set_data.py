@@ -1,16 +1,12 @@
+"""Developer probe: nngp_set_data wall time (host arrays in) at n = 10^6, m = 15; NNGP_TRACE=1 prints its phases."""
 import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from spnngp_b200 import Engine
 from bench import make_workload
-n, m = 1000000, 15
-wl = make_workload(n, m)
+wl = make_workload(1000000, 15)
 eng = Engine(0)
-t = time.perf_counter(); idx, dist, lu = eng.mk_nn_indx(wl["coords"], m, "cb"); print("knn cb 1st", time.perf_counter() - t)
-t = time.perf_counter(); idx, dist, lu = eng.mk_nn_indx(wl["coords"], m, "cb"); print("knn cb 2nd", time.perf_counter() - t)
+idx, dist, lu = eng.mk_nn_indx(wl["coords"], 15, "cb")
 for k in range(4):
-    t = time.perf_counter(); eng.set_data(wl["coords"], idx, lu, wl["X"], wl["y"], m); print("set_data", k, time.perf_counter() - t)
-import ctypes as C
-from spnngp_b200.engine import colmajor, _i32, _f64
-t = time.perf_counter(); c = colmajor(wl["coords"]); X = colmajor(wl["X"]); y = _f64(wl["y"]); i2 = _i32(idx); l2 = _i32(lu); print("python marshalling", time.perf_counter() - t)
+    t = time.perf_counter(); eng.set_data(wl["coords"], idx, lu, wl["X"], wl["y"], 15); print(f"set_data {k}: {(time.perf_counter()-t)*1e3:.2f} ms", flush=True)
