@@ -35,7 +35,16 @@ def _worker(rank, world, rdzv, q):
     starting = {"beta": [0.0, 0.0], "sigma.sq": 5.0, "tau.sq": 1.0, "phi": 6.0}
     tuning = {"sigma.sq": 0.03, "tau.sq": 0.03, "phi": 0.03}
     bs, ts, acc = eng.rnngp(0, [2.0, 5.0], [2.0, 1.0], [3.0, 300.0], None, starting, tuning, 25, R.rnorm, R.runif)
-    q.put((rank, out, S, qr, ts, acc))
+    # k-fold scores with the parameter sets split over the ranks: a second engine WITHOUT the location-sharding
+    # communicator (every rank fits the whole fold for its own sets), one torch allreduce at the end
+    from spnngp_b200.dist import conj_kfold_sharded, make_allreduce
+    d = np.load(os.path.join(ROOT, "tests", "golden", "kfold_n600_m10.npz"))
+    eng2 = Engine(rank)
+    scores = conj_kfold_sharded(eng2, d["y"], d["X"], d["coords"], int(d["m"]), 2, d["matern_theta_alpha"], d["sigmaSqIG"],
+                                d["ho_idx"], "cb", rank=rank, world=world,
+                                allreduce=make_allreduce(device=torch.device("cuda", rank)))
+    eng2.close()
+    q.put((rank, out, S, qr, ts, acc, scores))
     eng.close()
     dist.destroy_process_group()
 
@@ -69,4 +78,7 @@ def test_two_rank_nccl_matches_single_gpu(tmp_path, port):
         assert np.allclose(r[1], out, rtol=1e-12) and np.allclose(r[2], S, rtol=1e-11) and abs(r[3] - qr) < 1e-11 * abs(qr)
         assert r[5] == acc and np.allclose(r[4], ts, rtol=1e-10)
     assert np.array_equal(res[0][4], res[1][4])  # both ranks hold the same chain
+    d = np.load(os.path.join(ROOT, "tests", "golden", "kfold_n600_m10.npz"))
+    for r in res:  # parameter sets sharded over the ranks: every rank ends up with the reference's score matrix
+        assert np.max(np.abs(r[6] - d["matern_scores"]) / np.abs(d["matern_scores"])) < 1e-10
     eng.close()

@@ -120,3 +120,20 @@ def test_conj_kfold_golden(engine):
         assert np.array_equal(a + b, got)
     brute = engine.conj_kfold(d["y"], d["X"], d["coords"], int(d["m"]), 0, d["exp_theta_alpha"], d["sigmaSqIG"], d["ho_idx"], "brute")
     assert np.max(np.abs(brute - d["exp_scores"]) / np.abs(d["exp_scores"])) < 1e-10  # tie-free sites: brute == cb
+
+
+@pytest.mark.parametrize("cov,search", [(0, "cb"), (3, "brute")])
+def test_conj_kfold_midsize_vs_oracle(engine, port, cov, search):
+    """nngp_conj_kfold at n = 12,000 (2 folds, 3 parameter sets) against the oracle's restatement of the R loop:
+    ordered search, query search, fit and scores all go through the device path."""
+    from oracle import pyoracle as po
+    n, m, k_fold = 12000, 15, 2
+    prob = make_problem(n, m, seed=51 + cov, domain=np.sqrt(n / 5000.0))
+    rng = np.random.default_rng(52)
+    ho = np.stack([np.sort(rng.choice(n, n // 4, replace=False)) for _ in range(k_fold)]).astype(np.int32)
+    ta = np.array([[3.0, 0.1], [6.0, 0.3], [12.0, 1.0]]).T
+    ig = [2.0, float(np.var(prob["y"]))]
+    port.set_threads(8)
+    ref = po.conj_kfold(port, port, prob["y"], prob["X"], prob["coords"], m, cov, ta, ig, ho, search)
+    got = engine.conj_kfold(prob["y"], prob["X"], prob["coords"], m, cov, ta, ig, ho, search)
+    assert np.max(np.abs(got - ref) / np.abs(ref)) < 1e-10
