@@ -1,4 +1,4 @@
-// bf_ws_kernel.cu -- warp-specialised B/F + log-likelihood kernel for m <= 16.
+// bf_ws_kernel.cu -- warp-specialised B/F + log-likelihood kernel for 6 <= m <= 24.
 //
 // Same mathematics as bf_tpl_kernel.cu (one lane owns one location; reference sites: updateBF
 // src/rNNGP.cpp:46-101, updateConjBF src/cNNGP.cpp:24-69, Q src/util.cpp:261-280, prediction solves
@@ -6,26 +6,33 @@
 // single-role kernel showed its three phases have opposite needs: the covariance build (70% of the
 // instructions) runs at the FP64 pipe's cadence, while the gathers and the Cholesky chain are latency-
 // bound, and with ~1 warp per scheduler nothing overlaps them (FP64 pipe 32% busy overall).  Here a CTA
-// of 4 warps pipelines TILES of 32 locations through two shared-memory stages:
+// pipelines TILES of 32 locations through two shared-memory stages:
 //
-//   producer warps 1..3 : gather neighbour ids -> cp.async sites and residuals into the stage, then
-//                         each evaluates one third of the tile's m(m-1)/2 + m correlations
-//   consumer warp 0     : Cholesky + solves of the previous tile, B/F stores, sum log F / Q terms
+//   producer warps 1..NP : gather neighbour ids -> cp.async sites and residuals into the stage, then
+//                          each evaluates its share of the tile's m(m-1)/2 + m correlations
+//                          (NP = 3; Matern 5)
+//   consumer warp 0      : Cholesky + solves of the previous tile, B/F stores, sum log F / Q terms
 //
 // hand-off with named barriers (bar.arrive / bar.sync, ids 1..4 = full/empty per stage, id 5 = producers'
-// own rendezvous).  Two CTAs per SM (2 x 2 stages x 46 KB) put two latency-bound consumers on one
-// scheduler and two FP64-bound producers on each of the other three.
+// own rendezvous).  Two CTAs per SM (2 x 2 stages x 46 KB; one CTA for the 20 / 24 capacities).
 //
 // Measured at n = 10^6, m = 15 (ms per launch; exponential / Matern): cooperative kernel 1.11 / 1.79,
-// single-role one-lane kernel 0.90 / 2.63, this kernel 0.62 / 1.11 (history: 0.72 / 1.63 with a static tile
+// single-role one-lane kernel 0.90 / 2.63, this kernel 0.62 / 0.85.  History: 0.72 / 1.63 with a static tile
 // split and gathers inside the producers' critical path; dynamic tiles + the Matern series/quadrature paths
-// -> 0.71 / 1.20; gathers software-pipelined one tile ahead -> 0.62 / 1.11).  The exponential kernel is
-// consumer-bound (the Cholesky chain of one tile takes ~9k cycles, B stores ~2k); Matern is bound by the
-// FP64 issue rate of the three producer schedulers (3, 4 or 5 producer warps measure the same).  Variants
-// tried and rejected (all ~0.91-1.01 ms): one 8-warp CTA with a consumer and a producer on every scheduler
-// (the producer's DFMA stream starves the consumer's dependent chain); 2-4 consumers packed on scheduler 0
-// with 6 producers on schedulers 1-3 (the fully unrolled solve, 30 KB of code per consumer, thrashes the
-// instruction cache: ncu stall_no_instruction 40-49% in the solve).
+// -> 0.71 / 1.20; gathers software-pipelined one tile ahead -> 0.62 / 1.11; table-driven log/exp -> 0.99;
+// launch-level 9-term Matern series -> 0.95; producer loop trimmed (pre-multiplied work list, no clamp, integer
+// slow-path test, negated coefficients) -> 0.88; five Matern producer warps -> 0.86; 4-column Cholesky blocks for
+// the other models 0.64 -> 0.62.  ncu now: FP64 pipe 45-50% busy, issue slots 46%, shared-memory pipe ~60%; every
+// warp of a CTA is busy about equally long -- latency-bound on all sides (stall_wait and stall_short_scoreboard
+// ~1.1 per issued instruction each), not bound by one role.
+// Variants tried and rejected: one 8-warp CTA with a consumer and a producer on every scheduler (the producer's
+// DFMA stream starves the consumer's dependent chain); 2-4 consumers packed on scheduler 0 with 6 producers on
+// schedulers 1-3 (the fully unrolled solve, 30 KB of code per consumer, thrashes the instruction cache: ncu
+// stall_no_instruction 40-49% in the solve); Matern batches of 6 / 8 chains; batches drawn dynamically from a
+// shared counter; unequal static shares; 6 Matern producers (spills at 128 registers); 4 / 5 producers for the
+// exponential kernel (0.75 / 0.71 with 4-column blocks, 0.68 / 0.65 with 2-column blocks vs 0.62); the table-driven
+// exp for the exponential / gaussian producers; a log table replicated per quarter-warp lane (no bank conflicts, same
+// time).  The -D knobs below keep those experiments reproducible (tools/build_variant.sh + tools/ab_bench.py).
 #include <stdlib.h>
 
 
@@ -34,6 +41,9 @@
 #ifndef NNGP_WS_EXP_TAB
 #define NNGP_WS_EXP_TAB 0  // 1: exponential / gaussian producers use the table-driven exp -- measured SLOWER (0.619 -> 0.665 ms,
                            // gaussian 0.569 -> 0.646): the lookups' shared-memory latency outweighs the 8 FP64 instructions saved
+#endif
+#ifndef NNGP_WS_NP
+#define NNGP_WS_NP 3  // producer warps of the exponential / spherical / gaussian kernels
 #endif
 #ifndef NNGP_WS_MATERN_NP
 #define NNGP_WS_MATERN_NP 5  // producer warps of the Matern kernels: 3 / 4 / 5 / 6 -> 0.879 / 0.927 / 0.859 / 0.957 ms (n = 1e6, m = 15)
@@ -293,7 +303,11 @@ __global__ void __launch_bounds__(32 * (1 + NP), (MC <= 16) ? 2 : 1) bf_ws_kerne
       // Cholesky block width: 4 columns where the consumer is the critical path and registers allow (exponential at
       // m = 15: W = 2 / 3 / 4 -> 0.642 / 0.629 / 0.620 ms; gaussian 0.600 -> 0.571).  Matern (168 registers with five
       // producers) keeps 2, and so do the small capacities, where W = 4 measured slower (m = 10: 0.307 -> 0.343 ms).
+#ifdef NNGP_WS_CHOLW  // experiment builds
+      constexpr int kCholW = kIsMatern<COV> ? 2 : NNGP_WS_CHOLW;
+#else
       constexpr int kCholW = (!kIsMatern<COV> && MC >= 12 && MC <= 16) ? 4 : 2;
+#endif
       const bool ok = tpl_solve<MC, kCholW>(A, cv + lane, dv, mi, diag, &Fsum);
       if (!ok && active) failed = min(failed, (int)min(i + 1, (long long)INT_MAX - 1));
       const double Fv = diag - Fsum;
@@ -418,12 +432,12 @@ static cudaError_t ws_launch_one(const BfLaunch &P, int grid_x, cudaStream_t str
 template <int MC>
 static cudaError_t ws_launch_cov(const BfLaunch &P, int cov, int grid_x, cudaStream_t stream) {
   switch (cov) {
-    case NNGP_COV_EXPONENTIAL: return ws_launch_one<MC, NNGP_COV_EXPONENTIAL, 3>(P, grid_x, stream);
-    case NNGP_COV_SPHERICAL: return ws_launch_one<MC, NNGP_COV_SPHERICAL, 3>(P, grid_x, stream);
+    case NNGP_COV_EXPONENTIAL: return ws_launch_one<MC, NNGP_COV_EXPONENTIAL, NNGP_WS_NP>(P, grid_x, stream);
+    case NNGP_COV_SPHERICAL: return ws_launch_one<MC, NNGP_COV_SPHERICAL, NNGP_WS_NP>(P, grid_x, stream);
     case NNGP_COV_MATERN:
       if (P.matern_short) return ws_launch_one<MC, NNGP_COV_MATERN_SHORT, NNGP_WS_MATERN_NP>(P, grid_x, stream);
       return ws_launch_one<MC, NNGP_COV_MATERN, NNGP_WS_MATERN_NP>(P, grid_x, stream);
-    case NNGP_COV_GAUSSIAN: return ws_launch_one<MC, NNGP_COV_GAUSSIAN, 3>(P, grid_x, stream);
+    case NNGP_COV_GAUSSIAN: return ws_launch_one<MC, NNGP_COV_GAUSSIAN, NNGP_WS_NP>(P, grid_x, stream);
     default: return cudaErrorInvalidValue;
   }
 }
