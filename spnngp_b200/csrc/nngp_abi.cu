@@ -51,6 +51,16 @@ static int ensure_dev(nngp_ctx *c, Tp *&p, size_t &cap_bytes, size_t count) {
   p = nullptr;
   cap_bytes = 0;
   cudaError_t e = cudaMalloc(&p, bytes);
+  if (e == cudaErrorMemoryAllocation) {
+    // the scratch pool (DevBuf, nngp_ctx.h) keeps freed blocks cached: hand them back and try once more
+    cudaGetLastError();
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) {
+      cudaStreamSynchronize(c->stream);
+      cudaMemPoolTrimTo(pool, 0);
+    }
+    e = cudaMalloc(&p, bytes);
+  }
   if (e != cudaSuccess) return ctx_cuda(c, e, "cudaMalloc (model buffer)");
   cap_bytes = bytes;
   return NNGP_OK;
