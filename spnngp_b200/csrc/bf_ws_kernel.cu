@@ -92,7 +92,12 @@ __global__ void __launch_bounds__(32 * (1 + NP), (MC <= 16) ? 2 : 1) bf_ws_kerne
   constexpr int kBatch = kTplBatch<COV>;
   // who stores a solved tile's weights: the producers where the consumer is the critical path (0.62 -> 0.59 ms,
   // spherical), the consumer for Matern, whose producers are the critical path (1.11 vs 1.15 ms)
+#ifdef NNGP_WS_PSTORE  // experiment builds: 1 = producers copy B out for every model (Matern with five producers: 0.850 ->
+                       // 0.878 ms), 0 = the consumer always does
+  constexpr bool kProducersStoreB = (NNGP_WS_PSTORE != 0);
+#else
   constexpr bool kProducersStoreB = !kIsMatern<COV>;
+#endif
   __shared__ TplEnt<COV> ent[kTplMaxEnt];
   __shared__ int ebeg[NP + 1];
   __shared__ long long next_tile[8];  // ring of claimed tiles, slot j & 7 (>= ntiles: no more work)
