@@ -431,6 +431,61 @@ def cpu_baseline_leg(args, wl, nnIndx, lu, cov, starting, tuning, pri):
             "updateBF_loc_per_s": n / t_bf}
 
 
+def cpu_baseline_other_configs(args):
+    """`--cpu-configs`: the reference's own CPU code (oracle/_ref; rank 0, no GPU work) on bounded samples of the other
+    BASELINE configs, next to which tools/bench_configs.py's GPU timings are read -- SURVEY §8(d) "CPU baseline timing".
+    Prints one JSON line."""
+    from oracle import pyoracle as po
+    cores = os.cpu_count() or 1
+    if not po.Ref.available():
+        print(json.dumps({"impl": "reference", "cpu_configs": None, "unavailable": "oracle/_ref not built"}))
+        return 0
+    ref = po.Ref(); port = po.Port(); port.set_threads(cores)
+    rng = np.random.default_rng(11)
+    out = {"cores": cores, "kind": "reference", "threads": cores}
+
+    def timed(f):
+        t = time.perf_counter(); r = f(); return time.perf_counter() - t, r
+
+    def by_x(c):
+        return c[np.argsort(c[:, 0], kind="stable")]
+
+    # configs[4]: ordered search
+    c = by_x(rng.random((1000000, 2)) * np.sqrt(1000000 / 5000.0))
+    t, (idx6, _, lu6) = timed(lambda: ref.mk_nn_indx_cb(c, 15, threads=cores))
+    out["mkNNIndxCB_n1e6_m15_s"] = t
+    t, _ = timed(lambda: ref.mk_nn_indx_cb(c, 32, threads=cores)); out["mkNNIndxCB_n1e6_m32_s"] = t
+    t, _ = timed(lambda: ref.mk_nn_indx(c[:100000], 15, threads=cores)); out["mkNNIndx_brute_n1e5_m15_s"] = t
+    # configs[3]: a slice of the prediction job, q = 5,000 sites x S = 1,000 samples at n = 10^6
+    n, q, S = 1000000, 5000, 1000
+    X = np.column_stack([np.ones(n), rng.standard_normal(n)]); beta = np.array([1.0, 5.0])
+    y = X @ beta + rng.standard_normal(n)
+    c0 = rng.random((q, 2)) * np.sqrt(n / 5000.0); X0 = np.column_stack([np.ones(q), rng.standard_normal(q)])
+    nn0 = port.nn_query(c, c0, 15)
+    bs = beta[:, None] + 0.05 * rng.standard_normal((2, S))
+    th = np.tile(np.array([[5.0], [1.0], [6.0]]), (1, S))
+    ref.set_seed(1)
+    t, _ = timed(lambda: ref.predict(X, y, c, 15, X0, c0, nn0, bs, th, 0, nThreads=cores))
+    out["rNNGPPredict_q5000_S1000_s"] = t
+    out["rNNGPPredict_draws_per_s"] = q * S / t
+    # configs[1]: one fold's fit + hold-out prediction for ONE parameter set at BCEF's fold size
+    n2, n_ho = 150974, 37743
+    c2 = by_x(rng.random((n2, 2)) * np.array([21.5, 17.0]))
+    X2 = np.column_stack([np.ones(n2), rng.standard_normal(n2)]); y2 = X2 @ beta + rng.standard_normal(n2)
+    t_nn, (idx2, _, lu2) = timed(lambda: ref.mk_nn_indx_cb(c2, 15, threads=cores))
+    ch = rng.random((n_ho, 2)) * np.array([21.5, 17.0]); Xh = np.column_stack([np.ones(n_ho), rng.standard_normal(n_ho)])
+    nnh = port.nn_query(c2, ch, 15)
+    t_fit, _ = timed(lambda: ref.cnngp(y2, X2, c2, np.array([[3.0], [0.25]]), idx2, lu2, Xh, ch, nnh, 15, [2.0, 1.0], 0,
+                                        nThreads=cores))
+    out["cNNGP_one_set_one_fold_s"] = t_fit
+    out["mkNNIndxCB_fold_n151k_s"] = t_nn
+    out["spConjNNGP_kfold_5x25_extrapolated_s"] = 5 * (t_nn + 25 * t_fit)
+    out["note"] = ("reference C++ (oracle/_ref) with OpenMP on the box's host cores; the prediction and k-fold figures are "
+                   "bounded samples, linear in q*S and in folds*sets; the RANN query search is not included")
+    print(json.dumps({"impl": "reference", "cpu_configs": out}), flush=True)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -444,10 +499,14 @@ def main():
     ap.add_argument("--ref-budget-s", type=float, default=150.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--py-allreduce", action="store_true", help="sum partials through torch.distributed in Python")
+    ap.add_argument("--cpu-configs", action="store_true",
+                    help="time the reference's CPU code on samples of BASELINE configs[1], [3], [4] (no GPU work)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.cpu_configs:
+        return cpu_baseline_other_configs(args) if rank == 0 else 0
     if args.impl == "reference":
         return run_reference(args, rank, world)
     return run_b200(args, rank, world, local_rank)
