@@ -181,6 +181,7 @@ int nngp_mk_u_indx(nngp_ctx *c, int n, int m, const int *nnIndx, int search_type
     NNGP_CUDA(c, d_keys2.alloc(ib)); NNGP_CUDA(c, d_vals2.alloc(ib)); NNGP_CUDA(c, d_u.alloc(ib)); NNGP_CUDA(c, d_ui.alloc(ib));
     NNGP_CUDA(c, d_counts.alloc((size_t)n * sizeof(int)));
     std::vector<StageJob> up{{StageJob::RAW, d_nn.p, nnIndx, ib, 0}};
+    NNGP_CUDA(c, cudaStreamSynchronize(c->stream));  // recycled pool block: the stager writes from its own streams
     NNGP_CUDA(c, c->stager->run(up, nullptr));
     NNGP_CUDA(c, cudaMemsetAsync(d_counts.p, 0, (size_t)n * sizeof(int), c->stream));
     NNGP_CUDA(c, uindx_keys_launch(d_nn.as<int>(), nIndx, d_keys.as<int>(), d_vals.as<int>(), d_counts.as<int>(), c->stream));

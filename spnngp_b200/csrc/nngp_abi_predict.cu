@@ -157,6 +157,7 @@ int nngp_rnngp_predict(nngp_ctx *c, int cov, int q, const double *X0, const doub
 
   Dev d_beta, d_samples, d_z, d_y0;
   NNGP_CUDA(c, d_beta.alloc((size_t)p * S * sizeof(double)));
+  NNGP_CUDA(c, cudaStreamSynchronize(c->stream));  // pool blocks are recycled in stream order; the copies below are not
   NNGP_CUDA(c, cudaMemcpy(d_beta.p, betaSamples, (size_t)p * S * sizeof(double), cudaMemcpyHostToDevice));
   std::vector<int> flat;
   std::vector<int> gofs(groups.size() + 1, 0);
@@ -237,6 +238,7 @@ static int cnngp_impl(nngp_ctx *c, int cov, int g, const double *thetaAlpha, con
   std::vector<double> bh_local(p);
   if (score) {
     NNGP_CUDA(c, d_obs.alloc((size_t)n0 * sizeof(double)));
+    NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
     NNGP_CUDA(c, cudaMemcpy(d_obs.p, y0Obs, (size_t)n0 * sizeof(double), cudaMemcpyHostToDevice));
     NNGP_CUDA(c, d_sc.alloc((size_t)2 * g * sizeof(double)));
     NNGP_CUDA(c, cudaMemsetAsync(d_sc.p, 0, (size_t)2 * g * sizeof(double), c->stream));
