@@ -101,3 +101,58 @@ def test_shards_add_up_full_size(full):
         acc += e.bf_loglik(0, [theta], [full["beta"]], slots=[0])[0]
     e.close()
     assert np.allclose(acc, whole[0], rtol=1e-12)
+
+
+def test_ordered_search_n1e7_m32_properties(engine):
+    """BASELINE configs[4] at full size (n = 10^7, m = 32, code-book): list invariants over every location and an
+    exhaustive check of sampled locations (ids bit-exact, ties impossible on continuous random sites)."""
+    n, m = 10000000, 32
+    rng = np.random.default_rng(20251)
+    coords = rng.random((n, 2)) * np.sqrt(n / 5000.0)
+    coords = coords[np.argsort(coords[:, 0], kind="stable")]
+    idx, dist, lu = engine.mk_nn_indx(coords, m, "cb")
+    off = m * (m - 1) // 2
+    assert lu[m] == off and lu[n + m] == m and lu[n - 1] == off + (n - 1 - m) * m
+    rows = idx[off:].reshape(-1, m); drows = dist[off:].reshape(-1, m)
+    assert rows.shape[0] == n - m
+    step = 1 << 20  # blockwise to bound the temporaries
+    for a in range(0, n - m, step):
+        b = min(a + step, n - m)
+        r = rows[a:b]; d = drows[a:b]
+        assert (r < np.arange(m + a, m + b)[:, None]).all() and (r >= 0).all()      # predecessors only
+        assert (np.diff(d, axis=1) >= 0).all()                                       # ascending distance
+    for s in rng.integers(m, n, 12):                                                 # exhaustive, sampled
+        d2 = ((coords[:s] - coords[s]) ** 2).sum(axis=1)
+        best = np.argpartition(d2, m)[:m]
+        best = best[np.argsort(d2[best], kind="stable")]
+        assert np.array_equal(rows[s - m], best.astype(np.int32))
+        assert np.array_equal(drows[s - m], np.sqrt(d2[best]))
+
+
+def test_prediction_n0_1e6_properties(engine, full):
+    """BASELINE configs[3] at its full number of sites (n0 = 10^6; 24 samples keep the arrays small): site shards
+    reproduce the whole, the draws are affine in the normals with a per-site scale that does not depend on the
+    sample when theta is constant, and the query search is idempotent."""
+    q, S = 1000000, 24
+    rng = np.random.default_rng(20252)
+    W = np.sqrt(N / 5000.0)
+    c0 = rng.random((q, 2)) * W
+    X0 = np.column_stack([np.ones(q), rng.standard_normal(q)])
+    nn0 = engine.nn_query(full["coords"], c0, M)
+    assert np.array_equal(nn0, engine.nn_query(full["coords"], c0, M))
+    nn = nn0.reshape(M, q)
+    assert (nn >= 0).all() and (nn < N).all()
+    d = np.sqrt(((full["coords"][nn[:, :5000]] - c0[None, :5000]) ** 2).sum(axis=2))
+    assert (np.diff(d, axis=0) >= 0).all()                                           # ascending distance per site
+    engine.set_data(full["coords"], full["idx"], full["lu"], full["X"], full["y"], M)
+    beta = full["beta"][:, None] + 0.01 * rng.standard_normal((2, S))
+    theta = np.tile(np.array([[5.0], [1.0], [6.0]]), (1, S))
+    z1 = rng.standard_normal(q * S); z0 = np.zeros(q * S)
+    y1 = engine.rnngp_predict(0, X0, c0, nn0, beta, theta, z1)
+    y0 = engine.rnngp_predict(0, X0, c0, nn0, beta, theta, z0)
+    sd = (y1 - y0) / z1.reshape(q, S)
+    assert np.all(sd > 0) and np.max(np.abs(sd / sd[:, :1] - 1.0)) < 1e-6          # one scale per site: sqrt(F_i)
+    assert sd.max() ** 2 <= 6.0 * (1 + 1e-12)                                        # F_i <= sigma.sq + tau.sq
+    a = engine.rnngp_predict(0, X0, c0, nn0, beta, theta, z1, site_range=(0, 400000))
+    b = engine.rnngp_predict(0, X0, c0, nn0, beta, theta, z1, site_range=(400000, q))
+    assert np.array_equal(a[:400000], y1[:400000]) and np.array_equal(b[400000:], y1[400000:])
