@@ -55,11 +55,14 @@ __device__ __forceinline__ void tpl_decode_ent(uint2 w, unsigned &ok, unsigned &
   ol = w.x >> 16;
   od = w.y;
 }
+#ifndef NNGP_OTHER_BATCH
+#define NNGP_OTHER_BATCH 8  // exponential / spherical / gaussian (4 / 6 / 12 measured 0.628 / 0.629 / 0.659 vs 0.619 ms)
+#endif
 #ifndef NNGP_MATERN_BATCH
 #define NNGP_MATERN_BATCH 4  // 6 and 8 measured slower (0.97 / 0.96 vs 0.95 ms): the register file is full at 4 chains
 #endif
 template <int COV>
-constexpr int kTplBatch = kIsMatern<COV> ? NNGP_MATERN_BATCH : 8;  // entries evaluated together (independent chains)
+constexpr int kTplBatch = kIsMatern<COV> ? NNGP_MATERN_BATCH : NNGP_OTHER_BATCH;  // entries evaluated together (independent chains)
 
 // Batches of UNR entries: all loads, then UNR independent evaluation chains, then all stores.
 // (A plain unrolled loop is serialised by ptxas: it cannot prove that the store of entry e does not
