@@ -43,3 +43,12 @@ extern "C" double host_t_short_max(double nu) {
   nngp::MaternConsts mc; nngp::matern_prepare(nu, &mc);
   return mc.t_short_max;
 }
+// integer threshold of the producers' "may need slow()" test (matern_set_phi) and the bound it stands for
+extern "C" int host_d2_slow_hi(double nu, double phi, int use_short, double *t_fast_max) {
+  nngp::MaternConsts mc; nngp::matern_prepare(nu, &mc);
+  nngp::MaternSeriesParams ms; nngp::matern_series_params(mc, &ms);
+  if (use_short && mc.use_series) ms.t_fast_max = mc.t_short_max;
+  nngp::matern_set_phi(&ms, phi);
+  *t_fast_max = ms.t_fast_max;
+  return ms.d2_slow_hi;
+}

@@ -150,6 +150,31 @@ def test_matern_short_series_on_host_vs_mpmath(tmp_path):
     assert L.host_t_short_max(1.0) == 0.0 and L.host_t_short_max(2.0005) == 0.0  # integer nu: no series at all
 
 
+def test_integer_slow_path_threshold_is_conservative(tmp_path):
+    """matern_set_phi: the producers test `hi32(d2) >= d2_slow_hi` instead of `phi^2 d2 / 4 > t_fast_max`.  Every d2 the
+    integer test lets through must satisfy the floating-point bound (up to rounding), and it must not be grossly
+    pessimistic (it may only flag d2 within one high-word step, 2^-20 relative, below the bound)."""
+    L = _build_host("besselk_host.cpp", str(tmp_path / "libbk.so"))
+    L.host_d2_slow_hi.restype = C.c_int
+    L.host_d2_slow_hi.argtypes = [C.c_double, C.c_double, C.c_int, C.POINTER(C.c_double)]
+    rng = np.random.default_rng(9)
+    for nu in (0.3, 0.75, 1.5, 2.5):
+        for phi in (0.01, 0.7, 6.0, 123.0, 4.0e4):
+            for short in (0, 1):
+                tmax = C.c_double(0.0)
+                thr = L.host_d2_slow_hi(nu, phi, short, C.byref(tmax))
+                bound = tmax.value / (0.25 * phi * phi)                       # d2 at which t reaches t_fast_max
+                d2 = bound * np.exp(rng.uniform(-3e-6, 3e-6, 20000))           # a cloud around the bound
+                d2 = np.concatenate([d2, bound * np.array([0.0, 1e-300, 0.5, 0.999999, 1.0, 1.000001, 2.0, 1e30])])
+                hi = (d2.view(np.int64) >> 32).astype(np.int64)
+                passed = hi < thr                                               # the integer test says "fast path"
+                t = 0.25 * phi * phi * d2
+                assert np.all(t[passed] <= tmax.value * (1 + 4e-16))
+                assert np.all(passed[d2 < bound * (1 - 2.0 ** -19)])           # not pessimistic beyond one high-word step
+    tmax = C.c_double(0.0)
+    assert L.host_d2_slow_hi(1.0, 6.0, 0, C.byref(tmax)) == 0                   # integer nu: every entry takes slow()
+
+
 def test_device_fastmath_on_host(tmp_path):
     """Branch-free sqrt / exp of spnngp_b200/csrc/fastmath.cuh (host build) vs libm."""
     L = _build_host("fastmath_host.cpp", str(tmp_path / "libfm.so"))
