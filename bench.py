@@ -42,6 +42,13 @@ def flops_per_location(m: int, fused: bool = True) -> float:
     return f + (2 * m + 4 if fused else 0)
 
 
+def workload_label(n: int, m: int, cov: str) -> str:
+    """config.workload, identical in both arms."""
+    tag = (" (BASELINE.json configs[2])" if (n, m, cov) == (1000000, 15, "matern") else
+           " (BASELINE.json configs[0])" if (n, m, cov) == (5000, 15, "exponential") else "")
+    return f"rNNGP response model n={n} m={m} p=2 cov={cov}{tag}"
+
+
 def bytes_per_location(m: int) -> float:
     """Algorithmic bytes per location with B, F stored: coords 16 + nnIndx 4m + B 8m + F 8 + resid 8."""
     return 32 + 12 * m
@@ -224,8 +231,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "rNNGP_mcmc_iter_per_s", "value": value, "unit": "iter/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"rNNGP response model n={n_full} m={m} p=2 cov={args.cov}", "n": n_full, "m": m,
-                   "cov_model": args.cov, "sampler": "reference (src/rNNGP.cpp), OpenMP"},
+        "config": {"workload": workload_label(n_full, m, args.cov), "n": n_full, "m": m, "cov_model": args.cov, "p": 2,
+                   "sampler": "reference (src/rNNGP.cpp), OpenMP"},
         "cpu_baseline": {"value": value, "unit": "iter/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -369,9 +376,7 @@ def run_b200(args, rank, world, local_rank):
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": f"rNNGP response model n={n} m={m} p=2 cov={args.cov}"
-                + (" (BASELINE.json configs[2])" if (n, m, args.cov) == (1000000, 15, "matern") else
-                   " (BASELINE.json configs[0])" if (n, m, args.cov) == (5000, 15, "exponential") else ""),
+                "workload": workload_label(n, m, args.cov),
                 "n": n, "m": m, "cov_model": args.cov, "p": 2,
                 "sampler": "reference-faithful: 2 B/F solves + 2 Q per iteration, one batched launch" if args.mode == 0
                 else "double-buffered: 1 B/F solve + 1 Q-only pass per iteration",
