@@ -62,3 +62,15 @@ def test_product_code_never_touches_the_oracle():
                 if re.search(r"oracle[/.]|liboracle|pyoracle|_ref/", txt):
                     bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_tools_do_not_use_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may touch oracle/ (task rule): the developer probes
+    under tools/ get their neighbour lists from the engine's own search."""
+    bad = []
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith((".py", ".sh")):
+            txt = open(os.path.join(ROOT, "tools", f), errors="ignore").read()
+            if re.search(r"from oracle|import oracle|pyoracle|oracle/", txt):
+                bad.append(f)
+    assert not bad, bad
