@@ -279,6 +279,7 @@ __global__ void __launch_bounds__(128, (M <= 16 ? 4 : 2)) bf_kernel(const __grid
       th.out[1] = b;
       const int fv = atomicExch(th.fail, INT_MAX);
       th.out[2] = (fv != INT_MAX) ? 1.0 : 0.0;  // summed across ranks so that every rank sees a failure
+      th.out[3] = 0.0;
       *th.fail_out = fv;
       *th.ticket = 0u;
     }
@@ -290,13 +291,10 @@ __global__ void __launch_bounds__(128, (M <= 16 ? 4 : 2)) bf_kernel(const __grid
 template <int M, int COV>
 static cudaError_t launch_one(const BfLaunch &P, int grid_x, cudaStream_t stream) {
   using Geo = BfGeo<M>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(bf_kernel<M, COV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)Geo::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  // the attribute is per device and cheap to set: set it on every launch (a process may drive several GPUs)
+  cudaError_t e = cudaFuncSetAttribute(bf_kernel<M, COV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)Geo::kSmemBytes);
+  if (e != cudaSuccess) return e;
   dim3 grid(grid_x, P.nbatch, 1);
   bf_kernel<M, COV><<<grid, Geo::kThreads, Geo::kSmemBytes, stream>>>(P);
   return cudaGetLastError();
@@ -396,7 +394,12 @@ int bf_grid_max(int m, long long nloc, int sms) {
   return a;
 }
 
+int tri_capacity_for_m(int m);
+cudaError_t tri_launch(const BfLaunch &P, int cov, int grid_x, cudaStream_t stream);
+
 cudaError_t bf_launch(const BfLaunch &P, int cov, int grid_x, cudaStream_t stream) {
+  // resident distance triangle given (nngp_set_data built it): stream it instead of gathering sites (bf_tri_kernel.cu)
+  if (P.tri != nullptr && !P.site_mode && tri_capacity_for_m(P.m) > 0) return tri_launch(P, cov, grid_x, stream);
   switch (kernel_for(P.m, cov)) {
     case KERNEL_WS: return ws_launch(P, cov, grid_x, stream);
     case KERNEL_TPL: return tpl_launch(P, cov, grid_x, stream);

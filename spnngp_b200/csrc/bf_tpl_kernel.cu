@@ -224,6 +224,7 @@ __global__ void __launch_bounds__(32) bf_tpl_kernel(const __grid_constant__ BfLa
       th.out[1] = b;
       const int fv = atomicExch(th.fail, INT_MAX);
       th.out[2] = (fv != INT_MAX) ? 1.0 : 0.0;  // summed across ranks so that every rank sees a failure
+      th.out[3] = 0.0;
       *th.fail_out = fv;
       *th.ticket = 0u;
     }

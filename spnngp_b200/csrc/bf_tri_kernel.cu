@@ -1,0 +1,553 @@
+// bf_tri_kernel.cu -- B/F + log-likelihood kernel over the resident DISTANCE TRIANGLE (6 <= m <= 24).
+//
+// Same mathematics as the other B/F kernels (reference: updateBF src/rNNGP.cpp:46-101, updateConjBF
+// src/cNNGP.cpp:24-69, Q src/util.cpp:261-280), different data path.  The distances between a location's
+// m + 1 sites -- the arguments of spCor (src/util.cpp:208-245; dist2 src/util.cpp:51-53) -- do not depend on
+// theta, and a sampler evaluates the same geometry thousands of times.  nngp_set_data therefore builds them
+// once (tri_cache.cu: m(m+1)/2 doubles per location, tile-major, bit-equal to the reference's dist2) and this
+// kernel STREAMS them: on B200 the FP64 pipe (34 TFLOP/s) is the scarce resource and HBM (6.5 TB/s) is not --
+// recomputing a distance costs 15 FP64 instructions (gather, d^2, sqrt), reading it costs 8 bytes.
+//
+//   n = 10^6, m = 15:  0.96 GB of distances + 0.21 GB of ids / weights / variances per launch (HBM floor 0.18 ms),
+//                      ~3,500 FP64 warp instructions per 32-location tile (FP64 floor 0.19 ms).
+//
+// One persistent CTA per SM, 12 warps in three warpgroups with `setmaxnreg`:
+//   warpgroup 0 (232 registers): warps 0..NC-1 CONSUMERS -- one tile each: ragged-row fix-up, Cholesky + solves
+//                                (tpl_solve), log F, the quadratic-form terms, weights out through a bulk store;
+//                                warp 3 LOADER -- claims tiles (one atomic per tile), issues the 1-D bulk copies
+//                                (TMA) of the tile's distances [and of the resident weights of the current theta]
+//                                and the cp.async gathers of the neighbours' residuals
+//   warpgroups 1, 2 (136 registers; 128 x 232 + 256 x 136 = the 384 x 168 the CTA was launched with): 8 PRODUCER warps -- turn the stage's distances into covariances in place,
+//                                sigma^2 rho(D): rows of 32 doubles at immediate offsets, NU independent chains
+// Stages of one tile each travel  loader -> producers -> consumer -> loader  on mbarriers (full / built / empty).
+// Per-tile partial sums are written to a tile-indexed array and added in tile order by the last CTA, so the result
+// does not depend on which CTA drew which tile.
+#include <stdlib.h>
+
+#include "tpl_device.cuh"
+
+namespace nngp {
+
+#ifndef NNGP_TRI_UNR
+#define NNGP_TRI_UNR 5  // rows (independent chains) per producer batch
+#endif
+#ifndef NNGP_TRI_UNR_MATERN
+#define NNGP_TRI_UNR_MATERN 4
+#endif
+
+template <int MC>
+struct TriGeo {
+  static constexpr int NE = MC * (MC - 1) / 2;
+  static constexpr int OFF_CV = 0;                          // MC rows: c -> y -> weights, [k][lane]
+  static constexpr int OFF_A = OFF_CV + MC * 256;           // NE rows: strict lower triangle, packed, [entry][lane]
+  static constexpr int OFF_RR = OFF_A + NE * 256;           // MC + 1 rows: residuals of the neighbours, own in row MC
+  static constexpr int OFF_BC = OFF_RR + (MC + 1) * 256;    // 32 x m weights of the current theta, [lane][k]
+  static constexpr int kStageBytes = OFF_BC + MC * 256;
+  static constexpr int kConsBytes = 2 * MC * 256;           // per consumer: 1/diag rows, weight staging [lane][k]
+  static constexpr int kTabBytes = (32 + 128) * 8;
+  static constexpr int kMiscBytes = kTabBytes + 512;        // + mbarriers, tile ring
+  static constexpr int kAvail = 227 * 1024 - kMiscBytes;
+  static constexpr int stages_for(int nc) { return (kAvail - nc * kConsBytes) / kStageBytes; }
+  static constexpr int NC = stages_for(3) >= 5 ? 3 : (stages_for(2) >= 4 ? 2 : 1);
+  static constexpr int S = stages_for(NC) > 6 ? 6 : stages_for(NC);
+  static_assert(S >= 2, "tile does not fit shared memory twice");
+  static constexpr int OFF_CONS = S * kStageBytes;
+  static constexpr int OFF_TAB = OFF_CONS + NC * kConsBytes;
+  static constexpr int OFF_BAR = OFF_TAB + kTabBytes;       // 3 S mbarriers, then the tile ring (S long long)
+  static constexpr int kSmemBytes = OFF_BAR + 512;
+  static constexpr int kThreads = 384;
+  static constexpr int kProducers = 8;
+};
+
+// ---- mbarrier / bulk-copy primitives (PTX) ---------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n .reg .pred p;\n TRI_WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra TRI_DONE_%=;\n"
+      " bra TRI_WAIT_%=;\n TRI_DONE_%=:\n}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+// arrive on `bar` once all cp.async of this thread issued so far have landed (counts as one pending arrival)
+__device__ __forceinline__ void cp_async_mbar_arrive(unsigned bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 8-byte cp.async that writes zeros when `valid` is false (src-size 0: nothing is read)
+__device__ __forceinline__ void cp_async8_zfill(void *smem_dst, const void *gsrc, bool valid) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gsrc), "r"(valid ? 8 : 0) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, unsigned src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// tile of 32 complete (m-neighbour) rows: its weights are one contiguous run of 32 m doubles in B
+__device__ __forceinline__ bool tri_tile_is_full(long long base, int m, long long loc_end) {
+  return base >= m && base + 32 <= loc_end;
+}
+
+// ---- sigma^2 rho(D) from the DISTANCE --------------------------------------------------------------
+template <int COV>
+struct FromDist;
+template <>
+struct FromDist<NNGP_COV_EXPONENTIAL> {
+  double nphi, sig;
+  __device__ __forceinline__ FromDist(const BfTheta &t, const double *) : nphi(-t.phi), sig(t.sigmaSq) {}
+  __device__ __forceinline__ double operator()(double D) const { return sig * nngp_exp_nonpos(nphi * D); }
+};
+template <>
+struct FromDist<NNGP_COV_GAUSSIAN> {
+  double nphi2, sig;
+  __device__ __forceinline__ FromDist(const BfTheta &t, const double *) : nphi2(-(t.phi * t.phi)), sig(t.sigmaSq) {}
+  __device__ __forceinline__ double operator()(double D) const { return sig * nngp_exp_nonpos(nphi2 * (D * D)); }
+};
+template <>
+struct FromDist<NNGP_COV_SPHERICAL> {
+  double phi, rng, sig;
+  __device__ __forceinline__ FromDist(const BfTheta &t, const double *) : phi(t.phi), rng(1.0 / t.phi), sig(t.sigmaSq) {}
+  __device__ __forceinline__ double operator()(double D) const {  // src/util.cpp:221-227; D = 0 gives exactly 1
+    const double pd = phi * D;
+    const double v = 1.0 - 1.5 * pd + 0.5 * (pd * pd * pd);
+    return (D <= rng) ? sig * v : 0.0;
+  }
+};
+
+// One batch of NU rows of 32 doubles at `p + u * stride_bytes`: all loads, NU independent chains, all stores.
+template <int COV, int NU>
+__device__ __forceinline__ void tri_rows(unsigned char *p, int stride_bytes, const FromDist<COV> &f) {
+  double v[NU];
+#pragma unroll
+  for (int u = 0; u < NU; ++u) v[u] = *reinterpret_cast<const double *>(p + u * stride_bytes);
+#pragma unroll
+  for (int u = 0; u < NU; ++u) v[u] = f(v[u]);
+#pragma unroll
+  for (int u = 0; u < NU; ++u) *reinterpret_cast<double *>(p + u * stride_bytes) = v[u];
+}
+// Matern: the series in t = (phi D / 2)^2 (matern_series.cuh) with the table-driven log / exp; the rare arguments
+// outside the straight-line path are re-evaluated afterwards, like the gather kernels do (tpl_device.cuh)
+template <int COV, int NU>
+__device__ __forceinline__ void tri_rows_matern(unsigned char *p, int stride_bytes, const Cor<COV> &cor, double sig) {
+  double d2[NU], v[NU];
+#pragma unroll
+  for (int u = 0; u < NU; ++u) {
+    const double D = *reinterpret_cast<const double *>(p + u * stride_bytes);
+    d2[u] = D * D;
+  }
+#pragma unroll
+  for (int u = 0; u < NU; ++u) v[u] = sig * cor.fast_tab(d2[u]);
+  bool any = false;
+#pragma unroll
+  for (int u = 0; u < NU; ++u) any |= cor.maybe_slow(d2[u]);
+  if (any) {
+#pragma unroll
+    for (int u = 0; u < NU; ++u)
+      if (cor.needs_slow(d2[u])) v[u] = sig * cor.slow(d2[u]);
+  }
+#pragma unroll
+  for (int u = 0; u < NU; ++u) *reinterpret_cast<double *>(p + u * stride_bytes) = v[u];
+}
+
+// rows [r0, r1) of the stage's transform region, this warp's lane; rows >= m of the CV block are padding (m < MC)
+template <int MC, int COV, typename Fn>
+__device__ __forceinline__ void tri_transform(unsigned char *stage, int lane, int r0, int r1, int m, const Fn &rows) {
+  // logical row r: r < m -> CV row r; else A row r - m.  Byte offset = r * 256 + (r >= m ? (MC - m) * 256 : 0)
+  constexpr int NU = kIsMatern<COV> ? NNGP_TRI_UNR_MATERN : NNGP_TRI_UNR;
+  unsigned char *base = stage + lane * 8;
+  const int pad = (MC - m) * 256;
+  int r = r0;
+  if (r < m) {  // the (short) part of this warp's range inside the CV block: single rows
+    const int e = r1 < m ? r1 : m;
+    for (; r < e; ++r) rows(base + r * 256, 0, 1);
+  }
+  unsigned char *p = base + r * 256 + pad;
+  for (; r + NU <= r1; r += NU, p += NU * 256) rows(p, 256, NU);
+  for (; r < r1; ++r, p += 256) rows(p, 0, 1);
+}
+
+template <int MC, int COV>
+__global__ void __launch_bounds__(384, 1) bf_tri_kernel(const __grid_constant__ BfLaunch P) {
+  using G = TriGeo<MC>;
+  constexpr int S = G::S, NC = G::NC;
+  constexpr bool kMat = kIsMatern<COV>;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const BfTheta &th = P.th[blockIdx.y];
+  const int m = P.m;
+  const int ne = m * (m - 1) / 2;
+  const double *__restrict__ resid = th.resid;
+  const bool with_cur = th.Bcur != nullptr && resid != nullptr;
+  const long long nloc = (long long)P.loc_end - P.loc_begin;
+  const long long ntiles = (nloc + 31) / 32;
+  unsigned char *smem = tpl_smem;
+  const unsigned bar0 = smem_u32(smem + G::OFF_BAR);
+  auto bar_full = [&](int s) { return bar0 + 8u * s; };
+  auto bar_built = [&](int s) { return bar0 + 8u * (S + s); };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (2 * S + s); };
+  volatile long long *ring = reinterpret_cast<volatile long long *>(smem + G::OFF_BAR + 8 * 3 * S);
+  double *s_tab = reinterpret_cast<double *>(smem + G::OFF_TAB);
+  __shared__ double red[3][12];
+  __shared__ int last_flag;
+
+  // ---- one-time setup ---------------------------------------------------------------------------------
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar_full(s), 1 + 32);          // expect_tx arrival of the loader's lane 0 + 32 cp.async arrivals
+      mbar_init(bar_built(s), G::kProducers);  // one arrival per producer warp
+      mbar_init(bar_empty(s), 1);              // the consumer
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (kMat) {
+    for (int x = tid; x < 32; x += G::kThreads) s_tab[x] = kExpTab32[x];
+    for (int x = tid; x < 128; x += G::kThreads) s_tab[32 + x] = kLogTab64[x];
+  }
+  for (int s = 0; s < S; ++s) {  // zero padding (m < MC) and the residual rows; the bulk copies never touch them
+    double *st = reinterpret_cast<double *>(smem + s * G::kStageBytes);
+    for (int x = tid; x < (MC - m) * 32; x += G::kThreads) st[G::OFF_CV / 8 + m * 32 + x] = 0.0;
+    for (int x = tid; x < (G::NE - ne) * 32; x += G::kThreads) st[G::OFF_A / 8 + ne * 32 + x] = 0.0;
+    for (int x = tid; x < (MC + 1) * 32; x += G::kThreads) st[G::OFF_RR / 8 + x] = 0.0;
+  }
+  __syncthreads();
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    if (warp == 3) {
+      // ================================ loader =========================================================
+      // Tile sequence of this CTA: T(j) = blockIdx.x + j gridDim.x for j < S (static: spreads the slow head of the
+      // ordering over the CTAs), then S gridDim.x + (atomic counter).  Software pipeline so that the warp never waits
+      // for global memory: at trip j the copies of T(j) are issued with neighbour ids that were loaded during trip
+      // j - 1, the ids of T(j+1) are requested, and the atomic that claims T(j+2) is outstanding in lane 0.
+      const unsigned tri_bytes_a = (unsigned)ne * 256u, tri_bytes_c = (unsigned)m * 256u;
+      const size_t tile_doubles = (size_t)(ne + m) * 32;
+      int ids_cur[MC], ids_nxt[MC];
+      auto load_ids = [&](long long tile, int(&ids)[MC]) {
+        const int *src = P.nnT + (size_t)tile * m * 32 + lane;
+#pragma unroll
+        for (int k = 0; k < MC; ++k) ids[k] = (k < m) ? __ldg(src + k * 32) : -1;
+      };
+      long long t_cur = blockIdx.x, t_nxt = (long long)blockIdx.x + gridDim.x;
+      unsigned claim = 0u;
+      bool pending = false;
+      if (resid != nullptr && t_cur < ntiles) load_ids(t_cur, ids_cur);
+      int done_markers = 0;
+      for (int j = 0;; ++j) {
+        const int s = j % S;
+        if (j > 0) {  // T(j+1): static, or the claim issued one trip ago
+          if (pending) t_nxt = (long long)S * gridDim.x + __shfl_sync(0xffffffffu, claim, 0);
+          else t_nxt = (long long)blockIdx.x + (long long)(j + 1) * gridDim.x;
+        }
+        pending = false;
+        if (j + 2 >= S && t_nxt < ntiles) {  // claim T(j+2)
+          if (lane == 0) claim = atomicAdd(th.tile_counter, 1u);
+          pending = true;
+        } else if (j + 2 >= S) {
+          pending = true;  // past the end: stay there without touching the counter
+          claim = 0x7fffffffu;
+        }
+        if (resid != nullptr && t_nxt < ntiles) load_ids(t_nxt, ids_nxt);
+        if (j >= S) mbar_wait(bar_empty(s), ((j / S) - 1) & 1);
+        if (t_cur >= ntiles) {  // end of work: NC consecutive markers, one per consumer (they take the stages round-robin)
+          if (lane == 0) ring[s] = -1;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_full(s));
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_full(s)) : "memory");  // the 32 "cp.async" slots
+          if (++done_markers == NC) break;
+          t_cur = t_nxt;
+          continue;
+        }
+        unsigned char *st = smem + s * G::kStageBytes;
+        const long long base = P.loc_begin + t_cur * 32;
+        if (lane == 0) {
+          ring[s] = t_cur;
+          const unsigned extra = (with_cur && tri_tile_is_full(base, m, P.loc_end)) ? (unsigned)m * 256u : 0u;
+          mbar_expect_tx(bar_full(s), tri_bytes_a + tri_bytes_c + extra);
+          const double *src = P.tri + (size_t)t_cur * tile_doubles;
+          bulk_g2s(smem_u32(st + G::OFF_CV), src, tri_bytes_c, bar_full(s));
+          bulk_g2s(smem_u32(st + G::OFF_A), src + (size_t)m * 32, tri_bytes_a, bar_full(s));
+          if (extra) bulk_g2s(smem_u32(st + G::OFF_BC), th.Bcur + nn_offset(base, m), extra, bar_full(s));
+        }
+        if (resid != nullptr) {
+          double *rr = reinterpret_cast<double *>(st + G::OFF_RR) + lane;
+          long long i = base + lane;
+          if (i >= P.loc_end) i = (long long)P.loc_end - 1;
+#pragma unroll
+          for (int k = 0; k < MC; ++k)
+            if (k < m) cp_async8_zfill(&rr[k * 32], &resid[ids_cur[k] >= 0 ? ids_cur[k] : 0], ids_cur[k] >= 0);
+          cp_async8(&rr[MC * 32], &resid[i]);
+#pragma unroll
+          for (int k = 0; k < MC; ++k) ids_cur[k] = ids_nxt[k];
+        }
+        cp_async_mbar_arrive(bar_full(s));
+        t_cur = t_nxt;
+      }
+    } else if (warp < NC) {
+      // ================================ consumers ======================================================
+      unsigned char *cons = smem + G::OFF_CONS + warp * G::kConsBytes;
+      double *dv = reinterpret_cast<double *>(cons) + lane;
+      double *bo = reinterpret_cast<double *>(cons + MC * 256);  // [lane][k], the image of the tile's block of B
+      const double diag = th.sigmaSq + th.tauSq;
+      int failed = INT_MAX;
+      bool store_pending = false;
+      for (int j = warp;; j += NC) {
+        const int s = j % S;
+        unsigned char *st = smem + s * G::kStageBytes;
+        double *A = reinterpret_cast<double *>(st + G::OFF_A) + lane;
+        double *cv = reinterpret_cast<double *>(st + G::OFF_CV);
+        const double *rr = reinterpret_cast<const double *>(st + G::OFF_RR);
+        const double *bc = reinterpret_cast<const double *>(st + G::OFF_BC);
+        mbar_wait(bar_built(s), (j / S) & 1);
+        const long long tile = ring[s];
+        if (tile < 0) break;
+        const long long base = P.loc_begin + tile * 32;
+        const bool active = base + lane < P.loc_end;
+        const long long i = active ? base + lane : (long long)P.loc_end - 1;
+        const int mi = nn_count(i, m);
+        const long long off = nn_offset(i, m);
+        const bool full = tri_tile_is_full(base, m, P.loc_end);
+        double fcur = 1.0;
+        if (with_cur) fcur = __ldg(&th.Fcur[i]);
+        if (mi < m) {  // ragged start of the ordering: identity-pad rows >= m_i
+          for (int k = mi; k < m; ++k) {
+            cv[k * 32 + lane] = 0.0;
+            for (int l = 0; l < k; ++l) A[(k * (k - 1) / 2 + l) * 32] = 0.0;
+          }
+          for (int k = 0; k < mi; ++k)  // and the columns of the rows that do exist stay as they are
+            ;
+        }
+        // Q term of the RESIDENT factors (current theta of the sampler) with the same residuals
+        double qcur_part = 0.0;
+        if (with_cur) {
+          if (full) {
+#pragma unroll
+            for (int k = 0; k < MC; ++k)
+              if (k < m) qcur_part = fma(bc[lane * m + k], rr[k * 32 + lane], qcur_part);
+          } else {
+            for (int k = 0; k < mi; ++k) qcur_part = fma(__ldg(&th.Bcur[off + k]), rr[k * 32 + lane], qcur_part);
+          }
+        }
+        double Fsum;
+        constexpr int kCholW = (MC >= 12 && MC <= 16) ? 4 : 2;
+        const bool ok = tpl_solve<MC, kCholW>(A, cv + lane, dv, mi, diag, &Fsum);
+        if (!ok && active) failed = min(failed, (int)min(i + 1, (long long)INT_MAX - 1));
+        const double Fv = diag - Fsum;
+        double part = 0.0;
+        if (resid != nullptr) {
+#pragma unroll
+          for (int k = 0; k < MC; ++k) part = fma(cv[k * 32 + lane], rr[k * 32 + lane], part);
+        }
+        const double r_own = rr[MC * 32 + lane];
+        if (th.B != nullptr) {
+          if (full) {
+            if (store_pending) {
+              if (lane == 0) bulk_wait_read0();
+              __syncwarp();
+            }
+#pragma unroll
+            for (int k = 0; k < MC; ++k)
+              if (k < m) bo[lane * m + k] = cv[k * 32 + lane];
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              bulk_s2g(th.B + nn_offset(base, m), smem_u32(bo), (unsigned)m * 256u);
+              bulk_commit();
+            }
+            store_pending = true;
+          } else if (active) {
+            for (int k = 0; k < mi; ++k) th.B[off + k] = cv[k * 32 + lane];
+          }
+        }
+        fence_proxy_async();  // this warp's generic-proxy accesses to the stage precede the next bulk copy into it
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty(s));
+        if (th.F != nullptr && active) th.F[i] = Fv;
+        double lt = 0.0, qt = 0.0, qc = 0.0;
+        if (active) {
+          lt = (Fv > 0.0) ? nngp_log_pos(Fv) : log(Fv);
+          if (resid != nullptr) {
+            const double e = r_own - part;
+            qt = e * e * nngp_rcp_pos(Fv);
+            if (with_cur) {
+              const double ec = r_own - qcur_part;
+              qc = ec * ec / fcur;
+            }
+          }
+        }
+#pragma unroll
+        for (int sft = 16; sft >= 1; sft >>= 1) {
+          lt += __shfl_down_sync(0xffffffffu, lt, sft);
+          qt += __shfl_down_sync(0xffffffffu, qt, sft);
+          qc += __shfl_down_sync(0xffffffffu, qc, sft);
+        }
+        if (lane == 0) {
+          th.partials[4 * tile] = lt;
+          th.partials[4 * tile + 1] = qt;
+          th.partials[4 * tile + 2] = qc;
+        }
+      }
+      if (store_pending && lane == 0) bulk_wait0();
+      if (failed != INT_MAX) atomicMin(th.fail, failed);
+    }
+  } else {
+    // ================================ producers ========================================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 136;");
+    const int pw = warp - 4;
+    const int nrows = ne + m;
+    const int r0 = (nrows * pw) / G::kProducers, r1 = (nrows * (pw + 1)) / G::kProducers;
+    int markers = 0;
+    for (int j = 0;; ++j) {
+      const int s = j % S;
+      mbar_wait(bar_full(s), (j / S) & 1);
+      const long long tile = ring[s];
+      if (tile >= 0) {
+        unsigned char *st = smem + s * G::kStageBytes;
+        if constexpr (kMat) {
+          auto body = [&](auto idx) {
+            constexpr int B = decltype(idx)::value;
+            const Cor<COV> cor(P.th[B], s_tab);
+            const double sig = P.th[B].sigmaSq;
+            tri_transform<MC, COV>(st, lane, r0, r1, m, [&](unsigned char *p, int stride, int nu) {
+              if (nu == 1) tri_rows_matern<COV, 1>(p, stride, cor, sig);
+              else tri_rows_matern<COV, NNGP_TRI_UNR_MATERN>(p, stride, cor, sig);
+            });
+          };
+          switch (blockIdx.y) {  // compile-time set index: the series coefficients stay constant-bank operands
+            case 0: body(std::integral_constant<int, 0>()); break;
+            case 1: body(std::integral_constant<int, 1>()); break;
+            case 2: body(std::integral_constant<int, 2>()); break;
+            default: body(std::integral_constant<int, 3>()); break;
+          }
+        } else {
+          const FromDist<COV> f(th, nullptr);
+          tri_transform<MC, COV>(st, lane, r0, r1, m, [&](unsigned char *p, int stride, int nu) {
+            if (nu == 1) tri_rows<COV, 1>(p, stride, f);
+            else tri_rows<COV, NNGP_TRI_UNR>(p, stride, f);
+          });
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_built(s));
+      if (tile < 0 && ++markers == NC) break;  // the markers pass through, so that every consumer sees one
+    }
+  }
+
+  // ---- grid reduction: the last CTA to finish adds the per-tile partials in tile order --------------------
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    const unsigned int tk = atomicAdd(th.ticket, 1u);
+    last_flag = (tk == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last_flag) {
+    __threadfence();
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (long long t = tid; t < ntiles; t += G::kThreads) {
+      a += __ldcg(&th.partials[4 * t]);
+      b += __ldcg(&th.partials[4 * t + 1]);
+      c += __ldcg(&th.partials[4 * t + 2]);
+    }
+#pragma unroll
+    for (int sft = 16; sft >= 1; sft >>= 1) {
+      a += __shfl_down_sync(0xffffffffu, a, sft);
+      b += __shfl_down_sync(0xffffffffu, b, sft);
+      c += __shfl_down_sync(0xffffffffu, c, sft);
+    }
+    if (lane == 0) {
+      red[0][warp] = a;
+      red[1][warp] = b;
+      red[2][warp] = c;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double o0 = 0.0, o1 = 0.0, o2 = 0.0;
+      for (int w = 0; w < 12; ++w) {
+        o0 += red[0][w];
+        o1 += red[1][w];
+        o2 += red[2][w];
+      }
+      const int fv = atomicExch(th.fail, INT_MAX);
+      th.out[0] = o0;
+      th.out[1] = o1;
+      th.out[2] = (fv != INT_MAX) ? 1.0 : 0.0;
+      th.out[3] = o2;
+      *th.fail_out = fv;
+      *th.tile_counter = 0u;
+      *th.ticket = 0u;
+    }
+  }
+}
+
+// ---- launcher ---------------------------------------------------------------------------------------
+template <int MC, int COV>
+static cudaError_t tri_launch_one(const BfLaunch &P, int grid_x, cudaStream_t stream) {
+  using G = TriGeo<MC>;
+  cudaError_t e = cudaFuncSetAttribute(bf_tri_kernel<MC, COV>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  dim3 grid(grid_x, P.nbatch, 1);
+  bf_tri_kernel<MC, COV><<<grid, G::kThreads, G::kSmemBytes, stream>>>(P);
+  return cudaGetLastError();
+}
+
+template <int MC>
+static cudaError_t tri_launch_cov(const BfLaunch &P, int cov, int grid_x, cudaStream_t stream) {
+  switch (cov) {
+    case NNGP_COV_EXPONENTIAL: return tri_launch_one<MC, NNGP_COV_EXPONENTIAL>(P, grid_x, stream);
+    case NNGP_COV_SPHERICAL: return tri_launch_one<MC, NNGP_COV_SPHERICAL>(P, grid_x, stream);
+    case NNGP_COV_MATERN:
+      if (P.matern_short) return tri_launch_one<MC, NNGP_COV_MATERN_SHORT>(P, grid_x, stream);
+      return tri_launch_one<MC, NNGP_COV_MATERN>(P, grid_x, stream);
+    case NNGP_COV_GAUSSIAN: return tri_launch_one<MC, NNGP_COV_GAUSSIAN>(P, grid_x, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+int tri_capacity_for_m(int m) {
+  static const int caps[7] = {8, 10, 12, 15, 16, 20, 24};
+  if (m < 6) return 0;
+  for (int c : caps)
+    if (m <= c) return c;
+  return 0;
+}
+
+int tri_grid_for(long long nloc, int sms) {
+  const long long need = (nloc + 31) / 32;
+  long long g = sms;
+  if (need < g) g = need;
+  return (int)(g < 1 ? 1 : g);
+}
+
+cudaError_t tri_launch(const BfLaunch &P, int cov, int grid_x, cudaStream_t stream) {
+  switch (tri_capacity_for_m(P.m)) {
+#ifdef NNGP_TRI_ONLY15
+    case 15: return tri_launch_cov<15>(P, cov, grid_x, stream);
+#else
+    case 8: return tri_launch_cov<8>(P, cov, grid_x, stream);
+    case 10: return tri_launch_cov<10>(P, cov, grid_x, stream);
+    case 12: return tri_launch_cov<12>(P, cov, grid_x, stream);
+    case 15: return tri_launch_cov<15>(P, cov, grid_x, stream);
+    case 16: return tri_launch_cov<16>(P, cov, grid_x, stream);
+    case 20: return tri_launch_cov<20>(P, cov, grid_x, stream);
+    case 24: return tri_launch_cov<24>(P, cov, grid_x, stream);
+#endif
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace nngp

@@ -408,6 +408,7 @@ __global__ void __launch_bounds__(32 * (1 + NP), (MC <= 16) ? 2 : 1) bf_ws_kerne
       th.out[1] = o1;
       const int fv = atomicExch(th.fail, INT_MAX);
       th.out[2] = (fv != INT_MAX) ? 1.0 : 0.0;
+      th.out[3] = 0.0;
       *th.fail_out = fv;
       *th.tile_counter = 0u;
       *th.ticket = 0u;

@@ -68,13 +68,17 @@ static int ensure_dev(nngp_ctx *c, Tp *&p, size_t &cap_bytes, size_t count) {
 
 static void free_model(nngp_ctx *c) {
   free_dev(c->d_coords);
-  free_dev(c->d_nnIndx);
+  free_dev(c->d_nnIndx_store);
+  c->d_nnIndx = nullptr;
   free_dev(c->d_X);
   free_dev(c->d_y);
   for (int s = 0; s < 2; s++) {
-    free_dev(c->d_B[s]);
-    free_dev(c->d_F[s]);
+    free_dev(c->d_B_store[s]);
+    free_dev(c->d_F_store[s]);
+    c->d_B[s] = c->d_F[s] = nullptr;
   }
+  free_dev(c->d_tri);
+  c->tri_cap = 0;
   for (int b = 0; b < NNGP_MAX_BATCH; b++) free_dev(c->d_resid[b]);
   free_dev(c->d_beta);
   free_dev(c->d_partials);
@@ -158,9 +162,9 @@ int nngp_create(int device, void *stream_handle, nngp_ctx **out) {
     NNGP_CUDA(c, cudaMemcpy(c->d_fail, init, sizeof init, cudaMemcpyHostToDevice));
   }
   NNGP_CUDA(c, cudaMalloc(&c->d_mat, NNGP_MAX_BATCH * sizeof(MaternConsts)));
-  NNGP_CUDA(c, cudaHostAlloc(&c->h_out, 3 * NNGP_MAX_BATCH * sizeof(double), cudaHostAllocMapped));
-  NNGP_CUDA(c, cudaMalloc(&c->d_red, 3 * NNGP_MAX_BATCH * sizeof(double)));
-  NNGP_CUDA(c, cudaHostAlloc(&c->h_red, 3 * NNGP_MAX_BATCH * sizeof(double), cudaHostAllocDefault));
+  NNGP_CUDA(c, cudaHostAlloc(&c->h_out, kBfOutStride * NNGP_MAX_BATCH * sizeof(double), cudaHostAllocMapped));
+  NNGP_CUDA(c, cudaMalloc(&c->d_red, kBfOutStride * NNGP_MAX_BATCH * sizeof(double)));
+  NNGP_CUDA(c, cudaHostAlloc(&c->h_red, kBfOutStride * NNGP_MAX_BATCH * sizeof(double), cudaHostAllocDefault));
   NNGP_CUDA(c, cudaHostAlloc(&c->h_fail, NNGP_MAX_BATCH * sizeof(int), cudaHostAllocMapped));
   NNGP_CUDA(c, cudaHostAlloc(&c->h_mat, NNGP_MAX_BATCH * sizeof(MaternConsts), cudaHostAllocDefault));
   NNGP_CUDA(c, cudaEventCreate(&c->ev0));
@@ -212,6 +216,10 @@ int nngp_set_option(nngp_ctx *c, const char *name, int value) {
     c->opt_matern_short = value ? 1 : 0;
     return NNGP_OK;
   }
+  if (!strcmp(name, "tri_cache")) {  // takes effect at the next nngp_set_data
+    c->opt_tri = value ? 1 : 0;
+    return NNGP_OK;
+  }
   return ctx_fail(c, NNGP_EINVAL, std::string("nngp_set_option: unknown option ") + name);
 }
 
@@ -219,6 +227,14 @@ int nngp_get_option(nngp_ctx *c, const char *name, int *value) {
   if (!c || !name || !value) return NNGP_EINVAL;
   if (!strcmp(name, "matern_short")) {
     *value = c->opt_matern_short;
+    return NNGP_OK;
+  }
+  if (!strcmp(name, "tri_cache")) {
+    *value = c->opt_tri;
+    return NNGP_OK;
+  }
+  if (!strcmp(name, "tri_cache_used")) {  // 1 when the B/F launches of this data set stream the resident distance triangle
+    *value = c->d_tri != nullptr && c->tri_on;
     return NNGP_OK;
   }
   if (!strcmp(name, "matern_short_used")) {  // parameter sets of the last likelihood launch that ran the short series
@@ -253,9 +269,18 @@ int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const 
   // would otherwise dominate a short fit: the whole-call path is measured end to end by bench.py)
   c->n = n; c->m = m; c->p = p; c->loc_begin = loc_begin; c->loc_end = loc_end;
   c->rep_ready = false;
+  c->tri_on = false;
   c->has_nn = (nnIndx != nullptr);  // NULL: prediction-only use (sites, X, y), no B/F storage
   c->nIndx = c->has_nn ? nn_offset(n, m) : 0;  // == (1+m)/2*m + (n-m-1)*m for n > m
-  const long long nI = c->nIndx > 0 ? c->nIndx : 1;
+  // this shard's slice of the CSR arrays; the virtual bases (nngp_ctx.h) make global offsets work on the slice
+  c->csr_begin = c->has_nn ? nn_offset(loc_begin, m) : 0;
+  c->csr_end = c->has_nn ? nn_offset(loc_end, m) : 0;
+  const long long nI = c->csr_end > c->csr_begin ? c->csr_end - c->csr_begin : 1;
+  const long long nF = loc_end > loc_begin ? loc_end - loc_begin : 1;
+  // B: complete rows of a 32-location tile must start 16-byte aligned (bulk copies): one element of padding when the
+  // CSR offset of the first such tile, relative to the shard, is odd (all later tiles follow in steps of 32 m)
+  const long long first_full = loc_begin < m ? loc_begin + ((m - loc_begin + 31) / 32) * 32 : loc_begin;
+  const long long b_pad = c->has_nn ? ((nn_offset(first_full, m) - c->csr_begin) & 1) : 0;
   int rc;
 #define NNGP_ENSURE(ptr, slot, count)                                     \
   do {                                                                    \
@@ -263,7 +288,8 @@ int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const 
     if (rc) return rc;                                                    \
   } while (0)
   NNGP_ENSURE(c->d_coords, 0, n);
-  NNGP_ENSURE(c->d_nnIndx, 1, nI);
+  NNGP_ENSURE(c->d_nnIndx_store, 1, nI);
+  c->d_nnIndx = c->d_nnIndx_store - c->csr_begin;
   if (p > 0) {
     NNGP_ENSURE(c->d_X, 2, (size_t)n * p);
     NNGP_ENSURE(c->d_y, 3, n);
@@ -277,7 +303,9 @@ int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const 
     }
     std::vector<StageJob> jobs;
     jobs.push_back({StageJob::XY_INTERLEAVE, c->d_coords, coords, (size_t)n * sizeof(double2), n});
-    if (c->nIndx > 0) jobs.push_back({StageJob::INT_RANGE, c->d_nnIndx, nnIndx, (size_t)c->nIndx * sizeof(int), n});
+    if (c->csr_end > c->csr_begin)
+      jobs.push_back({StageJob::INT_RANGE, c->d_nnIndx_store, nnIndx + c->csr_begin,
+                      (size_t)(c->csr_end - c->csr_begin) * sizeof(int), n});
     if (p > 0) {
       jobs.push_back({StageJob::RAW, c->d_X, X, (size_t)n * p * sizeof(double), 0});
       jobs.push_back({StageJob::RAW, c->d_y, y, (size_t)n * sizeof(double), 0});
@@ -304,8 +332,28 @@ int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const 
     NNGP_CUDA(c, xy_rows_launch(c->d_X, c->d_y, n, p, c->d_Xy, c->sms, c->stream));
   }
   for (int s = 0; s < 2 && c->has_nn; s++) {
-    NNGP_ENSURE(c->d_B[s], 9 + s, nI);
-    NNGP_ENSURE(c->d_F[s], 11 + s, n);
+    NNGP_ENSURE(c->d_B_store[s], 9 + s, nI + 2);
+    NNGP_ENSURE(c->d_F_store[s], 11 + s, nF);
+    c->d_B[s] = c->d_B_store[s] + b_pad - c->csr_begin;
+    c->d_F[s] = c->d_F_store[s] - loc_begin;
+  }
+  if (c->has_nn && c->opt_tri && tri_capacity_for_m(m) > 0 && loc_end > loc_begin) {
+    // resident distance triangle (tri_cache.cu): m(m+1)/2 doubles per location, built once per data set
+    const size_t need = tri_cache_doubles(m, (long long)loc_end - loc_begin);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const bool fits = c->tri_cap >= need * sizeof(double) || need * sizeof(double) + ((size_t)2 << 30) < free_b + c->tri_cap;
+    if (fits) {
+      rc = ensure_dev(c, c->d_tri, c->tri_cap, need);
+      if (rc == NNGP_OK) {
+        NNGP_CUDA(c, tri_build_launch(c->d_coords, c->d_nnIndx, m, loc_begin, loc_end, c->d_tri, c->stream));
+        c->launches++;
+        c->tri_on = true;
+      } else if (rc != NNGP_ENOMEM) {
+        return rc;
+      }
+    }
+    tr.mark("distance triangle");
   }
   c->pair_d2_q99 = 1e300;
   if (c->has_nn && (long long)loc_end > m && loc_end > loc_begin) {
@@ -332,9 +380,9 @@ int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const 
   }
   const long long nloc = (long long)loc_end - loc_begin;
   const int K = p + 1, npairs = K * (K + 1) / 2;
-  // per parameter set: 2 doubles per CTA or per 32-location tile, whichever is more (site-mode chunks are <= 2^20)
+  // per parameter set: 2 doubles per CTA or 4 per 32-location tile, whichever is more (site-mode chunks are <= 2^20)
   const long long tiles_max = ((nloc > (1 << 20) ? nloc : (1 << 20)) + 31) / 32;
-  const long long per_set = 2 * (tiles_max > bf_grid_max(m, (long long)1 << 40, c->sms) ? tiles_max : bf_grid_max(m, (long long)1 << 40, c->sms));
+  const long long per_set = 4 * (tiles_max > bf_grid_max(m, (long long)1 << 40, c->sms) ? tiles_max : bf_grid_max(m, (long long)1 << 40, c->sms));
   c->partials_stride = (size_t)per_set;
   size_t need = (size_t)NNGP_MAX_BATCH * per_set;
   size_t need2 = (size_t)q_forms_grid(nloc) * npairs;
@@ -355,8 +403,12 @@ static int prepare_bf(nngp_ctx *c, int cov, int nbatch, const double *theta, con
   if (nbatch < 1 || nbatch > NNGP_MAX_BATCH) return ctx_fail(c, NNGP_EINVAL, "nbatch must be in 1..4");
   if (cov < 0 || cov > 3) return ctx_fail(c, NNGP_EINVAL, "cov.model is not correctly specified");
   if (beta && c->p == 0) return ctx_fail(c, NNGP_EINVAL, "beta given but the model has no covariates");
-  const int grid = bf_grid_any(c->m, cov, (long long)c->loc_end - c->loc_begin, c->sms);
+  const bool tri = c->tri_on && c->d_tri != nullptr;
+  const int grid = tri ? tri_grid_for((long long)c->loc_end - c->loc_begin, c->sms)
+                       : bf_grid_any(c->m, cov, (long long)c->loc_end - c->loc_begin, c->sms);
   memset(P, 0, sizeof *P);
+  P->tri = tri ? c->d_tri : nullptr;
+  P->nnT = tri ? reinterpret_cast<const int *>(c->d_tri + tri_ids_offset(c->m, (long long)c->loc_end - c->loc_begin)) : nullptr;
   memset(c->bf_short, 0, sizeof c->bf_short);
   P->coords = c->d_coords;
   P->nnIndx = c->d_nnIndx;
@@ -393,7 +445,7 @@ static int prepare_bf(nngp_ctx *c, int cov, int nbatch, const double *theta, con
       th.mat = c->d_mat + b;
       // short series: 99 % of the locations keep t = phi^2 d^2 / 4 of every pair inside its range
       const double t99 = 0.25 * t[2] * t[2] * c->pair_d2_q99;
-      c->bf_short[b] = (c->opt_matern_short && th.ms.use_series && bf_has_matern_short(c->m) &&
+      c->bf_short[b] = (c->opt_matern_short && th.ms.use_series && (tri || bf_has_matern_short(c->m)) &&
                         t99 <= c->h_mat[b].t_short_max) ? 1 : 0;
       if (c->bf_short[b]) th.ms.t_fast_max = c->h_mat[b].t_short_max;
       matern_set_phi(&th.ms, t[2]);
@@ -403,7 +455,7 @@ static int prepare_bf(nngp_ctx *c, int cov, int nbatch, const double *theta, con
     th.B = store ? c->d_B[slot] : nullptr;
     th.F = store ? c->d_F[slot] : nullptr;
     th.resid = beta ? c->d_resid[b] : nullptr;
-    th.out = (c->comm ? c->d_red : out_dev) + 3 * b;  // device buffer when the result is reduced over ranks
+    th.out = (c->comm ? c->d_red : out_dev) + kBfOutStride * b;  // device buffer when the result is reduced over ranks
     th.partials = c->d_partials + c->partials_stride * b;
     th.ticket = c->d_ticket + b;
     th.tile_counter = c->d_ticket + NNGP_MAX_BATCH + b;
@@ -474,18 +526,19 @@ static void share_resid(nngp_ctx *c, BfLaunch *P) {
 static int finish_bf(nngp_ctx *c, int nbatch, bool have_q, double *out) {
   const double *res = c->h_out;
   if (c->comm) {  // sum (logDet, Q, fail flag) over the ranks on the device, then one small copy back
-    int rc = comm_allreduce_dev(c, c->d_red, 3 * nbatch);
+    int rc = comm_allreduce_dev(c, c->d_red, kBfOutStride * nbatch);
     if (rc) return rc;
-    NNGP_CUDA(c, cudaMemcpyAsync(c->h_red, c->d_red, 3 * nbatch * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    NNGP_CUDA(c, cudaMemcpyAsync(c->h_red, c->d_red, kBfOutStride * nbatch * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     res = c->h_red;
   }
   NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
   int status = 0;
   bool any_rank_failed = false;
   for (int b = 0; b < nbatch; b++) {
-    out[2 * b] = res[3 * b];
-    out[2 * b + 1] = have_q ? res[3 * b + 1] : 0.0;
-    if (res[3 * b + 2] > 0.0) any_rank_failed = true;
+    out[2 * b] = res[kBfOutStride * b];
+    out[2 * b + 1] = have_q ? res[kBfOutStride * b + 1] : 0.0;
+    c->last_qcur[b] = res[kBfOutStride * b + 3];
+    if (res[kBfOutStride * b + 2] > 0.0) any_rank_failed = true;
     if (c->h_fail[b] != INT_MAX && (status == 0 || c->h_fail[b] < status)) status = c->h_fail[b];
   }
   if (status == 0 && any_rank_failed) status = INT_MAX;  // the failing location lives on another rank
@@ -622,8 +675,14 @@ int nngp_get_bf(nngp_ctx *c, int slot, double *B, double *F) {
   if (c->n == 0 || !c->has_nn) return ctx_fail(c, NNGP_ESTATE, "nngp_get_bf before nngp_set_data");
   NNGP_CUDA(c, cudaSetDevice(c->device));
   NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (B && c->nIndx > 0) NNGP_CUDA(c, cudaMemcpy(B, c->d_B[slot], (size_t)c->nIndx * sizeof(double), cudaMemcpyDeviceToHost));
-  if (F) NNGP_CUDA(c, cudaMemcpy(F, c->d_F[slot], (size_t)c->n * sizeof(double), cudaMemcpyDeviceToHost));
+  // storage is sharded: this context holds [csr_begin, csr_end) of B and [loc_begin, loc_end) of F; the rest of the
+  // caller's arrays is left untouched
+  if (B && c->csr_end > c->csr_begin)
+    NNGP_CUDA(c, cudaMemcpy(B + c->csr_begin, c->d_B[slot] + c->csr_begin, (size_t)(c->csr_end - c->csr_begin) * sizeof(double),
+                            cudaMemcpyDeviceToHost));
+  if (F && c->loc_end > c->loc_begin)
+    NNGP_CUDA(c, cudaMemcpy(F + c->loc_begin, c->d_F[slot] + c->loc_begin, (size_t)(c->loc_end - c->loc_begin) * sizeof(double),
+                            cudaMemcpyDeviceToHost));
   return NNGP_OK;
 }
 

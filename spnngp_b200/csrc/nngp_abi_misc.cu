@@ -144,7 +144,7 @@ int nngp_comm_init(nngp_ctx *c, const char id[128], int rank, int nranks) {
 }
 
 int nngp_comm_allreduce_sum(nngp_ctx *c, double *buf, int len) {
-  if (!c || !buf || len < 1 || len > 3 * NNGP_MAX_BATCH) return NNGP_EINVAL;
+  if (!c || !buf || len < 1 || len > nngp::kBfOutStride * NNGP_MAX_BATCH) return NNGP_EINVAL;
   if (!c->comm) return NNGP_OK;
   NNGP_CUDA(c, cudaSetDevice(c->device));
   memcpy(c->h_red, buf, len * sizeof(double));

@@ -15,6 +15,8 @@ __host__ __device__ __forceinline__ long long nn_offset(long long i, int m) {
 }
 __host__ __device__ __forceinline__ int nn_count(long long i, int m) { return i < m ? (int)i : m; }
 
+constexpr int kBfOutStride = 4;  // doubles per parameter set in the result block of a B/F launch
+
 // One parameter set of a batched B/F launch.
 struct BfTheta {
   double sigmaSq, tauSq, phi;
@@ -23,8 +25,12 @@ struct BfTheta {
   double *B;            // nIndx weights (or nullptr: do not store)
   double *F;            // n conditional variances (or nullptr)
   const double *resid;  // n residuals r = X beta - y (or nullptr: no quadratic form)
-  double *out;          // 3 doubles: sum log F, Q over [loc_begin, loc_end), 1.0 if a factorisation failed
-  double *partials;     // scratch: 2 doubles per CTA (static kernels) or per 32-location tile (dynamic tiles)
+  // bf_tri_kernel only: resident factors of ANOTHER parameter set (the sampler's current theta); when given, the launch
+  // also returns Q(Bcur, Fcur, resid, resid) -- the residual gathers are shared (double-buffered sampler, one launch)
+  const double *Bcur;
+  const double *Fcur;
+  double *out;          // kBfOutStride doubles: sum log F, Q over [loc_begin, loc_end), 1.0 if a factorisation failed, Q of (Bcur, Fcur)
+  double *partials;     // scratch: 2 doubles per CTA (static kernels) or 4 per 32-location tile (dynamic tiles)
   unsigned int *ticket; // zero-initialised, self-resetting
   unsigned int *tile_counter;  // zero-initialised, self-resetting: next tile to hand out (bf_ws_kernel)
   int *fail;            // device: min over failing locations of (i + 1); INT_MAX when none; self-resetting
@@ -46,6 +52,10 @@ struct BfLaunch {
   // Matern: every parameter set of this launch may use the short series (th.ms.t_fast_max set accordingly);
   // only bf_ws_kernel has that variant, the other kernels ignore the flag (their t_fast_max is 1)
   int matern_short;
+  // resident distance triangle (tri_cache.cu) of the locations [loc_begin, loc_end): tile t (32 locations) holds
+  // m(m+1)/2 rows of 32 doubles -- m rows location <-> neighbour k, then the packed pairs (k, l), l < k.  NULL: gather kernels.
+  const double *tri;
+  const int *nnT;  // tile-major neighbour ids behind the triangle: tile t, row k, lane -> N(i, k) or -1
   BfTheta th[NNGP_MAX_BATCH];
 };
 

@@ -28,12 +28,26 @@ struct nngp_ctx {
   long long nIndx = 0;
   bool has_nn = false;  // false when only sites/X/y were given (prediction-only use)
   double2 *d_coords = nullptr;  // n interleaved sites
-  int *d_nnIndx = nullptr;      // reference CSR
+  // Storage is SHARDED: only the slice of nnIndx / B / F that belongs to [loc_begin, loc_end) is allocated and
+  // uploaded (n = 10^7, m = 32 is 1.28 + 2 x 2.56 GB when replicated).  The kernels keep indexing with the
+  // reference's global CSR offsets (src/util.cpp:55-70) through VIRTUAL base pointers = allocation - first index of
+  // the shard, valid for [csr_begin, csr_end) resp. [loc_begin, loc_end) only.
+  long long csr_begin = 0, csr_end = 0;
+  int *d_nnIndx_store = nullptr;
+  double *d_B_store[2] = {nullptr, nullptr};
+  double *d_F_store[2] = {nullptr, nullptr};
+  int *d_nnIndx = nullptr;      // reference CSR (virtual base)
   double *d_X = nullptr;        // n x p column-major
   double *d_y = nullptr;
   double *d_Xy = nullptr;       // [X y] as rows, n x roundup4(p+1) row-major, zero padded (q_forms gathers)
-  double *d_B[2] = {nullptr, nullptr};  // two slots: current / candidate
+  double *d_B[2] = {nullptr, nullptr};  // two slots: current / candidate (virtual bases; complete rows of a 32-location
+                                        // tile start 16-byte aligned, so bulk copies can move them)
   double *d_F[2] = {nullptr, nullptr};
+  // resident distance triangle of the shard (tri_cache.cu), NULL when disabled / m not served / out of memory
+  double *d_tri = nullptr;
+  size_t tri_cap = 0;
+  int opt_tri = 1;  // nngp_set_option("tri_cache", 0/1)
+  bool tri_on = false;  // d_tri describes the current data set
   double *d_resid[NNGP_MAX_BATCH] = {};
   double *d_beta = nullptr;             // NNGP_MAX_BATCH x p
   nngp::MaternConsts *d_mat = nullptr;  // NNGP_MAX_BATCH
@@ -72,6 +86,7 @@ struct nngp_ctx {
   double pair_d2_q99 = 1e300;    // 99 % quantile over this shard's locations of the largest squared pair distance
   unsigned int *d_hist = nullptr;
   unsigned char bf_short[NNGP_MAX_BATCH] = {};  // decision of the last prepare_bf, per parameter set
+  double last_qcur[NNGP_MAX_BATCH] = {};  // Q of the resident factors returned by the last launch (BfTheta::Bcur)
 
   // multi-GPU: NCCL communicator over the ranks of a sharded fit (nngp_comm_init); when set, the
   // results of nngp_bf_loglik / nngp_q_resid / nngp_q_forms are summed over the ranks on the device
@@ -159,6 +174,15 @@ int bf_grid_for(int m, long long nloc, int sms);
 int bf_grid_any(int m, int cov, long long nloc, int sms);
 int bf_grid_max(int m, long long nloc, int sms);
 cudaError_t bf_launch(const BfLaunch &P, int cov, int grid_x, cudaStream_t stream);
+
+// bf_tri_kernel.cu / tri_cache.cu
+int tri_capacity_for_m(int m);
+int tri_grid_for(long long nloc, int sms);
+cudaError_t tri_launch(const BfLaunch &P, int cov, int grid_x, cudaStream_t stream);
+size_t tri_cache_doubles(int m, long long nloc);
+size_t tri_ids_offset(int m, long long nloc);
+cudaError_t tri_build_launch(const double2 *coords, const int *nnIndx, int m, int loc_begin, int loc_end, double *tri,
+                             cudaStream_t stream);
 
 // q_kernels.cu
 cudaError_t resid_launch(const double *X, const double *y, const double *beta, int n, int p, double *r, int sms,

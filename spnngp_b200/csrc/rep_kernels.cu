@@ -110,6 +110,8 @@ __global__ void __launch_bounds__(256) rep_add_mean_kernel(const double *__restr
 // Level structure of the neighbour graph (host pass over the ids taken back from the device).
 int rep_prepare(nngp_ctx *c) {
   if (c->rep_ready) return NNGP_OK;
+  if (c->loc_begin != 0 || c->loc_end != c->n)
+    return ctx_fail(c, NNGP_ESTATE, "replicates need the whole location range on one GPU (the recurrence is serial in the ordering)");
   const int n = c->n, m = c->m;
   std::vector<int> idx((size_t)(c->nIndx > 0 ? c->nIndx : 1)), lev((size_t)n), perm((size_t)n);
   if (c->nIndx > 0)

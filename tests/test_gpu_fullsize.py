@@ -62,6 +62,33 @@ def test_bf_loglik_full_size_against_oracle(engine, port, full):
     assert abs(engine.q_resid(0, full["beta"]) - Qo) <= TOL * abs(Qo)
 
 
+@pytest.mark.parametrize("short", [1, 0])
+def test_matern_headline_config_against_oracle(engine, port, full, short):
+    """BASELINE configs[2] verbatim -- Matern, theta = (5, 1, 6, 0.75), n = 10^6, m = 15: the kernel variant the bench
+    times (launch-level short series, `matern_short_used == 1`) and the full series, every B, F, logDet and Q against
+    the oracle (updateBF src/rNNGP.cpp:46-101 with spCor's Matern branch src/util.cpp:233-237), <= 1e-10."""
+    theta = [5.0, 1.0, 6.0, 0.75]
+    engine.set_data(full["coords"], full["idx"], full["lu"], full["X"], full["y"], M)
+    engine.set_option("matern_short", short)
+    try:
+        out = engine.bf_loglik(2, [theta], [full["beta"]], slots=[0])
+        assert engine.get_option("matern_short_used") == short
+        B, F = engine.get_bf(0)
+    finally:
+        engine.set_option("matern_short", 1)
+    Bo, Fo, ld, info = port.update_bf(full["coords"], full["idx"], full["lu"], N, M, theta, 2)
+    assert info == 0
+    r = full["X"] @ full["beta"] - full["y"]
+    Qo = port.q(Bo, Fo, r, r, N, full["idx"], full["lu"])
+    nI = len(full["idx"])
+    assert relerr(F, Fo) < TOL, relerr(F, Fo)
+    assert relerr_norm(B[:nI], Bo[:nI]) < TOL, relerr_norm(B[:nI], Bo[:nI])
+    rows = B[full["lu"][M]:nI].reshape(-1, M); rows_o = Bo[full["lu"][M]:nI].reshape(-1, M)
+    scale = np.abs(rows_o).max(axis=1, keepdims=True)                      # per-location scale of the weight vector
+    assert np.max(np.abs(rows - rows_o) / scale) < TOL
+    assert abs(out[0, 0] - ld) <= TOL * abs(ld) and abs(out[0, 1] - Qo) <= TOL * abs(Qo)
+
+
 @pytest.mark.parametrize("cov,theta", [(0, [5.0, 1.0, 6.0]), (2, [5.0, 1.0, 6.0, 0.75]), (3, [5.0, 1.0, 6.0]), (1, [5.0, 1.0, 6.0])])
 def test_bf_properties_full_size(engine, full, cov, theta):
     """(sigma.sq, tau.sq) -> c (sigma.sq, tau.sq) leaves B unchanged, scales F by c, shifts logDet by n log c and

@@ -135,3 +135,46 @@ def test_glue_kfold_symbol_against_golden(glue):
     got = np.ctypeslib.as_array(glue.lib.REAL(out), shape=(2 * g,)).copy().reshape(2, g).T
     glue.reset()
     assert np.max(np.abs(got - d["exp_scores"]) / np.abs(d["exp_scores"])) < 1e-10
+
+
+def _config0_problem(port):
+    """BASELINE configs[0] / SURVEY 8(d) C1: n = 5,000 sites ~ U(0,1)^2, x = [1, N(0,1)], beta = (1, 5), sigma.sq = 5,
+    tau.sq = 1, phi = 6 (man/spNNGP.Rd:231-246), y = X beta + w + eps with w a dense exponential-GP draw; m = 15,
+    neighbours by the code-book search."""
+    n, m = 5000, 15
+    rng = np.random.default_rng(1)
+    coords = rng.random((n, 2))
+    coords = coords[np.argsort(coords[:, 0], kind="stable")]
+    X = np.column_stack([np.ones(n), rng.standard_normal(n)])
+    d = np.sqrt(((coords[:, None, :] - coords[None, :, :]) ** 2).sum(axis=2))
+    L = np.linalg.cholesky(5.0 * np.exp(-6.0 * d) + 1e-10 * np.eye(n))
+    y = X @ np.array([1.0, 5.0]) + L @ rng.standard_normal(n) + rng.standard_normal(n)
+    idx, dist, lu = port.mk_nn_indx_cb(coords, m)
+    return dict(n=n, m=m, coords=coords, X=X, y=y, nnIndx=idx, nnIndxLU=lu)
+
+
+@pytest.mark.parametrize("tune", [0.5, 0.05])
+def test_config0_chain_1000_iterations_against_reference(glue, ref, port, tune):
+    """BASELINE configs[0] verbatim: spNNGP method = 'response', n = 5,000, exponential, n.neighbors = 15, 1,000 MCMC
+    samples, search.type = 'cb', set.seed(1).  The whole theta / beta chain of the `.Call` layer over the CUDA engine,
+    in both sampler modes, against the reference's own `rNNGP` (src/rNNGP.cpp:272-378) run on the same inputs
+    with the same RNG stream: identical accept decisions, theta to 1e-9, beta to 1e-7."""
+    prob = _config0_problem(port)
+    starting = {"beta": [0.0, 0.0], "sigma.sq": 5.0, "tau.sq": 1.0, "phi": 6.0}
+    tuning = {"sigma.sq": tune, "tau.sq": tune, "phi": tune}
+    args = (prob["y"], prob["X"], prob["coords"], 0, prob["nnIndx"], prob["nnIndxLU"], prob["m"], [2.0, 5.0], [2.0, 1.0],
+            [3.0, 300.0], None, starting, tuning, 1000)
+    ref.set_seed(1)
+    want = ref.rnngp(*args, nThreads=os.cpu_count())
+    moves = int((np.diff(want["p_theta_samples"][0]) != 0).sum())
+    assert moves > (100 if tune < 0.1 else 3)  # the chain does move: accept decisions are being compared
+    for mode in ("0", "1"):
+        os.environ["NNGP_SAMPLER_MODE"] = mode
+        try:
+            glue.lib.rshim_set_seed(1)
+            got = po.call_rnngp(glue, *args)
+        finally:
+            os.environ.pop("NNGP_SAMPLER_MODE", None)
+        assert int((np.diff(got["p_theta_samples"][0]) != 0).sum()) == moves
+        assert np.allclose(got["p_theta_samples"], want["p_theta_samples"], rtol=1e-9, atol=0)
+        assert np.allclose(got["p_beta_samples"], want["p_beta_samples"], rtol=1e-7, atol=1e-9)
