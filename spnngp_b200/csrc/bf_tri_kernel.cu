@@ -130,25 +130,25 @@ struct FromDist<NNGP_COV_SPHERICAL> {
   }
 };
 
-// One batch of NU rows of 32 doubles at `p + u * stride_bytes`: all loads, NU independent chains, all stores.
+// One batch of NU rows of 32 doubles (this lane's element of each): all loads, NU independent chains, all stores.
 template <int COV, int NU>
-__device__ __forceinline__ void tri_rows(unsigned char *p, int stride_bytes, const FromDist<COV> &f) {
+__device__ __forceinline__ void tri_rows(unsigned char *const (&p)[NU], const FromDist<COV> &f) {
   double v[NU];
 #pragma unroll
-  for (int u = 0; u < NU; ++u) v[u] = *reinterpret_cast<const double *>(p + u * stride_bytes);
+  for (int u = 0; u < NU; ++u) v[u] = *reinterpret_cast<const double *>(p[u]);
 #pragma unroll
   for (int u = 0; u < NU; ++u) v[u] = f(v[u]);
 #pragma unroll
-  for (int u = 0; u < NU; ++u) *reinterpret_cast<double *>(p + u * stride_bytes) = v[u];
+  for (int u = 0; u < NU; ++u) *reinterpret_cast<double *>(p[u]) = v[u];
 }
 // Matern: the series in t = (phi D / 2)^2 (matern_series.cuh) with the table-driven log / exp; the rare arguments
 // outside the straight-line path are re-evaluated afterwards, like the gather kernels do (tpl_device.cuh)
 template <int COV, int NU>
-__device__ __forceinline__ void tri_rows_matern(unsigned char *p, int stride_bytes, const Cor<COV> &cor, double sig) {
+__device__ __forceinline__ void tri_rows_matern(unsigned char *const (&p)[NU], const Cor<COV> &cor, double sig) {
   double d2[NU], v[NU];
 #pragma unroll
   for (int u = 0; u < NU; ++u) {
-    const double D = *reinterpret_cast<const double *>(p + u * stride_bytes);
+    const double D = *reinterpret_cast<const double *>(p[u]);
     d2[u] = D * D;
   }
 #pragma unroll
@@ -162,24 +162,39 @@ __device__ __forceinline__ void tri_rows_matern(unsigned char *p, int stride_byt
       if (cor.needs_slow(d2[u])) v[u] = sig * cor.slow(d2[u]);
   }
 #pragma unroll
-  for (int u = 0; u < NU; ++u) *reinterpret_cast<double *>(p + u * stride_bytes) = v[u];
+  for (int u = 0; u < NU; ++u) *reinterpret_cast<double *>(p[u]) = v[u];
 }
 
-// rows [r0, r1) of the stage's transform region, this warp's lane; rows >= m of the CV block are padding (m < MC)
-template <int MC, int COV, typename Fn>
-__device__ __forceinline__ void tri_transform(unsigned char *stage, int lane, int r0, int r1, int m, const Fn &rows) {
-  // logical row r: r < m -> CV row r; else A row r - m.  Byte offset = r * 256 + (r >= m ? (MC - m) * 256 : 0)
-  constexpr int NU = kIsMatern<COV> ? NNGP_TRI_UNR_MATERN : NNGP_TRI_UNR;
+template <int COV>
+constexpr int kTriUnr = kIsMatern<COV> ? NNGP_TRI_UNR_MATERN : NNGP_TRI_UNR;
+// FP64 instructions per correlation (SASS counts), for the producers' shares
+template <int COV>
+constexpr int kTriRowCost = kIsMatern<COV> ? 55 : (COV == NNGP_COV_SPHERICAL ? 7 : 21);
+
+// Whole batches [b0, b1) of the stage's m(m+1)/2 logical rows (row r < m: c row r, else packed-triangle row r - m, which
+// sits (MC - m) rows further when m < MC); `tail`: this warp also takes the rows left over after the last whole batch.
+template <int MC, int COV, typename Fn1, typename FnN>
+__device__ __forceinline__ void tri_transform(unsigned char *stage, int lane, int b0, int b1, bool tail, int m,
+                                              const Fn1 &one, const FnN &many) {
+  constexpr int NU = kTriUnr<COV>;
   unsigned char *base = stage + lane * 8;
   const int pad = (MC - m) * 256;
-  int r = r0;
-  if (r < m) {  // the (short) part of this warp's range inside the CV block: single rows
-    const int e = r1 < m ? r1 : m;
-    for (; r < e; ++r) rows(base + r * 256, 0, 1);
+  for (int b = b0; b < b1; ++b) {
+    unsigned char *p[NU];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      const int r = b * NU + u;
+      p[u] = base + r * 256 + (r >= m ? pad : 0);
+    }
+    many(p);
   }
-  unsigned char *p = base + r * 256 + pad;
-  for (; r + NU <= r1; r += NU, p += NU * 256) rows(p, 256, NU);
-  for (; r < r1; ++r, p += 256) rows(p, 0, 1);
+  if (tail) {
+    const int nrows = m * (m + 1) / 2;
+    for (int r = (nrows / NU) * NU; r < nrows; ++r) {
+      unsigned char *p[1] = {base + r * 256 + (r >= m ? pad : 0)};
+      one(p);
+    }
+  }
 }
 
 template <int MC, int COV>
@@ -204,6 +219,7 @@ __global__ void __launch_bounds__(384, 1) bf_tri_kernel(const __grid_constant__ 
   double *s_tab = reinterpret_cast<double *>(smem + G::OFF_TAB);
   __shared__ double red[3][12];
   __shared__ int last_flag;
+  __shared__ int bbeg[G::kProducers + 1];  // batches of producer warp pw: [bbeg[pw], bbeg[pw + 1])
 
   // ---- one-time setup ---------------------------------------------------------------------------------
   if (tid == 0) {
@@ -213,6 +229,29 @@ __global__ void __launch_bounds__(384, 1) bf_tri_kernel(const __grid_constant__ 
       mbar_init(bar_empty(s), 1);              // the consumer
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid == 0) {
+    // Shares of the producer warps, so that the four schedulers carry equal FP64 work: warp w issues on scheduler
+    // w & 3, schedulers 0..NC-1 also run a consumer (C instructions per tile, one tile in NC), scheduler 3 the loader.
+    const int nrows = m * (m + 1) / 2, nb = nrows / kTriUnr<COV>;
+    const float C = (float)(m * m * m) / 6.f + 2.f * m * m + 25.f * m, Tp = (float)nrows * kTriRowCost<COV>;
+    float f[4], fs = 0.f;
+    for (int q = 0; q < 4; ++q) {
+      f[q] = fmaxf(0.25f * NC * (C + Tp) - (q < NC ? C : 0.f), 0.f);
+      fs += f[q];
+    }
+    float acc = 0.f;
+    int prev = 0, cnt[G::kProducers];
+    for (int q = 0; q < 4; ++q) {
+      acc += f[q] / fs;
+      const int upto = (q == 3) ? nb : min(nb, (int)(acc * nb + 0.5f));
+      const int nq = upto - prev;
+      prev = upto;
+      cnt[q] = nq / 2;
+      cnt[q + 4] = nq - nq / 2;
+    }
+    bbeg[0] = 0;
+    for (int w = 0; w < G::kProducers; ++w) bbeg[w + 1] = bbeg[w] + cnt[w];
   }
   if (kMat) {
     for (int x = tid; x < 32; x += G::kThreads) s_tab[x] = kExpTab32[x];
@@ -408,8 +447,8 @@ __global__ void __launch_bounds__(384, 1) bf_tri_kernel(const __grid_constant__ 
     // ================================ producers ========================================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 136;");
     const int pw = warp - 4;
-    const int nrows = ne + m;
-    const int r0 = (nrows * pw) / G::kProducers, r1 = (nrows * (pw + 1)) / G::kProducers;
+    const int b0 = bbeg[pw], b1 = bbeg[pw + 1];
+    const bool tail = (pw == 0);
     int markers = 0;
     for (int j = 0;; ++j) {
       const int s = j % S;
@@ -422,10 +461,9 @@ __global__ void __launch_bounds__(384, 1) bf_tri_kernel(const __grid_constant__ 
             constexpr int B = decltype(idx)::value;
             const Cor<COV> cor(P.th[B], s_tab);
             const double sig = P.th[B].sigmaSq;
-            tri_transform<MC, COV>(st, lane, r0, r1, m, [&](unsigned char *p, int stride, int nu) {
-              if (nu == 1) tri_rows_matern<COV, 1>(p, stride, cor, sig);
-              else tri_rows_matern<COV, NNGP_TRI_UNR_MATERN>(p, stride, cor, sig);
-            });
+            tri_transform<MC, COV>(
+                st, lane, b0, b1, tail, m, [&](unsigned char *const(&p)[1]) { tri_rows_matern<COV, 1>(p, cor, sig); },
+                [&](unsigned char *const(&p)[kTriUnr<COV>]) { tri_rows_matern<COV, kTriUnr<COV>>(p, cor, sig); });
           };
           switch (blockIdx.y) {  // compile-time set index: the series coefficients stay constant-bank operands
             case 0: body(std::integral_constant<int, 0>()); break;
@@ -435,10 +473,9 @@ __global__ void __launch_bounds__(384, 1) bf_tri_kernel(const __grid_constant__ 
           }
         } else {
           const FromDist<COV> f(th, nullptr);
-          tri_transform<MC, COV>(st, lane, r0, r1, m, [&](unsigned char *p, int stride, int nu) {
-            if (nu == 1) tri_rows<COV, 1>(p, stride, f);
-            else tri_rows<COV, NNGP_TRI_UNR>(p, stride, f);
-          });
+          tri_transform<MC, COV>(
+              st, lane, b0, b1, tail, m, [&](unsigned char *const(&p)[1]) { tri_rows<COV, 1>(p, f); },
+              [&](unsigned char *const(&p)[kTriUnr<COV>]) { tri_rows<COV, kTriUnr<COV>>(p, f); });
         }
       }
       __syncwarp();

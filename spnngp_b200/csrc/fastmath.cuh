@@ -194,17 +194,31 @@ NNGP_FM double nngp_log_pos(double x) {
 //        log x = k ln2 + (-log rc_i) + log1p(r), log1p by its degree-8 Taylor polynomial        (truncation 2e-18)
 // Absolute error ~1e-16 (max of the result's ulp and 1e-16); the log is NOT relatively accurate next to x = 1,
 // which the callers (t^nu = exp(nu log t), log F summed over locations) do not need.
+// Constants of the two table-driven kernels whose low 32 bits are not zero: as literals each costs two UMOV / IMAD.MOV
+// per use (seen in SASS: 42 UMOV per batch of four Matern correlations); from the constant bank they are plain
+// operands of the DFMA.
+#if defined(__CUDACC__)
+static __constant__ double kTabC[14] = {
+#else
+static const double kTabC[14] = {
+#endif
+    46.166241308446828384,                  // 0: 32 / ln 2
+    -6.93147180369123816490e-01 / 32.0,     // 1: -ln2_hi / 32
+    -1.90821492927058770002e-10 / 32.0,     // 2: -ln2_lo / 32
+    1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0,  // 3..6: exp polynomial
+    1.0 / 7.0, -1.0 / 6.0, 1.0 / 5.0, 1.0 / 3.0,      // 7..10: log1p polynomial (-1/8, -1/4, -1/2 are exact immediates)
+    6.93147180369123816490e-01, 1.90821492927058770002e-10,  // 11, 12: ln2_hi, ln2_lo
+    0.0};
+
 NNGP_FM double nngp_exp_tab(double x, const double *etab) {
-  const double L2E32 = 46.166241308446828384;  // 32 / ln 2
-  const double LN2_32_HI = 6.93147180369123816490e-01 / 32.0, LN2_32_LO = 1.90821492927058770002e-10 / 32.0;
   const double SHIFTER = 6755399441055744.0;
-  const double t = fma(x, L2E32, SHIFTER);
+  const double t = fma(x, kTabC[0], SHIFTER);
   const double n = t - SHIFTER;
-  double r = fma(n, -LN2_32_HI, x);
-  r = fma(n, -LN2_32_LO, r);
-  double q = fma(r, 1.0 / 720.0, 1.0 / 120.0);
-  q = fma(q, r, 1.0 / 24.0);
-  q = fma(q, r, 1.0 / 6.0);
+  double r = fma(n, kTabC[1], x);
+  r = fma(n, kTabC[2], r);
+  double q = fma(r, kTabC[3], kTabC[4]);
+  q = fma(q, r, kTabC[5]);
+  q = fma(q, r, kTabC[6]);
   q = fma(q, r, 0.5);
   q = fma(q * r, r, r);  // r + r^2 (1/2 + ...)
 #if defined(__CUDA_ARCH__)
@@ -234,7 +248,7 @@ NNGP_FM double nngp_exp_tab(double x, const double *etab) {
 // so that the 8 lanes of one 128-bit shared-memory wavefront never share a bank group; ltab then points at the lane's copy)
 template <int LSTRIDE = 1>
 NNGP_FM double nngp_log_tab(double x, const double *ltab /* 64 pairs {rc, -log rc} */) {
-  const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
+  const double ln2_hi = kTabC[11], ln2_lo = kTabC[12];
 #if defined(__CUDA_ARCH__)
   const int hx = __double2hiint(x);
   const int lx = __double2loint(x);
@@ -258,11 +272,11 @@ NNGP_FM double nngp_log_tab(double x, const double *ltab /* 64 pairs {rc, -log r
   const double rc = ltab[2 * idx * LSTRIDE], lc = ltab[2 * idx * LSTRIDE + 1];
 #endif
   const double r = fma(m, rc, -1.0);
-  double p = fma(r, -1.0 / 8.0, 1.0 / 7.0);
-  p = fma(p, r, -1.0 / 6.0);
-  p = fma(p, r, 1.0 / 5.0);
+  double p = fma(r, -1.0 / 8.0, kTabC[7]);
+  p = fma(p, r, kTabC[8]);
+  p = fma(p, r, kTabC[9]);
   p = fma(p, r, -1.0 / 4.0);
-  p = fma(p, r, 1.0 / 3.0);
+  p = fma(p, r, kTabC[10]);
   p = fma(p, r, -0.5);
   const double dk = (double)k;
   p = fma(p * r, r, r);  // log1p(r)
