@@ -1,4 +1,4 @@
-// bf_tri_kernel.cu -- B/F + log-likelihood kernel over the resident DISTANCE TRIANGLE (6 <= m <= 24).
+// bf_tri_kernel.cu -- B/F + log-likelihood kernel over the resident DISTANCE TRIANGLE (2 <= m <= 26).
 //
 // Same mathematics as the other B/F kernels (reference: updateBF src/rNNGP.cpp:46-101, updateConjBF
 // src/cNNGP.cpp:24-69, Q src/util.cpp:261-280), different data path.  The distances between a location's
@@ -8,20 +8,30 @@
 // kernel STREAMS them: on B200 the FP64 pipe (34 TFLOP/s) is the scarce resource and HBM (6.5 TB/s) is not --
 // recomputing a distance costs 15 FP64 instructions (gather, d^2, sqrt), reading it costs 8 bytes.
 //
-//   n = 10^6, m = 15:  0.96 GB of distances + 0.21 GB of ids / weights / variances per launch (HBM floor 0.18 ms),
-//                      ~3,500 FP64 warp instructions per 32-location tile (FP64 floor 0.19 ms).
+//   n = 10^6, m = 15:  0.96 GB of distances + 0.27 GB of ids / weights / variances per launch (HBM floor 0.19 ms),
+//                      ~3,700 (exponential) / ~7,700 (Matern) FP64 warp instructions per 32-location tile
+//                      (FP64 floor 0.20 / 0.42 ms).
 //
 // One persistent CTA per SM, 12 warps in three warpgroups with `setmaxnreg`:
-//   warpgroup 0 (232 registers): warps 0..NC-1 CONSUMERS -- one tile each: ragged-row fix-up, Cholesky + solves
-//                                (tpl_solve), log F, the quadratic-form terms, weights out through a bulk store;
+//   warpgroup 0 (232 registers): warps 0..NC-1 CONSUMERS -- one tile each: ragged-row fix-up, blocked Cholesky +
+//                                solves (tri_solve below), log F, the quadratic-form terms, weights out through a
+//                                bulk store;
 //                                warp 3 LOADER -- claims tiles (one atomic per tile), issues the 1-D bulk copies
 //                                (TMA) of the tile's distances [and of the resident weights of the current theta]
 //                                and the cp.async gathers of the neighbours' residuals
-//   warpgroups 1, 2 (136 registers; 128 x 232 + 256 x 136 = the 384 x 168 the CTA was launched with): 8 PRODUCER warps -- turn the stage's distances into covariances in place,
-//                                sigma^2 rho(D): rows of 32 doubles at immediate offsets, NU independent chains
+//   warpgroups 1, 2 (136 registers; 128 x 232 + 256 x 136 = the 384 x 168 the CTA was launched with):
+//                                8 PRODUCER warps -- turn the stage's distances into covariances in place,
+//                                sigma^2 rho(D): rows of 32 doubles, NU independent chains per batch
 // Stages of one tile each travel  loader -> producers -> consumer -> loader  on mbarriers (full / built / empty).
+// The geometry (rows per stage, number of stages S, consumers NC) is a run-time function of m (tri_geometry): one
+// instantiation per correlation model serves every m; nothing is padded.
 // Per-tile partial sums are written to a tile-indexed array and added in tile order by the last CTA, so the result
 // does not depend on which CTA drew which tile.
+//
+// The solve is a BLOCKED Cholesky with rolled loops (4 x 4 register tiles over the per-lane matrix in shared memory),
+// not the fully unrolled column sweep of tpl_device.cuh: ncu showed the unrolled solve (36 KB of straight-line code
+// per consumer, executed once per tile) stalled on instruction fetch for 55 % of its samples; the rolled form is
+// ~700 instructions.
 #include <stdlib.h>
 
 #include "tpl_device.cuh"
@@ -35,29 +45,48 @@ namespace nngp {
 #define NNGP_TRI_UNR_MATERN 4
 #endif
 
-template <int MC>
-struct TriGeo {
-  static constexpr int NE = MC * (MC - 1) / 2;
-  static constexpr int OFF_CV = 0;                          // MC rows: c -> y -> weights, [k][lane]
-  static constexpr int OFF_A = OFF_CV + MC * 256;           // NE rows: strict lower triangle, packed, [entry][lane]
-  static constexpr int OFF_RR = OFF_A + NE * 256;           // MC + 1 rows: residuals of the neighbours, own in row MC
-  static constexpr int OFF_BC = OFF_RR + (MC + 1) * 256;    // 32 x m weights of the current theta, [lane][k]
-  static constexpr int kStageBytes = OFF_BC + MC * 256;
-  static constexpr int kConsBytes = 2 * MC * 256;           // per consumer: 1/diag rows, weight staging [lane][k]
-  static constexpr int kTabBytes = (32 + 128) * 8;
-  static constexpr int kMiscBytes = kTabBytes + 512;        // + mbarriers, tile ring
-  static constexpr int kAvail = 227 * 1024 - kMiscBytes;
-  static constexpr int stages_for(int nc) { return (kAvail - nc * kConsBytes) / kStageBytes; }
-  static constexpr int NC = stages_for(3) >= 5 ? 3 : (stages_for(2) >= 4 ? 2 : 1);
-  static constexpr int S = stages_for(NC) > 6 ? 6 : stages_for(NC);
-  static_assert(S >= 2, "tile does not fit shared memory twice");
-  static constexpr int OFF_CONS = S * kStageBytes;
-  static constexpr int OFF_TAB = OFF_CONS + NC * kConsBytes;
-  static constexpr int OFF_BAR = OFF_TAB + kTabBytes;       // 3 S mbarriers, then the tile ring (S long long)
-  static constexpr int kSmemBytes = OFF_BAR + 512;
-  static constexpr int kThreads = 384;
-  static constexpr int kProducers = 8;
+constexpr int kTriMaxM = 26;       // two stages still fit shared memory
+constexpr int kTriMaxStages = 6;
+constexpr int kTriThreads = 384;
+constexpr int kTriProducers = 8;
+constexpr int kTriTabBytes = (32 + 128) * 8;
+constexpr int kTriBarBytes = 512;  // 3 x 6 mbarriers, then the tile ring (6 long long)
+
+// Shared-memory geometry of the kernel for a given m (bytes; every region is a whole number of 256-byte rows).
+struct TriGeom {
+  int off_cv, off_a, off_rr, off_bc, stage_bytes;  // within a stage: c -> y -> weights | packed strict lower triangle |
+                                                   // residuals of the neighbours, own in row m | weights of the current theta
+  int cons_bytes;                                  // per consumer: 1/diag rows, weight staging [lane][k]
+  int S, NC;
+  int off_cons, off_tab, off_bar, smem_bytes;
 };
+__host__ __device__ inline TriGeom tri_geometry(int m) {
+  TriGeom g;
+  const int ne = m * (m - 1) / 2;
+  g.off_cv = 0;
+  g.off_a = m * 256;
+  g.off_rr = g.off_a + ne * 256;
+  g.off_bc = g.off_rr + (m + 1) * 256;
+  g.stage_bytes = g.off_bc + m * 256;
+  g.cons_bytes = 2 * m * 256;
+  const int avail = 227 * 1024 - kTriTabBytes - kTriBarBytes - 1024;  // 1 KB: the kernel's static shared memory
+  g.NC = 3;
+  g.S = (avail - 3 * g.cons_bytes) / g.stage_bytes;
+  if (g.S < 5) {
+    g.NC = 2;
+    g.S = (avail - 2 * g.cons_bytes) / g.stage_bytes;
+    if (g.S < 4) {
+      g.NC = 1;
+      g.S = (avail - g.cons_bytes) / g.stage_bytes;
+    }
+  }
+  if (g.S > kTriMaxStages) g.S = kTriMaxStages;
+  g.off_cons = g.S * g.stage_bytes;
+  g.off_tab = g.off_cons + g.NC * g.cons_bytes;
+  g.off_bar = g.off_tab + kTriTabBytes;
+  g.smem_bytes = g.off_bar + kTriBarBytes;
+  return g;
+}
 
 // ---- mbarrier / bulk-copy primitives (PTX) ---------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -171,66 +200,226 @@ constexpr int kTriUnr = kIsMatern<COV> ? NNGP_TRI_UNR_MATERN : NNGP_TRI_UNR;
 template <int COV>
 constexpr int kTriRowCost = kIsMatern<COV> ? 55 : (COV == NNGP_COV_SPHERICAL ? 7 : 21);
 
-// Whole batches [b0, b1) of the stage's m(m+1)/2 logical rows (row r < m: c row r, else packed-triangle row r - m, which
-// sits (MC - m) rows further when m < MC); `tail`: this warp also takes the rows left over after the last whole batch.
-template <int MC, int COV, typename Fn1, typename FnN>
+// Whole batches [b0, b1) of the stage's m(m+1)/2 rows (c rows, then the packed triangle: contiguous);
+// `tail`: this warp also takes the rows left over after the last whole batch.
+template <int COV, typename Fn1, typename FnN>
 __device__ __forceinline__ void tri_transform(unsigned char *stage, int lane, int b0, int b1, bool tail, int m,
                                               const Fn1 &one, const FnN &many) {
   constexpr int NU = kTriUnr<COV>;
   unsigned char *base = stage + lane * 8;
-  const int pad = (MC - m) * 256;
   for (int b = b0; b < b1; ++b) {
     unsigned char *p[NU];
 #pragma unroll
-    for (int u = 0; u < NU; ++u) {
-      const int r = b * NU + u;
-      p[u] = base + r * 256 + (r >= m ? pad : 0);
-    }
+    for (int u = 0; u < NU; ++u) p[u] = base + (b * NU + u) * 256;
     many(p);
   }
   if (tail) {
     const int nrows = m * (m + 1) / 2;
     for (int r = (nrows / NU) * NU; r < nrows; ++r) {
-      unsigned char *p[1] = {base + r * 256 + (r >= m ? pad : 0)};
+      unsigned char *p[1] = {base + r * 256};
       one(p);
     }
   }
 }
 
-template <int MC, int COV>
-__global__ void __launch_bounds__(384, 1) bf_tri_kernel(const __grid_constant__ BfLaunch P) {
-  using G = TriGeo<MC>;
-  constexpr int S = G::S, NC = G::NC;
+// ---- the consumer's solve ----------------------------------------------------------------------------
+// Per lane: the (m+1) x (m+1) matrix  M = [C c; c' diag]  with C = sigma^2 rho(neighbours) + tau^2 I (strict lower
+// triangle packed in A, row i at A + i(i-1)/2 rows; unit rows for i >= mi), c in cv.  Left-looking Cholesky in 4 x 4
+// register tiles, block column by block column; the right-hand side rides along as row m, so row m ends up as
+// y = V^-1 c and its pivot as F = diag - |y|^2.  1 / V(j,j) goes to dv.  Rows past m in the last block are register-only
+// dummies (clamped loads, no stores).  Then V' B = y by blocks from the bottom; B overwrites cv.
+// Returns false if a pivot of C is not positive.
+__device__ __forceinline__ bool tri_solve(double *__restrict__ A, double *__restrict__ cv, double *__restrict__ dv,
+                                          int m, int mi, double diag, double *F_out) {
+  bool ok = true;
+  double F = diag;
+  auto rowp = [&](int i) -> double * { return (i < m) ? A + (i * (i - 1) / 2) * 32 : cv; };  // row m (and dummies): cv
+  const int nrb = (m + 4) >> 2;  // row blocks over rows 0..m
+#pragma unroll 1
+  for (int jb = 0; jb < nrb; ++jb) {
+    const int j0 = 4 * jb;
+    double *pj[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) pj[r] = rowp(min(j0 + r, m));
+    // ---- diagonal block ----
+    double d[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+      for (int c = 0; c < r; ++c) d[r][c] = pj[r][(j0 + c) * 32];
+      d[r][r] = (j0 + r < mi || j0 + r == m) ? diag : 1.0;
+    }
+#pragma unroll 1
+    for (int k = 0; k < j0; k += 4) {
+      double a[4][4];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) a[kk][r] = pj[r][(k + kk) * 32];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c <= r; ++c) d[r][c] = fma(-a[kk][r], a[kk][c], d[r][c]);
+    }
+    double ri[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const double piv = d[c][c];
+      if (j0 + c < mi && !(piv > 0.0)) ok = false;
+      if (j0 + c == m) F = piv;
+      ri[c] = nngp_rsqrt_pos(piv);
+#pragma unroll
+      for (int r = c + 1; r < 4; ++r) d[r][c] *= ri[c];
+#pragma unroll
+      for (int c2 = c + 1; c2 < 4; ++c2)
+#pragma unroll
+        for (int r = c2; r < 4; ++r) d[r][c2] = fma(-d[r][c], d[c2][c], d[r][c2]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (j0 + r < m) dv[(j0 + r) * 32] = ri[r];
+      if (j0 + r <= m) {
+#pragma unroll
+        for (int c = 0; c < r; ++c) pj[r][(j0 + c) * 32] = d[r][c];
+      }
+    }
+    // ---- blocks below ----
+#pragma unroll 1
+    for (int ib = jb + 1; ib < nrb; ++ib) {
+      const int i0 = 4 * ib;
+      double *pi[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) pi[r] = rowp(min(i0 + r, m));
+      double e[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) e[r][c] = pi[r][(j0 + c) * 32];
+#pragma unroll 1
+      for (int k = 0; k < j0; k += 4) {
+        double ai[4][4], aj[4][4];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            ai[kk][r] = pi[r][(k + kk) * 32];
+            aj[kk][r] = pj[r][(k + kk) * 32];
+          }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) e[r][c] = fma(-ai[kk][r], aj[kk][c], e[r][c]);
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {  // e <- e L^-T with the diagonal block still in registers
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+          for (int c2 = 0; c2 < c; ++c2) e[r][c] = fma(-e[r][c2], d[c][c2], e[r][c]);
+          e[r][c] *= ri[c];
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (i0 + r <= m) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) pi[r][(j0 + c) * 32] = e[r][c];
+        }
+    }
+  }
+  // ---- V' B = y, blocks of four unknowns from the bottom; B_i = 0 stands in for the dummies i >= m ----
+  const int nb = (m + 3) >> 2;
+#pragma unroll 1
+  for (int ib = nb - 1; ib >= 0; --ib) {
+    const int i0 = 4 * ib;
+    double w[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) w[c] = (i0 + c < m) ? cv[(i0 + c) * 32] : 0.0;
+#pragma unroll 1
+    for (int lb = nb - 1; lb > ib; --lb) {
+      const int l0 = 4 * lb;
+      double wl[4], v[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int i = min(l0 + r, m - 1);
+        wl[r] = (l0 + r < m) ? cv[i * 32] : 0.0;
+        const double *pr = A + (i * (i - 1) / 2 + i0) * 32;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[r][c] = pr[c * 32];
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) w[c] = fma(-v[r][c], wl[r], w[c]);
+    }
+    double t[4][4], rv[4];  // the diagonal block: t[r][c] = V(i0 + r, i0 + c), c < r
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = min(i0 + r, m - 1);
+      rv[r] = dv[i * 32];
+      const double *pr = A + (i * (i - 1) / 2 + i0) * 32;
+#pragma unroll
+      for (int c = 0; c < r; ++c) t[r][c] = (i0 + r < m) ? pr[c * 32] : 0.0;
+    }
+#pragma unroll
+    for (int c = 3; c >= 0; --c) {
+#pragma unroll
+      for (int r = c + 1; r < 4; ++r) w[c] = fma(-t[r][c], w[r], w[c]);
+      w[c] = (i0 + c < m) ? w[c] * rv[c] : 0.0;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (i0 + c < m) cv[(i0 + c) * 32] = w[c];
+  }
+  *F_out = F;
+  return ok;
+}
+
+template <int MC>
+__device__ __forceinline__ bool tri_solve_unrolled(double *A, double *cv, double *dv, int mi, double diag, double *F_out) {
+  double Fsum;
+  constexpr int kCholW = (MC >= 12 && MC <= 16) ? 4 : 2;
+  const bool ok = tpl_solve<MC, kCholW>(A, cv, dv, mi, diag, &Fsum);
+  *F_out = diag - Fsum;
+  return ok;
+}
+
+template <int COV>
+__global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_constant__ BfLaunch P) {
   constexpr bool kMat = kIsMatern<COV>;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const BfTheta &th = P.th[blockIdx.y];
   const int m = P.m;
   const int ne = m * (m - 1) / 2;
+  const TriGeom G = tri_geometry(m);
+  const int S = G.S, NC = G.NC;
   const double *__restrict__ resid = th.resid;
   const bool with_cur = th.Bcur != nullptr && resid != nullptr;
   const long long nloc = (long long)P.loc_end - P.loc_begin;
   const long long ntiles = (nloc + 31) / 32;
   unsigned char *smem = tpl_smem;
-  const unsigned bar0 = smem_u32(smem + G::OFF_BAR);
+  const unsigned bar0 = smem_u32(smem + G.off_bar);
   auto bar_full = [&](int s) { return bar0 + 8u * s; };
-  auto bar_built = [&](int s) { return bar0 + 8u * (S + s); };
-  auto bar_empty = [&](int s) { return bar0 + 8u * (2 * S + s); };
-  volatile long long *ring = reinterpret_cast<volatile long long *>(smem + G::OFF_BAR + 8 * 3 * S);
-  double *s_tab = reinterpret_cast<double *>(smem + G::OFF_TAB);
+  auto bar_built = [&](int s) { return bar0 + 8u * (kTriMaxStages + s); };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (2 * kTriMaxStages + s); };
+  volatile long long *ring = reinterpret_cast<volatile long long *>(smem + G.off_bar + 8 * 3 * kTriMaxStages);
+  double *s_tab = reinterpret_cast<double *>(smem + G.off_tab);
   __shared__ double red[3][12];
   __shared__ int last_flag;
-  __shared__ int bbeg[G::kProducers + 1];  // batches of producer warp pw: [bbeg[pw], bbeg[pw + 1])
+  __shared__ int bbeg[kTriProducers + 1];  // batches of producer warp pw: [bbeg[pw], bbeg[pw + 1])
 
   // ---- one-time setup ---------------------------------------------------------------------------------
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(bar_full(s), 1 + 32);          // expect_tx arrival of the loader's lane 0 + 32 cp.async arrivals
-      mbar_init(bar_built(s), G::kProducers);  // one arrival per producer warp
-      mbar_init(bar_empty(s), 1);              // the consumer
+      mbar_init(bar_full(s), 1 + 32);            // expect_tx arrival of the loader's lane 0 + 32 cp.async arrivals
+      mbar_init(bar_built(s), kTriProducers);    // one arrival per producer warp
+      mbar_init(bar_empty(s), 1);                // the consumer
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (tid == 0) {
     // Shares of the producer warps, so that the four schedulers carry equal FP64 work: warp w issues on scheduler
     // w & 3, schedulers 0..NC-1 also run a consumer (C instructions per tile, one tile in NC), scheduler 3 the loader.
     const int nrows = m * (m + 1) / 2, nb = nrows / kTriUnr<COV>;
@@ -241,7 +430,7 @@ __global__ void __launch_bounds__(384, 1) bf_tri_kernel(const __grid_constant__ 
       fs += f[q];
     }
     float acc = 0.f;
-    int prev = 0, cnt[G::kProducers];
+    int prev = 0, cnt[kTriProducers];
     for (int q = 0; q < 4; ++q) {
       acc += f[q] / fs;
       const int upto = (q == 3) ? nb : min(nb, (int)(acc * nb + 0.5f));
@@ -251,17 +440,15 @@ __global__ void __launch_bounds__(384, 1) bf_tri_kernel(const __grid_constant__ 
       cnt[q + 4] = nq - nq / 2;
     }
     bbeg[0] = 0;
-    for (int w = 0; w < G::kProducers; ++w) bbeg[w + 1] = bbeg[w] + cnt[w];
+    for (int w = 0; w < kTriProducers; ++w) bbeg[w + 1] = bbeg[w] + cnt[w];
   }
   if (kMat) {
-    for (int x = tid; x < 32; x += G::kThreads) s_tab[x] = kExpTab32[x];
-    for (int x = tid; x < 128; x += G::kThreads) s_tab[32 + x] = kLogTab64[x];
+    for (int x = tid; x < 32; x += kTriThreads) s_tab[x] = kExpTab32[x];
+    for (int x = tid; x < 128; x += kTriThreads) s_tab[32 + x] = kLogTab64[x];
   }
-  for (int s = 0; s < S; ++s) {  // zero padding (m < MC) and the residual rows; the bulk copies never touch them
-    double *st = reinterpret_cast<double *>(smem + s * G::kStageBytes);
-    for (int x = tid; x < (MC - m) * 32; x += G::kThreads) st[G::OFF_CV / 8 + m * 32 + x] = 0.0;
-    for (int x = tid; x < (G::NE - ne) * 32; x += G::kThreads) st[G::OFF_A / 8 + ne * 32 + x] = 0.0;
-    for (int x = tid; x < (MC + 1) * 32; x += G::kThreads) st[G::OFF_RR / 8 + x] = 0.0;
+  for (int s = 0; s < S; ++s) {  // residual rows: stay zero when the launch has no quadratic form
+    double *rr = reinterpret_cast<double *>(smem + s * G.stage_bytes + G.off_rr);
+    for (int x = tid; x < (m + 1) * 32; x += kTriThreads) rr[x] = 0.0;
   }
   __syncthreads();
 
@@ -273,85 +460,88 @@ __global__ void __launch_bounds__(384, 1) bf_tri_kernel(const __grid_constant__ 
       // ordering over the CTAs), then S gridDim.x + (atomic counter).  Software pipeline so that the warp never waits
       // for global memory: at trip j the copies of T(j) are issued with neighbour ids that were loaded during trip
       // j - 1, the ids of T(j+1) are requested, and the atomic that claims T(j+2) is outstanding in lane 0.
-      const unsigned tri_bytes_a = (unsigned)ne * 256u, tri_bytes_c = (unsigned)m * 256u;
+      const unsigned tri_bytes = (unsigned)(ne + m) * 256u;
       const size_t tile_doubles = (size_t)(ne + m) * 32;
-      int ids_cur[MC], ids_nxt[MC];
-      auto load_ids = [&](long long tile, int(&ids)[MC]) {
+      int ids_cur[kTriMaxM], ids_nxt[kTriMaxM];
+      auto load_ids = [&](long long tile, int(&ids)[kTriMaxM]) {
         const int *src = P.nnT + (size_t)tile * m * 32 + lane;
 #pragma unroll
-        for (int k = 0; k < MC; ++k) ids[k] = (k < m) ? __ldg(src + k * 32) : -1;
+        for (int k = 0; k < kTriMaxM; ++k) ids[k] = (k < m) ? __ldg(src + k * 32) : -1;
       };
       long long t_cur = blockIdx.x, t_nxt = (long long)blockIdx.x + gridDim.x;
       unsigned claim = 0u;
       bool pending = false;
       if (resid != nullptr && t_cur < ntiles) load_ids(t_cur, ids_cur);
-      int done_markers = 0;
+      int done_markers = 0, s = 0, use = 0;  // stage of trip j, and how often it has been used before
       for (int j = 0;; ++j) {
-        const int s = j % S;
         if (j > 0) {  // T(j+1): static, or the claim issued one trip ago
           if (pending) t_nxt = (long long)S * gridDim.x + __shfl_sync(0xffffffffu, claim, 0);
           else t_nxt = (long long)blockIdx.x + (long long)(j + 1) * gridDim.x;
         }
         pending = false;
-        if (j + 2 >= S && t_nxt < ntiles) {  // claim T(j+2)
-          if (lane == 0) claim = atomicAdd(th.tile_counter, 1u);
-          pending = true;
-        } else if (j + 2 >= S) {
-          pending = true;  // past the end: stay there without touching the counter
+        if (j + 2 >= S) {  // claim T(j+2); past the end: stay there without touching the counter
           claim = 0x7fffffffu;
+          if (t_nxt < ntiles && lane == 0) claim = atomicAdd(th.tile_counter, 1u);
+          pending = true;
         }
         if (resid != nullptr && t_nxt < ntiles) load_ids(t_nxt, ids_nxt);
-        if (j >= S) mbar_wait(bar_empty(s), ((j / S) - 1) & 1);
+        if (use > 0) mbar_wait(bar_empty(s), (use - 1) & 1);
         if (t_cur >= ntiles) {  // end of work: NC consecutive markers, one per consumer (they take the stages round-robin)
           if (lane == 0) ring[s] = -1;
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_full(s));
           asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_full(s)) : "memory");  // the 32 "cp.async" slots
           if (++done_markers == NC) break;
-          t_cur = t_nxt;
-          continue;
-        }
-        unsigned char *st = smem + s * G::kStageBytes;
-        const long long base = P.loc_begin + t_cur * 32;
-        if (lane == 0) {
-          ring[s] = t_cur;
-          const unsigned extra = (with_cur && tri_tile_is_full(base, m, P.loc_end)) ? (unsigned)m * 256u : 0u;
-          mbar_expect_tx(bar_full(s), tri_bytes_a + tri_bytes_c + extra);
-          const double *src = P.tri + (size_t)t_cur * tile_doubles;
-          bulk_g2s(smem_u32(st + G::OFF_CV), src, tri_bytes_c, bar_full(s));
-          bulk_g2s(smem_u32(st + G::OFF_A), src + (size_t)m * 32, tri_bytes_a, bar_full(s));
-          if (extra) bulk_g2s(smem_u32(st + G::OFF_BC), th.Bcur + nn_offset(base, m), extra, bar_full(s));
-        }
-        if (resid != nullptr) {
-          double *rr = reinterpret_cast<double *>(st + G::OFF_RR) + lane;
-          long long i = base + lane;
-          if (i >= P.loc_end) i = (long long)P.loc_end - 1;
+        } else {
+          unsigned char *st = smem + s * G.stage_bytes;
+          const long long base = P.loc_begin + t_cur * 32;
+          if (lane == 0) {
+            ring[s] = t_cur;
+            const unsigned extra = (with_cur && tri_tile_is_full(base, m, P.loc_end)) ? (unsigned)m * 256u : 0u;
+            mbar_expect_tx(bar_full(s), tri_bytes + extra);
+            // c rows and the packed triangle are adjacent in the cache and in the stage: one copy
+            bulk_g2s(smem_u32(st + G.off_cv), P.tri + (size_t)t_cur * tile_doubles, tri_bytes, bar_full(s));
+            if (extra) bulk_g2s(smem_u32(st + G.off_bc), th.Bcur + nn_offset(base, m), extra, bar_full(s));
+          }
+          if (resid != nullptr) {
+            double *rr = reinterpret_cast<double *>(st + G.off_rr) + lane;
+            long long i = base + lane;
+            if (i >= P.loc_end) i = (long long)P.loc_end - 1;
 #pragma unroll
-          for (int k = 0; k < MC; ++k)
-            if (k < m) cp_async8_zfill(&rr[k * 32], &resid[ids_cur[k] >= 0 ? ids_cur[k] : 0], ids_cur[k] >= 0);
-          cp_async8(&rr[MC * 32], &resid[i]);
+            for (int k = 0; k < kTriMaxM; ++k)
+              if (k < m) cp_async8_zfill(&rr[k * 32], &resid[ids_cur[k] >= 0 ? ids_cur[k] : 0], ids_cur[k] >= 0);
+            cp_async8(&rr[m * 32], &resid[i]);
 #pragma unroll
-          for (int k = 0; k < MC; ++k) ids_cur[k] = ids_nxt[k];
+            for (int k = 0; k < kTriMaxM; ++k) ids_cur[k] = ids_nxt[k];
+          }
+          cp_async_mbar_arrive(bar_full(s));
         }
-        cp_async_mbar_arrive(bar_full(s));
         t_cur = t_nxt;
+        if (++s == S) {
+          s = 0;
+          ++use;
+        }
       }
     } else if (warp < NC) {
       // ================================ consumers ======================================================
-      unsigned char *cons = smem + G::OFF_CONS + warp * G::kConsBytes;
+      unsigned char *cons = smem + G.off_cons + warp * G.cons_bytes;
       double *dv = reinterpret_cast<double *>(cons) + lane;
-      double *bo = reinterpret_cast<double *>(cons + MC * 256);  // [lane][k], the image of the tile's block of B
+      double *bo = reinterpret_cast<double *>(cons + m * 256);  // [lane][k], the image of the tile's block of B
       const double diag = th.sigmaSq + th.tauSq;
       int failed = INT_MAX;
       bool store_pending = false;
-      for (int j = warp;; j += NC) {
-        const int s = j % S;
-        unsigned char *st = smem + s * G::kStageBytes;
-        double *A = reinterpret_cast<double *>(st + G::OFF_A) + lane;
-        double *cv = reinterpret_cast<double *>(st + G::OFF_CV);
-        const double *rr = reinterpret_cast<const double *>(st + G::OFF_RR);
-        const double *bc = reinterpret_cast<const double *>(st + G::OFF_BC);
-        mbar_wait(bar_built(s), (j / S) & 1);
+      int s = warp, use = 0;
+      while (s >= S) {  // (NC <= S always; kept general)
+        s -= S;
+        ++use;
+      }
+      for (;;) {
+        unsigned char *st = smem + s * G.stage_bytes;
+        double *A = reinterpret_cast<double *>(st + G.off_a) + lane;
+        double *cv = reinterpret_cast<double *>(st + G.off_cv) + lane;
+        const double *rr = reinterpret_cast<const double *>(st + G.off_rr) + lane;
+        const double *bc = reinterpret_cast<const double *>(st + G.off_bc);
+        mbar_wait(bar_built(s), use & 1);
         const long long tile = ring[s];
         if (tile < 0) break;
         const long long base = P.loc_begin + tile * 32;
@@ -362,55 +552,59 @@ __global__ void __launch_bounds__(384, 1) bf_tri_kernel(const __grid_constant__ 
         const bool full = tri_tile_is_full(base, m, P.loc_end);
         double fcur = 1.0;
         if (with_cur) fcur = __ldg(&th.Fcur[i]);
-        if (mi < m) {  // ragged start of the ordering: identity-pad rows >= m_i
+        if (mi < m) {  // ragged start of the ordering: unit rows k >= m_i
           for (int k = mi; k < m; ++k) {
-            cv[k * 32 + lane] = 0.0;
+            cv[k * 32] = 0.0;
             for (int l = 0; l < k; ++l) A[(k * (k - 1) / 2 + l) * 32] = 0.0;
           }
-          for (int k = 0; k < mi; ++k)  // and the columns of the rows that do exist stay as they are
-            ;
         }
         // Q term of the RESIDENT factors (current theta of the sampler) with the same residuals
         double qcur_part = 0.0;
         if (with_cur) {
           if (full) {
-#pragma unroll
-            for (int k = 0; k < MC; ++k)
-              if (k < m) qcur_part = fma(bc[lane * m + k], rr[k * 32 + lane], qcur_part);
+#pragma unroll 4
+            for (int k = 0; k < m; ++k) qcur_part = fma(bc[lane * m + k], rr[k * 32], qcur_part);
           } else {
-            for (int k = 0; k < mi; ++k) qcur_part = fma(__ldg(&th.Bcur[off + k]), rr[k * 32 + lane], qcur_part);
+            for (int k = 0; k < mi; ++k) qcur_part = fma(__ldg(&th.Bcur[off + k]), rr[k * 32], qcur_part);
           }
         }
-        double Fsum;
-        constexpr int kCholW = (MC >= 12 && MC <= 16) ? 4 : 2;
-        const bool ok = tpl_solve<MC, kCholW>(A, cv + lane, dv, mi, diag, &Fsum);
+        // The usual neighbour counts take the fully unrolled column sweep (tpl_device.cuh; same layout when m equals its
+        // capacity): 12.4k cycles per tile against 16.4k for the rolled blocks at m = 15 (stall_wait on the loop-carried
+        // chains), in spite of its instruction-fetch stalls.  Every other m: the rolled blocked solve.
+        double Fv;
+        bool ok;
+        switch (m) {
+#ifndef NNGP_TRI_ROLLED_ONLY
+          case 10: ok = tri_solve_unrolled<10>(A, cv, dv, mi, diag, &Fv); break;
+          case 15: ok = tri_solve_unrolled<15>(A, cv, dv, mi, diag, &Fv); break;
+          case 20: ok = tri_solve_unrolled<20>(A, cv, dv, mi, diag, &Fv); break;
+#endif
+          default: ok = tri_solve(A, cv, dv, m, mi, diag, &Fv); break;
+        }
         if (!ok && active) failed = min(failed, (int)min(i + 1, (long long)INT_MAX - 1));
-        const double Fv = diag - Fsum;
-        double part = 0.0;
-        if (resid != nullptr) {
-#pragma unroll
-          for (int k = 0; k < MC; ++k) part = fma(cv[k * 32 + lane], rr[k * 32 + lane], part);
+        const bool to_bulk = th.B != nullptr && full;
+        if (to_bulk && store_pending) {
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
         }
-        const double r_own = rr[MC * 32 + lane];
-        if (th.B != nullptr) {
-          if (full) {
-            if (store_pending) {
-              if (lane == 0) bulk_wait_read0();
-              __syncwarp();
-            }
-#pragma unroll
-            for (int k = 0; k < MC; ++k)
-              if (k < m) bo[lane * m + k] = cv[k * 32 + lane];
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              bulk_s2g(th.B + nn_offset(base, m), smem_u32(bo), (unsigned)m * 256u);
-              bulk_commit();
-            }
-            store_pending = true;
-          } else if (active) {
-            for (int k = 0; k < mi; ++k) th.B[off + k] = cv[k * 32 + lane];
+        double part = 0.0;
+#pragma unroll 4
+        for (int k = 0; k < m; ++k) {  // residual rows are zero when the launch has no quadratic form
+          const double wk = cv[k * 32];
+          part = fma(wk, rr[k * 32], part);
+          if (to_bulk) bo[lane * m + k] = wk;
+        }
+        const double r_own = rr[m * 32];
+        if (to_bulk) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            bulk_s2g(th.B + nn_offset(base, m), smem_u32(bo), (unsigned)m * 256u);
+            bulk_commit();
           }
+          store_pending = true;
+        } else if (th.B != nullptr && active) {
+          for (int k = 0; k < mi; ++k) th.B[off + k] = cv[k * 32];
         }
         fence_proxy_async();  // this warp's generic-proxy accesses to the stage precede the next bulk copy into it
         __syncwarp();
@@ -439,6 +633,11 @@ __global__ void __launch_bounds__(384, 1) bf_tri_kernel(const __grid_constant__ 
           th.partials[4 * tile + 1] = qt;
           th.partials[4 * tile + 2] = qc;
         }
+        s += NC;
+        if (s >= S) {
+          s -= S;
+          ++use;
+        }
       }
       if (store_pending && lane == 0) bulk_wait0();
       if (failed != INT_MAX) atomicMin(th.fail, failed);
@@ -449,19 +648,18 @@ __global__ void __launch_bounds__(384, 1) bf_tri_kernel(const __grid_constant__ 
     const int pw = warp - 4;
     const int b0 = bbeg[pw], b1 = bbeg[pw + 1];
     const bool tail = (pw == 0);
-    int markers = 0;
-    for (int j = 0;; ++j) {
-      const int s = j % S;
-      mbar_wait(bar_full(s), (j / S) & 1);
+    int markers = 0, s = 0, use = 0;
+    for (;;) {
+      mbar_wait(bar_full(s), use & 1);
       const long long tile = ring[s];
       if (tile >= 0) {
-        unsigned char *st = smem + s * G::kStageBytes;
+        unsigned char *st = smem + s * G.stage_bytes;
         if constexpr (kMat) {
           auto body = [&](auto idx) {
             constexpr int B = decltype(idx)::value;
             const Cor<COV> cor(P.th[B], s_tab);
             const double sig = P.th[B].sigmaSq;
-            tri_transform<MC, COV>(
+            tri_transform<COV>(
                 st, lane, b0, b1, tail, m, [&](unsigned char *const(&p)[1]) { tri_rows_matern<COV, 1>(p, cor, sig); },
                 [&](unsigned char *const(&p)[kTriUnr<COV>]) { tri_rows_matern<COV, kTriUnr<COV>>(p, cor, sig); });
           };
@@ -473,7 +671,7 @@ __global__ void __launch_bounds__(384, 1) bf_tri_kernel(const __grid_constant__ 
           }
         } else {
           const FromDist<COV> f(th, nullptr);
-          tri_transform<MC, COV>(
+          tri_transform<COV>(
               st, lane, b0, b1, tail, m, [&](unsigned char *const(&p)[1]) { tri_rows<COV, 1>(p, f); },
               [&](unsigned char *const(&p)[kTriUnr<COV>]) { tri_rows<COV, kTriUnr<COV>>(p, f); });
         }
@@ -481,6 +679,10 @@ __global__ void __launch_bounds__(384, 1) bf_tri_kernel(const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_built(s));
       if (tile < 0 && ++markers == NC) break;  // the markers pass through, so that every consumer sees one
+      if (++s == S) {
+        s = 0;
+        ++use;
+      }
     }
   }
 
@@ -495,7 +697,7 @@ __global__ void __launch_bounds__(384, 1) bf_tri_kernel(const __grid_constant__ 
   if (last_flag) {
     __threadfence();
     double a = 0.0, b = 0.0, c = 0.0;
-    for (long long t = tid; t < ntiles; t += G::kThreads) {
+    for (long long t = tid; t < ntiles; t += kTriThreads) {
       a += __ldcg(&th.partials[4 * t]);
       b += __ldcg(&th.partials[4 * t + 1]);
       c += __ldcg(&th.partials[4 * t + 2]);
@@ -532,36 +734,17 @@ __global__ void __launch_bounds__(384, 1) bf_tri_kernel(const __grid_constant__ 
 }
 
 // ---- launcher ---------------------------------------------------------------------------------------
-template <int MC, int COV>
+template <int COV>
 static cudaError_t tri_launch_one(const BfLaunch &P, int grid_x, cudaStream_t stream) {
-  using G = TriGeo<MC>;
-  cudaError_t e = cudaFuncSetAttribute(bf_tri_kernel<MC, COV>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes);
+  const TriGeom G = tri_geometry(P.m);
+  cudaError_t e = cudaFuncSetAttribute(bf_tri_kernel<COV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
   if (e != cudaSuccess) return e;
   dim3 grid(grid_x, P.nbatch, 1);
-  bf_tri_kernel<MC, COV><<<grid, G::kThreads, G::kSmemBytes, stream>>>(P);
+  bf_tri_kernel<COV><<<grid, kTriThreads, G.smem_bytes, stream>>>(P);
   return cudaGetLastError();
 }
 
-template <int MC>
-static cudaError_t tri_launch_cov(const BfLaunch &P, int cov, int grid_x, cudaStream_t stream) {
-  switch (cov) {
-    case NNGP_COV_EXPONENTIAL: return tri_launch_one<MC, NNGP_COV_EXPONENTIAL>(P, grid_x, stream);
-    case NNGP_COV_SPHERICAL: return tri_launch_one<MC, NNGP_COV_SPHERICAL>(P, grid_x, stream);
-    case NNGP_COV_MATERN:
-      if (P.matern_short) return tri_launch_one<MC, NNGP_COV_MATERN_SHORT>(P, grid_x, stream);
-      return tri_launch_one<MC, NNGP_COV_MATERN>(P, grid_x, stream);
-    case NNGP_COV_GAUSSIAN: return tri_launch_one<MC, NNGP_COV_GAUSSIAN>(P, grid_x, stream);
-    default: return cudaErrorInvalidValue;
-  }
-}
-
-int tri_capacity_for_m(int m) {
-  static const int caps[7] = {8, 10, 12, 15, 16, 20, 24};
-  if (m < 6) return 0;
-  for (int c : caps)
-    if (m <= c) return c;
-  return 0;
-}
+int tri_capacity_for_m(int m) { return (m >= 2 && m <= kTriMaxM) ? m : 0; }
 
 int tri_grid_for(long long nloc, int sms) {
   const long long need = (nloc + 31) / 32;
@@ -571,18 +754,14 @@ int tri_grid_for(long long nloc, int sms) {
 }
 
 cudaError_t tri_launch(const BfLaunch &P, int cov, int grid_x, cudaStream_t stream) {
-  switch (tri_capacity_for_m(P.m)) {
-#ifdef NNGP_TRI_ONLY15
-    case 15: return tri_launch_cov<15>(P, cov, grid_x, stream);
-#else
-    case 8: return tri_launch_cov<8>(P, cov, grid_x, stream);
-    case 10: return tri_launch_cov<10>(P, cov, grid_x, stream);
-    case 12: return tri_launch_cov<12>(P, cov, grid_x, stream);
-    case 15: return tri_launch_cov<15>(P, cov, grid_x, stream);
-    case 16: return tri_launch_cov<16>(P, cov, grid_x, stream);
-    case 20: return tri_launch_cov<20>(P, cov, grid_x, stream);
-    case 24: return tri_launch_cov<24>(P, cov, grid_x, stream);
-#endif
+  if (!tri_capacity_for_m(P.m)) return cudaErrorInvalidValue;
+  switch (cov) {
+    case NNGP_COV_EXPONENTIAL: return tri_launch_one<NNGP_COV_EXPONENTIAL>(P, grid_x, stream);
+    case NNGP_COV_SPHERICAL: return tri_launch_one<NNGP_COV_SPHERICAL>(P, grid_x, stream);
+    case NNGP_COV_MATERN:
+      if (P.matern_short) return tri_launch_one<NNGP_COV_MATERN_SHORT>(P, grid_x, stream);
+      return tri_launch_one<NNGP_COV_MATERN>(P, grid_x, stream);
+    case NNGP_COV_GAUSSIAN: return tri_launch_one<NNGP_COV_GAUSSIAN>(P, grid_x, stream);
     default: return cudaErrorInvalidValue;
   }
 }
