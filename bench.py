@@ -11,8 +11,9 @@ beta, evaluate the log-likelihood (B/F solve + Q) at the current and at the prop
     python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path (oracle/_ref)
 
 Prints ONE JSON line on rank 0.  N > 1 is launched with torchrun (one rank per GPU): the locations are
-sharded over the ranks (strong scaling, total work fixed) and the likelihood partials are summed with an
-NCCL allreduce of 4 doubles per iteration.
+sharded over the ranks (strong scaling, total work fixed) and the likelihood partials (4 doubles per rank and
+iteration) are exchanged through the engine's shared-memory mailbox (include/nngp_b200.h: nngp_comm_init; set
+NNGP_REDUCE=nccl for the ncclAllReduce path).
 """
 from __future__ import annotations
 
@@ -49,9 +50,10 @@ def workload_label(n: int, m: int, cov: str) -> str:
     return f"rNNGP response model n={n} m={m} p=2 cov={cov}{tag}"
 
 
-def bytes_per_location(m: int) -> float:
-    """Algorithmic bytes per location with B, F stored: coords 16 + nnIndx 4m + B 8m + F 8 + resid 8."""
-    return 32 + 12 * m
+def bytes_per_location(m: int, tri: bool = False) -> float:
+    """Algorithmic bytes per location with B, F stored: coords 16 + nnIndx 4m + B 8m + F 8 + resid 8.
+    tri: the distance-triangle kernel streams the 8 * m(m+1)/2 bytes of resident pair distances instead of the sites."""
+    return (4 * m * (m + 1) + 16 + 12 * m) if tri else (32 + 12 * m)
 
 
 def make_workload(n: int, m: int, seed: int = 1):
@@ -328,6 +330,27 @@ def run_b200(args, rank, world, local_rank):
     h2d_step = data_bytes / args.steps + nb * (2 * 8 + 0)           # data set amortised + beta per launch
     d2h_step = nb * (2 * 8 + 4) + (acc_e / args.steps) * 9 * 8 + (2 + 3) * 8  # partials, S on accepts, samples
 
+    # ---- N > 1: self-check of the sharded numbers against the unsharded engine on rank 0 -------------------
+    parity = None
+    theta0 = [5.0, 1.0, 6.0, 0.75][: 4 if cov == 2 else 3]
+    if world > 1 and not args.no_parity:
+        out_sh = eng.bf_loglik(cov, [theta0], [wl["beta"]], slots=[0])           # every rank: summed over the shards
+        _, ts_sh, _ = chain(args.steps, args.mode)
+        if rank == 0:
+            full = Engine(local_rank, stream=stream.cuda_stream)
+            full.set_data(wl["coords"], nnIndx, lu, wl["X"], wl["y"], m)
+            out_1 = full.bf_loglik(cov, [theta0], [wl["beta"]], slots=[0])
+            R.rshim_set_seed(1)
+            _, ts_1, _ = full.rnngp(cov, pri["sigmaSqIG"], pri["tauSqIG"], pri["phiUnif"], pri["nuUnif"], starting, tuning,
+                                    args.steps, R.rnorm, R.runif, mode=args.mode)
+            full.close()
+            parity = {"rel_logdet": float(abs(out_sh[0, 0] - out_1[0, 0]) / abs(out_1[0, 0])),
+                      "rel_q": float(abs(out_sh[0, 1] - out_1[0, 1]) / abs(out_1[0, 1])),
+                      "chain_max_rel_diff_to_n1": float(np.max(np.abs(ts_sh - ts_1) / np.abs(ts_1))),
+                      "chain_equal_to_n1": bool(np.allclose(ts_sh, ts_1, rtol=1e-9, atol=0.0)),
+                      "note": "sharded vs unsharded engine on rank 0, same seed, after the timed region"}
+        barrier()
+
     launches_t = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(launches_t)
@@ -349,14 +372,15 @@ def run_b200(args, rank, world, local_rank):
         fp64_peak = eng.fp64_peak_tflops()
         peaks, peak_src = measured_peaks()
         fl = flops_per_location(m)
+        tri = bool(eng.get_option("tri_cache_used"))
         ach_tf = loc_s * fl / 1e12
-        ach_gbs = loc_s * bytes_per_location(m) / 1e9
+        ach_gbs = loc_s * bytes_per_location(m, tri) / 1e9
         roofline = {
             "bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
             "traffic": traffic_from_profile(n, m, args.cov),
-            "kernel": "bf_ws_kernel" if 6 <= m <= 24 else ("bf_tpl_kernel" if m <= 5 else "bf_kernel"),
+            "kernel": "bf_tri_kernel" if tri else ("bf_ws_kernel" if 6 <= m <= 24 else ("bf_tpl_kernel" if m <= 5 else "bf_kernel")),
             "kernel_ms": k_ms, "locations_per_launch": nloc, "updateBF_loc_per_s": loc_s,
-            "flops_per_location": fl, "bytes_per_location": bytes_per_location(m),
+            "flops_per_location": fl, "bytes_per_location": bytes_per_location(m, tri),
             "peak_source": "FP64 FMA peak measured live by nngp_fp64_peak (DFMA micro-benchmark; MEASURED_PEAKS.json has no "
                            "FP64 figure); transcendentals count as 1 flop (SURVEY §8d)",
             "hbm_view": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"],
@@ -379,10 +403,13 @@ def run_b200(args, rank, world, local_rank):
                 "workload": workload_label(n, m, args.cov),
                 "n": n, "m": m, "cov_model": args.cov, "p": 2,
                 "sampler": "reference-faithful: 2 B/F solves + 2 Q per iteration, one batched launch" if args.mode == 0
-                else "double-buffered: 1 B/F solve + 1 Q-only pass per iteration",
+                else "double-buffered: B, F of the current theta stay resident; one launch per iteration solves the "
+                     "candidate and re-forms Q of the current theta (identical chain, tests/test_gpu_golden_and_glue.py)",
                 "l2": f"inputs larger than L2: {bytes_per_location(m) * (hi - lo) / 1e6:.0f} MB touched per launch vs 126 MB L2"
                 if bytes_per_location(m) * (hi - lo) > 126e6 else "working set fits L2 at this shard size (no flush; strong scaling)",
-                "parallelism": f"locations sharded over {world} GPU(s); NCCL allreduce of 6 doubles per iteration on the kernel's stream",
+                "parallelism": f"locations (and their nnIndx / B / F / distance storage) sharded over {world} GPU(s); "
+                               + ("ncclAllReduce of the partials per iteration" if os.environ.get("NNGP_REDUCE") == "nccl" else
+                                  "partials stamped into a shared-memory mailbox by the kernel's last CTA, summed in rank order by every host"),
                 "acceptance_rate": acc / args.steps, "rng": "R-compatible Mersenne-Twister + inversion (librshim), seed 1",
             },
             "e2e": {"value": args.steps / e2e_s, "unit": "iter/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
@@ -390,6 +417,7 @@ def run_b200(args, rank, world, local_rank):
                     "note": "nngp_set_data from host buffers + K iterations + samples back, wall clock, max over ranks"},
             "gpu_launches": int(launches_t.item()),
             "clocks": clk,
+            "parity": parity,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "extra": {
@@ -500,7 +528,8 @@ def main():
     ap.add_argument("--n", type=int, default=1000000)
     ap.add_argument("--m", type=int, default=15)
     ap.add_argument("--cov", default="matern", choices=list(COV))
-    ap.add_argument("--mode", type=int, default=0, help="0 reference-faithful sampler, 1 double-buffered")
+    ap.add_argument("--no-parity", action="store_true", help="skip the N > 1 self-check against the unsharded engine")
+    ap.add_argument("--mode", type=int, default=1, help="1 double-buffered sampler (default), 0 reference-faithful")
     ap.add_argument("--ref-budget-s", type=float, default=150.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--py-allreduce", action="store_true", help="sum partials through torch.distributed in Python")

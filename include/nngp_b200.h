@@ -113,6 +113,14 @@ int nngp_set_data(nngp_ctx *ctx, int n, int m, int p, const double *coords, cons
 int nngp_bf_loglik(nngp_ctx *ctx, int cov_model, int nbatch, const double *theta, const double *beta,
                    const int *slots, double *out);
 
+/* The sampler's step in ONE launch: solve theta into slot_new as nngp_bf_loglik does, and with the same residual
+ * r = X beta - y also return Q of the factors already resident in slot_cur (the current theta of the chain, whose
+ * B and F do not change while only beta moves -- the work src/rNNGP.cpp:297-306 repeats every iteration).
+ *      theta: 4 doubles; beta: p doubles; out: (sum_i log F_i(theta), Q(theta), Q(slot_cur)).
+ * Kernels without the fused path (no resident distance triangle) run nngp_q_resid behind the launch. */
+int nngp_bf_loglik_cur(nngp_ctx *ctx, int cov_model, const double *theta, const double *beta, int slot_new,
+                       int slot_cur, double *out);
+
 /* The same launch with the vector to whiten given directly (n doubles) instead of r = X beta - y: Q = u' C~^-1 u.
  * With tau.sq = 0 and u = w this is the latent model's likelihood piece -- its tau.sq-free updateBF plus the
  * OpenMP reductions over b_i^2 / F_i and log F_i (src/sNNGP.cpp:24-65, 323-400). */
@@ -228,6 +236,13 @@ int nngp_rnngp_predict(nngp_ctx *ctx, int cov_model, int q, const double *X0, co
 int nngp_comm_unique_id(char id[128]);
 int nngp_comm_init(nngp_ctx *ctx, const char id[128], int rank, int nranks);
 int nngp_comm_allreduce_sum(nngp_ctx *ctx, double *buf, int len); /* host buffer, len <= 12; for tests/tools */
+/* The same sums for ranks that share one node WITHOUT NCCL: every rank's kernels store their partials, then a sequence
+ * stamp, into that rank's slot of a shared-memory mailbox; every host polls all slots and adds them in rank order
+ * (deterministic; no collective call, no device-to-host copy, no stream synchronisation on the sampler's critical path).
+ * nngp_comm_init sets the same mailbox up next to its NCCL communicator and uses it unless
+ * nngp_set_option("reduce_nccl", 1) / NNGP_REDUCE=nccl asks for ncclAllReduce.  key: 128 bytes, identical on all ranks
+ * of the job and unique to it (nngp_comm_unique_id provides one).  Ranks may share a GPU. */
+int nngp_comm_init_local(nngp_ctx *ctx, const char key[128], int rank, int nranks);
 void nngp_comm_destroy(nngp_ctx *ctx);
 
 /* ---- HBM-resident measurement helpers (bench.py `value`): time the likelihood launch with every

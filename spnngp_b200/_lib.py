@@ -43,9 +43,9 @@ class RnngpArgs(C.Structure):
 # every symbol include/nngp_b200.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
     "nngp_abi_version", "nngp_device_count", "nngp_create", "nngp_destroy", "nngp_last_error", "nngp_sync",
-    "nngp_mk_nn_indx", "nngp_mk_u_indx", "nngp_nn_query", "nngp_set_data", "nngp_bf_loglik", "nngp_bf_loglik_vec", "nngp_q_resid", "nngp_q_forms",
+    "nngp_mk_nn_indx", "nngp_mk_u_indx", "nngp_nn_query", "nngp_set_data", "nngp_bf_loglik", "nngp_bf_loglik_cur", "nngp_bf_loglik_vec", "nngp_q_resid", "nngp_q_forms",
     "nngp_get_bf", "nngp_rnngp", "nngp_rep_draw", "nngp_rnngp_replicated", "nngp_cnngp", "nngp_cnngp_score", "nngp_conj_kfold", "nngp_rnngp_predict", "nngp_time_bf_loglik", "nngp_launch_count", "nngp_set_option", "nngp_get_option",
-    "nngp_fp64_peak", "nngp_comm_unique_id", "nngp_comm_init", "nngp_comm_allreduce_sum", "nngp_comm_destroy",
+    "nngp_fp64_peak", "nngp_comm_unique_id", "nngp_comm_init", "nngp_comm_init_local", "nngp_comm_allreduce_sum", "nngp_comm_destroy",
 ]
 
 _lib = None
@@ -75,6 +75,7 @@ def load():
     L.nngp_set_data.argtypes = [vp, C.c_int, C.c_int, C.c_int, c_double_p, c_int_p, c_int_p, c_double_p, c_double_p,
                                 C.c_int, C.c_int]
     L.nngp_bf_loglik.argtypes = [vp, C.c_int, C.c_int, c_double_p, c_double_p, c_int_p, c_double_p]
+    L.nngp_bf_loglik_cur.argtypes = [vp, C.c_int, c_double_p, c_double_p, C.c_int, C.c_int, c_double_p]
     L.nngp_bf_loglik_vec.argtypes = [vp, C.c_int, C.c_int, c_double_p, c_double_p, c_int_p, c_double_p]
     L.nngp_q_resid.argtypes = [vp, C.c_int, c_double_p, c_double_p]
     L.nngp_q_forms.argtypes = [vp, C.c_int, c_double_p]
@@ -88,6 +89,7 @@ def load():
     L.nngp_fp64_peak.argtypes = [vp, c_double_p]
     L.nngp_comm_unique_id.argtypes = [C.c_char_p]
     L.nngp_comm_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
+    L.nngp_comm_init_local.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
     L.nngp_comm_allreduce_sum.argtypes = [vp, c_double_p, C.c_int]
     L.nngp_comm_destroy.restype = None
     L.nngp_comm_destroy.argtypes = [vp]

@@ -227,6 +227,8 @@ __global__ void __launch_bounds__(32) bf_tpl_kernel(const __grid_constant__ BfLa
       th.out[3] = 0.0;
       *th.fail_out = fv;
       *th.ticket = 0u;
+      __threadfence_system();  // results before the stamp, as seen by the polling host (and by peers' hosts)
+      *reinterpret_cast<volatile double *>(&th.out[kBfOutSeq]) = th.seq;
     }
   }
 }

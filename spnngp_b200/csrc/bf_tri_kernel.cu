@@ -729,6 +729,8 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
       *th.fail_out = fv;
       *th.tile_counter = 0u;
       *th.ticket = 0u;
+      __threadfence_system();  // results before the stamp, as seen by the polling host (and by peers' hosts)
+      *reinterpret_cast<volatile double *>(&th.out[kBfOutSeq]) = th.seq;
     }
   }
 }

@@ -412,6 +412,8 @@ __global__ void __launch_bounds__(32 * (1 + NP), (MC <= 16) ? 2 : 1) bf_ws_kerne
       *th.fail_out = fv;
       *th.tile_counter = 0u;
       *th.ticket = 0u;
+      __threadfence_system();  // results before the stamp, as seen by the polling host (and by peers' hosts)
+      *reinterpret_cast<volatile double *>(&th.out[kBfOutSeq]) = th.seq;
     }
   }
 }

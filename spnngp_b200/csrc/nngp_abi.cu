@@ -115,30 +115,12 @@ const char *nngp_last_error(const nngp_ctx *ctx) {
   return copy.c_str();
 }
 
-int nngp_create(int device, void *stream_handle, nngp_ctx **out) {
-  if (!out) return ctx_fail(nullptr, NNGP_EINVAL, "nngp_create: out is NULL");
-  *out = nullptr;
-  int ndev = 0;
-  cudaError_t e = cudaGetDeviceCount(&ndev);
-  if (e != cudaSuccess || ndev == 0) {
-    cudaGetLastError();
-    return ctx_fail(nullptr, NNGP_ENODEV,
-                    "nngp_create: no CUDA device visible (this library has no CPU fallback)");
-  }
-  if (device < 0) {
-    if (cudaGetDevice(&device) != cudaSuccess) device = 0;
-  }
-  if (device >= ndev) return ctx_fail(nullptr, NNGP_EINVAL, "nngp_create: device index out of range");
-  nngp_ctx *c = new nngp_ctx();
-  c->device = device;
+static int create_init(nngp_ctx *c, int device, void *stream_handle) {
   NNGP_CUDA(c, cudaSetDevice(device));
   int major = 0, sms = 0;
   cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  if (major < 10) {
-    delete c;
-    return ctx_fail(nullptr, NNGP_ENODEV, "nngp_create: device is not sm_100-class (kernels are built for sm_100a only)");
-  }
+  if (major < 10) return ctx_fail(nullptr, NNGP_ENODEV, "nngp_create: device is not sm_100-class (kernels are built for sm_100a only)");
   c->sms = sms > 0 ? sms : 148;
   if (stream_handle) {
     c->stream = (cudaStream_t)stream_handle;
@@ -166,9 +148,37 @@ int nngp_create(int device, void *stream_handle, nngp_ctx **out) {
   NNGP_CUDA(c, cudaMalloc(&c->d_red, kBfOutStride * NNGP_MAX_BATCH * sizeof(double)));
   NNGP_CUDA(c, cudaHostAlloc(&c->h_red, kBfOutStride * NNGP_MAX_BATCH * sizeof(double), cudaHostAllocDefault));
   NNGP_CUDA(c, cudaHostAlloc(&c->h_fail, NNGP_MAX_BATCH * sizeof(int), cudaHostAllocMapped));
+  {
+    int rc = mbox_local_init(c);
+    if (rc) return rc;
+  }
   NNGP_CUDA(c, cudaHostAlloc(&c->h_mat, NNGP_MAX_BATCH * sizeof(MaternConsts), cudaHostAllocDefault));
   NNGP_CUDA(c, cudaEventCreate(&c->ev0));
   NNGP_CUDA(c, cudaEventCreate(&c->ev1));
+  return NNGP_OK;
+}
+
+int nngp_create(int device, void *stream_handle, nngp_ctx **out) {
+  if (!out) return ctx_fail(nullptr, NNGP_EINVAL, "nngp_create: out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return ctx_fail(nullptr, NNGP_ENODEV,
+                    "nngp_create: no CUDA device visible (this library has no CPU fallback)");
+  }
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+  }
+  if (device >= ndev) return ctx_fail(nullptr, NNGP_EINVAL, "nngp_create: device index out of range");
+  nngp_ctx *c = new nngp_ctx();
+  c->device = device;
+  const int rc = create_init(c, device, stream_handle);
+  if (rc) {  // nothing half-built survives a failed create
+    nngp_destroy(c);
+    return rc;
+  }
   *out = c;
   return NNGP_OK;
 }
@@ -184,6 +194,8 @@ void nngp_destroy(nngp_ctx *c) {
   free_dev(c->d_fail);
   free_dev(c->d_mat);
   if (c->d_flush) cudaFree(c->d_flush);
+  nngp_comm_destroy(c);
+  mbox_release(c);
   if (c->h_out) cudaFreeHost(c->h_out);
   if (c->h_red) cudaFreeHost(c->h_red);
   free_dev(c->d_red);
@@ -220,6 +232,10 @@ int nngp_set_option(nngp_ctx *c, const char *name, int value) {
     c->opt_tri = value ? 1 : 0;
     return NNGP_OK;
   }
+  if (!strcmp(name, "reduce_nccl")) {  // 1: sums over ranks go through ncclAllReduce instead of the shared mailbox
+    c->opt_reduce_nccl = value ? 1 : 0;
+    return NNGP_OK;
+  }
   return ctx_fail(c, NNGP_EINVAL, std::string("nngp_set_option: unknown option ") + name);
 }
 
@@ -231,6 +247,14 @@ int nngp_get_option(nngp_ctx *c, const char *name, int *value) {
   }
   if (!strcmp(name, "tri_cache")) {
     *value = c->opt_tri;
+    return NNGP_OK;
+  }
+  if (!strcmp(name, "reduce_nccl")) {
+    *value = c->opt_reduce_nccl;
+    return NNGP_OK;
+  }
+  if (!strcmp(name, "mailbox_ranks")) {  // ranks whose slots this context reads (1: private mailbox)
+    *value = c->mbox_ranks;
     return NNGP_OK;
   }
   if (!strcmp(name, "tri_cache_used")) {  // 1 when the B/F launches of this data set stream the resident distance triangle
@@ -398,7 +422,7 @@ int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const 
 
 // Build the launch descriptor for `nbatch` parameter sets.  resid_on: form r = X beta - y first.
 static int prepare_bf(nngp_ctx *c, int cov, int nbatch, const double *theta, const double *beta, const int *slots,
-                      bool store, BfLaunch *P, int *grid_out) {
+                      bool store, BfLaunch *P, int *grid_out, int cur_slot = -1) {
   if (c->n == 0 || !c->has_nn) return ctx_fail(c, NNGP_ESTATE, "likelihood requested before nngp_set_data (with neighbours)");
   if (nbatch < 1 || nbatch > NNGP_MAX_BATCH) return ctx_fail(c, NNGP_EINVAL, "nbatch must be in 1..4");
   if (cov < 0 || cov > 3) return ctx_fail(c, NNGP_EINVAL, "cov.model is not correctly specified");
@@ -417,10 +441,11 @@ static int prepare_bf(nngp_ctx *c, int cov, int nbatch, const double *theta, con
   P->loc_begin = c->loc_begin;
   P->loc_end = c->loc_end;
   P->nbatch = nbatch;
-  double *out_dev = nullptr;
   int *fail_dev = nullptr;
-  NNGP_CUDA(c, cudaHostGetDevicePointer((void **)&out_dev, c->h_out, 0));
   NNGP_CUDA(c, cudaHostGetDevicePointer((void **)&fail_dev, c->h_fail, 0));
+  // results go to this rank's mailbox slot, stamped with a fresh sequence number (NCCL path: to d_red, reduced there)
+  const unsigned long long seq = ++c->seq;
+  double *out_dev = mbox_slot_dev(c, seq) + kMboxPayload;
   for (int b = 0; b < nbatch; b++) {
     const double *t = theta + 4 * b;
     if (!(t[0] > 0.0) || !(t[1] >= 0.0) || !(t[2] > 0.0)) return ctx_fail(c, NNGP_EINVAL, "theta out of range");
@@ -455,18 +480,29 @@ static int prepare_bf(nngp_ctx *c, int cov, int nbatch, const double *theta, con
     th.B = store ? c->d_B[slot] : nullptr;
     th.F = store ? c->d_F[slot] : nullptr;
     th.resid = beta ? c->d_resid[b] : nullptr;
-    th.out = (c->comm ? c->d_red : out_dev) + kBfOutStride * b;  // device buffer when the result is reduced over ranks
+    if (cur_slot >= 0 && tri && beta) {  // also return Q of the resident factors of `cur_slot` (bf_tri_kernel only)
+      th.Bcur = c->d_B[cur_slot];
+      th.Fcur = c->d_F[cur_slot];
+    }
+    th.out = (mbox_reduces(c) ? out_dev : c->d_red) + kBfOutStride * b;
+    th.seq = (double)seq;
     th.partials = c->d_partials + c->partials_stride * b;
     th.ticket = c->d_ticket + b;
     th.tile_counter = c->d_ticket + NNGP_MAX_BATCH + b;
     th.fail = c->d_fail + b;
     th.fail_out = fail_dev + b;
   }
-  if (cov == NNGP_COV_MATERN)  // full tables for the rare Temme / CF2 path (the series coefficients travel as parameters)
-    NNGP_CUDA(c, cudaMemcpyAsync(c->d_mat, c->h_mat, nbatch * sizeof(MaternConsts), cudaMemcpyHostToDevice, c->stream));
+  if (cov == NNGP_COV_MATERN) {  // full tables for the rare Temme / CF2 path (the series coefficients travel as parameters)
+    for (int b = 0; b < nbatch; b++) {
+      if (c->d_mat_nu[b] == theta[4 * b + 3]) continue;  // this slot already holds the tables of that smoothness
+      NNGP_CUDA(c, cudaMemcpyAsync(c->d_mat + b, c->h_mat + b, sizeof(MaternConsts), cudaMemcpyHostToDevice, c->stream));
+      c->d_mat_nu[b] = theta[4 * b + 3];
+    }
+  }
   if (beta) {
     memcpy(c->h_beta, beta, (size_t)nbatch * c->p * sizeof(double));
-    NNGP_CUDA(c, cudaMemcpyAsync(c->d_beta, c->h_beta, (size_t)nbatch * c->p * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (c->p > kResidBetaMax)  // otherwise beta rides in the residual kernel's parameters
+      NNGP_CUDA(c, cudaMemcpyAsync(c->d_beta, c->h_beta, (size_t)nbatch * c->p * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   }
   *grid_out = grid;
   return NNGP_OK;
@@ -480,7 +516,10 @@ static int enqueue_bf(nngp_ctx *c, int cov, const BfLaunch &P, int grid, bool wi
       for (int a = 0; a < b && !dup; a++)
         if (memcmp(c->h_beta + (size_t)a * c->p, c->h_beta + (size_t)b * c->p, c->p * sizeof(double)) == 0) dup = true;
       if (dup) continue;
-      NNGP_CUDA(c, resid_launch(c->d_X, c->d_y, c->d_beta + (size_t)b * c->p, c->n, c->p, c->d_resid[b], c->sms, c->stream));
+      if (c->p <= kResidBetaMax)
+        NNGP_CUDA(c, resid_launch_val(c->d_X, c->d_y, c->h_beta + (size_t)b * c->p, c->n, c->p, c->d_resid[b], c->sms, c->stream));
+      else
+        NNGP_CUDA(c, resid_launch(c->d_X, c->d_y, c->d_beta + (size_t)b * c->p, c->n, c->p, c->d_resid[b], c->sms, c->stream));
       c->launches++;
     }
   }
@@ -524,14 +563,18 @@ static void share_resid(nngp_ctx *c, BfLaunch *P) {
 
 // after the launch: sum over ranks if sharded, one stream sync, unpack (logDet, Q) per set, report failures
 static int finish_bf(nngp_ctx *c, int nbatch, bool have_q, double *out) {
-  const double *res = c->h_out;
-  if (c->comm) {  // sum (logDet, Q, fail flag) over the ranks on the device, then one small copy back
+  double sums[kBfOutStride * NNGP_MAX_BATCH];
+  const double *res = sums;
+  if (mbox_reduces(c)) {  // poll the stamps of every rank's result blocks, add them in rank order
+    int rc = mbox_wait_sets(c, c->seq, nbatch, sums);
+    if (rc) return rc;
+  } else {  // NCCL: sum (logDet, Q, fail flag) over the ranks on the device, then one small copy back
     int rc = comm_allreduce_dev(c, c->d_red, kBfOutStride * nbatch);
     if (rc) return rc;
     NNGP_CUDA(c, cudaMemcpyAsync(c->h_red, c->d_red, kBfOutStride * nbatch * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
     res = c->h_red;
   }
-  NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
   int status = 0;
   bool any_rank_failed = false;
   for (int b = 0; b < nbatch; b++) {
@@ -543,6 +586,23 @@ static int finish_bf(nngp_ctx *c, int nbatch, bool have_q, double *out) {
   }
   if (status == 0 && any_rank_failed) status = INT_MAX;  // the failing location lives on another rank
   if (status > 0) return ctx_fail(c, status, "c++ error: dpotrf failed (neighbour covariance not positive definite)");
+  return NNGP_OK;
+}
+
+// `len` doubles at d_src (this rank's part) -> their sum over the ranks, on the host
+static int reduce_small(nngp_ctx *c, double *d_src, int len, double *host) {
+  if (mbox_reduces(c) && len <= kMboxSlotDoubles - kMboxPayload) {
+    const unsigned long long seq = ++c->seq;
+    int rc = mbox_post_dev(c, d_src, len, seq);
+    if (rc) return rc;
+    return mbox_wait_payload(c, seq, len, host);
+  }
+  if (c->comm) {
+    int rc = comm_allreduce_dev(c, d_src, len);
+    if (rc) return rc;
+  }
+  NNGP_CUDA(c, cudaMemcpyAsync(host, d_src, len * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
   return NNGP_OK;
 }
 
@@ -558,6 +618,29 @@ int nngp_bf_loglik(nngp_ctx *c, int cov, int nbatch, const double *theta, const 
   rc = enqueue_bf(c, cov, P, grid, beta != nullptr);
   if (rc) return rc;
   return finish_bf(c, nbatch, beta != nullptr, out);
+}
+
+int nngp_bf_loglik_cur(nngp_ctx *c, int cov, const double *theta, const double *beta, int slot_new, int slot_cur,
+                       double *out) {
+  if (!c || !theta || !beta || !out || slot_new < 0 || slot_new > 1 || slot_cur < 0 || slot_cur > 1 || slot_new == slot_cur)
+    return NNGP_EINVAL;
+  NNGP_CUDA(c, cudaSetDevice(c->device));
+  BfLaunch P;
+  int grid = 0;
+  int rc = prepare_bf(c, cov, 1, theta, beta, &slot_new, true, &P, &grid, slot_cur);
+  if (rc) return rc;
+  rc = enqueue_bf(c, cov, P, grid, true);
+  if (rc) return rc;
+  double o2[2];
+  rc = finish_bf(c, 1, true, o2);
+  if (rc) return rc;
+  out[0] = o2[0];
+  out[1] = o2[1];
+  if (P.th[0].Bcur != nullptr) {  // the launch carried the resident factors along
+    out[2] = c->last_qcur[0];
+    return NNGP_OK;
+  }
+  return nngp_q_resid(c, slot_cur, beta, out + 2);  // kernels without that path: one more pass over B, F
 }
 
 int nngp_bf_loglik_vec(nngp_ctx *c, int cov, int nbatch, const double *theta, const double *u, const int *slots,
@@ -631,19 +714,16 @@ int nngp_q_resid(nngp_ctx *c, int slot, const double *beta, double *out) {
   if (c->n == 0 || c->p == 0 || !c->has_nn) return ctx_fail(c, NNGP_ESTATE, "nngp_q_resid before nngp_set_data");
   NNGP_CUDA(c, cudaSetDevice(c->device));
   memcpy(c->h_beta, beta, c->p * sizeof(double));
-  NNGP_CUDA(c, cudaMemcpyAsync(c->d_beta, c->h_beta, c->p * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  NNGP_CUDA(c, resid_launch(c->d_X, c->d_y, c->d_beta, c->n, c->p, c->d_resid[0], c->sms, c->stream));
+  if (c->p <= kResidBetaMax) {
+    NNGP_CUDA(c, resid_launch_val(c->d_X, c->d_y, c->h_beta, c->n, c->p, c->d_resid[0], c->sms, c->stream));
+  } else {
+    NNGP_CUDA(c, cudaMemcpyAsync(c->d_beta, c->h_beta, c->p * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    NNGP_CUDA(c, resid_launch(c->d_X, c->d_y, c->d_beta, c->n, c->p, c->d_resid[0], c->sms, c->stream));
+  }
   NNGP_CUDA(c, q_resid_launch(c->d_B[slot], c->d_F[slot], c->d_nnIndx, c->d_resid[0], c->m, c->loc_begin, c->loc_end,
                               c->d_partials, c->d_out, c->sms, c->stream));
   c->launches += 3;
-  if (c->comm) {
-    int rc = comm_allreduce_dev(c, c->d_out, 1);
-    if (rc) return rc;
-  }
-  NNGP_CUDA(c, cudaMemcpyAsync(c->h_out, c->d_out, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
-  out[0] = c->h_out[0];
-  return NNGP_OK;
+  return reduce_small(c, c->d_out, 1, out);
 }
 
 int nngp_q_forms(nngp_ctx *c, int slot, double *S) {
@@ -654,13 +734,9 @@ int nngp_q_forms(nngp_ctx *c, int slot, double *S) {
   NNGP_CUDA(c, q_forms_launch(c->d_B[slot], c->d_F[slot], c->d_nnIndx, c->d_Xy, c->n, c->p, c->m, c->loc_begin,
                               c->loc_end, c->d_partials, c->d_out, c->stream));
   c->launches += 2;
-  if (c->comm) {
-    int rc = comm_allreduce_dev(c, c->d_out, npairs);
-    if (rc) return rc;
-  }
   std::vector<double> packed(npairs);
-  NNGP_CUDA(c, cudaMemcpyAsync(packed.data(), c->d_out, npairs * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
+  int rc = reduce_small(c, c->d_out, npairs, packed.data());
+  if (rc) return rc;
   int e = 0;
   for (int d = 0; d < K; d++)
     for (int r = d; r < K; r++, e++) {
@@ -803,13 +879,12 @@ int nngp_rnngp(nngp_ctx *c, const nngp_rnngp_args *a, double *betaSamples, doubl
       logDetCur = red[0]; QCur = red[1]; logDetCand = red[2]; QCand = red[3];
     } else {
       // double-buffered: B,F of the current theta are still resident; only Q changes with beta
-      slots[0] = 1 - cur;
-      rc = nngp_bf_loglik(c, cov, 1, cand, beta.data(), slots, out);
+      // one launch: solve the candidate and, with the same residual gathers, Q of the resident factors
+      double o3[3];
+      rc = nngp_bf_loglik_cur(c, cov, cand, beta.data(), 1 - cur, cur, o3);
       if (rc) return rc;
-      red[2] = out[0]; red[3] = out[1];
-      rc = nngp_q_resid(c, cur, beta.data(), out);
-      if (rc) return rc;
-      red[0] = 0.0; red[1] = out[0];
+      red[2] = o3[0]; red[3] = o3[1];
+      red[0] = 0.0; red[1] = o3[2];
       if (a->allreduce) a->allreduce(red, 4, a->allreduce_user);
       QCur = red[1]; logDetCand = red[2]; QCand = red[3];
     }

@@ -15,7 +15,12 @@ __host__ __device__ __forceinline__ long long nn_offset(long long i, int m) {
 }
 __host__ __device__ __forceinline__ int nn_count(long long i, int m) { return i < m ? (int)i : m; }
 
-constexpr int kBfOutStride = 4;  // doubles per parameter set in the result block of a B/F launch
+// Result block of one parameter set of a B/F launch: 8 doubles (one 64-byte line of the rank's mailbox slot)
+//   [0] sum log F   [1] Q   [2] 1.0 if a factorisation failed   [3] Q of (Bcur, Fcur)   [4] the launch's sequence number,
+// written LAST behind a system-scope fence: the host polls it instead of synchronising the stream (nngp_ctx.h: mailbox)
+constexpr int kBfOutStride = 8;
+constexpr int kBfOutSeq = 4;
+constexpr int kResidBetaMax = 32;  // p up to which beta rides in the residual kernel's parameters
 
 // One parameter set of a batched B/F launch.
 struct BfTheta {
@@ -29,6 +34,7 @@ struct BfTheta {
   // also returns Q(Bcur, Fcur, resid, resid) -- the residual gathers are shared (double-buffered sampler, one launch)
   const double *Bcur;
   const double *Fcur;
+  double seq;           // completion stamp of this launch (an integer value), stored to out[kBfOutSeq] after the results
   double *out;          // kBfOutStride doubles: sum log F, Q over [loc_begin, loc_end), 1.0 if a factorisation failed, Q of (Bcur, Fcur)
   double *partials;     // scratch: 2 doubles per CTA (static kernels) or 4 per 32-location tile (dynamic tiles)
   unsigned int *ticket; // zero-initialised, self-resetting

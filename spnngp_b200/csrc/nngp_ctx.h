@@ -80,6 +80,7 @@ struct nngp_ctx {
     nngp::MaternConsts mc;
   } mat_cache[4];
   int mat_cache_next = 0;
+  double d_mat_nu[NNGP_MAX_BATCH] = {-1.0, -1.0, -1.0, -1.0};  // smoothness whose tables sit in d_mat[b]
 
   // Matern short series (matern_series.cuh): chosen per parameter set when phi^2/4 * pair_d2_q99 <= t_short_max(nu)
   int opt_matern_short = 1;      // nngp_set_option("matern_short", 0/1)
@@ -92,8 +93,22 @@ struct nngp_ctx {
   // results of nngp_bf_loglik / nngp_q_resid / nngp_q_forms are summed over the ranks on the device
   void *comm = nullptr;
   int comm_rank = 0, comm_size = 1;
-  double *d_red = nullptr;  // 3 * NNGP_MAX_BATCH doubles: kernel results, reduced in place
+  double *d_red = nullptr;  // kBfOutStride * NNGP_MAX_BATCH doubles: kernel results, reduced in place (NCCL path)
   double *h_red = nullptr;  // pinned copy
+
+  // MAILBOX (nngp_abi_misc.cu): how small results leave the device.  A ring of two slots per rank in mapped host memory;
+  // the kernel that finishes a reduction stores its numbers and then a sequence stamp straight into this rank's slot,
+  // the host polls the stamp -- no cudaMemcpy, no stream synchronisation.  With nngp_comm_init the ring lives in a
+  // POSIX shared-memory object registered by every rank of the node: each host reads ALL ranks' slots and adds them in
+  // rank order (deterministic, identical on every rank), which replaces ncclAllReduce + copy + sync for the 48..100
+  // bytes per iteration of a sharded fit.  nngp_set_option("reduce_nccl", 1) keeps the NCCL path (tested alternative).
+  double *mbox_h = nullptr;   // [2][mbox_ranks][kMboxSlotDoubles]
+  double *mbox_d = nullptr;   // device alias
+  size_t mbox_bytes = 0;
+  int mbox_ranks = 1, mbox_rank = 0;
+  bool mbox_shared = false;   // true: shm-backed (mbox_h came from mmap), false: cudaHostAlloc
+  int opt_reduce_nccl = 0;
+  unsigned long long seq = 0; // collective counter: the stamp of the most recent posting
 
   // timing
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -184,9 +199,27 @@ size_t tri_ids_offset(int m, long long nloc);
 cudaError_t tri_build_launch(const double2 *coords, const int *nnIndx, int m, int loc_begin, int loc_end, double *tri,
                              cudaStream_t stream);
 
+// nngp_abi_misc.cu: mailbox
+constexpr int kMboxSlotDoubles = 2304;  // [0] stamp of a generic posting, [8 ..] payload (B/F sets: 8 doubles each, own stamps)
+constexpr int kMboxPayload = 8;
+int mbox_local_init(nngp_ctx *c);
+void mbox_release(nngp_ctx *c);
+inline bool mbox_reduces(const nngp_ctx *c) { return c->comm == nullptr || (c->mbox_shared && !c->opt_reduce_nccl); }
+inline double *mbox_slot_dev(nngp_ctx *c, unsigned long long seq) {
+  return c->mbox_d + ((size_t)(seq & 1) * c->mbox_ranks + c->mbox_rank) * kMboxSlotDoubles;
+}
+// B/F form: waits for the stamps of `nbatch` result blocks of every rank, res[8 b + j] = sum over ranks (j < 4)
+int mbox_wait_sets(nngp_ctx *c, unsigned long long seq, int nbatch, double *res);
+// generic form: the device posts len doubles from d_src (a tiny kernel on the context stream); wait adds all ranks' copies
+int mbox_post_dev(nngp_ctx *c, const double *d_src, int len, unsigned long long seq);
+int mbox_wait_payload(nngp_ctx *c, unsigned long long seq, int len, double *sum);
+int mbox_host_allreduce(nngp_ctx *c, double *buf, int len);
+
 // q_kernels.cu
 cudaError_t resid_launch(const double *X, const double *y, const double *beta, int n, int p, double *r, int sms,
                          cudaStream_t stream);
+cudaError_t resid_launch_val(const double *X, const double *y, const double *beta_host, int n, int p, double *r, int sms,
+                             cudaStream_t stream);
 int q_resid_grid(int m, long long nloc, int sms);
 cudaError_t q_resid_launch(const double *B, const double *F, const int *nnIndx, const double *resid, int m,
                            int loc_begin, int loc_end, double *partials, double *out, int sms, cudaStream_t stream);

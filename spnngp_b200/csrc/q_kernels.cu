@@ -14,6 +14,21 @@
 
 namespace nngp {
 
+// beta travels as a kernel parameter when p <= kResidBetaMax: no host-to-device copy in front of every evaluation
+struct ResidBeta {
+  double b[kResidBetaMax];
+};
+__global__ void __launch_bounds__(256) resid_val_kernel(const double *__restrict__ X, const double *__restrict__ y,
+                                                        const __grid_constant__ ResidBeta beta, int n, int p,
+                                                        double *__restrict__ r) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double acc = 0.0;
+    for (int c = 0; c < p; ++c) acc = fma(__ldg(&X[(size_t)c * n + i]), beta.b[c], acc);
+    r[i] = acc - __ldg(&y[i]);
+  }
+}
+
 __global__ void __launch_bounds__(256) resid_kernel(const double *__restrict__ X, const double *__restrict__ y,
                                                     const double *__restrict__ beta, int n, int p,
                                                     double *__restrict__ r) {
@@ -258,6 +273,18 @@ cudaError_t resid_launch(const double *X, const double *y, const double *beta, i
   if (grid > sms * 8) grid = sms * 8;
   if (grid < 1) grid = 1;
   resid_kernel<<<grid, 256, 0, stream>>>(X, y, beta, n, p, r);
+  return cudaGetLastError();
+}
+
+// beta_host: p <= kResidBetaMax doubles on the host
+cudaError_t resid_launch_val(const double *X, const double *y, const double *beta_host, int n, int p, double *r, int sms,
+                             cudaStream_t stream) {
+  int grid = (n + 255) / 256;
+  if (grid > sms * 8) grid = sms * 8;
+  if (grid < 1) grid = 1;
+  ResidBeta b;
+  for (int c = 0; c < kResidBetaMax; ++c) b.b[c] = c < p ? beta_host[c] : 0.0;
+  resid_val_kernel<<<grid, 256, 0, stream>>>(X, y, b, n, p, r);
   return cudaGetLastError();
 }
 

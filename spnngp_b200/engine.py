@@ -7,6 +7,8 @@ from __future__ import annotations
 
 import ctypes as C
 
+import os
+
 import numpy as np
 
 from . import _lib
@@ -90,7 +92,7 @@ class Engine:
     def set_data(self, coords, nnIndx, nnIndxLU, X, y, m, loc_range=None):
         coords = colmajor(coords)
         n = coords.size // 2
-        nnIndx = _i32(nnIndx)
+        nnIndx = _i32(nnIndx) if nnIndx is not None else None  # None: prediction-only use (sites, X, y)
         lu = _i32(nnIndxLU) if nnIndxLU is not None else None
         if X is None:
             p = 0; Xf = None; yf = None
@@ -99,7 +101,7 @@ class Engine:
             p = X.shape[1]
             Xf = colmajor(X); yf = _f64(y)
         lo, hi = loc_range if loc_range is not None else (0, n)
-        self._check(self.lib.nngp_set_data(self.h, n, m, p, _dp(coords), _ip(nnIndx), _ip(lu) if lu is not None else None,
+        self._check(self.lib.nngp_set_data(self.h, n, m, p, _dp(coords), _ip(nnIndx) if nnIndx is not None else None, _ip(lu) if lu is not None else None,
                                            _dp(Xf) if Xf is not None else None, _dp(yf) if yf is not None else None,
                                            lo, hi))
         self.n, self.m, self.p = n, m, p
@@ -121,6 +123,16 @@ class Engine:
         sl = _i32(slots) if slots is not None else None
         out = np.zeros((nb, 2))
         self._check(self.lib.nngp_bf_loglik(self.h, cov, nb, _dp(th), bp, _ip(sl) if sl is not None else None, _dp(out)))
+        return out
+
+    def bf_loglik_cur(self, cov, theta, beta, slot_new, slot_cur):
+        """One launch of the sampler's step (nngp_bf_loglik_cur): solves `theta` into slot_new and returns
+        (sum log F(theta), Q(theta), Q of the factors resident in slot_cur), all with r = X beta - y."""
+        th = np.zeros(4); t = np.asarray(theta, dtype=np.float64).ravel(); th[: t.size] = t
+        b = _f64(beta)
+        assert b.size == self.p
+        out = np.zeros(3)
+        self._check(self.lib.nngp_bf_loglik_cur(self.h, cov, _dp(th), _dp(b), int(slot_new), int(slot_cur), _dp(out)))
         return out
 
     def bf_loglik_vec(self, cov, thetas, u, slots=None):
@@ -164,12 +176,19 @@ class Engine:
         self._check(self.lib.nngp_get_bf(self.h, slot, _dp(B), _dp(F)))
         return B, F
 
-    def comm_init_from_torch(self, group=None):
-        """Create the engine's NCCL communicator over the ranks of torch.distributed's default (or given)
-        group: rank 0 makes the id, torch broadcasts it.  Afterwards likelihood results are rank-summed."""
+    def comm_init_from_torch(self, group=None, nccl=True):
+        """Join the ranks of torch.distributed's default (or given) group: afterwards likelihood results are
+        rank-summed.  nccl=True: the engine's NCCL communicator plus the shared-memory mailbox (nngp_comm_init; rank 0
+        makes the id, torch broadcasts it).  nccl=False: the mailbox alone (nngp_comm_init_local) -- the ranks of one
+        node, which may even share a GPU; works over a gloo group."""
         import torch.distributed as dist
         world = dist.get_world_size(group); rank = dist.get_rank(group)
         if world == 1:
+            return
+        if not nccl:
+            obj = [os.urandom(128) if rank == 0 else None]
+            dist.broadcast_object_list(obj, src=0, group=group)
+            self._check(self.lib.nngp_comm_init_local(self.h, obj[0], rank, world))
             return
         buf = C.create_string_buffer(128)
         if rank == 0:
@@ -203,7 +222,7 @@ class Engine:
         return int(self.lib.nngp_launch_count(self.h))
 
     # ---- entry points ------------------------------------------------------------------------------
-    def rnngp(self, cov, sigmaSqIG, tauSqIG, phiUnif, nuUnif, starting, tuning, n_samples, rnorm, runif, mode=0,
+    def rnngp(self, cov, sigmaSqIG, tauSqIG, phiUnif, nuUnif, starting, tuning, n_samples, rnorm, runif, mode=1,
               verbose=False, n_report=100, printer=None, allreduce=None, rep_indx=None):
         """Response-model sampler on the data given to set_data (reference `rNNGP`, src/rNNGP.cpp:105).
         rnorm/runif: ctypes function pointers or Python callables (mu, sd) / (a, b).

@@ -54,8 +54,11 @@ void print_hook(const char *msg) { Rprintf("%s", msg); }
 void interrupt_hook(void) { R_CheckUserInterrupt(); }
 
 int sampler_mode() {
-  const char *e = getenv("NNGP_SAMPLER_MODE");  // 0 reference-faithful (default), 1 double-buffered
-  return (e && e[0] == '1') ? 1 : 0;
+  // 1 (default): double-buffered -- B, F of the current theta stay resident, one launch per iteration solves the
+  // candidate and re-forms Q of the current theta; 0: reference-faithful -- both solved anew every iteration
+  // (src/rNNGP.cpp:297-339).  Identical chains either way (tests/test_gpu_golden_and_glue.py).
+  const char *e = getenv("NNGP_SAMPLER_MODE");
+  return (e && e[0] == '0') ? 0 : 1;
 }
 
 SEXP named_list(const std::vector<const char *> &names, const std::vector<SEXP> &vals) {

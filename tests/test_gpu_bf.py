@@ -277,3 +277,26 @@ def test_matern_short_series_variant(engine, port, nu, m):
         assert np.array_equal(mixed[0], a[0]) and np.array_equal(mixed[1], b[0])
     finally:
         engine.set_option("matern_short", 1)
+
+
+@pytest.mark.parametrize("cov,theta,m", [(0, [5.0, 1.0, 6.0], 15), (2, [5.0, 1.0, 6.0, 0.75], 15), (1, [5.0, 1.0, 6.0], 9),
+                                         (3, [5.0, 1.0, 6.0], 30)])
+def test_fused_current_q_launch(engine, port, cov, theta, m):
+    """nngp_bf_loglik_cur: one launch returns the candidate's (logDet, Q) and Q of the factors resident in the other
+    slot -- equal to nngp_bf_loglik of the candidate and nngp_q_resid of the resident slot (src/rNNGP.cpp:297-306,
+    src/util.cpp:261-280); m = 30 takes the kernels without the fused path (falls back to the separate pass)."""
+    n = 5000
+    prob = make_problem(n, m, seed=11, port=port, domain=1.0)
+    engine.set_data(prob["coords"], prob["nnIndx"], prob["nnIndxLU"], prob["X"], prob["y"], m)
+    cand = list(theta); cand[0] *= 0.9; cand[2] *= 1.1
+    beta = prob["beta"] * 1.02
+    engine.bf_loglik(cov, [theta], [prob["beta"]], slots=[0])          # resident: theta in slot 0
+    got = engine.bf_loglik_cur(cov, cand, beta, 1, 0)
+    want_c = engine.bf_loglik(cov, [cand], [beta], slots=[1])[0]
+    want_q = engine.q_resid(0, beta)
+    assert np.allclose(got[:2], want_c, rtol=1e-13)
+    assert abs(got[2] - want_q) <= 1e-12 * abs(want_q)
+    r = prob["X"] @ beta - prob["y"]
+    Bo, Fo, ld, info = port.update_bf(prob["coords"], prob["nnIndx"], prob["nnIndxLU"], n, m, theta, cov)
+    Qo = port.q(Bo, Fo, r, r, n, prob["nnIndx"], prob["nnIndxLU"])
+    assert abs(got[2] - Qo) <= 1e-10 * abs(Qo)
