@@ -739,8 +739,14 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
 template <int COV>
 static cudaError_t tri_launch_one(const BfLaunch &P, int grid_x, cudaStream_t stream) {
   const TriGeom G = tri_geometry(P.m);
-  cudaError_t e = cudaFuncSetAttribute(bf_tri_kernel<COV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
-  if (e != cudaSuccess) return e;
+  static bool configured[64] = {};  // the attribute is per device; setting it costs a few microseconds of every launch
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(bf_tri_kernel<COV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
   dim3 grid(grid_x, P.nbatch, 1);
   bf_tri_kernel<COV><<<grid, kTriThreads, G.smem_bytes, stream>>>(P);
   return cudaGetLastError();

@@ -6,6 +6,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <chrono>
+
 #include <mutex>
 #include <string>
 #include <vector>
@@ -441,8 +443,8 @@ static int prepare_bf(nngp_ctx *c, int cov, int nbatch, const double *theta, con
   P->loc_begin = c->loc_begin;
   P->loc_end = c->loc_end;
   P->nbatch = nbatch;
-  int *fail_dev = nullptr;
-  NNGP_CUDA(c, cudaHostGetDevicePointer((void **)&fail_dev, c->h_fail, 0));
+  if (!c->h_fail_dev) NNGP_CUDA(c, cudaHostGetDevicePointer((void **)&c->h_fail_dev, c->h_fail, 0));
+  int *fail_dev = c->h_fail_dev;
   // results go to this rank's mailbox slot, stamped with a fresh sequence number (NCCL path: to d_red, reduced there)
   const unsigned long long seq = ++c->seq;
   double *out_dev = mbox_slot_dev(c, seq) + kMboxPayload;
@@ -562,7 +564,15 @@ static void share_resid(nngp_ctx *c, BfLaunch *P) {
 }
 
 // after the launch: sum over ranks if sharded, one stream sync, unpack (logDet, Q) per set, report failures
+static double wall_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 static int finish_bf(nngp_ctx *c, int nbatch, bool have_q, double *out) {
+  const double t_wait0 = wall_s();
+  struct WaitClock {
+    nngp_ctx *c;
+    double t0;
+    ~WaitClock() { c->trace_wait_s += wall_s() - t0; }
+  } wait_clock{c, t_wait0};
   double sums[kBfOutStride * NNGP_MAX_BATCH];
   const double *res = sums;
   if (mbox_reduces(c)) {  // poll the stamps of every rank's result blocks, add them in rank order
@@ -609,6 +619,7 @@ static int reduce_small(nngp_ctx *c, double *d_src, int len, double *host) {
 int nngp_bf_loglik(nngp_ctx *c, int cov, int nbatch, const double *theta, const double *beta, const int *slots,
                    double *out) {
   if (!c || !theta || !out) return NNGP_EINVAL;
+  const double t_enq0 = wall_s();
   NNGP_CUDA(c, cudaSetDevice(c->device));
   BfLaunch P;
   int grid = 0;
@@ -617,6 +628,7 @@ int nngp_bf_loglik(nngp_ctx *c, int cov, int nbatch, const double *theta, const 
   share_resid(c, &P);
   rc = enqueue_bf(c, cov, P, grid, beta != nullptr);
   if (rc) return rc;
+  c->trace_enqueue_s += wall_s() - t_enq0;
   return finish_bf(c, nbatch, beta != nullptr, out);
 }
 
@@ -624,6 +636,7 @@ int nngp_bf_loglik_cur(nngp_ctx *c, int cov, const double *theta, const double *
                        double *out) {
   if (!c || !theta || !beta || !out || slot_new < 0 || slot_new > 1 || slot_cur < 0 || slot_cur > 1 || slot_new == slot_cur)
     return NNGP_EINVAL;
+  const double t_enq0 = wall_s();
   NNGP_CUDA(c, cudaSetDevice(c->device));
   BfLaunch P;
   int grid = 0;
@@ -631,6 +644,7 @@ int nngp_bf_loglik_cur(nngp_ctx *c, int cov, const double *theta, const double *
   if (rc) return rc;
   rc = enqueue_bf(c, cov, P, grid, true);
   if (rc) return rc;
+  c->trace_enqueue_s += wall_s() - t_enq0;
   double o2[2];
   rc = finish_bf(c, 1, true, o2);
   if (rc) return rc;
@@ -824,9 +838,16 @@ int nngp_rnngp(nngp_ctx *c, const nngp_rnngp_args *a, double *betaSamples, doubl
   double logDetCur = out[0];
   if (a->allreduce) a->allreduce(&logDetCur, 1, a->allreduce_user);
 
+  // NNGP_TRACE_ITER=1: where one iteration's wall time goes (host clock; printed once per call on stderr)
+  const bool trace_iter = getenv("NNGP_TRACE_ITER") != nullptr;
+  double tr_forms = 0.0, tr_host = 0.0, tr_enqueue = 0.0, tr_wait = 0.0, tr_tail = 0.0;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  c->trace_enqueue_s = c->trace_wait_s = 0.0;
+
   bool thetaUpdate = true;
   int accept = 0, batchAccept = 0, status = 0, repCnt = 0;
   for (int s = 0; s < a->nSamples; s++) {
+    const double t_it0 = trace_iter ? now() : 0.0;
     if (thetaUpdate) {  // src/rNNGP.cpp:274-292
       thetaUpdate = false;
       rc = nngp_q_forms(c, cur, S.data());
@@ -841,6 +862,7 @@ int nngp_rnngp(nngp_ctx *c, const nngp_rnngp_args *a, double *betaSamples, doubl
       hl::symv(tmp_pp.data(), p, tmp_p.data(), mean.data());
       if (hl::chol(tmp_pp.data(), p)) return ctx_fail(c, NNGP_EINVAL, "c++ error: dpotrf failed (inverse of X'C^-1X)");
     }
+    const double t_it1 = trace_iter ? now() : 0.0;
     // beta ~ N(mean, (X'C^-1X)^-1): mvrnorm, src/util.cpp:28-41
     for (int i = 0; i < p; i++) beta[i] = a->rnorm(0.0, 1.0);
     hl::trmv_lower(tmp_pp.data(), p, beta.data());
@@ -862,6 +884,8 @@ int nngp_rnngp(nngp_ctx *c, const nngp_rnngp_args *a, double *betaSamples, doubl
       cand[3] = logit_inv_(a->rnorm(logit_(theta[3], a->nuUnif[0], a->nuUnif[1]), tuning[3]), a->nuUnif[0], a->nuUnif[1]);
 
     double QCur, logDetCand, QCand;
+    const double t_it2 = trace_iter ? now() : 0.0;
+    const double e0 = c->trace_enqueue_s, w0 = c->trace_wait_s;
     if (a->mode == 0) {
       // reference-faithful: re-solve the current theta and solve the candidate, one launch
       double th2[8], b2[2 * 64];
@@ -888,6 +912,7 @@ int nngp_rnngp(nngp_ctx *c, const nngp_rnngp_args *a, double *betaSamples, doubl
       if (a->allreduce) a->allreduce(red, 4, a->allreduce_user);
       QCur = red[1]; logDetCand = red[2]; QCand = red[3];
     }
+    const double t_it3 = trace_iter ? now() : 0.0;
     if (rep) {  // B, F of the current theta are in slot `cur` in both modes
       rc = rep_draw(c, cur, beta.data(), c->h_z, a->repSamples + (size_t)repCnt * c->n);
       if (rc) return rc;
@@ -918,6 +943,21 @@ int nngp_rnngp(nngp_ctx *c, const nngp_rnngp_args *a, double *betaSamples, doubl
     }
     status++;
     if (a->interrupt) a->interrupt();
+    if (trace_iter) {
+      tr_forms += t_it1 - t_it0;
+      tr_host += t_it2 - t_it1;
+      tr_enqueue += c->trace_enqueue_s - e0;
+      tr_wait += c->trace_wait_s - w0;
+      tr_tail += now() - t_it3;
+    }
+  }
+  if (trace_iter && a->nSamples > 0) {
+    const double k = 1e6 / a->nSamples;
+    fprintf(stderr,
+            "{\"trace\": \"nngp_rnngp\", \"rank\": %d, \"ranks\": %d, \"iterations\": %d, \"accepted\": %d, \"us_per_iteration\": "
+            "{\"q_forms_on_accepts\": %.1f, \"host_draws\": %.1f, \"prepare_and_launch\": %.1f, \"wait_for_stamps\": %.1f, "
+            "\"accept_and_store\": %.1f}}\n",
+            c->comm_rank, c->comm_size, a->nSamples, accept, tr_forms * k, tr_host * k, tr_enqueue * k, tr_wait * k, tr_tail * k);
   }
   if (a->verbose && a->print) {
     snprintf(line, sizeof line, "Sampled: %i of %i, %3.2f%%\n", a->nSamples, a->nSamples, 100.0); a->print(line);

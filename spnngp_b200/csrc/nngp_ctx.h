@@ -62,6 +62,7 @@ struct nngp_ctx {
   // pinned host staging
   double *h_out = nullptr;
   int *h_fail = nullptr;
+  int *h_fail_dev = nullptr;  // device alias of h_fail
   double *h_beta = nullptr;
   size_t h_beta_cap = 0;
   // replicated-data draws (rep_kernels.cu): level structure of the neighbour graph, built on first use
@@ -109,6 +110,7 @@ struct nngp_ctx {
   bool mbox_shared = false;   // true: shm-backed (mbox_h came from mmap), false: cudaHostAlloc
   int opt_reduce_nccl = 0;
   unsigned long long seq = 0; // collective counter: the stamp of the most recent posting
+  double trace_enqueue_s = 0.0, trace_wait_s = 0.0;  // host seconds spent preparing + launching / waiting for stamps
 
   // timing
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
