@@ -206,6 +206,7 @@ void nngp_destroy(nngp_ctx *c) {
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   delete c->stager;
+  delete c->stager2;
   if (c->d_rep_perm) cudaFree(c->d_rep_perm);
   if (c->d_rep_levoff) cudaFree(c->d_rep_levoff);
   if (c->d_rep_z) cudaFree(c->d_rep_z);

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <map>
+#include <thread>
 #include <vector>
 
 #include "host_linalg.h"
@@ -155,7 +156,7 @@ int nngp_rnngp_predict(nngp_ctx *c, int cov, int q, const double *X0, const doub
     }
   }
 
-  Dev d_beta, d_samples, d_z, d_y0;
+  Dev d_beta, d_samples, d_z;
   NNGP_CUDA(c, d_beta.alloc((size_t)p * S * sizeof(double)));
   NNGP_CUDA(c, cudaStreamSynchronize(c->stream));  // pool blocks are recycled in stream order; the copies below are not
   NNGP_CUDA(c, cudaMemcpy(d_beta.p, betaSamples, (size_t)p * S * sizeof(double), cudaMemcpyHostToDevice));
@@ -172,21 +173,35 @@ int nngp_rnngp_predict(nngp_ctx *c, int cov, int q, const double *X0, const doub
   long long cs_max = ((long long)1 << 30) / ((long long)8 * S);
   if (cs_max < 1024) cs_max = 1024;
   if (cs_max > 1 << 20) cs_max = 1 << 20;
-  for (int i0 = site_begin; i0 < site_end; i0 += (int)cs_max) {
+  // Full duplex: the draws of chunk k leave through a second pinned ring on their own thread while the normals of
+  // chunk k + 1 arrive and its solves run (two result buffers); src/rNNGPPredict.cpp:131-137,176-181 are these two
+  // q x S streams, and they, not the solves, bound a 10^6 x 1,000 job.
+  if (!c->stager) {
+    c->stager = new HostStager();
+    NNGP_CUDA(c, c->stager->init(c->device));
+  }
+  if (!c->stager2) {
+    c->stager2 = new HostStager();
+    NNGP_CUDA(c, c->stager2->init(c->device));
+  }
+  Dev d_y0b[2];
+  std::thread dl;
+  cudaError_t dl_err = cudaSuccess;
+  struct Joiner {  // never leave the download thread running behind an early return
+    std::thread &t;
+    ~Joiner() { if (t.joinable()) t.join(); }
+  } joiner{dl};
+  int kchunk = 0;
+  for (int i0 = site_begin; i0 < site_end; i0 += (int)cs_max, ++kchunk) {
     const int i1 = (int)std::min<long long>(site_end, (long long)i0 + cs_max);
     const int cs = i1 - i0;
+    Dev &d_y0 = d_y0b[kchunk & 1];
     SiteChunk ch;
     int rc = upload_chunk(c, ch, q, i0, i1, X0, coords0, nnIndx0);
     if (rc) return rc;
     NNGP_CUDA(c, d_z.alloc((size_t)cs * S * sizeof(double)));
-    NNGP_CUDA(c, d_y0.alloc((size_t)cs * S * sizeof(double)));
+    NNGP_CUDA(c, d_y0.alloc((size_t)cs * S * sizeof(double)));  // its previous content left with the download of chunk k - 2
     NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
-    // the normals in and the draws out go through the threaded pinned ring (host_stage.h): a q x S job is
-    // dominated by these two transfers, not by the solves
-    if (!c->stager) {
-      c->stager = new HostStager();
-      NNGP_CUDA(c, c->stager->init(c->device));
-    }
     {
       std::vector<StageJob> up{{StageJob::RAW, d_z.p, z + (size_t)i0 * S, (size_t)cs * S * sizeof(double), 0}};
       NNGP_CUDA(c, c->stager->run(up, nullptr));
@@ -200,14 +215,20 @@ int nngp_rnngp_predict(nngp_ctx *c, int cov, int q, const double *X0, const doub
       c->launches++;
     }
     NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (dl.joinable()) dl.join();  // the download of chunk k - 1 ran alongside this chunk's upload and solves
+    NNGP_CUDA(c, dl_err);
     // y0 is q x S column-major on the host: column s of the chunk is contiguous on both sides
-    {
+    const double *src = d_y0.as<double>();
+    HostStager *st2 = c->stager2;
+    dl = std::thread([=, &dl_err] {
       std::vector<StageJob> down((size_t)S);
       for (int s = 0; s < S; s++)
-        down[s] = {StageJob::RAW, y0 + (size_t)s * q + i0, d_y0.as<double>() + (size_t)s * cs, (size_t)cs * sizeof(double), 0};
-      NNGP_CUDA(c, c->stager->run_d2h(down));
-    }
+        down[s] = {StageJob::RAW, y0 + (size_t)s * q + i0, src + (size_t)s * cs, (size_t)cs * sizeof(double), 0};
+      dl_err = st2->run_d2h(down);
+    });
   }
+  if (dl.joinable()) dl.join();
+  NNGP_CUDA(c, dl_err);
   return NNGP_OK;
 }
 

@@ -73,6 +73,7 @@ struct nngp_ctx {
   double *h_z = nullptr;  // pinned, n doubles
   size_t h_z_cap = 0;
   nngp::HostStager *stager = nullptr;  // pinned upload ring of nngp_set_data (host_stage.h)
+  nngp::HostStager *stager2 = nullptr; // second ring: downloads that overlap uploads (nngp_rnngp_predict)
   size_t cap[16] = {};  // capacities (bytes) of the grow-only model buffers, see nngp_set_data
   nngp::MaternConsts *h_mat = nullptr;
   // last few prepared smoothness values (the sampler re-evaluates its current theta every iteration)

@@ -32,10 +32,19 @@ def by_x(c):
 
 
 if "kfold" in which:  # ---- configs[1] ----------------------------------------------------------------------------
-    n, m, k_fold = 188717, 15, 5
-    c = by_x(rng.random((n, 2)) * np.array([21.5, 17.0]))
-    X = np.column_stack([np.ones(n), rng.standard_normal(n)])
-    y = X @ np.array([1.0, 5.0]) + 2.0 * np.sin(c[:, 0]) * np.cos(c[:, 1]) + rng.standard_normal(n)
+    m, k_fold = 15, 5
+    bcef = os.path.join(ROOT, "data", "bcef.npz")
+    real = os.path.exists(bcef)
+    if real:  # the reference's data set (tools/read_bcef.py): FCH ~ PTC on all 188,717 rows, ordered by x
+        d = np.load(bcef)
+        c = np.column_stack([d["x"], d["y"]]); o = np.argsort(c[:, 0], kind="stable"); c = c[o]
+        y = d["FCH"][o]; X = np.column_stack([np.ones(len(y)), d["PTC"][o]])
+        n = len(y)
+    else:
+        n = 188717
+        c = by_x(rng.random((n, 2)) * np.array([21.5, 17.0]))
+        X = np.column_stack([np.ones(n), rng.standard_normal(n)])
+        y = X @ np.array([1.0, 5.0]) + 2.0 * np.sin(c[:, 0]) * np.cos(c[:, 1]) + rng.standard_normal(n)
     ta = np.array([[ph, al] for ph in (0.3, 0.6, 1.5, 3, 6) for al in (0.05, 0.1, 0.25, 0.5, 1)]).T
     n_ho = n // k_fold
     ho = np.stack([np.sort(rng.choice(n, n_ho, replace=False)) for _ in range(k_fold)]).astype(np.int32)
@@ -49,9 +58,12 @@ if "kfold" in which:  # ---- configs[1] ----------------------------------------
     t_fit, fit = timed(lambda: eng.cnngp(0, ta[:, best:best + 1], ig))
     out["conj_kfold"] = dict(n=n, m=m, g=25, k_fold=k_fold, n_ho=n_ho, kfold_s=t, final_search_s=t_nn, final_fit_s=t_fit,
                              best_set=best, best_theta_alpha=ta[:, best].tolist(), crps_best=float(scores[best, 1]),
+                             rmspe_best=float(scores[best, 0]), beta_hat=np.asarray(fit["beta_hat"]).ravel().tolist(),
                              fits_per_s=25 * k_fold / t,
-                             note="synthetic sites on BCEF's 21.5 x 17 km extent; exponential; 125 fits of ~151k "
-                                  "locations + 125 x 37.7k hold-out predictions, scores formed on the device")
+                             data="BCEF (data/BCEF.rda of the reference package, FCH ~ PTC, all 188,717 rows)" if real else
+                                  "synthetic sites on BCEF's 21.5 x 17 km extent",
+                             note="exponential; 125 fits of ~151k locations + 125 x 37.7k hold-out predictions, scores "
+                                  "formed on the device")
     print("kfold", out["conj_kfold"], flush=True)
 
 if "predict" in which:  # ---- configs[3] --------------------------------------------------------------------------
