@@ -93,6 +93,7 @@ int site_solve(nngp_ctx *c, int cov, const double *t, SiteChunk &ch) {
     matern_series_params(c->h_mat[0], &th.ms);
     matern_set_phi(&th.ms, t[2]);
     NNGP_CUDA(c, cudaMemcpyAsync(c->d_mat, c->h_mat, sizeof(MaternConsts), cudaMemcpyHostToDevice, c->stream));
+    c->d_mat_nu[0] = t[3];  // what slot 0 of the device tables holds now (prepare_bf skips uploads it believes current)
     th.mat = c->d_mat;
   }
   double *out_dev = nullptr;
@@ -184,6 +185,8 @@ int nngp_rnngp_predict(nngp_ctx *c, int cov, int q, const double *X0, const doub
     c->stager2 = new HostStager();
     NNGP_CUDA(c, c->stager2->init(c->device));
   }
+  const char *dup_env = getenv("NNGP_PREDICT_DUPLEX");
+  const bool duplex = !(dup_env && dup_env[0] == '0');
   Dev d_y0b[2];
   std::thread dl;
   cudaError_t dl_err = cudaSuccess;
@@ -226,6 +229,7 @@ int nngp_rnngp_predict(nngp_ctx *c, int cov, int q, const double *X0, const doub
         down[s] = {StageJob::RAW, y0 + (size_t)s * q + i0, src + (size_t)s * cs, (size_t)cs * sizeof(double), 0};
       dl_err = st2->run_d2h(down);
     });
+    if (!duplex) dl.join();  // NNGP_PREDICT_DUPLEX=0: one direction at a time (A/B switch)
   }
   if (dl.joinable()) dl.join();
   NNGP_CUDA(c, dl_err);
