@@ -174,6 +174,10 @@ int nngp_rnngp_predict(nngp_ctx *c, int cov, int q, const double *X0, const doub
   long long cs_max = ((long long)1 << 30) / ((long long)8 * S);
   if (cs_max < 1024) cs_max = 1024;
   if (cs_max > 1 << 20) cs_max = 1 << 20;
+  if (const char *e = getenv("NNGP_PREDICT_CHUNK")) {  // tests: many small chunks
+    const long long v = atoll(e);
+    if (v >= 32 && v < cs_max) cs_max = v;
+  }
   // Full duplex: the draws of chunk k leave through a second pinned ring on their own thread while the normals of
   // chunk k + 1 arrive and its solves run (two result buffers); src/rNNGPPredict.cpp:131-137,176-181 are these two
   // q x S streams, and they, not the solves, bound a 10^6 x 1,000 job.

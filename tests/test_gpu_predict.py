@@ -1,4 +1,6 @@
 """GPU parity: kNN + solve prediction paths (rNNGPPredict, cNNGP) through the C ABI vs the CPU oracle."""
+import os
+
 import numpy as np
 import pytest
 
@@ -41,6 +43,39 @@ def test_rnngp_predict_parity(engine, port, cov, m):
     a = engine.rnngp_predict(cov, X0, coords0, nn0, beta, theta, z, site_range=(0, 100))
     b = engine.rnngp_predict(cov, X0, coords0, nn0, beta, theta, z, site_range=(100, q))
     assert np.array_equal(a[:100], got[:100]) and np.array_equal(b[100:], got[100:])
+    # prediction-only context: no neighbour structure of the fit is needed (the C ABI's nnIndx = NULL mode)
+    engine.set_data(prob["coords"], None, None, prob["X"], prob["y"], m)
+    assert np.array_equal(engine.rnngp_predict(cov, X0, coords0, nn0, beta, theta, z), got)
+    with pytest.raises(Exception):
+        engine.bf_loglik(cov, [theta[:, 0]], None)  # a likelihood needs the neighbours
+
+
+def test_rnngp_predict_many_chunks_full_duplex(engine, port):
+    """Several site chunks (NNGP_PREDICT_CHUNK = 512 sites): the overlapped download of chunk k with the upload
+    and solves of chunk k + 1 (two result buffers, second pinned ring) leaves every draw where the serial path puts it."""
+    rng = np.random.default_rng(9)
+    m, q, S = 10, 3000, 64
+    prob = make_problem(1200, m, seed=33, port=port, domain=0.5)
+    coords0 = rng.random((q, 2)) * 0.5
+    X0 = np.column_stack([np.ones(q), rng.standard_normal(q)])
+    nn0 = port.nn_query(prob["coords"], coords0, m)
+    theta = np.tile(np.array([[5.0], [1.0], [6.0]]), (1, S)); theta[2, S // 2:] = 7.0
+    os.environ["NNGP_PREDICT_CHUNK"] = "512"
+    beta = np.array([[1.0], [5.0]]) + 0.1 * rng.standard_normal((2, S))
+    z = rng.standard_normal(q * S)
+    engine.set_data(prob["coords"], prob["nnIndx"], prob["nnIndxLU"], prob["X"], prob["y"], m)
+    try:
+        got = engine.rnngp_predict(0, X0, coords0, nn0, beta, theta, z)
+        os.environ["NNGP_PREDICT_DUPLEX"] = "0"
+        serial = engine.rnngp_predict(0, X0, coords0, nn0, beta, theta, z)
+    finally:
+        os.environ.pop("NNGP_PREDICT_DUPLEX", None)
+        os.environ.pop("NNGP_PREDICT_CHUNK", None)
+    assert np.array_equal(got, serial)
+    sub = slice(0, 40)  # and against the oracle on a slice of the samples
+    ref, st = port.predict(prob["X"], prob["y"], prob["coords"], m, X0, coords0, nn0, beta[:, sub], theta[:, sub], 0,
+                           z.reshape(q, S)[:, sub].ravel())
+    assert st == 0 and np.max(np.abs(got[:, sub] - ref)) < 1e-10 * np.abs(ref).max()
 
 
 @pytest.mark.parametrize("cov,m", [(0, 15), (2, 10), (3, 20)])
