@@ -532,7 +532,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=1000000)
+    ap.add_argument("--n", "--locations", type=int, default=1000000)
     ap.add_argument("--m", type=int, default=15)
     ap.add_argument("--cov", default="matern", choices=list(COV))
     ap.add_argument("--no-parity", action="store_true", help="skip the N > 1 self-check against the unsharded engine")

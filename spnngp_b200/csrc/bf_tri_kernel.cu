@@ -48,36 +48,43 @@ namespace nngp {
 constexpr int kTriMaxM = 26;       // two stages still fit shared memory
 constexpr int kTriMaxStages = 6;
 constexpr int kTriThreads = 384;
-constexpr int kTriProducers = 8;
+constexpr int kTriProducers = 8;  // at most (seven when the loader takes warp 4)
+template <int COV>
+constexpr bool kTriWant4 = !(COV == 2 || COV == 4);  // Matern keeps three consumers and eight producers
 constexpr int kTriTabBytes = (32 + 128) * 8;
-constexpr int kTriBarBytes = 512;  // 3 x 6 mbarriers, then the tile ring (6 long long)
+constexpr int kTriBarBytes = 512;  // 4 x 6 mbarriers, then the tile ring (6 long long)
 
 // Shared-memory geometry of the kernel for a given m (bytes; every region is a whole number of 256-byte rows).
 struct TriGeom {
-  int off_cv, off_a, off_rr, off_bc, stage_bytes;  // within a stage: c -> y -> weights | packed strict lower triangle |
-                                                   // residuals of the neighbours, own in row m | weights of the current theta
-  int cons_bytes;                                  // per consumer: 1/diag rows, weight staging [lane][k]
+  int off_cv, off_a, off_rr, stage_bytes;  // within a stage: c -> y -> weights | packed strict lower triangle |
+                                           // residuals of the neighbours, own in row m
+  int cons_bytes;                          // per consumer: 1/diag rows during the solve, then the weight staging [lane][k]
   int S, NC;
   int off_cons, off_tab, off_bar, smem_bytes;
 };
-__host__ __device__ inline TriGeom tri_geometry(int m) {
+// want4: four consumers when six stages fit (models whose consumers are the critical path); the loader then moves to
+// warp 4 and seven producer warps remain.
+__host__ __device__ inline TriGeom tri_geometry(int m, bool want4) {
   TriGeom g;
   const int ne = m * (m - 1) / 2;
   g.off_cv = 0;
   g.off_a = m * 256;
   g.off_rr = g.off_a + ne * 256;
-  g.off_bc = g.off_rr + (m + 1) * 256;
-  g.stage_bytes = g.off_bc + m * 256;
-  g.cons_bytes = 2 * m * 256;
+  g.stage_bytes = g.off_rr + (m + 1) * 256;
+  g.cons_bytes = m * 256;
   const int avail = 227 * 1024 - kTriTabBytes - kTriBarBytes - 1024;  // 1 KB: the kernel's static shared memory
-  g.NC = 3;
-  g.S = (avail - 3 * g.cons_bytes) / g.stage_bytes;
-  if (g.S < 5) {
-    g.NC = 2;
-    g.S = (avail - 2 * g.cons_bytes) / g.stage_bytes;
-    if (g.S < 4) {
-      g.NC = 1;
-      g.S = (avail - g.cons_bytes) / g.stage_bytes;
+  g.NC = 4;
+  g.S = (avail - 4 * g.cons_bytes) / g.stage_bytes;
+  if (!want4 || g.S < 6) {
+    g.NC = 3;
+    g.S = (avail - 3 * g.cons_bytes) / g.stage_bytes;
+    if (g.S < 5) {
+      g.NC = 2;
+      g.S = (avail - 2 * g.cons_bytes) / g.stage_bytes;
+      if (g.S < 4) {
+        g.NC = 1;
+        g.S = (avail - g.cons_bytes) / g.stage_bytes;
+      }
     }
   }
   if (g.S > kTriMaxStages) g.S = kTriMaxStages;
@@ -395,8 +402,9 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
   const BfTheta &th = P.th[blockIdx.y];
   const int m = P.m;
   const int ne = m * (m - 1) / 2;
-  const TriGeom G = tri_geometry(m);
+  const TriGeom G = tri_geometry(m, P.tri_want4 != 0);
   const int S = G.S, NC = G.NC;
+  const int loader_warp = (NC == 4) ? 4 : 3, first_producer = loader_warp + 1, nprod = 12 - first_producer;
   const double *__restrict__ resid = th.resid;
   const bool with_cur = th.Bcur != nullptr && resid != nullptr;
   const long long nloc = (long long)P.loc_end - P.loc_begin;
@@ -406,7 +414,8 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
   auto bar_full = [&](int s) { return bar0 + 8u * s; };
   auto bar_built = [&](int s) { return bar0 + 8u * (kTriMaxStages + s); };
   auto bar_empty = [&](int s) { return bar0 + 8u * (2 * kTriMaxStages + s); };
-  volatile long long *ring = reinterpret_cast<volatile long long *>(smem + G.off_bar + 8 * 3 * kTriMaxStages);
+  auto bar_rr = [&](int s) { return bar0 + 8u * (3 * kTriMaxStages + s); };
+  volatile long long *ring = reinterpret_cast<volatile long long *>(smem + G.off_bar + 8 * 4 * kTriMaxStages);
   double *s_tab = reinterpret_cast<double *>(smem + G.off_tab);
   __shared__ double red[3][12];
   __shared__ int last_flag;
@@ -415,29 +424,42 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
   // ---- one-time setup ---------------------------------------------------------------------------------
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(bar_full(s), 1 + 32);            // expect_tx arrival of the loader's lane 0 + 32 cp.async arrivals
-      mbar_init(bar_built(s), kTriProducers);    // one arrival per producer warp
+      mbar_init(bar_full(s), 1);                 // expect_tx arrival of the loader's lane 0: the distances have landed
+      mbar_init(bar_rr(s), 32);                  // 32 cp.async arrivals: the residual gathers have landed -- a barrier of
+                                                 // their own, only the consumer needs them: behind bar_full their L2
+                                                 // latency sat on the producers' critical path (spherical 0.47 -> ms)
+      mbar_init(bar_built(s), nprod);            // one arrival per producer warp
       mbar_init(bar_empty(s), 1);                // the consumer
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     // Shares of the producer warps, so that the four schedulers carry equal FP64 work: warp w issues on scheduler
-    // w & 3, schedulers 0..NC-1 also run a consumer (C instructions per tile, one tile in NC), scheduler 3 the loader.
+    // w & 3; schedulers 0..NC-1 also run a consumer (C instructions per tile, one tile in NC); a scheduler whose only
+    // producer would carry a whole quarter alone gets less (that warp would pace every tile).
     const int nrows = m * (m + 1) / 2, nb = nrows / kTriUnr<COV>;
     const float C = (float)(m * m * m) / 6.f + 2.f * m * m + 25.f * m, Tp = (float)nrows * kTriRowCost<COV>;
+    int np[4] = {0, 0, 0, 0};
+    for (int w = first_producer; w < 12; ++w) np[w & 3]++;
     float f[4], fs = 0.f;
     for (int q = 0; q < 4; ++q) {
       f[q] = fmaxf(0.25f * NC * (C + Tp) - (q < NC ? C : 0.f), 0.f);
+      if (np[q] == 1) f[q] *= 0.6f;
+      if (np[q] == 0) f[q] = 0.f;
       fs += f[q];
     }
     float acc = 0.f;
-    int prev = 0, cnt[kTriProducers];
+    int prev = 0, cnt[kTriProducers] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int q = 0; q < 4; ++q) {
       acc += f[q] / fs;
       const int upto = (q == 3) ? nb : min(nb, (int)(acc * nb + 0.5f));
-      const int nq = upto - prev;
+      int nq = upto - prev, left = np[q];
       prev = upto;
-      cnt[q] = nq / 2;
-      cnt[q + 4] = nq - nq / 2;
+      for (int w = first_producer; w < 12; ++w)
+        if ((w & 3) == q) {
+          const int take = nq / left;
+          cnt[w - first_producer] = take;
+          nq -= take;
+          --left;
+        }
     }
     bbeg[0] = 0;
     for (int w = 0; w < kTriProducers; ++w) bbeg[w + 1] = bbeg[w] + cnt[w];
@@ -452,81 +474,88 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
   }
   __syncthreads();
 
+  auto run_loader = [&]() {
+    // ================================ loader =========================================================
+    // Tile sequence of this CTA: T(j) = blockIdx.x + j gridDim.x for j < S (static: spreads the slow head of the
+    // ordering over the CTAs), then S gridDim.x + (atomic counter).  Software pipeline so that the warp never waits
+    // for global memory: at trip j the copies of T(j) are issued with neighbour ids that were loaded during trip
+    // j - 1, the ids of T(j+1) are requested, and the atomic that claims T(j+2) is outstanding in lane 0.
+    const unsigned tri_bytes = (unsigned)(ne + m) * 256u;
+    const size_t tile_doubles = (size_t)(ne + m) * 32;
+    int ids_a[kTriMaxM], ids_b[kTriMaxM];  // ping-pong: the ids a trip loads are first READ one trip later (a register
+                                           // copy at the end of the trip would wait for the loads right away)
+    auto load_ids = [&](long long tile, int(&ids)[kTriMaxM]) {
+      const int *src = P.nnT + (size_t)tile * m * 32 + lane;
+#pragma unroll
+      for (int k = 0; k < kTriMaxM; ++k) ids[k] = (k < m) ? __ldg(src + k * 32) : -1;
+    };
+    long long t_cur = blockIdx.x, t_nxt = (long long)blockIdx.x + gridDim.x;
+    unsigned claim = 0u;
+    bool pending = false;
+    if (resid != nullptr && t_cur < ntiles) load_ids(t_cur, ids_a);
+    int done_markers = 0, s = 0, use = 0, j = 0;  // stage of trip j, and how often it has been used before
+    // one trip: issue T(j) with `ids_use`, request the ids of T(j+1) into `ids_load`; false when the work is over
+    auto trip = [&](int(&ids_use)[kTriMaxM], int(&ids_load)[kTriMaxM]) -> bool {
+      if (j > 0) {  // T(j+1): static, or the claim issued one trip ago
+        if (pending) t_nxt = (long long)S * gridDim.x + __shfl_sync(0xffffffffu, claim, 0);
+        else t_nxt = (long long)blockIdx.x + (long long)(j + 1) * gridDim.x;
+      }
+      pending = false;
+      if (j + 2 >= S) {  // claim T(j+2); past the end: stay there without touching the counter
+        claim = 0x7fffffffu;
+        if (t_nxt < ntiles && lane == 0) claim = atomicAdd(th.tile_counter, 1u);
+        pending = true;
+      }
+      if (resid != nullptr && t_nxt < ntiles) load_ids(t_nxt, ids_load);
+      if (use > 0) mbar_wait(bar_empty(s), (use - 1) & 1);
+      if (t_cur >= ntiles) {  // end of work: NC consecutive markers, one per consumer (they take the stages round-robin)
+        if (lane == 0) ring[s] = -1;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full(s));
+        if (++done_markers == NC) return false;
+      } else {
+        unsigned char *st = smem + s * G.stage_bytes;
+        const long long base = P.loc_begin + t_cur * 32;
+        if (lane == 0) {
+          ring[s] = t_cur;
+          mbar_expect_tx(bar_full(s), tri_bytes);
+          // c rows and the packed triangle are adjacent in the cache and in the stage: one copy
+          bulk_g2s(smem_u32(st + G.off_cv), P.tri + (size_t)t_cur * tile_doubles, tri_bytes, bar_full(s));
+        }
+        if (resid != nullptr) {
+          double *rr = reinterpret_cast<double *>(st + G.off_rr) + lane;
+          long long i = base + lane;
+          if (i >= P.loc_end) i = (long long)P.loc_end - 1;
+#pragma unroll
+          for (int k = 0; k < kTriMaxM; ++k)
+            if (k < m) cp_async8_zfill(&rr[k * 32], &resid[ids_use[k] >= 0 ? ids_use[k] : 0], ids_use[k] >= 0);
+          cp_async8(&rr[m * 32], &resid[i]);
+        }
+        cp_async_mbar_arrive(bar_rr(s));
+      }
+      t_cur = t_nxt;
+      if (++s == S) {
+        s = 0;
+        ++use;
+      }
+      ++j;
+      return true;
+    };
+    for (;;) {
+      if (!trip(ids_a, ids_b)) break;
+      if (!trip(ids_b, ids_a)) break;
+    }
+  };
+
   if (warp < 4) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    if (warp == 3) {
-      // ================================ loader =========================================================
-      // Tile sequence of this CTA: T(j) = blockIdx.x + j gridDim.x for j < S (static: spreads the slow head of the
-      // ordering over the CTAs), then S gridDim.x + (atomic counter).  Software pipeline so that the warp never waits
-      // for global memory: at trip j the copies of T(j) are issued with neighbour ids that were loaded during trip
-      // j - 1, the ids of T(j+1) are requested, and the atomic that claims T(j+2) is outstanding in lane 0.
-      const unsigned tri_bytes = (unsigned)(ne + m) * 256u;
-      const size_t tile_doubles = (size_t)(ne + m) * 32;
-      int ids_cur[kTriMaxM], ids_nxt[kTriMaxM];
-      auto load_ids = [&](long long tile, int(&ids)[kTriMaxM]) {
-        const int *src = P.nnT + (size_t)tile * m * 32 + lane;
-#pragma unroll
-        for (int k = 0; k < kTriMaxM; ++k) ids[k] = (k < m) ? __ldg(src + k * 32) : -1;
-      };
-      long long t_cur = blockIdx.x, t_nxt = (long long)blockIdx.x + gridDim.x;
-      unsigned claim = 0u;
-      bool pending = false;
-      if (resid != nullptr && t_cur < ntiles) load_ids(t_cur, ids_cur);
-      int done_markers = 0, s = 0, use = 0;  // stage of trip j, and how often it has been used before
-      for (int j = 0;; ++j) {
-        if (j > 0) {  // T(j+1): static, or the claim issued one trip ago
-          if (pending) t_nxt = (long long)S * gridDim.x + __shfl_sync(0xffffffffu, claim, 0);
-          else t_nxt = (long long)blockIdx.x + (long long)(j + 1) * gridDim.x;
-        }
-        pending = false;
-        if (j + 2 >= S) {  // claim T(j+2); past the end: stay there without touching the counter
-          claim = 0x7fffffffu;
-          if (t_nxt < ntiles && lane == 0) claim = atomicAdd(th.tile_counter, 1u);
-          pending = true;
-        }
-        if (resid != nullptr && t_nxt < ntiles) load_ids(t_nxt, ids_nxt);
-        if (use > 0) mbar_wait(bar_empty(s), (use - 1) & 1);
-        if (t_cur >= ntiles) {  // end of work: NC consecutive markers, one per consumer (they take the stages round-robin)
-          if (lane == 0) ring[s] = -1;
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_full(s));
-          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_full(s)) : "memory");  // the 32 "cp.async" slots
-          if (++done_markers == NC) break;
-        } else {
-          unsigned char *st = smem + s * G.stage_bytes;
-          const long long base = P.loc_begin + t_cur * 32;
-          if (lane == 0) {
-            ring[s] = t_cur;
-            const unsigned extra = (with_cur && tri_tile_is_full(base, m, P.loc_end)) ? (unsigned)m * 256u : 0u;
-            mbar_expect_tx(bar_full(s), tri_bytes + extra);
-            // c rows and the packed triangle are adjacent in the cache and in the stage: one copy
-            bulk_g2s(smem_u32(st + G.off_cv), P.tri + (size_t)t_cur * tile_doubles, tri_bytes, bar_full(s));
-            if (extra) bulk_g2s(smem_u32(st + G.off_bc), th.Bcur + nn_offset(base, m), extra, bar_full(s));
-          }
-          if (resid != nullptr) {
-            double *rr = reinterpret_cast<double *>(st + G.off_rr) + lane;
-            long long i = base + lane;
-            if (i >= P.loc_end) i = (long long)P.loc_end - 1;
-#pragma unroll
-            for (int k = 0; k < kTriMaxM; ++k)
-              if (k < m) cp_async8_zfill(&rr[k * 32], &resid[ids_cur[k] >= 0 ? ids_cur[k] : 0], ids_cur[k] >= 0);
-            cp_async8(&rr[m * 32], &resid[i]);
-#pragma unroll
-            for (int k = 0; k < kTriMaxM; ++k) ids_cur[k] = ids_nxt[k];
-          }
-          cp_async_mbar_arrive(bar_full(s));
-        }
-        t_cur = t_nxt;
-        if (++s == S) {
-          s = 0;
-          ++use;
-        }
-      }
+    if (warp == loader_warp) {
+      run_loader();
     } else if (warp < NC) {
       // ================================ consumers ======================================================
       unsigned char *cons = smem + G.off_cons + warp * G.cons_bytes;
-      double *dv = reinterpret_cast<double *>(cons) + lane;
-      double *bo = reinterpret_cast<double *>(cons + m * 256);  // [lane][k], the image of the tile's block of B
+      double *dv = reinterpret_cast<double *>(cons) + lane;  // [k][lane]: 1 / V(k,k) during the solve ...
+      double *bo = reinterpret_cast<double *>(cons);         // ... then [lane][k], the image of the tile's block of B
       const double diag = th.sigmaSq + th.tauSq;
       int failed = INT_MAX;
       bool store_pending = false;
@@ -540,7 +569,6 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
         double *A = reinterpret_cast<double *>(st + G.off_a) + lane;
         double *cv = reinterpret_cast<double *>(st + G.off_cv) + lane;
         const double *rr = reinterpret_cast<const double *>(st + G.off_rr) + lane;
-        const double *bc = reinterpret_cast<const double *>(st + G.off_bc);
         mbar_wait(bar_built(s), use & 1);
         const long long tile = ring[s];
         if (tile < 0) break;
@@ -552,6 +580,7 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
         const bool full = tri_tile_is_full(base, m, P.loc_end);
         double fcur = 1.0;
         if (with_cur) fcur = __ldg(&th.Fcur[i]);
+        const unsigned rr_parity = use & 1;
         if (mi < m) {  // ragged start of the ordering: unit rows k >= m_i
           for (int k = mi; k < m; ++k) {
             cv[k * 32] = 0.0;
@@ -561,12 +590,15 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
         // Q term of the RESIDENT factors (current theta of the sampler) with the same residuals
         double qcur_part = 0.0;
         if (with_cur) {
-          if (full) {
-#pragma unroll 4
-            for (int k = 0; k < m; ++k) qcur_part = fma(bc[lane * m + k], rr[k * 32], qcur_part);
-          } else {
-            for (int k = 0; k < mi; ++k) qcur_part = fma(__ldg(&th.Bcur[off + k]), rr[k * 32], qcur_part);
-          }
+          mbar_wait(bar_rr(s), rr_parity);
+          // the location's m resident weights are 8 m contiguous bytes: the 32 rows of a tile share ~30 cache lines
+#pragma unroll 5
+          for (int k = 0; k < mi; ++k) qcur_part = fma(__ldg(&th.Bcur[off + k]), rr[k * 32], qcur_part);
+        }
+        if (store_pending) {  // the staging area doubles as the solve's 1 / diag rows: the last bulk store must have read it
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+          store_pending = false;
         }
         // The usual neighbour counts take the fully unrolled column sweep (tpl_device.cuh; same layout when m equals its
         // capacity): 12.4k cycles per tile against 16.4k for the rolled blocks at m = 15 (stall_wait on the loop-carried
@@ -582,11 +614,9 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
           default: ok = tri_solve(A, cv, dv, m, mi, diag, &Fv); break;
         }
         if (!ok && active) failed = min(failed, (int)min(i + 1, (long long)INT_MAX - 1));
+        if (!with_cur) mbar_wait(bar_rr(s), rr_parity);  // long landed by now: the solve took microseconds
         const bool to_bulk = th.B != nullptr && full;
-        if (to_bulk && store_pending) {
-          if (lane == 0) bulk_wait_read0();
-          __syncwarp();
-        }
+        __syncwarp();  // every lane is done with the 1 / diag rows
         double part = 0.0;
 #pragma unroll 4
         for (int k = 0; k < m; ++k) {  // residual rows are zero when the launch has no quadratic form
@@ -645,7 +675,10 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
   } else {
     // ================================ producers ========================================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 136;");
-    const int pw = warp - 4;
+    if (warp == loader_warp) {
+      run_loader();
+    } else {
+    const int pw = warp - first_producer;
     const int b0 = bbeg[pw], b1 = bbeg[pw + 1];
     const bool tail = (pw == 0);
     int markers = 0, s = 0, use = 0;
@@ -683,6 +716,7 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
         s = 0;
         ++use;
       }
+    }
     }
   }
 
@@ -737,8 +771,17 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
 
 // ---- launcher ---------------------------------------------------------------------------------------
 template <int COV>
-static cudaError_t tri_launch_one(const BfLaunch &P, int grid_x, cudaStream_t stream) {
-  const TriGeom G = tri_geometry(P.m);
+static cudaError_t tri_launch_one(const BfLaunch &P0, int grid_x, cudaStream_t stream) {
+  static int want4_env = -2;  // NNGP_TRI_NC4 = 0 / 1 overrides the per-model choice (A/B measurements)
+  if (want4_env == -2) {
+    const char *e = getenv("NNGP_TRI_NC4");
+    want4_env = e ? atoi(e) : -1;
+  }
+  BfLaunch P = P0;
+  // measured (n = 10^6, m = 15, same box): with the quadratic form the loader's gathers pace a four-consumer CTA
+  // (exponential 0.498 vs 0.466 ms, spherical 0.446 vs 0.412), without it four consumers win (0.416 vs 0.433, 0.331 vs 0.366)
+  P.tri_want4 = want4_env >= 0 ? want4_env : ((kTriWant4<COV> && P.th[0].resid == nullptr) ? 1 : 0);
+  const TriGeom G = tri_geometry(P.m, P.tri_want4 != 0);
   static bool configured[64] = {};  // the attribute is per device; setting it costs a few microseconds of every launch
   int dev = 0;
   cudaGetDevice(&dev);

@@ -146,7 +146,12 @@ __device__ __forceinline__ void tpl_chol_block(double *A, double *cv, double *dv
       else a[c][i] = cv[(J0 + c) * 32];
     }
   }
+#ifdef NNGP_CHOL_KROLL  // experiment builds: k loop rolled in steps of NNGP_CHOL_KROLL (code 3x smaller)
+  constexpr int kKRoll = NNGP_CHOL_KROLL;
+#pragma unroll kKRoll
+#else
 #pragma unroll  // (a rolled k loop, unroll 2 or 4, shrinks the code 3x but measured 3-8% slower: less load hoisting)
+#endif
   for (int k = 0; k < J0; ++k) {
     double vc[NW];
 #pragma unroll
