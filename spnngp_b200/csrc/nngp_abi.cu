@@ -383,21 +383,52 @@ int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const 
     tr.mark("distance triangle");
   }
   c->pair_d2_q99 = 1e300;
-  if (c->has_nn && (long long)loc_end > m && loc_end > loc_begin) {
-    // 99 % quantile of the largest squared pair distance inside a neighbourhood (stat_kernels.cu)
+  const bool have_pairs = c->has_nn && (long long)loc_end > m && loc_end > loc_begin;
+  if (have_pairs || (c->has_nn && c->mbox_shared)) {
+    // 99 % quantile of the largest squared pair distance inside a neighbourhood (stat_kernels.cu).  In a sharded fit
+    // the histograms of all ranks are added first (through the mailbox, a few rounds of < 2,300 counts), so that every
+    // rank -- and every shard layout -- takes the same Matern series decision as the unsharded fit.
     const int nb = pair_d2_hist_bins();
-    if (!c->d_hist) NNGP_CUDA(c, cudaMalloc(&c->d_hist, nb * sizeof(unsigned int)));
-    NNGP_CUDA(c, pair_d2_hist_launch(c->d_coords, c->d_nnIndx, m, loc_begin, loc_end, c->d_hist, c->stream));
-    c->launches++;
-    std::vector<unsigned int> hist((size_t)nb);
-    NNGP_CUDA(c, cudaMemcpyAsync(hist.data(), c->d_hist, nb * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
-    NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
-    unsigned long long total = 0, above = 0;
-    for (int b = 0; b < nb; b++) total += hist[b];
+    std::vector<unsigned int> hist((size_t)nb, 0u);
+    if (have_pairs) {
+      if (!c->d_hist) NNGP_CUDA(c, cudaMalloc(&c->d_hist, nb * sizeof(unsigned int)));
+      NNGP_CUDA(c, pair_d2_hist_launch(c->d_coords, c->d_nnIndx, m, loc_begin, loc_end, c->d_hist, c->stream));
+      c->launches++;
+      NNGP_CUDA(c, cudaMemcpyAsync(hist.data(), c->d_hist, nb * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+      NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    std::vector<double> cnt(hist.begin(), hist.end());
+    if (c->mbox_shared) {
+      // only the occupied range travels: its bounds are agreed first (min / max through two sums of indicator-free values)
+      int lo = nb, hi = -1;
+      for (int b = 0; b < nb; b++)
+        if (hist[b]) {
+          if (b < lo) lo = b;
+          hi = b;
+        }
+      // agree on [min lo, max hi] over the ranks: post every rank's pair and scan them
+      std::vector<double> bounds((size_t)2 * c->mbox_ranks, 0.0);
+      bounds[2 * c->mbox_rank] = (double)lo;
+      bounds[2 * c->mbox_rank + 1] = (double)hi;
+      rc = mbox_host_allreduce(c, bounds.data(), 2 * c->mbox_ranks);
+      if (rc) return rc;
+      for (int r = 0; r < c->mbox_ranks; r++) {
+        if ((int)bounds[2 * r] < lo) lo = (int)bounds[2 * r];
+        if ((int)bounds[2 * r + 1] > hi) hi = (int)bounds[2 * r + 1];
+      }
+      const int chunk = kMboxSlotDoubles - kMboxPayload;
+      for (int b0 = lo; b0 <= hi; b0 += chunk) {
+        const int len = (hi + 1 - b0 < chunk) ? hi + 1 - b0 : chunk;
+        rc = mbox_host_allreduce(c, cnt.data() + b0, len);
+        if (rc) return rc;
+      }
+    }
+    double total = 0, above = 0;
+    for (int b = 0; b < nb; b++) total += cnt[b];
     int b = nb - 1;
     for (; b > 0; b--) {
-      if ((above + hist[b]) * 100ull > total) break;  // more than 1 % of the locations at or above this bin
-      above += hist[b];
+      if ((above + cnt[b]) * 100.0 > total) break;  // more than 1 % of the locations at or above this bin
+      above += cnt[b];
     }
     const unsigned long long edge = (unsigned long long)(b + 1) << 48;  // upper edge of bin b
     double v;
