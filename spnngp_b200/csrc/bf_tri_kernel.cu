@@ -795,7 +795,10 @@ static cudaError_t tri_launch_one(const BfLaunch &P0, int grid_x, cudaStream_t s
   return cudaGetLastError();
 }
 
-int tri_capacity_for_m(int m) { return (m >= 2 && m <= kTriMaxM) ? m : 0; }
+// Where this kernel is the fastest one (n = 3 x 10^5, ms per launch, tri / gather kernel): m = 15: 0.14 / 0.19; m = 20:
+// 0.50 / 0.44; m = 24: 1.13 / 0.70; m = 26: 1.17 / 1.75.  From m = 20 on only one consumer and two or three stages fit
+// (tri_geometry), and bf_ws_kernel's two-stage CTA wins until its capacities end at 24.
+int tri_capacity_for_m(int m) { return ((m >= 2 && m <= 19) || (m >= 25 && m <= kTriMaxM)) ? m : 0; }
 
 int tri_grid_for(long long nloc, int sms) {
   const long long need = (nloc + 31) / 32;
