@@ -328,19 +328,33 @@ int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const 
       c->stager = new HostStager();
       NNGP_CUDA(c, c->stager->init(c->device));
     }
+    // The REPLICATED arrays (sites, X, y) of a sharded fit: every rank uploads 1 / N of them from its host copy and
+    // the ranks exchange the pieces over NVLink (grouped ncclBroadcast, one root per piece) -- host-to-device traffic per
+    // rank drops N-fold, which is what made nngp_set_data slower with every added GPU (8 ranks x 40 MB through one host).
+    const char *gmin = getenv("NNGP_GATHER_MIN");  // sites from which the exchange pays (tests lower it)
+    const bool gather = c->comm != nullptr && c->comm_size > 1 && n >= (gmin ? atoi(gmin) : (1 << 16)) && !getenv("NNGP_NO_GATHER");
+    const long long s0 = gather ? (long long)n * c->comm_rank / c->comm_size : 0;
+    const long long s1 = gather ? (long long)n * (c->comm_rank + 1) / c->comm_size : n;
     std::vector<StageJob> jobs;
-    jobs.push_back({StageJob::XY_INTERLEAVE, c->d_coords, coords, (size_t)n * sizeof(double2), n});
+    // (XY_INTERLEAVE reads y at src + n doubles: a shifted src addresses the same pair of columns from site s0 on)
+    jobs.push_back({StageJob::XY_INTERLEAVE, c->d_coords + s0, coords + s0, (size_t)(s1 - s0) * sizeof(double2), n});
     if (c->csr_end > c->csr_begin)
       jobs.push_back({StageJob::INT_RANGE, c->d_nnIndx_store, nnIndx + c->csr_begin,
                       (size_t)(c->csr_end - c->csr_begin) * sizeof(int), n});
     if (p > 0) {
-      jobs.push_back({StageJob::RAW, c->d_X, X, (size_t)n * p * sizeof(double), 0});
-      jobs.push_back({StageJob::RAW, c->d_y, y, (size_t)n * sizeof(double), 0});
+      for (int col = 0; col < p; col++)
+        jobs.push_back({StageJob::RAW, c->d_X + (size_t)col * n + s0, X + (size_t)col * n + s0, (size_t)(s1 - s0) * sizeof(double), 0});
+      jobs.push_back({StageJob::RAW, c->d_y + s0, y + s0, (size_t)(s1 - s0) * sizeof(double), 0});
     }
     bool bad_id = false;
     tr.mark("buffers");
     NNGP_CUDA(c, c->stager->run(jobs, &bad_id));
     tr.mark("staged upload");
+    if (gather) {
+      rc = comm_exchange_replicated(c, c->d_coords, c->d_X, c->d_y, n, p);
+      if (rc) return rc;
+      tr.mark("exchange of the replicated arrays");
+    }
     if (bad_id) {
       c->n = 0;
       return ctx_fail(c, NNGP_EINVAL, "nngp_set_data: neighbour index out of range");

@@ -76,7 +76,7 @@ typedef struct ncclComm *ncclComm_t;
 #define NCCL_UNIQUE_ID_BYTES 128
 typedef struct { char internal[NCCL_UNIQUE_ID_BYTES]; } ncclUniqueId;
 typedef enum { ncclSuccess = 0 } ncclResult_t;
-typedef enum { ncclDouble = 8 } ncclDataType_t;
+typedef enum { ncclChar = 0, ncclDouble = 8 } ncclDataType_t;
 typedef enum { ncclSum = 0 } ncclRedOp_t;
 }
 
@@ -88,6 +88,9 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -110,6 +113,9 @@ static NcclApi *nccl_api(std::string *why) {
     api.AllReduce = (decltype(api.AllReduce))dlsym(api.handle, "ncclAllReduce");
     api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
     api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
+    api.Broadcast = (decltype(api.Broadcast))dlsym(api.handle, "ncclBroadcast");
+    api.GroupStart = (decltype(api.GroupStart))dlsym(api.handle, "ncclGroupStart");
+    api.GroupEnd = (decltype(api.GroupEnd))dlsym(api.handle, "ncclGroupEnd");
     if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce) err = "libnccl lacks the expected symbols";
   });
   if (!err.empty()) {
@@ -268,6 +274,27 @@ int comm_allreduce_dev(nngp_ctx *c, double *d_buf, int len) {
   if (!api) return ctx_fail(c, NNGP_ESTATE, why);
   ncclResult_t r = api->AllReduce(d_buf, d_buf, (size_t)len, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream);
   if (r != ncclSuccess) return ctx_fail(c, NNGP_ECUDA, std::string("ncclAllReduce: ") + (api->GetErrorString ? api->GetErrorString(r) : "error"));
+  return NNGP_OK;
+}
+
+int comm_exchange_replicated(nngp_ctx *c, double2 *coords, double *X, double *y, int n, int p) {
+  std::string why;
+  NcclApi *api = nccl_api(&why);
+  if (!api || !api->Broadcast || !api->GroupStart || !api->GroupEnd) return ctx_fail(c, NNGP_ESTATE, "libnccl lacks ncclBroadcast / ncclGroupStart");
+  ncclComm_t comm = (ncclComm_t)c->comm;
+  const int N = c->comm_size;
+  bool ok = api->GroupStart() == ncclSuccess;
+  for (int r = 0; r < N && ok; r++) {  // piece of root r, in place on every rank
+    const long long s0 = (long long)n * r / N, s1 = (long long)n * (r + 1) / N;
+    if (s1 <= s0) continue;
+    ok = ok && api->Broadcast(coords + s0, coords + s0, (size_t)(s1 - s0) * sizeof(double2), ncclChar, r, comm, c->stream) == ncclSuccess;
+    for (int col = 0; col < p && ok; col++)
+      ok = api->Broadcast(X + (size_t)col * n + s0, X + (size_t)col * n + s0, (size_t)(s1 - s0) * sizeof(double), ncclChar, r, comm, c->stream) == ncclSuccess;
+    if (p > 0) ok = ok && api->Broadcast(y + s0, y + s0, (size_t)(s1 - s0) * sizeof(double), ncclChar, r, comm, c->stream) == ncclSuccess;
+  }
+  ok = (api->GroupEnd() == ncclSuccess) && ok;
+  if (!ok) return ctx_fail(c, NNGP_ECUDA, "ncclBroadcast of the replicated arrays failed");
+  c->launches += 1;
   return NNGP_OK;
 }
 

@@ -202,6 +202,9 @@ size_t tri_ids_offset(int m, long long nloc);
 cudaError_t tri_build_launch(const double2 *coords, const int *nnIndx, int m, int loc_begin, int loc_end, double *tri,
                              cudaStream_t stream);
 
+// nngp_abi_misc.cu: every rank holds sites [n r / N, n (r+1) / N) of the replicated arrays -> every rank holds all of them
+int comm_exchange_replicated(nngp_ctx *c, double2 *coords, double *X, double *y, int n, int p);
+
 // nngp_abi_misc.cu: mailbox
 constexpr int kMboxSlotDoubles = 2304;  // [0] stamp of a generic posting, [8 ..] payload (B/F sets: 8 doubles each, own stamps)
 constexpr int kMboxPayload = 8;

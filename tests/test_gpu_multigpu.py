@@ -19,6 +19,7 @@ def _worker(rank, world, rdzv, q):
     from spnngp_b200.dist import shard_range
     from tests.util import make_problem
     torch.cuda.set_device(rank)
+    os.environ["NNGP_GATHER_MIN"] = "1000"  # exercise the NVLink exchange of the replicated arrays at this small n
     dist.init_process_group("nccl", init_method=f"file://{rdzv}", rank=rank, world_size=world,
                             device_id=torch.device("cuda", rank))
     port = po.Port(); port.set_threads(2)
