@@ -1,5 +1,5 @@
 """BASELINE.json configs[1], [3], [4] at their full sizes on one GPU (not the contract bench, which is configs[2]).
-Host wall clock around the public calls (host arrays in, results out).  Writes gpurun_out/r01_config_timings.json.
+Host wall clock around the public calls (host arrays in, results out).  Writes gpurun_out/r02_config_timings.json.
 
   configs[1]  spConjNNGP, BCEF shape: n = 188,717, theta.alpha 5 x 5 grid, k.fold = 5, m = 15 -> nngp_conj_kfold + final fit
   configs[3]  predict.NNGP: n0 = 10^6 sites x 1,000 posterior samples at n = 10^6 (four site slices of 250k)
@@ -115,7 +115,7 @@ if "knn" in which:  # ---- configs[4] ------------------------------------------
     out["knn"] = knn
 
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-path = os.path.join(ROOT, "gpurun_out", "r01_config_timings.json")
+path = os.path.join(ROOT, "gpurun_out", "r02_config_timings.json")
 old = json.load(open(path)) if os.path.exists(path) else {}
 old.update(out)
 json.dump(old, open(path, "w"), indent=1)
