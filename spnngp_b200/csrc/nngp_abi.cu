@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <chrono>
+#include <future>
 
 #include <mutex>
 #include <string>
@@ -192,6 +193,8 @@ void nngp_destroy(nngp_ctx *c) {
   free_model(c);
   free_dev(c->d_ticket);
   free_dev(c->d_hist);
+  if (c->h_hist) cudaFreeHost(c->h_hist);
+  if (c->ev_hist) cudaEventDestroy(c->ev_hist);
   free_dev(c->d_Xy);
   free_dev(c->d_fail);
   free_dev(c->d_mat);
@@ -272,6 +275,52 @@ int nngp_get_option(nngp_ctx *c, const char *name, int *value) {
   return ctx_fail(c, NNGP_EINVAL, std::string("nngp_get_option: unknown option ") + name);
 }
 
+// Second half of the pair-distance quantile (see nngp_set_data): histogram -> [sum over ranks] -> 99 % quantile.
+static int pair_quantile_finish(nngp_ctx *c) {
+  if (!c->hist_pending) return NNGP_OK;
+  c->hist_pending = false;
+  const int nb = pair_d2_hist_bins();
+  NNGP_CUDA(c, cudaEventSynchronize(c->ev_hist));
+  const unsigned int *hist = c->h_hist;
+  std::vector<double> cnt(hist, hist + nb);
+  if (c->mbox_shared) {
+    // only the occupied range travels: every rank posts its bounds, all take the union
+    int lo = nb, hi = -1;
+    for (int b = 0; b < nb; b++)
+      if (hist[b]) {
+        if (b < lo) lo = b;
+        hi = b;
+      }
+    std::vector<double> bounds((size_t)2 * c->mbox_ranks, 0.0);
+    bounds[2 * c->mbox_rank] = (double)lo;
+    bounds[2 * c->mbox_rank + 1] = (double)hi;
+    int rc = mbox_host_allreduce(c, bounds.data(), 2 * c->mbox_ranks);
+    if (rc) return rc;
+    for (int r = 0; r < c->mbox_ranks; r++) {
+      if ((int)bounds[2 * r] < lo) lo = (int)bounds[2 * r];
+      if ((int)bounds[2 * r + 1] > hi) hi = (int)bounds[2 * r + 1];
+    }
+    const int chunk = kMboxSlotDoubles - kMboxPayload;
+    for (int b0 = lo; b0 <= hi; b0 += chunk) {
+      const int len = (hi + 1 - b0 < chunk) ? hi + 1 - b0 : chunk;
+      rc = mbox_host_allreduce(c, cnt.data() + b0, len);
+      if (rc) return rc;
+    }
+  }
+  double total = 0, above = 0;
+  for (int b = 0; b < nb; b++) total += cnt[b];
+  int b = nb - 1;
+  for (; b > 0; b--) {
+    if ((above + cnt[b]) * 100.0 > total) break;  // more than 1 % of the locations at or above this bin
+    above += cnt[b];
+  }
+  const unsigned long long edge = (unsigned long long)(b + 1) << 48;  // upper edge of bin b
+  double v;
+  memcpy(&v, &edge, sizeof v);
+  if (total > 0 && b + 1 < 0x7ff0) c->pair_d2_q99 = v;
+  return NNGP_OK;
+}
+
 int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const int *nnIndx, const int *nnIndxLU,
                   const double *X, const double *y, int loc_begin, int loc_end) {
   if (!c) return NNGP_EINVAL;
@@ -280,14 +329,19 @@ int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const 
   if (p > 0 && (!X || !y)) return ctx_fail(c, NNGP_EINVAL, "nngp_set_data: X / y missing");
   if (loc_begin < 0 || loc_end > n || loc_begin > loc_end) return ctx_fail(c, NNGP_EINVAL, "nngp_set_data: bad shard range");
   PhaseTrace tr("nngp_set_data");
-  if (nnIndxLU) {  // must be the closed form of src/util.cpp:55-70 (offset = running sum of the counts min(i, m))
-    long long run = 0;
-    int bad = 0;
-    for (int i = 1; i < n; i++) {
-      run += (i - 1 < m) ? i - 1 : m;
-      bad |= (nnIndxLU[i] != (int)run) | (nnIndxLU[n + i] != ((i < m) ? i : m));
-    }
-    if (bad) return ctx_fail(c, NNGP_EINVAL, "nngp_set_data: nnIndxLU is not the reference's closed-form layout");
+  // nnIndxLU must be the closed form of src/util.cpp:55-70 (offset = running sum of the counts min(i, m)); the pass over
+  // its 8 n bytes runs on its own thread next to the staged upload and is collected behind it
+  std::future<int> lu_bad;
+  if (nnIndxLU) {
+    lu_bad = std::async(std::launch::async, [=] {
+      long long run = 0;
+      int bad = 0;
+      for (int i = 1; i < n; i++) {
+        run += (i - 1 < m) ? i - 1 : m;
+        bad |= (nnIndxLU[i] != (int)run) | (nnIndxLU[n + i] != ((i < m) ? i : m));
+      }
+      return bad;
+    });
   }
   NNGP_CUDA(c, cudaSetDevice(c->device));
   NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -359,6 +413,10 @@ int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const 
       c->n = 0;
       return ctx_fail(c, NNGP_EINVAL, "nngp_set_data: neighbour index out of range");
     }
+    if (lu_bad.valid() && lu_bad.get()) {
+      c->n = 0;
+      return ctx_fail(c, NNGP_EINVAL, "nngp_set_data: nnIndxLU is not the reference's closed-form layout");
+    }
   }
   if (p > 0) {
     NNGP_ENSURE(c->d_beta, 4, (size_t)NNGP_MAX_BATCH * p);
@@ -397,57 +455,30 @@ int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const 
     tr.mark("distance triangle");
   }
   c->pair_d2_q99 = 1e300;
+  c->hist_pending = false;
   const bool have_pairs = c->has_nn && (long long)loc_end > m && loc_end > loc_begin;
   if (have_pairs || (c->has_nn && c->mbox_shared)) {
-    // 99 % quantile of the largest squared pair distance inside a neighbourhood (stat_kernels.cu).  In a sharded fit
-    // the histograms of all ranks are added first (through the mailbox, a few rounds of < 2,300 counts), so that every
-    // rank -- and every shard layout -- takes the same Matern series decision as the unsharded fit.
+    // 99 % quantile of the largest squared pair distance inside a neighbourhood (stat_kernels.cu): only the Matern
+    // series choice needs it, so an unsharded context launches the histogram here and reads it when the first Matern
+    // likelihood is prepared (pair_quantile_finish).  In a sharded fit the histograms of all ranks are added first
+    // (through the mailbox, a few rounds of < 2,300 counts), so that every rank -- and every shard layout -- takes the
+    // same decision as the unsharded fit; that exchange is collective and stays here.
     const int nb = pair_d2_hist_bins();
-    std::vector<unsigned int> hist((size_t)nb, 0u);
+    if (!c->h_hist) NNGP_CUDA(c, cudaHostAlloc(&c->h_hist, nb * sizeof(unsigned int), cudaHostAllocDefault));
+    if (!c->ev_hist) NNGP_CUDA(c, cudaEventCreateWithFlags(&c->ev_hist, cudaEventDisableTiming));
+    memset(c->h_hist, 0, nb * sizeof(unsigned int));
     if (have_pairs) {
       if (!c->d_hist) NNGP_CUDA(c, cudaMalloc(&c->d_hist, nb * sizeof(unsigned int)));
       NNGP_CUDA(c, pair_d2_hist_launch(c->d_coords, c->d_nnIndx, m, loc_begin, loc_end, c->d_hist, c->stream));
       c->launches++;
-      NNGP_CUDA(c, cudaMemcpyAsync(hist.data(), c->d_hist, nb * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
-      NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
+      NNGP_CUDA(c, cudaMemcpyAsync(c->h_hist, c->d_hist, nb * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+      NNGP_CUDA(c, cudaEventRecord(c->ev_hist, c->stream));
     }
-    std::vector<double> cnt(hist.begin(), hist.end());
+    c->hist_pending = true;
     if (c->mbox_shared) {
-      // only the occupied range travels: its bounds are agreed first (min / max through two sums of indicator-free values)
-      int lo = nb, hi = -1;
-      for (int b = 0; b < nb; b++)
-        if (hist[b]) {
-          if (b < lo) lo = b;
-          hi = b;
-        }
-      // agree on [min lo, max hi] over the ranks: post every rank's pair and scan them
-      std::vector<double> bounds((size_t)2 * c->mbox_ranks, 0.0);
-      bounds[2 * c->mbox_rank] = (double)lo;
-      bounds[2 * c->mbox_rank + 1] = (double)hi;
-      rc = mbox_host_allreduce(c, bounds.data(), 2 * c->mbox_ranks);
+      rc = pair_quantile_finish(c);
       if (rc) return rc;
-      for (int r = 0; r < c->mbox_ranks; r++) {
-        if ((int)bounds[2 * r] < lo) lo = (int)bounds[2 * r];
-        if ((int)bounds[2 * r + 1] > hi) hi = (int)bounds[2 * r + 1];
-      }
-      const int chunk = kMboxSlotDoubles - kMboxPayload;
-      for (int b0 = lo; b0 <= hi; b0 += chunk) {
-        const int len = (hi + 1 - b0 < chunk) ? hi + 1 - b0 : chunk;
-        rc = mbox_host_allreduce(c, cnt.data() + b0, len);
-        if (rc) return rc;
-      }
     }
-    double total = 0, above = 0;
-    for (int b = 0; b < nb; b++) total += cnt[b];
-    int b = nb - 1;
-    for (; b > 0; b--) {
-      if ((above + cnt[b]) * 100.0 > total) break;  // more than 1 % of the locations at or above this bin
-      above += cnt[b];
-    }
-    const unsigned long long edge = (unsigned long long)(b + 1) << 48;  // upper edge of bin b
-    double v;
-    memcpy(&v, &edge, sizeof v);
-    if (total > 0 && b + 1 < 0x7ff0) c->pair_d2_q99 = v;
     tr.mark("row layout + pair-distance histogram");
   }
   const long long nloc = (long long)loc_end - loc_begin;
@@ -504,6 +535,10 @@ static int prepare_bf(nngp_ctx *c, int cov, int nbatch, const double *theta, con
     th.mat = nullptr;
     if (cov == NNGP_COV_MATERN) {
       if (!(t[3] > 0.0)) return ctx_fail(c, NNGP_EINVAL, "matern nu must be > 0");
+      if (c->hist_pending) {
+        int rcq = pair_quantile_finish(c);
+        if (rcq) return rcq;
+      }
       int hit = -1;
       for (int k = 0; k < 4; k++)
         if (c->mat_cache[k].nu == t[3]) hit = k;

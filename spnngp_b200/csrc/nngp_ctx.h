@@ -88,6 +88,9 @@ struct nngp_ctx {
   int opt_matern_short = 1;      // nngp_set_option("matern_short", 0/1)
   double pair_d2_q99 = 1e300;    // 99 % quantile over this shard's locations of the largest squared pair distance
   unsigned int *d_hist = nullptr;
+  unsigned int *h_hist = nullptr;   // pinned copy, filled asynchronously behind the histogram kernel
+  cudaEvent_t ev_hist = nullptr;
+  bool hist_pending = false;        // the quantile has not been formed from h_hist yet (pair_quantile_finish)
   unsigned char bf_short[NNGP_MAX_BATCH] = {};  // decision of the last prepare_bf, per parameter set
   double last_qcur[NNGP_MAX_BATCH] = {};  // Q of the resident factors returned by the last launch (BfTheta::Bcur)
 
