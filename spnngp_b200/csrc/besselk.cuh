@@ -8,6 +8,7 @@
 // the host per parameter set (matern_prepare) and handed to the kernel by value, so the device loops
 // contain no divisions except the one CF2 needs.
 #pragma once
+#include <cmath>
 #include <math.h>
 #include <string.h>
 
@@ -78,42 +79,46 @@ struct MaternConsts {
 };
 
 // Nodes and normalised weights of the n-point Gauss-Laguerre rule for t^a e^-t, a > -1 (Golub-Welsch:
-// eigenvalues of the Jacobi matrix by implicit QL in long double; weight = squared first component of
-// the eigenvector).
-inline void gauss_laguerre_rule(int n, long double a, double *t, double *w) {
-  long double d[64], e[64], z[64];
+// eigenvalues of the Jacobi matrix by implicit QL; weight = squared first component of the eigenvector).
+// Real: the iteration runs in double (nodes to ~1e-15 of the largest, far below the 4e-13 truncation error of the
+// 16-node rule it feeds, matern_gl) -- the x87 long double version cost 15 us per new smoothness, which the sampler
+// pays on every iteration's critical path; long double remains available for the host tests.
+template <typename Real>
+inline void gauss_laguerre_rule_t(int n, Real a, double *t, double *w) {
+  Real d[64], e[64], z[64];
+  const Real eps = (sizeof(Real) > 8) ? (Real)1e-22L : (Real)1.2e-16;
   for (int i = 0; i < n; i++) {
-    d[i] = 2.0L * i + a + 1.0L;
-    e[i] = (i + 1 < n) ? sqrtl((long double)(i + 1) * ((long double)(i + 1) + a)) : 0.0L;  // couples i, i+1
-    z[i] = (i == 0) ? 1.0L : 0.0L;
+    d[i] = (Real)2 * i + a + (Real)1;
+    e[i] = (i + 1 < n) ? std::sqrt((Real)(i + 1) * ((Real)(i + 1) + a)) : (Real)0;  // couples i, i+1
+    z[i] = (i == 0) ? (Real)1 : (Real)0;
   }
   for (int l = 0; l < n; l++) {
     for (int iter = 0; iter < 300; iter++) {
       int mm = l;
       for (; mm < n - 1; mm++) {
-        const long double dd = fabsl(d[mm]) + fabsl(d[mm + 1]);
-        if (fabsl(e[mm]) <= 1e-22L * dd) break;
+        const Real dd = std::fabs(d[mm]) + std::fabs(d[mm + 1]);
+        if (std::fabs(e[mm]) <= eps * dd) break;
       }
       if (mm == l) break;
-      long double g = (d[l + 1] - d[l]) / (2.0L * e[l]);
-      long double r = sqrtl(g * g + 1.0L);
-      g = d[mm] - d[l] + e[l] / (g + copysignl(r, g));
-      long double sn = 1.0L, cs = 1.0L, pp = 0.0L;
+      Real g = (d[l + 1] - d[l]) / ((Real)2 * e[l]);
+      Real r = std::sqrt(g * g + (Real)1);
+      g = d[mm] - d[l] + e[l] / (g + std::copysign(r, g));
+      Real sn = 1, cs = 1, pp = 0;
       int i = mm - 1;
       for (; i >= l; i--) {
-        long double f = sn * e[i];
-        const long double b = cs * e[i];
-        r = sqrtl(f * f + g * g);  // entries are O(n): no overflow guard needed (hypotl is 5x slower)
+        Real f = sn * e[i];
+        const Real b = cs * e[i];
+        r = std::sqrt(f * f + g * g);  // entries are O(n): no overflow guard needed (hypot is 5x slower)
         e[i + 1] = r;
-        if (r == 0.0L) {
+        if (r == (Real)0) {
           d[i + 1] -= pp;
-          e[mm] = 0.0L;
+          e[mm] = 0;
           break;
         }
         sn = f / r;
         cs = g / r;
         g = d[i + 1] - pp;
-        r = (d[i] - g) * sn + 2.0L * cs * b;
+        r = (d[i] - g) * sn + (Real)2 * cs * b;
         pp = sn * r;
         d[i + 1] = g + pp;
         g = cs * r - b;
@@ -121,16 +126,23 @@ inline void gauss_laguerre_rule(int n, long double a, double *t, double *w) {
         z[i + 1] = sn * z[i] + cs * f;
         z[i] = cs * z[i] - sn * f;
       }
-      if (r == 0.0L && i >= l) continue;
+      if (r == (Real)0 && i >= l) continue;
       d[l] -= pp;
       e[l] = g;
-      e[mm] = 0.0L;
+      e[mm] = 0;
     }
   }
   for (int i = 0; i < n; i++) {
     t[i] = (double)d[i];
     w[i] = (double)(z[i] * z[i]);
   }
+}
+inline void gauss_laguerre_rule(int n, long double a, double *t, double *w) {
+#ifdef NNGP_GL_LONG_DOUBLE
+  gauss_laguerre_rule_t<long double>(n, a, t, w);
+#else
+  gauss_laguerre_rule_t<double>(n, (double)a, t, w);
+#endif
 }
 
 // ---- host side: constants per nu -------------------------------------------------------------
@@ -209,7 +221,7 @@ inline void matern_prepare(double nu, MaternConsts *mc) {
       };
       double lo = 0.0, hi = 1.0;
       if (tail(hi) <= 1e-16) lo = hi;
-      for (int it = 0; it < 50 && lo < hi; it++) {
+      for (int it = 0; it < 16 && lo < hi; it++) {  // `lo` always satisfies the bound: 16 halvings resolve it to 1.5e-5
         const double mid = 0.5 * (lo + hi);
         if (tail(mid) <= 1e-16) lo = mid;
         else hi = mid;
