@@ -795,10 +795,21 @@ static cudaError_t tri_launch_one(const BfLaunch &P0, int grid_x, cudaStream_t s
   return cudaGetLastError();
 }
 
-// Where this kernel is the fastest one (n = 3 x 10^5, ms per launch, tri / gather kernel): m = 15: 0.14 / 0.19; m = 20:
-// 0.50 / 0.44; m = 24: 1.13 / 0.70; m = 26: 1.17 / 1.75.  From m = 20 on only one consumer and two or three stages fit
-// (tri_geometry), and bf_ws_kernel's two-stage CTA wins until its capacities end at 24.
-int tri_capacity_for_m(int m) { return ((m >= 2 && m <= 19) || (m >= 25 && m <= kTriMaxM)) ? m : 0; }
+// Where this kernel is the fastest one (n = 5 x 10^5, ms per launch, exponential / Matern: this kernel vs the gather
+// kernels): m = 5: 0.148 / 0.163 vs 0.068 / 0.126; 8: 0.179 / 0.209 vs 0.121 / 0.171; 10: 0.174 / 0.215 vs 0.166 / 0.226;
+// 12: 0.267 / 0.320 vs 0.239 / 0.297; 13: 0.290 / 0.357 vs 0.292 / 0.380; 14: 0.296 / 0.374 vs 0.309 / 0.424;
+// 15: 0.233 / 0.324 vs 0.310 / 0.426; 16: 0.414 / 0.522 vs 0.400 / 0.505; 17: 0.553 / 0.668 vs 0.726 / 0.871;
+// 18: 0.564 / 0.694 vs 0.717 / 0.880; 20 (n = 3 x 10^5): 0.50 / 0.56 vs 0.44 / 0.56; 24: 1.13 vs 0.70; 26: 1.17 / 1.27 vs 1.75 / 2.48.
+// Small m: per-tile hand-offs outweigh the saved distance arithmetic; 16: the rolled solve loses to bf_ws_kernel's
+// unrolled one; from 20 on only one consumer and two or three stages fit (tri_geometry) and bf_ws_kernel's two-stage
+// CTA wins until its capacities end at 24.  nngp_set_option("tri_force", 1) serves every 2 <= m <= 26 (tests).
+static bool tri_is_fastest(int m) { return (m >= 13 && m <= 15) || (m >= 17 && m <= 19) || m == 25 || m == 26; }
+static int g_tri_force = 0;
+void tri_set_force(int on) { g_tri_force = on; }
+int tri_capacity_for_m(int m) {
+  if (m < 2 || m > kTriMaxM) return 0;
+  return (g_tri_force || tri_is_fastest(m)) ? m : 0;
+}
 
 int tri_grid_for(long long nloc, int sms) {
   const long long need = (nloc + 31) / 32;

@@ -198,6 +198,7 @@ cudaError_t bf_launch(const BfLaunch &P, int cov, int grid_x, cudaStream_t strea
 
 // bf_tri_kernel.cu / tri_cache.cu
 int tri_capacity_for_m(int m);
+void tri_set_force(int on);
 int tri_grid_for(long long nloc, int sms);
 cudaError_t tri_launch(const BfLaunch &P, int cov, int grid_x, cudaStream_t stream);
 size_t tri_cache_doubles(int m, long long nloc);

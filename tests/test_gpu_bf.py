@@ -300,3 +300,17 @@ def test_fused_current_q_launch(engine, port, cov, theta, m):
     Bo, Fo, ld, info = port.update_bf(prob["coords"], prob["nnIndx"], prob["nnIndxLU"], n, m, theta, cov)
     Qo = port.q(Bo, Fo, r, r, n, prob["nnIndx"], prob["nnIndxLU"])
     assert abs(got[2] - Qo) <= 1e-10 * abs(Qo)
+
+
+@pytest.mark.parametrize("cov", [0, 1, 2, 3])
+@pytest.mark.parametrize("n,m", [(700, 3), (2500, 9), (3000, 12), (2100, 16), (1900, 20), (1500, 26), (40, 14), (33, 2)])
+def test_distance_triangle_kernel_every_m(engine, port, cov, n, m):
+    """bf_tri_kernel serves 2 <= m <= 26 (run-time geometry, rolled blocked Cholesky; unrolled sweep at 10 / 15 / 20) but is
+    selected only where it is the fastest kernel: `tri_force` routes every m through it -- B, F, logDet, Q vs the oracle."""
+    prob = make_problem(n, m, seed=2 * n + m, port=port, domain=np.sqrt(n / 5000.0))
+    engine.set_option("tri_force", 1)
+    try:
+        _check(engine, port, prob, cov, THETA[cov])
+        assert engine.get_option("tri_cache_used") == 1
+    finally:
+        engine.set_option("tri_force", 0)

@@ -17,6 +17,7 @@ t = time.time()
 prob = make_problem(n, m, seed=1, domain=np.sqrt(n / 5000.0))
 eng = Engine(0)
 eng.set_option("tri_cache", int(os.environ.get("NNGP_TRI", "1")))
+eng.set_option("tri_force", int(os.environ.get("NNGP_TRI_FORCE", "0")))
 prob["nnIndx"], _, prob["nnIndxLU"] = eng.mk_nn_indx(prob["coords"], m, "cb")
 t = time.time()
 eng.set_data(prob["coords"], prob["nnIndx"], prob["nnIndxLU"], prob["X"], prob["y"], m)

@@ -12,6 +12,7 @@ from tests.util import make_problem  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 ms = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [15]
 eng = Engine(0)
+eng.set_option("tri_force", 1)  # every m through the distance-triangle kernel, not only where it is fastest
 for m in ms:
     prob = make_problem(n, m, seed=1, domain=np.sqrt(n / 5000.0))
     prob["nnIndx"], _, prob["nnIndxLU"] = eng.mk_nn_indx(prob["coords"], m, "cb")

@@ -14,6 +14,7 @@ m = int(sys.argv[2]) if len(sys.argv) > 2 else 15
 prob = make_problem(n, m, seed=1, domain=np.sqrt(n / 5000.0))
 eng = Engine(0)
 eng.set_option("tri_cache", int(os.environ.get("NNGP_TRI", "1")))
+eng.set_option("tri_force", int(os.environ.get("NNGP_TRI_FORCE", "0")))
 prob["nnIndx"], _, prob["nnIndxLU"] = eng.mk_nn_indx(prob["coords"], m, "cb")
 eng.set_data(prob["coords"], prob["nnIndx"], prob["nnIndxLU"], prob["X"], prob["y"], m)
 for name, cov, theta in [("exponential", 0, [5, 1, 6]), ("spherical", 1, [5, 1, 6]), ("matern", 2, [5, 1, 6, 0.75])]:
