@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <chrono>
+#include <functional>
 #include <future>
 
 #include <mutex>
@@ -717,8 +718,20 @@ int nngp_bf_loglik(nngp_ctx *c, int cov, int nbatch, const double *theta, const 
   return finish_bf(c, nbatch, beta != nullptr, out);
 }
 
-int nngp_bf_loglik_cur(nngp_ctx *c, int cov, const double *theta, const double *beta, int slot_new, int slot_cur,
-                       double *out) {
+// make sure the Matern tables of smoothness nu sit in the context's small cache (what prepare_bf looks up)
+static void matern_cache_warm(nngp_ctx *c, double nu) {
+  if (!(nu > 0.0)) return;
+  for (int k = 0; k < 4; k++)
+    if (c->mat_cache[k].nu == nu) return;
+  const int hit = c->mat_cache_next;
+  c->mat_cache_next = (c->mat_cache_next + 1) & 3;
+  matern_prepare(nu, &c->mat_cache[hit].mc);
+  c->mat_cache[hit].nu = nu;
+}
+
+// `between` (may be empty) runs on the host after the launch has been queued and before its result is awaited
+static int bf_loglik_cur_impl(nngp_ctx *c, int cov, const double *theta, const double *beta, int slot_new, int slot_cur,
+                              double *out, const std::function<void()> &between) {
   if (!c || !theta || !beta || !out || slot_new < 0 || slot_new > 1 || slot_cur < 0 || slot_cur > 1 || slot_new == slot_cur)
     return NNGP_EINVAL;
   const double t_enq0 = wall_s();
@@ -730,6 +743,7 @@ int nngp_bf_loglik_cur(nngp_ctx *c, int cov, const double *theta, const double *
   rc = enqueue_bf(c, cov, P, grid, true);
   if (rc) return rc;
   c->trace_enqueue_s += wall_s() - t_enq0;
+  if (between) between();
   double o2[2];
   rc = finish_bf(c, 1, true, o2);
   if (rc) return rc;
@@ -740,6 +754,11 @@ int nngp_bf_loglik_cur(nngp_ctx *c, int cov, const double *theta, const double *
     return NNGP_OK;
   }
   return nngp_q_resid(c, slot_cur, beta, out + 2);  // kernels without that path: one more pass over B, F
+}
+
+int nngp_bf_loglik_cur(nngp_ctx *c, int cov, const double *theta, const double *beta, int slot_new, int slot_cur,
+                       double *out) {
+  return bf_loglik_cur_impl(c, cov, theta, beta, slot_new, slot_cur, out, nullptr);
 }
 
 int nngp_bf_loglik_vec(nngp_ctx *c, int cov, int nbatch, const double *theta, const double *u, const int *slots,
@@ -929,6 +948,30 @@ int nngp_rnngp(nngp_ctx *c, const nngp_rnngp_args *a, double *betaSamples, doubl
   auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   c->trace_enqueue_s = c->trace_wait_s = 0.0;
 
+  // Draws of the NEXT iteration taken while this iteration's kernel runs (mode 1).  The reference consumes a fixed
+  // sequence per iteration -- p normals for beta, [n for a replicate,] 3 or 4 for the proposals, one uniform
+  // (src/rNNGP.cpp:295-349) -- none of which depends on the accept decision, so taking the uniform of iteration s and
+  // the raw normals of iteration s + 1 early leaves the stream, and the chain, unchanged; rnorm(mu, sd) is
+  // mu + sd * norm_rand() (nmath/rnorm.c), formed below without contraction.  With them both possible candidates of
+  // iteration s + 1 are known, and the Matern tables of both smoothness values are prepared while the GPU works
+  // (8-14 us each, otherwise on the critical path of every iteration).
+  struct Predrawn {
+    bool have = false;
+    double u = 0.0, zp[4] = {0, 0, 0, 0};
+    std::vector<double> zb;
+  } pre;
+  pre.zb.resize(p);
+  const bool can_predraw = (a->mode != 0) && getenv("NNGP_NO_PREDRAW") == nullptr;
+  auto mul_rn = [](double x, double y) { volatile double r = x * y; return (double)r; };  // product rounded on its own
+  auto propose = [&](const double *from, const double *z, double *to) {  // src/rNNGP.cpp:327-333 with the normals given
+    to[2] = logit_inv_(logit_(from[2], a->phiUnif[0], a->phiUnif[1]) + mul_rn(tuning[2], z[0]), a->phiUnif[0], a->phiUnif[1]);
+    to[0] = exp(log(from[0]) + mul_rn(tuning[0], z[1]));
+    to[1] = exp(log(from[1]) + mul_rn(tuning[1], z[2]));
+    to[3] = 0.0;
+    if (cov == NNGP_COV_MATERN)
+      to[3] = logit_inv_(logit_(from[3], a->nuUnif[0], a->nuUnif[1]) + mul_rn(tuning[3], z[3]), a->nuUnif[0], a->nuUnif[1]);
+  };
+
   bool thetaUpdate = true;
   int accept = 0, batchAccept = 0, status = 0, repCnt = 0;
   for (int s = 0; s < a->nSamples; s++) {
@@ -949,7 +992,9 @@ int nngp_rnngp(nngp_ctx *c, const nngp_rnngp_args *a, double *betaSamples, doubl
     }
     const double t_it1 = trace_iter ? now() : 0.0;
     // beta ~ N(mean, (X'C^-1X)^-1): mvrnorm, src/util.cpp:28-41
-    for (int i = 0; i < p; i++) beta[i] = a->rnorm(0.0, 1.0);
+    const bool have_pre = pre.have;  // this iteration's draws were taken during the previous kernel
+    pre.have = false;
+    for (int i = 0; i < p; i++) beta[i] = have_pre ? pre.zb[i] : a->rnorm(0.0, 1.0);
     hl::trmv_lower(tmp_pp.data(), p, beta.data());
     for (int i = 0; i < p; i++) beta[i] += mean[i];
 
@@ -962,11 +1007,38 @@ int nngp_rnngp(nngp_ctx *c, const nngp_rnngp_args *a, double *betaSamples, doubl
     }
 
     // proposals, in the reference's draw order phi, sigma.sq, tau.sq[, nu] (src/rNNGP.cpp:327-333)
-    cand[2] = logit_inv_(a->rnorm(logit_(theta[2], a->phiUnif[0], a->phiUnif[1]), tuning[2]), a->phiUnif[0], a->phiUnif[1]);
-    cand[0] = exp(a->rnorm(log(theta[0]), tuning[0]));
-    cand[1] = exp(a->rnorm(log(theta[1]), tuning[1]));
-    if (cov == NNGP_COV_MATERN)
-      cand[3] = logit_inv_(a->rnorm(logit_(theta[3], a->nuUnif[0], a->nuUnif[1]), tuning[3]), a->nuUnif[0], a->nuUnif[1]);
+    if (have_pre) {
+      propose(theta, pre.zp, cand);
+    } else {
+      cand[2] = logit_inv_(a->rnorm(logit_(theta[2], a->phiUnif[0], a->phiUnif[1]), tuning[2]), a->phiUnif[0], a->phiUnif[1]);
+      cand[0] = exp(a->rnorm(log(theta[0]), tuning[0]));
+      cand[1] = exp(a->rnorm(log(theta[1]), tuning[1]));
+      if (cov == NNGP_COV_MATERN)
+        cand[3] = logit_inv_(a->rnorm(logit_(theta[3], a->nuUnif[0], a->nuUnif[1]), tuning[3]), a->nuUnif[0], a->nuUnif[1]);
+    }
+    // what the host does while the kernel runs: this iteration's uniform, the next iteration's normals, both of its
+    // possible Matern preparations
+    const bool next_rep = a->repIndx && a->repSamples && s + 1 < a->nSamples && a->repIndx[s + 1];
+    const bool predraw = can_predraw && !rep && !next_rep && s + 1 < a->nSamples;
+    double u_accept = 0.0;
+    bool have_u = false;
+    auto between = [&]() {
+      if (!predraw) return;
+      u_accept = a->runif(0.0, 1.0);
+      have_u = true;
+      for (int i = 0; i < p; i++) pre.zb[i] = a->rnorm(0.0, 1.0);
+      // draw order phi, sigma.sq, tau.sq[, nu]; rnorm(mu, 0) returns mu WITHOUT consuming a normal (nmath/rnorm.c)
+      const double sd[4] = {tuning[2], tuning[0], tuning[1], tuning[3]};
+      for (int k = 0; k < nTheta; k++) pre.zp[k] = (sd[k] == 0.0) ? 0.0 : a->rnorm(0.0, 1.0);
+      pre.have = true;
+      if (cov == NNGP_COV_MATERN) {
+        double t1[4], t2[4];
+        propose(theta, pre.zp, t1);  // if this iteration's candidate is rejected
+        propose(cand, pre.zp, t2);   // if it is accepted
+        matern_cache_warm(c, t1[3]);
+        matern_cache_warm(c, t2[3]);
+      }
+    };
 
     double QCur, logDetCand, QCand;
     const double t_it2 = trace_iter ? now() : 0.0;
@@ -990,7 +1062,7 @@ int nngp_rnngp(nngp_ctx *c, const nngp_rnngp_args *a, double *betaSamples, doubl
       // double-buffered: B,F of the current theta are still resident; only Q changes with beta
       // one launch: solve the candidate and, with the same residual gathers, Q of the resident factors
       double o3[3];
-      rc = nngp_bf_loglik_cur(c, cov, cand, beta.data(), 1 - cur, cur, o3);
+      rc = bf_loglik_cur_impl(c, cov, cand, beta.data(), 1 - cur, cur, o3, between);
       if (rc) return rc;
       red[2] = o3[0]; red[3] = o3[1];
       red[0] = 0.0; red[1] = o3[2];
@@ -1005,7 +1077,7 @@ int nngp_rnngp(nngp_ctx *c, const nngp_rnngp_args *a, double *betaSamples, doubl
     }
     const double lpCur = log_post_(logDetCur, QCur, theta, a);
     const double lpCand = log_post_(logDetCand, QCand, cand, a);
-    if (a->runif(0.0, 1.0) <= exp(lpCand - lpCur)) {  // src/rNNGP.cpp:349
+    if ((have_u ? u_accept : a->runif(0.0, 1.0)) <= exp(lpCand - lpCur)) {  // src/rNNGP.cpp:349
       thetaUpdate = true;
       memcpy(theta, cand, sizeof theta);
       cur = 1 - cur;

@@ -178,3 +178,39 @@ def test_config0_chain_1000_iterations_against_reference(glue, ref, port, tune):
         assert int((np.diff(got["p_theta_samples"][0]) != 0).sum()) == moves
         assert np.allclose(got["p_theta_samples"], want["p_theta_samples"], rtol=1e-9, atol=0)
         assert np.allclose(got["p_beta_samples"], want["p_beta_samples"], rtol=1e-7, atol=1e-9)
+
+
+@pytest.mark.parametrize("tuning", [{"sigma.sq": 0.05, "tau.sq": 0.0, "phi": 0.05, "nu": 0.0},
+                                    {"sigma.sq": 0.1, "tau.sq": 0.1, "phi": 0.1, "nu": 0.03}])
+def test_matern_chain_with_predrawn_normals_against_reference(glue, ref, port, tuning):
+    """The double-buffered sampler takes the next iteration's draws while the kernel runs (nngp_abi.cu: Predrawn).  The
+    stream must stay the reference's: Matern chain, 120 iterations, with and without zero proposal scales (rnorm(mu, 0)
+    returns mu without consuming a normal, nmath/rnorm.c), against the reference's own rNNGP and against the same
+    engine with the pre-draw switched off; the RNG ends in the same state (the next uniform agrees)."""
+    rng = np.random.default_rng(5)
+    n, m = 900, 10
+    coords = rng.random((n, 2)); coords = coords[np.argsort(coords[:, 0], kind="stable")]
+    X = np.column_stack([np.ones(n), rng.standard_normal(n)])
+    y = X @ np.array([1.0, 5.0]) + np.sin(4 * coords[:, 0]) + 0.5 * rng.standard_normal(n)
+    idx, _, lu = port.mk_nn_indx_cb(coords, m)
+    starting = {"beta": [0.0, 0.0], "sigma.sq": 2.0, "tau.sq": 0.5, "phi": 6.0, "nu": 0.8}
+    args = (y, X, coords, 2, idx, lu, m, [2.0, 2.0], [2.0, 0.5], [3.0, 30.0], [0.3, 1.6], starting, tuning, 120)
+    ref.set_seed(11)
+    want = ref.rnngp(*args)
+    u_ref = ref.runif() if hasattr(ref, "runif") else None
+    got = {}
+    for pre in ("on", "off"):
+        if pre == "off":
+            os.environ["NNGP_NO_PREDRAW"] = "1"
+        try:
+            glue.lib.rshim_set_seed(11)
+            got[pre] = po.call_rnngp(glue, *args)
+            got[pre + "_u"] = float(glue.lib.unif_rand()) if hasattr(glue.lib, "unif_rand") else None
+        finally:
+            os.environ.pop("NNGP_NO_PREDRAW", None)
+    assert np.array_equal(got["on"]["p_theta_samples"], got["off"]["p_theta_samples"])
+    assert np.array_equal(got["on"]["p_beta_samples"], got["off"]["p_beta_samples"])
+    assert got["on_u"] == got["off_u"]  # same RNG state after the run
+    assert int((np.diff(want["p_theta_samples"][0]) != 0).sum()) > 5
+    assert np.allclose(got["on"]["p_theta_samples"], want["p_theta_samples"], rtol=1e-9, atol=0)
+    assert np.allclose(got["on"]["p_beta_samples"], want["p_beta_samples"], rtol=1e-7, atol=1e-9)
