@@ -39,7 +39,8 @@ enum {
   NNGP_ENODEV = -2,  /* no usable CUDA device */
   NNGP_ECUDA = -3,   /* CUDA runtime error, see nngp_last_error */
   NNGP_ENOMEM = -4,
-  NNGP_ESTATE = -5   /* call order (e.g. likelihood before nngp_set_data) */
+  NNGP_ESTATE = -5,  /* call order (e.g. likelihood before nngp_set_data) */
+  NNGP_EINTR = -6    /* the caller's interrupt hook asked to stop */
 };
 
 #define NNGP_MAX_M 32     /* neighbours per location handled by the warp-group solver */
@@ -57,7 +58,7 @@ typedef double (*nngp_runif_fn)(double a, double b);
 /* progress text hook (Rprintf); may be NULL */
 typedef void (*nngp_print_fn)(const char *msg);
 /* polled once per MCMC iteration / prediction chunk (R_CheckUserInterrupt); may be NULL */
-typedef void (*nngp_interrupt_fn)(void);
+typedef int (*nngp_interrupt_fn)(void);  /* polled once per iteration; nonzero: stop -- the call unwinds normally and returns NNGP_EINTR */
 
 /* ---- lifecycle ------------------------------------------------------------------------------ */
 int nngp_abi_version(void);
@@ -185,7 +186,7 @@ int nngp_rep_draw(nngp_ctx *ctx, int slot, const double *beta, const double *z, 
  * nSamples x p column-major (R/generics.R:252-259), thetaSamples nTheta x nSamples, repSamples n x nSamples.
  * rnorm is called n times per sample, in the reference's order. */
 int nngp_rnngp_replicated(nngp_ctx *ctx, int cov_model, const double *betaSamples, const double *thetaSamples,
-                          int nSamples, double (*rnorm)(double mu, double sd), void (*interrupt)(void),
+                          int nSamples, double (*rnorm)(double mu, double sd), nngp_interrupt_fn interrupt,
                           double *repSamples);
 
 /* `cNNGP` (src/cNNGP.cpp:73-357): conjugate model for g parameter sets.  thetaAlpha is nTheta x g

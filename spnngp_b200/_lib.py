@@ -18,7 +18,7 @@ c_int_p = C.POINTER(C.c_int)
 RNORM_FN = C.CFUNCTYPE(C.c_double, C.c_double, C.c_double)
 RUNIF_FN = C.CFUNCTYPE(C.c_double, C.c_double, C.c_double)
 PRINT_FN = C.CFUNCTYPE(None, C.c_char_p)
-INTERRUPT_FN = C.CFUNCTYPE(None)
+INTERRUPT_FN = C.CFUNCTYPE(C.c_int)  # nonzero: stop (the call returns NNGP_EINTR)
 ALLREDUCE_FN = C.CFUNCTYPE(None, c_double_p, C.c_int, C.c_void_p)
 
 

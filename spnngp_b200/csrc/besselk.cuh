@@ -21,7 +21,10 @@
 namespace nngp {
 
 constexpr int kMatSeriesTerms = 14;  // t^k/(k!)^2-like decay: 1e-17 relative at t = 1 by k = 13
-constexpr int kMatShortTerms = 9;    // truncated series for small arguments (dense neighbourhoods), see t_short_max
+#ifndef NNGP_MAT_SHORT_TERMS
+#define NNGP_MAT_SHORT_TERMS 9
+#endif
+constexpr int kMatShortTerms = NNGP_MAT_SHORT_TERMS;    // truncated series for small arguments (dense neighbourhoods), see t_short_max
 constexpr int kMatExtTerms = 32;     // 6.25^k / (k!)^2 < 1e-19 by k = 31
 constexpr int kTemmeTerms = 24;  // (x^2/4)^i / i! < 1e-18 well before i = 24 for x <= 2
 constexpr int kCf2Tab = 64;      // tabulated reciprocals for the first CF2 iterations

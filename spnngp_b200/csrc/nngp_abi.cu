@@ -1099,7 +1099,7 @@ int nngp_rnngp(nngp_ctx *c, const nngp_rnngp_args *a, double *betaSamples, doubl
       status = 0;
     }
     status++;
-    if (a->interrupt) a->interrupt();
+    if (a->interrupt && a->interrupt()) return ctx_fail(c, NNGP_EINTR, "interrupted by the caller");
     if (trace_iter) {
       tr_forms += t_it1 - t_it0;
       tr_host += t_it2 - t_it1;
@@ -1133,7 +1133,7 @@ int nngp_rep_draw(nngp_ctx *c, int slot, const double *beta, const double *z, do
 }
 
 int nngp_rnngp_replicated(nngp_ctx *c, int cov, const double *betaSamples, const double *thetaSamples, int nSamples,
-                          double (*rnorm)(double, double), void (*interrupt)(void), double *repSamples) {
+                          double (*rnorm)(double, double), nngp_interrupt_fn interrupt, double *repSamples) {
   if (!c || !betaSamples || !thetaSamples || !rnorm || !repSamples || nSamples < 0) return NNGP_EINVAL;
   if (c->n == 0 || c->p == 0 || !c->has_nn) return ctx_fail(c, NNGP_ESTATE, "nngp_rnngp_replicated before nngp_set_data");
   if (cov < 0 || cov > 3) return ctx_fail(c, NNGP_EINVAL, "cov.model is not correctly specified");
@@ -1157,7 +1157,7 @@ int nngp_rnngp_replicated(nngp_ctx *c, int cov, const double *betaSamples, const
     for (int j = 0; j < p; j++) beta[j] = betaSamples[(size_t)j * nSamples + s];  // nSamples x p (R/generics.R:252)
     rc = rep_draw(c, slot, beta.data(), c->h_z, repSamples + (size_t)s * c->n);
     if (rc) return rc;
-    if (interrupt) interrupt();
+    if (interrupt && interrupt()) return ctx_fail(c, NNGP_EINTR, "interrupted by the caller");
   }
   return NNGP_OK;
 }

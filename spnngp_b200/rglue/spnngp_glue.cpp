@@ -51,7 +51,11 @@ void check(int rc) {
 double rnorm_hook(double mu, double sd) { return rnorm(mu, sd); }
 double runif_hook(double a, double b) { return runif(a, b); }
 void print_hook(const char *msg) { Rprintf("%s", msg); }
-void interrupt_hook(void) { R_CheckUserInterrupt(); }
+// R_CheckUserInterrupt longjmps: called from inside the engine it would skip the destructors of live C++ frames
+// (host vectors, pooled device buffers) and PutRNGstate.  R_ToplevelExec contains the jump; the hook only reports it,
+// the engine unwinds normally with NNGP_EINTR, and the glue raises the R error after its own clean-up.
+void check_interrupt_fn(void *) { R_CheckUserInterrupt(); }
+int interrupt_hook(void) { return R_ToplevelExec(check_interrupt_fn, nullptr) ? 0 : 1; }
 
 int sampler_mode() {
   // 1 (default): double-buffered -- B, F of the current theta stay resident, one launch per iteration solves the

@@ -202,6 +202,18 @@ void REprintf(const char *fmt, ...) {
 }
 void R_FlushConsole(void) { fflush(stdout); }
 void R_CheckUserInterrupt(void) {}
+// Runs fun(data) in a context that a jump to top level cannot leave; TRUE when fun returned normally.  The stand-in has
+// no interrupts to deliver; rshim_raise_interrupt() makes the next call report one (tests).
+static int g_pending_interrupt = 0;
+void rshim_raise_interrupt(void) { g_pending_interrupt = 1; }
+Rboolean R_ToplevelExec(void (*fun)(void *), void *data) {
+  if (g_pending_interrupt) {
+    g_pending_interrupt = 0;
+    return FALSE;
+  }
+  fun(data);
+  return TRUE;
+}
 
 void Rf_error(const char *fmt, ...) {
   char buf[1024];

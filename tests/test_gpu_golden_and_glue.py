@@ -214,3 +214,21 @@ def test_matern_chain_with_predrawn_normals_against_reference(glue, ref, port, t
     assert int((np.diff(want["p_theta_samples"][0]) != 0).sum()) > 5
     assert np.allclose(got["on"]["p_theta_samples"], want["p_theta_samples"], rtol=1e-9, atol=0)
     assert np.allclose(got["on"]["p_beta_samples"], want["p_beta_samples"], rtol=1e-7, atol=1e-9)
+
+
+def test_interrupt_unwinds_and_leaves_the_engine_usable(glue):
+    """A user interrupt during `rNNGP`: the hook reports it (R_ToplevelExec contains R's jump), the engine returns
+    NNGP_EINTR through its normal return path, the glue raises the R error after PutRNGstate -- and the next call works."""
+    d = np.load(os.path.join(G, "chain_n300_m10.npz"))
+    starting = {"beta": [0.0, 0.0], "sigma.sq": 5.0, "tau.sq": 1.0, "phi": 6.0}
+    tuning = {"sigma.sq": 0.05, "tau.sq": 0.05, "phi": 0.05}
+    args = (d["y"], d["X"], d["coords"], 0, d["nnIndx"], d["nnIndxLU"], int(d["m"]), [2.0, 5.0], [2.0, 1.0], [3.0, 300.0], None,
+            starting, tuning, 40)
+    glue.lib.rshim_set_seed(1)
+    glue.lib.rshim_raise_interrupt()
+    with pytest.raises(RuntimeError, match="interrupted"):
+        po.call_rnngp(glue, *args)
+    glue.reset()
+    glue.lib.rshim_set_seed(1)
+    out = po.call_rnngp(glue, *args)
+    assert np.allclose(out["p_theta_samples"], d["exp_theta"], rtol=1e-9)
