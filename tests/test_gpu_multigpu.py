@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, rdzv, q):
+def _worker(rank, world, rdzv, q, reduce="mailbox"):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -20,6 +20,7 @@ def _worker(rank, world, rdzv, q):
     from tests.util import make_problem
     torch.cuda.set_device(rank)
     os.environ["NNGP_GATHER_MIN"] = "1000"  # exercise the NVLink exchange of the replicated arrays at this small n
+    os.environ["NNGP_REDUCE"] = reduce      # "nccl": sums over ranks by ncclAllReduce instead of the shared-memory mailbox
     dist.init_process_group("nccl", init_method=f"file://{rdzv}", rank=rank, world_size=world,
                             device_id=torch.device("cuda", rank))
     port = po.Port(); port.set_threads(2)
@@ -50,7 +51,8 @@ def _worker(rank, world, rdzv, q):
     dist.destroy_process_group()
 
 
-def test_two_rank_nccl_matches_single_gpu(tmp_path, port):
+@pytest.mark.parametrize("reduce", ["mailbox", "nccl"])
+def test_two_rank_nccl_matches_single_gpu(tmp_path, port, reduce):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
@@ -59,7 +61,7 @@ def test_two_rank_nccl_matches_single_gpu(tmp_path, port):
     from tests.util import make_problem
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(k, 2, str(tmp_path / "rdzv"), q)) for k in range(2)]
+    procs = [ctx.Process(target=_worker, args=(k, 2, str(tmp_path / "rdzv"), q, reduce)) for k in range(2)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=300) for _ in procs], key=lambda r: r[0])
