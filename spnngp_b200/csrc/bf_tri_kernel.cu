@@ -50,6 +50,10 @@ constexpr int kTriMaxStages = 6;
 constexpr int kTriThreads = 384;
 constexpr int kTriProducers = 8;  // at most (seven when the loader takes warp 4)
 template <int COV>
+constexpr int kTriConsumerWeight = 10;  // tenths; see the shares in the kernel's set-up.  Measured (n = 10^6, m = 15, ms,
+                                        // exponential / spherical / Matern): 0 (even split) 0.473 / 0.432 / 0.667; 10: 0.467 / 0.414 /
+                                        // 0.647; 18: 0.501 / 0.445 / 0.693; 28: 0.597 / 0.447 / 0.854 (scheduler 3's two warps pace the tile)
+template <int COV>
 constexpr bool kTriWant4 = !(COV == 2 || COV == 4);  // Matern keeps three consumers and eight producers
 constexpr int kTriTabBytes = (32 + 128) * 8;
 constexpr int kTriBarBytes = 512;  // 4 x 6 mbarriers, then the tile ring (6 long long)
@@ -436,7 +440,9 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
     // w & 3; schedulers 0..NC-1 also run a consumer (C instructions per tile, one tile in NC); a scheduler whose only
     // producer would carry a whole quarter alone gets less (that warp would pace every tile).
     const int nrows = m * (m + 1) / 2, nb = nrows / kTriUnr<COV>;
-    const float C = (float)(m * m * m) / 6.f + 2.f * m * m + 25.f * m, Tp = (float)nrows * kTriRowCost<COV>;
+    // tri_cw: the consumer's weight in tenths (its dependent chains suffer from sharing a scheduler more than its
+    // instruction count says)
+    const float C = ((float)(m * m * m) / 6.f + 2.f * m * m + 25.f * m) * 0.1f * (float)P.tri_cw, Tp = (float)nrows * kTriRowCost<COV>;
     int np[4] = {0, 0, 0, 0};
     for (int w = first_producer; w < 12; ++w) np[w & 3]++;
     float f[4], fs = 0.f;
@@ -777,7 +783,13 @@ static cudaError_t tri_launch_one(const BfLaunch &P0, int grid_x, cudaStream_t s
     const char *e = getenv("NNGP_TRI_NC4");
     want4_env = e ? atoi(e) : -1;
   }
+  static int cw_env = -2;  // NNGP_TRI_CW: consumer weight of the producers' shares, in tenths
+  if (cw_env == -2) {
+    const char *e = getenv("NNGP_TRI_CW");
+    cw_env = e ? atoi(e) : -1;
+  }
   BfLaunch P = P0;
+  P.tri_cw = cw_env > 0 ? cw_env : kTriConsumerWeight<COV>;
   // measured (n = 10^6, m = 15, same box): with the quadratic form the loader's gathers pace a four-consumer CTA
   // (exponential 0.498 vs 0.466 ms, spherical 0.446 vs 0.412), without it four consumers win (0.416 vs 0.433, 0.331 vs 0.366)
   P.tri_want4 = want4_env >= 0 ? want4_env : ((kTriWant4<COV> && P.th[0].resid == nullptr) ? 1 : 0);

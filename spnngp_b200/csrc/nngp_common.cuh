@@ -61,6 +61,7 @@ struct BfLaunch {
   // resident distance triangle (tri_cache.cu) of the locations [loc_begin, loc_end): tile t (32 locations) holds
   // m(m+1)/2 rows of 32 doubles -- m rows location <-> neighbour k, then the packed pairs (k, l), l < k.  NULL: gather kernels.
   const double *tri;
+  int tri_cw;      // bf_tri_kernel: weight of a consumer in the producers' shares, in tenths (set by its launcher)
   int tri_want4;   // bf_tri_kernel: four consumers / six stages when they fit (set by its launcher)
   const int *nnT;  // tile-major neighbour ids behind the triangle: tile t, row k, lane -> N(i, k) or -1
   BfTheta th[NNGP_MAX_BATCH];
