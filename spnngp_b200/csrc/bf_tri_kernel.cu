@@ -49,6 +49,14 @@ constexpr int kTriMaxM = 26;       // two stages still fit shared memory
 constexpr int kTriMaxStages = 6;
 constexpr int kTriThreads = 384;
 constexpr int kTriProducers = 8;  // at most (seven when the loader takes warp 4)
+// Register split of the CTA's pool (384 x 168): consumers / producers 232 / 136, or "slim" 200 / 152 for models whose
+// producers are the critical path and want one more evaluation chain per batch (NNGP_TRI_SLIM=1 builds: Matern with five
+// chains at 152 registers and a 3-column consumer at 200 measured 0.665 vs 0.648 ms -- not taken)
+#ifndef NNGP_TRI_SLIM
+#define NNGP_TRI_SLIM 0
+#endif
+template <int COV>
+constexpr bool kTriSlim = NNGP_TRI_SLIM && (COV == 2 || COV == 4);
 template <int COV>
 constexpr int kTriConsumerWeight = 10;  // tenths; see the shares in the kernel's set-up.  Measured (n = 10^6, m = 15, ms,
                                         // exponential / spherical / Matern): 0 (even split) 0.473 / 0.432 / 0.667; 10: 0.467 / 0.414 /
@@ -206,7 +214,7 @@ __device__ __forceinline__ void tri_rows_matern(unsigned char *const (&p)[NU], c
 }
 
 template <int COV>
-constexpr int kTriUnr = kIsMatern<COV> ? NNGP_TRI_UNR_MATERN : NNGP_TRI_UNR;
+constexpr int kTriUnr = kIsMatern<COV> ? (NNGP_TRI_SLIM ? NNGP_TRI_UNR_MATERN + 1 : NNGP_TRI_UNR_MATERN) : NNGP_TRI_UNR;
 // FP64 instructions per correlation (SASS counts), for the producers' shares
 template <int COV>
 constexpr int kTriRowCost = kIsMatern<COV> ? 55 : (COV == NNGP_COV_SPHERICAL ? 7 : 21);
@@ -390,10 +398,10 @@ __device__ __forceinline__ bool tri_solve(double *__restrict__ A, double *__rest
   return ok;
 }
 
-template <int MC>
+template <int MC, bool kSlim>
 __device__ __forceinline__ bool tri_solve_unrolled(double *A, double *cv, double *dv, int mi, double diag, double *F_out) {
   double Fsum;
-  constexpr int kCholW = (MC >= 12 && MC <= 16) ? 4 : 2;
+  constexpr int kCholW = (MC >= 12 && MC <= 16) ? (kSlim ? 3 : 4) : 2;  // kSlim: the consumer runs at 200 registers
   const bool ok = tpl_solve<MC, kCholW>(A, cv, dv, mi, diag, &Fsum);
   *F_out = diag - Fsum;
   return ok;
@@ -554,7 +562,8 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
   };
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    if constexpr (kTriSlim<COV>) asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     if (warp == loader_warp) {
       run_loader();
     } else if (warp < NC) {
@@ -613,9 +622,9 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
         bool ok;
         switch (m) {
 #ifndef NNGP_TRI_ROLLED_ONLY
-          case 10: ok = tri_solve_unrolled<10>(A, cv, dv, mi, diag, &Fv); break;
-          case 15: ok = tri_solve_unrolled<15>(A, cv, dv, mi, diag, &Fv); break;
-          case 20: ok = tri_solve_unrolled<20>(A, cv, dv, mi, diag, &Fv); break;
+          case 10: ok = tri_solve_unrolled<10, kTriSlim<COV>>(A, cv, dv, mi, diag, &Fv); break;
+          case 15: ok = tri_solve_unrolled<15, kTriSlim<COV>>(A, cv, dv, mi, diag, &Fv); break;
+          case 20: ok = tri_solve_unrolled<20, kTriSlim<COV>>(A, cv, dv, mi, diag, &Fv); break;
 #endif
           default: ok = tri_solve(A, cv, dv, m, mi, diag, &Fv); break;
         }
@@ -680,7 +689,8 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
     }
   } else {
     // ================================ producers ========================================================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 136;");
+    if constexpr (kTriSlim<COV>) asm volatile("setmaxnreg.dec.sync.aligned.u32 152;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 136;");
     if (warp == loader_warp) {
       run_loader();
     } else {
