@@ -28,6 +28,10 @@ import time
 
 import numpy as np
 
+# stdout carries ONE JSON line: NCCL_DEBUG=VERSION makes libnccl print its banner there
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
