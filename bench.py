@@ -260,7 +260,7 @@ def run_b200(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from spnngp_b200 import Engine, _lib
-    from spnngp_b200.dist import make_allreduce, shard_range
+    from spnngp_b200.dist import balanced_shard_range, make_allreduce, shard_range
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device visible; spnngp_b200 has no CPU fallback (use --impl reference)")
@@ -314,6 +314,24 @@ def run_b200(args, rank, world, local_rank):
         return float(ms.item()), acc, eng.launch_count() - l0
 
     # ---- HBM-resident: data uploaded once, then W warm-up and K timed iterations -----------------------
+    shard_sizes = None
+    if world > 1 and not args.no_balance:
+        # shard boundaries equalised by measured launch time (setup, like the neighbour search): the head of the ordering
+        # is more expensive per location for Matern, and the slowest rank paces every iteration (spnngp_b200/dist.py)
+        theta_b = [5.0, 1.0, 6.0, 0.75][: 4 if cov == 2 else 3]
+
+        def gather(x):
+            t = torch.zeros(world, dtype=torch.float64, device=dev)
+            t[rank] = x
+            dist.all_reduce(t)
+            return t.cpu().tolist()
+
+        lo, hi = balanced_shard_range(
+            eng, n, m, rank, world,
+            lambda a, b: eng.set_data(wl["coords"], nnIndx, lu, wl["X"], wl["y"], m, loc_range=(a, b)),
+            lambda: (eng.time_bf_loglik(cov, [theta_b], [wl["beta"]], iters=3), eng.time_bf_loglik(cov, [theta_b], [wl["beta"]], iters=20))[1],
+            gather)
+        shard_sizes = [int(v) for v in gather(float(hi - lo))]
     eng.set_data(wl["coords"], nnIndx, lu, wl["X"], wl["y"], m, loc_range=(lo, hi))
     chain(max(args.warmup, 3), args.mode)
     clocks = ClockSampler(local_rank)
@@ -420,6 +438,7 @@ def run_b200(args, rank, world, local_rank):
                 "parallelism": f"locations (and their nnIndx / B / F / distance storage) sharded over {world} GPU(s); "
                                + ("ncclAllReduce of the partials per iteration" if os.environ.get("NNGP_REDUCE") == "nccl" else
                                   "partials stamped into a shared-memory mailbox by the kernel's last CTA, summed in rank order by every host"),
+                "shard_sizes": shard_sizes,
                 "acceptance_rate": acc / args.steps, "rng": "R-compatible Mersenne-Twister + inversion (librshim), seed 1",
             },
             "e2e": {"value": args.steps / e2e_s, "unit": "iter/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
@@ -539,6 +558,7 @@ def main():
     ap.add_argument("--n", "--locations", type=int, default=1000000)
     ap.add_argument("--m", type=int, default=15)
     ap.add_argument("--cov", default="matern", choices=list(COV))
+    ap.add_argument("--no-balance", action="store_true", help="N > 1: keep the neighbour-count shard boundaries (no timing-based rebalancing)")
     ap.add_argument("--no-parity", action="store_true", help="skip the N > 1 self-check against the unsharded engine")
     ap.add_argument("--mode", type=int, default=1, help="1 double-buffered sampler (default), 0 reference-faithful")
     ap.add_argument("--ref-budget-s", type=float, default=150.0)
