@@ -254,11 +254,19 @@ int nngp_time_bf_loglik(nngp_ctx *ctx, int cov_model, int nbatch, const double *
 /* FP64 FMA throughput of this device measured with a DFMA micro-benchmark (TFLOP/s, FMA = 2 flops):
  * the roofline denominator for the B/F kernels (MEASURED_PEAKS.json has no FP64 figure). */
 int nngp_fp64_peak(nngp_ctx *ctx, double *tflops);
+/* Page-locked host memory (cudaHostAlloc).  Optional: every entry point takes ordinary pageable arrays (R vectors) and
+ * stages them through an internal pinned ring at the host's memcpy rate; arrays that ARE page-locked -- from this call,
+ * or cudaHostRegister'ed by the caller -- are recognised (cudaPointerGetAttributes) and moved by direct DMA at the
+ * PCIe rate.  Matters for the q x nSamples streams of nngp_rnngp_predict (src/rNNGPPredict.cpp:131-137,176-181). */
+int nngp_host_alloc(nngp_ctx *ctx, size_t bytes, void **out);
+int nngp_host_free(nngp_ctx *ctx, void *p);
 /* Tuning switches (tests and A/B measurements; defaults are the fast settings).
- *   "matern_short" (default 1): let Matern launches use the 9-term series when the data set's neighbourhoods are
- *   dense enough for it (dropped terms < 1e-16, see csrc/matern_series.cuh); 0 forces the 14-term series. */
+ *   "matern_short" (default 2): let Matern launches use a truncated series when the data set's neighbourhoods are
+ *   dense enough for it (dropped terms < 1e-16, see csrc/matern_series.cuh): 2 = the 5-term series where it holds
+ *   (distance-triangle kernel), else the 9-term one; 1 = at most the 9-term series; 0 forces the 14-term series. */
 int nngp_set_option(nngp_ctx *ctx, const char *name, int value);
-/* reads an option back; "matern_short_used": how many parameter sets of the last likelihood launch ran the short series */
+/* reads an option back; "matern_short_used": how many parameter sets of the last likelihood launch ran a truncated
+ * series, "matern_tiny_used": how many of them the 5-term one */
 int nngp_get_option(nngp_ctx *ctx, const char *name, int *value);
 /* number of kernel launches issued by this context so far (bench.py `gpu_launches`) */
 long long nngp_launch_count(const nngp_ctx *ctx);

@@ -45,7 +45,7 @@ ABI_SYMBOLS = [
     "nngp_abi_version", "nngp_device_count", "nngp_create", "nngp_destroy", "nngp_last_error", "nngp_sync",
     "nngp_mk_nn_indx", "nngp_mk_u_indx", "nngp_nn_query", "nngp_set_data", "nngp_bf_loglik", "nngp_bf_loglik_cur", "nngp_bf_loglik_vec", "nngp_q_resid", "nngp_q_forms",
     "nngp_get_bf", "nngp_rnngp", "nngp_rep_draw", "nngp_rnngp_replicated", "nngp_cnngp", "nngp_cnngp_score", "nngp_conj_kfold", "nngp_rnngp_predict", "nngp_time_bf_loglik", "nngp_launch_count", "nngp_set_option", "nngp_get_option",
-    "nngp_fp64_peak", "nngp_comm_unique_id", "nngp_comm_init", "nngp_comm_init_local", "nngp_comm_allreduce_sum", "nngp_comm_destroy",
+    "nngp_fp64_peak", "nngp_host_alloc", "nngp_host_free", "nngp_comm_unique_id", "nngp_comm_init", "nngp_comm_init_local", "nngp_comm_allreduce_sum", "nngp_comm_destroy",
 ]
 
 _lib = None
@@ -87,6 +87,8 @@ def load():
     L.nngp_time_bf_loglik.argtypes = [vp, C.c_int, C.c_int, c_double_p, c_double_p, C.c_int, C.c_int,
                                       C.POINTER(C.c_float)]
     L.nngp_fp64_peak.argtypes = [vp, c_double_p]
+    L.nngp_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(C.c_void_p)]
+    L.nngp_host_free.argtypes = [vp, C.c_void_p]
     L.nngp_comm_unique_id.argtypes = [C.c_char_p]
     L.nngp_comm_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
     L.nngp_comm_init_local.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]

@@ -25,6 +25,10 @@ constexpr int kMatSeriesTerms = 14;  // t^k/(k!)^2-like decay: 1e-17 relative at
 #define NNGP_MAT_SHORT_TERMS 9
 #endif
 constexpr int kMatShortTerms = NNGP_MAT_SHORT_TERMS;    // truncated series for small arguments (dense neighbourhoods), see t_short_max
+#ifndef NNGP_MAT_TINY_TERMS
+#define NNGP_MAT_TINY_TERMS 5
+#endif
+constexpr int kMatTinyTerms = NNGP_MAT_TINY_TERMS;      // a still shorter one for very dense neighbourhoods (bf_tri_kernel only), see t_tiny_max
 constexpr int kMatExtTerms = 32;     // 6.25^k / (k!)^2 < 1e-19 by k = 31
 constexpr int kTemmeTerms = 24;  // (x^2/4)^i / i! < 1e-18 well before i = 24 for x <= 2
 constexpr int kCf2Tab = 64;      // tabulated reciprocals for the first CF2 iterations
@@ -34,6 +38,7 @@ constexpr int kGlNodes = 16;     // generalised Gauss-Laguerre rule for phi D > 
 // parameters (constant bank, no upload, static operand addresses).
 struct MaternSeriesParams {
   double nu;
+  double nu32, nu32_log2e;  // 32 nu and 32 nu log2(e): t^nu = 2^(y/32), y = 32 nu log2 t (nngp_pow_tab)
   double t_ext_max;  // largest t = (phi D / 2)^2 served by the extended series (beyond: Gauss-Laguerre, matern_gl)
   double t_fast_max; // largest t the straight-line path serves: 1 for the full series, t_short_max for the short one
   int use_series;
@@ -74,6 +79,7 @@ struct MaternConsts {
   // largest t for which the first kMatShortTerms terms of both sums are enough: the dropped terms
   // sum_{k >= kMatShortTerms} (|ea_k| + t^nu |eb_k|) t^k stay below 1e-16 (absolute; rho is O(1) there)
   double t_short_max;
+  double t_tiny_max;  // the same bound for the first kMatTinyTerms terms
   // Gauss-Laguerre rule for the weight t^(nu-1/2) e^-t (nodes, weights normalised to sum 1) and
   // gl_c = sqrt(pi/2) / (2^(nu-1) Gamma(nu)): the large-argument path, see matern_gl()
   double gl_t[kGlNodes];
@@ -211,25 +217,30 @@ inline void matern_prepare(double nu, MaternConsts *mc) {
       for (int k = 0; k < kMatSeriesTerms; k++) mc->sa[k] = mc->sb[k] = 0.0;
       for (int k = 0; k < kMatExtTerms; k++) mc->ea[k] = mc->eb[k] = 0.0;
     }
-    mc->t_short_max = 0.0;
+    mc->t_short_max = mc->t_tiny_max = 0.0;
     if (mc->use_series) {
-      auto tail = [&](double t) {
-        double sa_t = 0.0, sb_t = 0.0, pw = pow(t, (double)kMatShortTerms);
-        for (int k = kMatShortTerms; k < kMatExtTerms; k++) {
+      auto tail = [&](double t, int first) {
+        double sa_t = 0.0, sb_t = 0.0, pw = 1.0;
+        for (int k = 0; k < first; k++) pw *= t;
+        for (int k = first; k < kMatExtTerms; k++) {
           sa_t += fabs(mc->ea[k]) * pw;
           sb_t += fabs(mc->eb[k]) * pw;
           pw *= t;
         }
         return sa_t + pow(t, nu) * sb_t;
       };
-      double lo = 0.0, hi = 1.0;
-      if (tail(hi) <= 1e-16) lo = hi;
-      for (int it = 0; it < 16 && lo < hi; it++) {  // `lo` always satisfies the bound: 16 halvings resolve it to 1.5e-5
-        const double mid = 0.5 * (lo + hi);
-        if (tail(mid) <= 1e-16) lo = mid;
-        else hi = mid;
-      }
-      mc->t_short_max = lo;
+      auto largest_t = [&](int first) {
+        double lo = 0.0, hi = 1.0;
+        if (tail(hi, first) <= 1e-16) lo = hi;
+        for (int it = 0; it < 16 && lo < hi; it++) {  // `lo` always satisfies the bound: 16 halvings resolve it to 1.5e-5
+          const double mid = 0.5 * (lo + hi);
+          if (tail(mid, first) <= 1e-16) lo = mid;
+          else hi = mid;
+        }
+        return lo;
+      };
+      mc->t_short_max = largest_t(kMatShortTerms);
+      mc->t_tiny_max = largest_t(kMatTinyTerms);
     }
   }
   gauss_laguerre_rule(kGlNodes, (long double)nu - 0.5L, mc->gl_t, mc->gl_w);
@@ -367,6 +378,8 @@ NNGP_HD double matern_cor(double x, const MaternConsts &mc) {
 
 inline void matern_series_params(const MaternConsts &mc, MaternSeriesParams *ms) {
   ms->nu = mc.nu;
+  ms->nu32 = 32.0 * mc.nu;
+  ms->nu32_log2e = (double)(32.0L * (long double)mc.nu * 1.442695040888963407359925L);
   ms->use_series = mc.use_series;
   // cancellation of the two sums grows like e^(2 phi D) / |sin(nu pi)|: keep ~1e-12 absolute
   const double snp = fabs(sin(3.14159265358979323846 * mc.nu));

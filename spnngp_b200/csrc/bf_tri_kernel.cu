@@ -44,6 +44,12 @@ namespace nngp {
 #ifndef NNGP_TRI_UNR_MATERN
 #define NNGP_TRI_UNR_MATERN 4
 #endif
+#ifndef NNGP_TRI_SIG_FOLD
+#define NNGP_TRI_SIG_FOLD 1  // Matern: sigma^2 multiplied into the series coefficients on the host (one FP64 instruction per entry)
+#endif
+#ifndef NNGP_TRI_MATERN_COST
+#define NNGP_TRI_MATERN_COST 52  // FP64 instructions per Matern correlation (9-term series), for the producers' shares
+#endif
 
 constexpr int kTriMaxM = 26;       // two stages still fit shared memory
 constexpr int kTriMaxStages = 6;
@@ -56,13 +62,13 @@ constexpr int kTriProducers = 8;  // at most (seven when the loader takes warp 4
 #define NNGP_TRI_SLIM 0
 #endif
 template <int COV>
-constexpr bool kTriSlim = NNGP_TRI_SLIM && (COV == 2 || COV == 4);
+constexpr bool kTriSlim = NNGP_TRI_SLIM && kIsMatern<COV>;
 template <int COV>
 constexpr int kTriConsumerWeight = 10;  // tenths; see the shares in the kernel's set-up.  Measured (n = 10^6, m = 15, ms,
                                         // exponential / spherical / Matern): 0 (even split) 0.473 / 0.432 / 0.667; 10: 0.467 / 0.414 /
                                         // 0.647; 18: 0.501 / 0.445 / 0.693; 28: 0.597 / 0.447 / 0.854 (scheduler 3's two warps pace the tile)
 template <int COV>
-constexpr bool kTriWant4 = !(COV == 2 || COV == 4);  // Matern keeps three consumers and eight producers
+constexpr bool kTriWant4 = !kIsMatern<COV>;  // Matern keeps three consumers and eight producers
 constexpr int kTriTabBytes = (32 + 128) * 8;
 constexpr int kTriBarBytes = 512;  // 4 x 6 mbarriers, then the tile ring (6 long long)
 
@@ -204,7 +210,7 @@ __device__ __forceinline__ void tri_rows_matern(unsigned char *const (&p)[NU], c
     d2[u] = D * D;
   }
 #pragma unroll
-  for (int u = 0; u < NU; ++u) v[u] = sig * cor.fast_tab(d2[u]);
+  for (int u = 0; u < NU; ++u) v[u] = NNGP_TRI_SIG_FOLD ? cor.fast_tab(d2[u]) : sig * cor.fast_tab(d2[u]);  // folded: sigma^2 rides in the series coefficients (tri_launch_one)
   bool any = false;
 #pragma unroll
   for (int u = 0; u < NU; ++u) any |= cor.maybe_slow(d2[u]);
@@ -221,7 +227,7 @@ template <int COV>
 constexpr int kTriUnr = kIsMatern<COV> ? (NNGP_TRI_SLIM ? NNGP_TRI_UNR_MATERN + 1 : NNGP_TRI_UNR_MATERN) : NNGP_TRI_UNR;
 // FP64 instructions per correlation (SASS counts), for the producers' shares
 template <int COV>
-constexpr int kTriRowCost = kIsMatern<COV> ? 55 : (COV == NNGP_COV_SPHERICAL ? 7 : 21);
+constexpr int kTriRowCost = COV == NNGP_COV_MATERN_TINY ? NNGP_TRI_MATERN_COST - 8 : (kIsMatern<COV> ? NNGP_TRI_MATERN_COST : (COV == NNGP_COV_SPHERICAL ? 7 : 21));
 
 // Whole batches [b0, b1) of the stage's m(m+1)/2 rows (c rows, then the packed triangle: contiguous);
 // `tail`: this warp also takes the rows left over after the last whole batch.
@@ -813,6 +819,15 @@ static cudaError_t tri_launch_one(const BfLaunch &P0, int grid_x, cudaStream_t s
     cw_env = e ? atoi(e) : -1;
   }
   BfLaunch P = P0;
+  if constexpr (kIsMatern<COV> && NNGP_TRI_SIG_FOLD) {
+    // sigma^2 folded into the series coefficients of this launch's copy: the producers' fast path returns sigma^2 rho
+    // (one multiplication less per entry; exact for the powers of two of the scaling tests); slow() keeps its own tables
+    for (int b = 0; b < P.nbatch; b++)
+      for (int k = 0; k < kMatSeriesTerms; k++) {
+        P.th[b].ms.sa[k] *= P.th[b].sigmaSq;
+        P.th[b].ms.sb[k] *= P.th[b].sigmaSq;
+      }
+  }
   P.tri_cw = cw_env > 0 ? cw_env : kTriConsumerWeight<COV>;
   // measured (n = 10^6, m = 15, same box): with the quadratic form the loader's gathers pace a four-consumer CTA
   // (exponential 0.498 vs 0.466 ms, spherical 0.446 vs 0.412), without it four consumers win (0.416 vs 0.433, 0.331 vs 0.366)
@@ -860,6 +875,7 @@ cudaError_t tri_launch(const BfLaunch &P, int cov, int grid_x, cudaStream_t stre
     case NNGP_COV_EXPONENTIAL: return tri_launch_one<NNGP_COV_EXPONENTIAL>(P, grid_x, stream);
     case NNGP_COV_SPHERICAL: return tri_launch_one<NNGP_COV_SPHERICAL>(P, grid_x, stream);
     case NNGP_COV_MATERN:
+      if (P.matern_short == 2) return tri_launch_one<NNGP_COV_MATERN_TINY>(P, grid_x, stream);
       if (P.matern_short) return tri_launch_one<NNGP_COV_MATERN_SHORT>(P, grid_x, stream);
       return tri_launch_one<NNGP_COV_MATERN>(P, grid_x, stream);
     case NNGP_COV_GAUSSIAN: return tri_launch_one<NNGP_COV_GAUSSIAN>(P, grid_x, stream);

@@ -10,8 +10,9 @@ namespace nngp {
 
 // Kernel-template code of the short-series Matern variant (not an ABI value: the C ABI's cov_model stays 0..3).
 constexpr int NNGP_COV_MATERN_SHORT = 4;
+constexpr int NNGP_COV_MATERN_TINY = 5;  // kMatTinyTerms terms (bf_tri_kernel only; the other kernels run SHORT instead)
 template <int COV>
-constexpr bool kIsMatern = (COV == NNGP_COV_MATERN || COV == NNGP_COV_MATERN_SHORT);
+constexpr bool kIsMatern = (COV == NNGP_COV_MATERN || COV == NNGP_COV_MATERN_SHORT || COV == NNGP_COV_MATERN_TINY);
 
 // Every functor maps the SQUARED distance to the correlation.  fast() is straight-line code valid for
 // most arguments; needs_slow() flags the rare arguments that must be re-evaluated with slow().
@@ -89,6 +90,19 @@ struct Cor<NNGP_COV_MATERN_SHORT> : Cor<NNGP_COV_MATERN> {
   __device__ __forceinline__ Cor(const BfTheta &t, const double *tab_ = nullptr) : Cor<NNGP_COV_MATERN>(t, tab_) {}
   __device__ __forceinline__ double fast_tab(double d2) const {
     return matern_series_tab<kMatShortTerms>(q4 * d2, ms, tab, ltab);
+  }
+  __device__ __forceinline__ double fast(double d2) const { return fast_tab(d2); }
+  __device__ __forceinline__ bool needs_slow(double d2) const { return q4 * d2 > ms.t_fast_max; }
+  __device__ __forceinline__ double operator()(double d2) const { return needs_slow(d2) ? slow(d2) : fast(d2); }
+};
+
+// ... and to kMatTinyTerms terms for t <= MaternConsts::t_tiny_max (very dense neighbourhoods: at n = 10^6, m = 15, phi = 6 every
+// pair of a neighbourhood has t ~ 3e-4, where the sixth term is already below 1e-19)
+template <>
+struct Cor<NNGP_COV_MATERN_TINY> : Cor<NNGP_COV_MATERN> {
+  __device__ __forceinline__ Cor(const BfTheta &t, const double *tab_ = nullptr) : Cor<NNGP_COV_MATERN>(t, tab_) {}
+  __device__ __forceinline__ double fast_tab(double d2) const {
+    return matern_series_tab<kMatTinyTerms>(q4 * d2, ms, tab, ltab);
   }
   __device__ __forceinline__ double fast(double d2) const { return fast_tab(d2); }
   __device__ __forceinline__ bool needs_slow(double d2) const { return q4 * d2 > ms.t_fast_max; }

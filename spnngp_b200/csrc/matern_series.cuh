@@ -32,18 +32,24 @@ NNGP_FM double matern_series(double t, const MaternSeriesParams &mc) {
 }
 
 // matern_series with the table-driven log / exp (tab: 32 doubles of kExpTab32, then the 64 pairs of kLogTab64, in
-// shared memory): 26 fewer FP64 instructions of ~95 per correlation.
+// shared memory): 26 fewer FP64 instructions of ~95 per correlation; log and exp fused in base 2 (nngp_pow_tab): 2 more.
 #ifndef NNGP_LOGTAB_REP
 #define NNGP_LOGTAB_REP 0  // 1: the kernel staged 8 interleaved copies of the log table (one per quarter-warp lane)
 #endif
 constexpr int kLogTabStride = NNGP_LOGTAB_REP ? 8 : 1;
+#ifndef NNGP_POW_FUSED
+#define NNGP_POW_FUSED 1  // t^nu by nngp_pow_tab (log and exp fused in base 2) instead of exp_tab(nu * log_tab(t))
+#endif
 
 // tab: kExpTab32; ltab: the log table (this lane's copy when replicated)
 template <int NT = kMatSeriesTerms>
 NNGP_FM double matern_series_tab(double t, const MaternSeriesParams &mc, const double *tab, const double *ltab) {
   // t = 0 (coincident sites) needs no guard here: the table log reads it as 2^-1023, so t^nu ~ 0 and rho = sa[0] = 1
-  const double L = nngp_log_tab<kLogTabStride>(t, ltab);
-  const double pw = nngp_exp_tab(mc.nu * L, tab);  // t^nu
+#if NNGP_POW_FUSED
+  const double pw = nngp_pow_tab<kLogTabStride>(t, mc.nu32, mc.nu32_log2e, tab, ltab);  // t^nu
+#else
+  const double pw = nngp_exp_tab(mc.nu * nngp_log_tab<kLogTabStride>(t, ltab), tab);  // t^nu
+#endif
   double pa = mc.sa[NT - 1], pb = mc.sb[NT - 1];
 #pragma unroll
   for (int k = NT - 2; k >= 0; --k) {

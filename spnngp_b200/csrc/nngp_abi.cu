@@ -232,7 +232,7 @@ long long nngp_launch_count(const nngp_ctx *c) { return c ? c->launches : 0; }
 int nngp_set_option(nngp_ctx *c, const char *name, int value) {
   if (!c || !name) return NNGP_EINVAL;
   if (!strcmp(name, "matern_short")) {
-    c->opt_matern_short = value ? 1 : 0;
+    c->opt_matern_short = value < 0 ? 0 : (value > 2 ? 2 : value);  // 0: full series; 1: at most the short one; 2: tiny allowed
     return NNGP_OK;
   }
   if (!strcmp(name, "tri_cache")) {  // takes effect at the next nngp_set_data
@@ -274,7 +274,12 @@ int nngp_get_option(nngp_ctx *c, const char *name, int *value) {
   }
   if (!strcmp(name, "matern_short_used")) {  // parameter sets of the last likelihood launch that ran the short series
     *value = 0;
-    for (int b = 0; b < NNGP_MAX_BATCH; b++) *value += c->bf_short[b];
+    for (int b = 0; b < NNGP_MAX_BATCH; b++) *value += c->bf_short[b] != 0;
+    return NNGP_OK;
+  }
+  if (!strcmp(name, "matern_tiny_used")) {  // ... and how many of them the kMatTinyTerms-term one (bf_tri_kernel)
+    *value = 0;
+    for (int b = 0; b < NNGP_MAX_BATCH; b++) *value += c->bf_short[b] == 2;
     return NNGP_OK;
   }
   return ctx_fail(c, NNGP_EINVAL, std::string("nngp_get_option: unknown option ") + name);
@@ -560,7 +565,8 @@ static int prepare_bf(nngp_ctx *c, int cov, int nbatch, const double *theta, con
       const double t99 = 0.25 * t[2] * t[2] * c->pair_d2_q99;
       c->bf_short[b] = (c->opt_matern_short && th.ms.use_series && (tri || bf_has_matern_short(c->m)) &&
                         t99 <= c->h_mat[b].t_short_max) ? 1 : 0;
-      if (c->bf_short[b]) th.ms.t_fast_max = c->h_mat[b].t_short_max;
+      if (c->bf_short[b] && c->opt_matern_short >= 2 && tri && t99 <= c->h_mat[b].t_tiny_max) c->bf_short[b] = 2;
+      if (c->bf_short[b]) th.ms.t_fast_max = (c->bf_short[b] == 2) ? c->h_mat[b].t_tiny_max : c->h_mat[b].t_short_max;
       matern_set_phi(&th.ms, t[2]);
     }
     const int slot = slots ? slots[b] : (b & 1);
@@ -611,23 +617,24 @@ static int enqueue_bf(nngp_ctx *c, int cov, const BfLaunch &P, int grid, bool wi
       c->launches++;
     }
   }
-  int nshort = 0;
-  if (cov == NNGP_COV_MATERN)
-    for (int b = 0; b < P.nbatch; b++) nshort += c->bf_short[b];
-  if (nshort == 0 || nshort == P.nbatch) {
-    if (nshort == 0) {
-      NNGP_CUDA(c, bf_launch(P, cov, grid, c->stream));
-    } else {
-      BfLaunch Ps = P;
-      Ps.matern_short = 1;
-      NNGP_CUDA(c, bf_launch(Ps, cov, grid, c->stream));
+  // Matern: one launch per series variant present in the batch (0 full, 1 short, 2 tiny), so that the result of a
+  // parameter set never depends on what it was batched with (the sampler's current and candidate phi may straddle a
+  // variant's range); a homogeneous batch -- the usual case -- is one launch
+  int have[3] = {0, 0, 0};
+  for (int b = 0; b < P.nbatch; b++) have[cov == NNGP_COV_MATERN ? c->bf_short[b] : 0]++;
+  for (int v = 0; v < 3; v++) {
+    if (!have[v]) continue;
+    if (have[v] == P.nbatch) {
+      if (v == 0) {
+        NNGP_CUDA(c, bf_launch(P, cov, grid, c->stream));
+      } else {
+        BfLaunch Ps = P;
+        Ps.matern_short = v;
+        NNGP_CUDA(c, bf_launch(Ps, cov, grid, c->stream));
+      }
+      c->launches++;
+      return NNGP_OK;
     }
-    c->launches++;
-    return NNGP_OK;
-  }
-  // mixed batch (the sampler's current and candidate phi straddle the short series' range): one launch per
-  // variant, so that the result of a parameter set never depends on what it was batched with
-  for (int v = 0; v < 2; v++) {
     BfLaunch Pv = P;
     Pv.nbatch = 0;
     for (int b = 0; b < P.nbatch; b++)

@@ -25,6 +25,21 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, 
 
 using namespace nngp;
 
+// Page-locked host arrays for callers that can place their big inputs / outputs there (the q x S normals and draws of
+// nngp_rnngp_predict): the transfer paths DMA straight from / to such arrays instead of staging through the pinned ring.
+extern "C" int nngp_host_alloc(nngp_ctx *c, size_t bytes, void **out) {
+  if (!c || !out) return NNGP_EINVAL;
+  NNGP_CUDA(c, cudaSetDevice(c->device));
+  NNGP_CUDA(c, cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+  return NNGP_OK;
+}
+
+extern "C" int nngp_host_free(nngp_ctx *c, void *p) {
+  if (!c) return NNGP_EINVAL;
+  if (p) NNGP_CUDA(c, cudaFreeHost(p));
+  return NNGP_OK;
+}
+
 extern "C" int nngp_fp64_peak(nngp_ctx *c, double *tflops) {
   if (!c || !tflops) return NNGP_EINVAL;
   NNGP_CUDA(c, cudaSetDevice(c->device));

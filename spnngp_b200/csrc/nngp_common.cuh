@@ -55,8 +55,9 @@ struct BfLaunch {
   const double2 *sites;  // q interleaved query sites
   const int *nn0;        // q x m column-major neighbour ids (R/generics.R:642 layout)
   int q;
-  // Matern: every parameter set of this launch may use the short series (th.ms.t_fast_max set accordingly);
-  // only bf_ws_kernel has that variant, the other kernels ignore the flag (their t_fast_max is 1)
+  // Matern: every parameter set of this launch may use a truncated series (th.ms.t_fast_max set accordingly): 1 = the
+  // short one (bf_ws_kernel, bf_tri_kernel), 2 = the tiny one (bf_tri_kernel; bf_ws_kernel runs the short one instead);
+  // the other kernels ignore the flag (their t_fast_max is 1)
   int matern_short;
   // resident distance triangle (tri_cache.cu) of the locations [loc_begin, loc_end): tile t (32 locations) holds
   // m(m+1)/2 rows of 32 doubles -- m rows location <-> neighbour k, then the packed pairs (k, l), l < k.  NULL: gather kernels.

@@ -85,7 +85,7 @@ struct nngp_ctx {
   double d_mat_nu[NNGP_MAX_BATCH] = {-1.0, -1.0, -1.0, -1.0};  // smoothness whose tables sit in d_mat[b]
 
   // Matern short series (matern_series.cuh): chosen per parameter set when phi^2/4 * pair_d2_q99 <= t_short_max(nu)
-  int opt_matern_short = 1;      // nngp_set_option("matern_short", 0/1)
+  int opt_matern_short = 2;      // nngp_set_option("matern_short", 0/1/2): 0 full series, 1 at most the short one, 2 tiny allowed
   double pair_d2_q99 = 1e300;    // 99 % quantile over this shard's locations of the largest squared pair distance
   unsigned int *d_hist = nullptr;
   unsigned int *h_hist = nullptr;   // pinned copy, filled asynchronously behind the histogram kernel

@@ -204,6 +204,23 @@ class Engine:
         self._check(self.lib.nngp_comm_allreduce_sum(self.h, _dp(a), a.size))
         return a
 
+    def pinned_array(self, count, dtype=np.float64):
+        """A page-locked numpy array (include/nngp_b200.h: nngp_host_alloc): inputs / outputs placed in such arrays are
+        moved by direct DMA instead of through the staging ring.  Freed by `free_pinned` (or with the process)."""
+        dt = np.dtype(dtype)
+        ptr = C.c_void_p()
+        self._check(self.lib.nngp_host_alloc(self.h, int(count) * dt.itemsize, C.byref(ptr)))
+        buf = (C.c_char * (int(count) * dt.itemsize)).from_address(ptr.value)
+        a = np.frombuffer(buf, dtype=dt, count=int(count))
+        self._pinned = getattr(self, "_pinned", {})
+        self._pinned[a.ctypes.data] = ptr
+        return a
+
+    def free_pinned(self, a):
+        ptr = getattr(self, "_pinned", {}).pop(a.ctypes.data, None)
+        if ptr is not None:
+            self._check(self.lib.nngp_host_free(self.h, ptr))
+
     def fp64_peak_tflops(self):
         out = np.zeros(1)
         self._check(self.lib.nngp_fp64_peak(self.h, _dp(out)))
@@ -280,15 +297,19 @@ class Engine:
                                                    _lib.INTERRUPT_FN(0), _dp(out)))
         return out[: self.n * S].reshape(S, self.n).T.copy()
 
-    def rnngp_predict(self, cov, X0, coords0, nnIndx0, beta_samples, theta_samples, z, site_range=None):
+    def rnngp_predict(self, cov, X0, coords0, nnIndx0, beta_samples, theta_samples, z, site_range=None, out=None):
         """Posterior predictive draws (reference `rNNGPPredict`, src/rNNGPPredict.cpp:25).
         beta_samples p x S, theta_samples nTheta x S, nnIndx0 flat q*m column-major, z flat q*S (z[i*S+s]).
-        Returns q x S."""
+        Returns q x S.  `out`: optional flat q*S float64 array for the draws (e.g. `pinned_array`: direct DMA)."""
         X0 = np.asarray(X0, dtype=np.float64).reshape(-1, self.p); q = X0.shape[0]
         bs = np.asarray(beta_samples, dtype=np.float64); S = bs.shape[1]
         x0f = colmajor(X0); c0 = colmajor(coords0); nn0 = _i32(nnIndx0)
         bsf = colmajor(bs); tsf = colmajor(np.asarray(theta_samples, dtype=np.float64)); zf = _f64(z)
-        y0 = np.zeros(q * S)
+        if out is not None:
+            assert out.dtype == np.float64 and out.size == q * S and out.flags.c_contiguous
+            y0 = out
+        else:
+            y0 = np.zeros(q * S)
         lo, hi = site_range if site_range is not None else (0, q)
         self._check(self.lib.nngp_rnngp_predict(self.h, cov, q, _dp(x0f), _dp(c0), _ip(nn0), S, _dp(bsf), _dp(tsf),
                                                 _dp(zf), _dp(y0), lo, hi))

@@ -43,6 +43,17 @@ extern "C" double host_t_short_max(double nu) {
   nngp::MaternConsts mc; nngp::matern_prepare(nu, &mc);
   return mc.t_short_max;
 }
+// tiny series (kMatTinyTerms terms, bf_tri_kernel) and the largest t it is used for
+extern "C" double host_matern_series_tiny(double t, double nu) {
+  nngp::MaternConsts mc; nngp::matern_prepare(nu, &mc);
+  if (!mc.use_series) return -1.0;
+  nngp::MaternSeriesParams ms; nngp::matern_series_params(mc, &ms);
+  return nngp::matern_series<nngp::kMatTinyTerms>(t, ms);
+}
+extern "C" double host_t_tiny_max(double nu) {
+  nngp::MaternConsts mc; nngp::matern_prepare(nu, &mc);
+  return mc.t_tiny_max;
+}
 // integer threshold of the producers' "may need slow()" test (matern_set_phi) and the bound it stands for
 extern "C" int host_d2_slow_hi(double nu, double phi, int use_short, double *t_fast_max) {
   nngp::MaternConsts mc; nngp::matern_prepare(nu, &mc);
@@ -51,4 +62,13 @@ extern "C" int host_d2_slow_hi(double nu, double phi, int use_short, double *t_f
   nngp::matern_set_phi(&ms, phi);
   *t_fast_max = ms.t_fast_max;
   return ms.d2_slow_hi;
+}
+// the series exactly as the producers evaluate it: table-driven t^nu (nngp_pow_tab), NT terms
+extern "C" double host_matern_series_tab(double t, double nu, int terms) {
+  nngp::MaternConsts mc; nngp::matern_prepare(nu, &mc);
+  if (!mc.use_series) return -1.0;
+  nngp::MaternSeriesParams ms; nngp::matern_series_params(mc, &ms);
+  if (terms == nngp::kMatTinyTerms) return nngp::matern_series_tab<nngp::kMatTinyTerms>(t, ms, nngp::kExpTab32, nngp::kLogTab64);
+  if (terms == nngp::kMatShortTerms) return nngp::matern_series_tab<nngp::kMatShortTerms>(t, ms, nngp::kExpTab32, nngp::kLogTab64);
+  return nngp::matern_series_tab<nngp::kMatSeriesTerms>(t, ms, nngp::kExpTab32, nngp::kLogTab64);
 }

@@ -266,6 +266,25 @@ def test_matern_short_series_variant(engine, port, nu, m):
         assert engine.get_option("matern_short_used") == 0
         assert relerr(Fs, Ff) < 1e-13 and relerr_norm(Bs, Bf) < 1e-13
         assert abs(outs[0, 0] - outf[0, 0]) < 1e-13 * abs(outf[0, 0])
+        # the 5-term series (distance-triangle kernel): phi small enough that 99 % of the neighbourhoods sit in its range
+        engine.set_option("matern_short", 2)
+        tiny = [5.0, 1.0, 0.25, nu]
+        Bt, Ft, outt = _check(engine, port, prob, 2, tiny)
+        used_tiny = engine.get_option("matern_tiny_used")
+        assert used_tiny == (1 if engine.get_option("tri_cache_used") else 0)
+        engine.set_option("matern_short", 0)
+        Bf2, Ff2, outf2 = _check(engine, port, prob, 2, tiny)
+        assert relerr(Ft, Ff2) < 1e-13 and relerr_norm(Bt, Bf2) < 1e-13
+        assert abs(outt[0, 0] - outf2[0, 0]) < 1e-13 * abs(outf2[0, 0])
+        if used_tiny:  # three variants in one batch: one launch each, results as if launched alone
+            engine.set_option("matern_short", 2)
+            beta = prob["beta"]
+            far3 = [5.0, 1.0, 60.0, nu]
+            mixed = engine.bf_loglik(2, [tiny, far3, theta], [beta, beta, beta], slots=[0, 1, 0])
+            assert engine.get_option("matern_short_used") == 2 and engine.get_option("matern_tiny_used") == 1
+            for k, th in enumerate((tiny, far3, theta)):
+                alone = engine.bf_loglik(2, [th], [beta], slots=[0])
+                assert np.array_equal(mixed[k], alone[0])
         engine.set_option("matern_short", 1)
         far = [5.0, 1.0, 60.0, nu]  # phi D ~ 5: outside the short range -> full series / quadrature
         beta = prob["beta"]
@@ -276,7 +295,7 @@ def test_matern_short_series_variant(engine, port, nu, m):
         assert engine.get_option("matern_short_used") == 0
         assert np.array_equal(mixed[0], a[0]) and np.array_equal(mixed[1], b[0])
     finally:
-        engine.set_option("matern_short", 1)
+        engine.set_option("matern_short", 2)
 
 
 @pytest.mark.parametrize("cov,theta,m", [(0, [5.0, 1.0, 6.0], 15), (2, [5.0, 1.0, 6.0, 0.75], 15), (1, [5.0, 1.0, 6.0], 9),

@@ -62,20 +62,23 @@ def test_bf_loglik_full_size_against_oracle(engine, port, full):
     assert abs(engine.q_resid(0, full["beta"]) - Qo) <= TOL * abs(Qo)
 
 
-@pytest.mark.parametrize("short", [1, 0])
-def test_matern_headline_config_against_oracle(engine, port, full, short):
+@pytest.mark.parametrize("short,phi", [(2, 6.0), (0, 6.0), (2, 0.6)])
+def test_matern_headline_config_against_oracle(engine, port, full, short, phi):
     """BASELINE configs[2] verbatim -- Matern, theta = (5, 1, 6, 0.75), n = 10^6, m = 15: the kernel variant the bench
-    times (launch-level short series, `matern_short_used == 1`) and the full series, every B, F, logDet and Q against
-    the oracle (updateBF src/rNNGP.cpp:46-101 with spCor's Matern branch src/util.cpp:233-237), <= 1e-10."""
-    theta = [5.0, 1.0, 6.0, 0.75]
+    times (default options: the launch-level 9-term series, `matern_short_used == 1`) and the full series, every B, F,
+    logDet and Q against the oracle (updateBF src/rNNGP.cpp:46-101 with spCor's Matern branch src/util.cpp:233-237),
+    <= 1e-10.  Third case: a decay ten times smaller, where the same data set falls into the 5-term series' range
+    (`matern_tiny_used == 1`)."""
+    theta = [5.0, 1.0, phi, 0.75]
     engine.set_data(full["coords"], full["idx"], full["lu"], full["X"], full["y"], M)
     engine.set_option("matern_short", short)
     try:
         out = engine.bf_loglik(2, [theta], [full["beta"]], slots=[0])
-        assert engine.get_option("matern_short_used") == short
+        assert engine.get_option("matern_short_used") == (short > 0)
+        assert engine.get_option("matern_tiny_used") == (short == 2 and phi < 1.0)
         B, F = engine.get_bf(0)
     finally:
-        engine.set_option("matern_short", 1)
+        engine.set_option("matern_short", 2)
     Bo, Fo, ld, info = port.update_bf(full["coords"], full["idx"], full["lu"], N, M, theta, 2)
     assert info == 0
     r = full["X"] @ full["beta"] - full["y"]

@@ -78,6 +78,35 @@ def test_rnngp_predict_many_chunks_full_duplex(engine, port):
     assert st == 0 and np.max(np.abs(got[:, sub] - ref)) < 1e-10 * np.abs(ref).max()
 
 
+def test_rnngp_predict_page_locked_arrays(engine, port):
+    """Normals and draws placed in page-locked arrays (nngp_host_alloc) travel by direct DMA instead of through the
+    staging ring (host_stage.h): same draws bit for bit as with pageable arrays, one chunk and many chunks."""
+    rng = np.random.default_rng(10)
+    m, q, S = 10, 5000, 80  # z: 3.2 MB, above the 2 MB threshold of the direct path
+    prob = make_problem(1500, m, seed=34, port=port, domain=0.5)
+    coords0 = rng.random((q, 2)) * 0.5
+    X0 = np.column_stack([np.ones(q), rng.standard_normal(q)])
+    nn0 = port.nn_query(prob["coords"], coords0, m)
+    beta, theta = _chain_like_samples(rng, S, 2, 2)
+    engine.set_data(prob["coords"], prob["nnIndx"], prob["nnIndxLU"], prob["X"], prob["y"], m)
+    z = rng.standard_normal(q * S)
+    want = engine.rnngp_predict(2, X0, coords0, nn0, beta, theta, z)
+    zp = engine.pinned_array(q * S); yp = engine.pinned_array(q * S)
+    try:
+        zp[:] = z
+        yp[:] = -1.0
+        got = engine.rnngp_predict(2, X0, coords0, nn0, beta, theta, zp, out=yp)
+        assert np.array_equal(got, want)
+        os.environ["NNGP_PREDICT_CHUNK"] = "1024"
+        yp[:] = -1.0
+        got = engine.rnngp_predict(2, X0, coords0, nn0, beta, theta, zp, out=yp)
+        assert np.array_equal(got, want)
+        got = got.copy()
+    finally:
+        os.environ.pop("NNGP_PREDICT_CHUNK", None)
+        engine.free_pinned(zp); engine.free_pinned(yp)
+
+
 @pytest.mark.parametrize("cov,m", [(0, 15), (2, 10), (3, 20)])
 def test_cnngp_parity(engine, port, cov, m):
     rng = np.random.default_rng(7 + cov)

@@ -150,6 +150,29 @@ def test_matern_short_series_on_host_vs_mpmath(tmp_path):
     assert L.host_t_short_max(1.0) == 0.0 and L.host_t_short_max(2.0005) == 0.0  # integer nu: no series at all
 
 
+def test_matern_tiny_series_on_host_vs_mpmath(tmp_path):
+    """The 5-term series (Cor<NNGP_COV_MATERN_TINY>, the variant BASELINE configs[2] runs: t ~ 3e-4 there) over its whole
+    range t <= t_tiny_max(nu): as accurate as the 14-term one (vs mpmath); the range covers the benchmark's
+    neighbourhoods with room to spare and lies inside the 9-term range."""
+    import mpmath as mp
+    L = _build_host("besselk_host.cpp", str(tmp_path / "libbk.so"))
+    L.host_matern_series_tiny.restype = C.c_double; L.host_matern_series_tiny.argtypes = [C.c_double, C.c_double]
+    L.host_t_tiny_max.restype = C.c_double; L.host_t_tiny_max.argtypes = [C.c_double]
+    L.host_t_short_max.restype = C.c_double; L.host_t_short_max.argtypes = [C.c_double]
+    mp.mp.dps = 40
+    worst = 0.0
+    for nu in (0.1, 0.3, 0.5, 0.75, 0.9, 1.2, 1.5, 1.9, 2.5, 3.3):
+        T = L.host_t_tiny_max(nu)
+        assert 1e-3 < T <= L.host_t_short_max(nu), (nu, T)
+        for f in (1e-12, 1e-6, 1e-3, 0.1, 0.5, 0.9, 1.0):
+            t = T * f
+            x = 2.0 * np.sqrt(t)
+            rho = mp.mpf(x) ** nu * mp.besselk(nu, x) / (mp.mpf(2) ** (nu - 1) * mp.gamma(nu))
+            worst = max(worst, float(abs((mp.mpf(L.host_matern_series_tiny(t, nu)) - rho) / rho)))
+    assert worst < 5e-14, worst
+    assert L.host_t_tiny_max(1.0) == 0.0 and L.host_t_tiny_max(2.0005) == 0.0  # integer nu: no series at all
+
+
 def test_integer_slow_path_threshold_is_conservative(tmp_path):
     """matern_set_phi: the producers test `hi32(d2) >= d2_slow_hi` instead of `phi^2 d2 / 4 > t_fast_max`.  Every d2 the
     integer test lets through must satisfy the floating-point bound (up to rounding), and it must not be grossly
@@ -217,6 +240,40 @@ def test_table_driven_exp_log_on_host(tmp_path):
         worst_abs = max(worst_abs, err / max(1.0, float(abs(r))))
     assert worst_abs < 3e-16, worst_abs
     assert abs(L.host_nngp_log_tab(1.0)) < 2e-17
+
+
+def test_fused_power_kernel_on_host(tmp_path):
+    """nngp_pow_tab (fastmath.cuh): x^nu = 2^(32 nu log2 x / 32) with the log's recombination and the exp's reduction
+    fused -- vs mpmath over the producers' range (t = (phi D / 2)^2 from 1e-30 to 4, nu from 0.05 to 5), relative error of
+    the order of |nu log x| ulps like exp(nu * log x); and the series evaluated through it (matern_series_tab) vs the
+    Matern correlation itself for all three series lengths."""
+    import mpmath as mp
+    L = _build_host("fastmath_host.cpp", str(tmp_path / "libfm3.so"))
+    L.host_nngp_pow_tab.restype = C.c_double; L.host_nngp_pow_tab.argtypes = [C.c_double, C.c_double]
+    mp.mp.dps = 40
+    rng = np.random.default_rng(5)
+    worst = 0.0
+    for nu in (0.05, 0.3, 0.5, 0.75, 1.5, 2.5, 5.0):
+        for x in np.concatenate([10 ** rng.uniform(-30, 0.6, 600), 1 + rng.uniform(-0.5, 1.0, 100), [1.0, 0.5, 2.0, 4.0]]):
+            r = mp.mpf(float(x)) ** mp.mpf(nu)
+            err = float(abs((mp.mpf(L.host_nngp_pow_tab(float(x), nu)) - r) / r))
+            worst = max(worst, err / max(1.0, abs(nu * np.log(x))))
+    assert worst < 6e-16, worst  # exp_tab(nu * log_tab(x)) measures 3.2e-16 on the same points
+    assert L.host_nngp_pow_tab(1.0, 0.75) == 1.0
+    assert 0.0 <= L.host_nngp_pow_tab(0.0, 0.75) < 1e-200 and L.host_nngp_pow_tab(1e-300, 5.0) == 0.0
+    Lb = _build_host("besselk_host.cpp", str(tmp_path / "libbk3.so"))
+    Lb.host_matern_series_tab.restype = C.c_double; Lb.host_matern_series_tab.argtypes = [C.c_double, C.c_double, C.c_int]
+    for name in ("host_t_tiny_max", "host_t_short_max"):
+        getattr(Lb, name).restype = C.c_double; getattr(Lb, name).argtypes = [C.c_double]
+    worst = 0.0
+    for nu in (0.1, 0.3, 0.75, 0.9, 1.5, 2.5, 3.3):
+        for terms, T in ((5, Lb.host_t_tiny_max(nu)), (9, Lb.host_t_short_max(nu)), (14, 1.0)):
+            for f in (1e-12, 1e-6, 1e-3, 0.03, 0.1, 0.5, 0.9, 1.0):
+                t = T * f
+                x = 2.0 * np.sqrt(t)
+                rho = mp.mpf(x) ** nu * mp.besselk(nu, x) / (mp.mpf(2) ** (nu - 1) * mp.gamma(nu))
+                worst = max(worst, float(abs((mp.mpf(Lb.host_matern_series_tab(t, nu, terms)) - rho) / rho)))
+    assert worst < 1e-13, worst
 
 
 def test_kats_on_the_oracle(port):

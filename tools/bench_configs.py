@@ -80,23 +80,34 @@ if "predict" in which:  # ---- configs[3] --------------------------------------
     base = np.array([[5.0], [1.0], [6.0], [0.75]]) * (1 + 0.02 * rng.standard_normal((4, distinct)))
     th = base[:, np.sort(rng.integers(0, distinct, S))]
     res = {}
+    qs = q // slices
+    zp = eng.pinned_array(qs * S); yp = eng.pinned_array(qs * S)  # page-locked arrays (nngp_host_alloc): direct DMA
     for cov, name in ((0, "exponential"), (2, "matern")):
-        t_nn = t_pred = 0.0
-        chk = 0.0
+        t_nn = t_pred = t_pin = 0.0
+        chk = chk_pin = 0.0
         for s in range(slices):
-            qs = q // slices
             c0 = rng.random((qs, 2)) * W
             X0 = np.column_stack([np.ones(qs), rng.standard_normal(qs)])
             z = rng.standard_normal(qs * S)
             dt, nn0 = timed(lambda: eng.nn_query(c, c0, m)); t_nn += dt
             dt, y0 = timed(lambda: eng.rnngp_predict(cov, X0, c0, nn0, bs, th[: (4 if cov == 2 else 3)], z)); t_pred += dt
             chk += float(np.mean(y0))
-            del z, y0
-        res[name] = dict(nn_query_s=t_nn, predict_s=t_pred, draws_per_s=q * S / t_pred, mean_of_draws=chk / slices)
+            del y0
+            zp[:] = z
+            del z
+            dt, y0 = timed(lambda: eng.rnngp_predict(cov, X0, c0, nn0, bs, th[: (4 if cov == 2 else 3)], zp, out=yp)); t_pin += dt
+            chk_pin += float(np.mean(y0))
+        res[name] = dict(nn_query_s=t_nn, predict_s=t_pred, draws_per_s=q * S / t_pred, mean_of_draws=chk / slices,
+                         predict_page_locked_s=t_pin, draws_per_s_page_locked=q * S / t_pin,
+                         transfer_GBps_each_way_page_locked=8.0 * q * S / t_pin / 1e9,
+                         same_draws=bool(chk == chk_pin))
         print("predict", name, res[name], flush=True)
+    eng.free_pinned(zp); eng.free_pinned(yp)
     out["predict"] = dict(n=n, q=q, S=S, distinct_theta=int(len(np.unique(th[2]))), site_slices=slices, **res,
                           note="host arrays in (z: q x S normals, 8 GB) and the q x S draws out (8 GB); the solves run "
-                               "once per distinct theta")
+                               "once per distinct theta.  predict_s: pageable arrays (what R hands over) staged through the "
+                               "pinned rings; predict_page_locked_s: the same call with z and the result in page-locked "
+                               "arrays (nngp_host_alloc / cudaHostRegister), moved by direct DMA, both directions at once")
 
 if "knn" in which:  # ---- configs[4] ------------------------------------------------------------------------------
     knn = {}
