@@ -51,7 +51,7 @@ namespace nngp {
 #define NNGP_TRI_MATERN_COST 52  // FP64 instructions per Matern correlation (9-term series), for the producers' shares
 #endif
 
-constexpr int kTriMaxM = 26;       // two stages still fit shared memory
+constexpr int kTriMaxM = 32;       // 27..32: ONE stage fits shared memory (loader, producers and the consumer take turns)
 constexpr int kTriMaxStages = 6;
 constexpr int kTriThreads = 384;
 constexpr int kTriProducers = 8;  // at most (seven when the loader takes warp 4)
@@ -408,6 +408,188 @@ __device__ __forceinline__ bool tri_solve(double *__restrict__ A, double *__rest
   return ok;
 }
 
+// ---- the same solve by a TEAM of warps on one tile (single-stage geometry, m >= 27) -----------------------------------
+// With one stage in shared memory the loader, the producers and the consumer take turns, and a lone consumer warp needs
+// ~60k cycles for the 33 x 33 factorisation (loads and dependent FMA chains of one warp).  The blocks of a block column
+// are independent given the columns before it, so every warp of the CTA but the loader joins in: team rank tw takes block
+// row jb + tw of column jb (rank 0 the diagonal block, which it also factors; (m + 4) / 4 <= 9 block rows, one block per
+// warp at most).  Two team barriers per column: diagonal factor published -> the others finish their block (e L^-T) ->
+// column published.  V' B = y runs right-looking with one barrier per block (rank 0 solves the 4 x 4 diagonal systems and
+// carries the block right above; the others subtract V(ib, jb)' w_ib from the blocks further up).  Every element sees the
+// same operations in the same order as in tri_solve: results are bit-identical to the one-warp solve.
+__device__ __forceinline__ void team_bar(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+
+__device__ __forceinline__ bool tri_solve_team(double *__restrict__ A, double *__restrict__ cv, double *__restrict__ dv, int m,
+                                               int mi, double diag, double *F_out, int tw, int nthreads) {
+  bool ok = true;
+  double F = diag;
+  auto rowp = [&](int i) -> double * { return (i < m) ? A + (i * (i - 1) / 2) * 32 : cv; };  // row m (and dummies): cv
+  const int nrb = (m + 4) >> 2;  // row blocks over rows 0..m
+#pragma unroll 1
+  for (int jb = 0; jb < nrb; ++jb) {
+    const int j0 = 4 * jb;
+    const int ib = jb + tw;
+    const bool have = ib < nrb;
+    double *pj[4], *pi[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      pj[r] = rowp(min(j0 + r, m));
+      pi[r] = rowp(min(4 * ib + r, m));
+    }
+    double e[4][4];
+    if (tw == 0) {
+      // ---- diagonal block: update (lower part), factor, publish ----
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) e[r][c] = 0.0;
+#pragma unroll
+        for (int c = 0; c < r; ++c) e[r][c] = pj[r][(j0 + c) * 32];
+        e[r][r] = (j0 + r < mi || j0 + r == m) ? diag : 1.0;
+      }
+#pragma unroll 1
+      for (int k = 0; k < j0; k += 2) {
+        double a[2][4];
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+          for (int r = 0; r < 4; ++r) a[kk][r] = pj[r][(k + kk) * 32];
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c <= r; ++c) e[r][c] = fma(-a[kk][r], a[kk][c], e[r][c]);
+      }
+      double ri[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const double piv = e[c][c];
+        if (j0 + c < mi && !(piv > 0.0)) ok = false;
+        if (j0 + c == m) F = piv;
+        ri[c] = nngp_rsqrt_pos(piv);
+#pragma unroll
+        for (int r = c + 1; r < 4; ++r) e[r][c] *= ri[c];
+#pragma unroll
+        for (int c2 = c + 1; c2 < 4; ++c2)
+#pragma unroll
+          for (int r = c2; r < 4; ++r) e[r][c2] = fma(-e[r][c], e[c2][c], e[r][c2]);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        if (j0 + r < m) dv[(j0 + r) * 32] = ri[r];
+        if (j0 + r <= m) {
+#pragma unroll
+          for (int c = 0; c < r; ++c) pj[r][(j0 + c) * 32] = e[r][c];
+        }
+      }
+    } else if (have) {
+      // ---- a block below: update with the columns before j0 ----
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) e[r][c] = pi[r][(j0 + c) * 32];
+#pragma unroll 1
+      for (int k = 0; k < j0; k += 2) {
+        double ai[2][4], aj[2][4];
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            ai[kk][r] = pi[r][(k + kk) * 32];
+            aj[kk][r] = pj[r][(k + kk) * 32];
+          }
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) e[r][c] = fma(-ai[kk][r], aj[kk][c], e[r][c]);
+      }
+    }
+    team_bar(nthreads);  // the factored diagonal block and its 1 / pivots are in shared memory
+    if (tw != 0 && have) {
+      double d[4][4], ri[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        ri[c] = dv[(j0 + c) * 32];
+#pragma unroll
+        for (int c2 = 0; c2 < c; ++c2) d[c][c2] = pj[c][(j0 + c2) * 32];
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {  // e <- e L^-T
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+          for (int c2 = 0; c2 < c; ++c2) e[r][c] = fma(-e[r][c2], d[c][c2], e[r][c]);
+          e[r][c] *= ri[c];
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (4 * ib + r <= m) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) pi[r][(j0 + c) * 32] = e[r][c];
+        }
+    }
+    team_bar(nthreads);  // column jb is final
+  }
+  // ---- V' B = y, right-looking from the bottom ----
+  const int nb = (m + 3) >> 2;
+#pragma unroll 1
+  for (int ib = nb - 1; ib >= 0; --ib) {
+    const int i0 = 4 * ib;
+    if (tw == 0) {
+      double w[4], t[4][4], rv[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) w[c] = (i0 + c < m) ? cv[(i0 + c) * 32] : 0.0;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int i = min(i0 + r, m - 1);
+        rv[r] = dv[i * 32];
+        const double *pr = A + (i * (i - 1) / 2 + i0) * 32;
+#pragma unroll
+        for (int c = 0; c < r; ++c) t[r][c] = (i0 + r < m) ? pr[c * 32] : 0.0;
+      }
+#pragma unroll
+      for (int c = 3; c >= 0; --c) {
+#pragma unroll
+        for (int r = c + 1; r < 4; ++r) w[c] = fma(-t[r][c], w[r], w[c]);
+        w[c] = (i0 + c < m) ? w[c] * rv[c] : 0.0;
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (i0 + c < m) cv[(i0 + c) * 32] = w[c];
+    }
+    if (ib == 0) break;
+    team_bar(nthreads);  // w_ib is final
+    // blocks above: y_jb -= V(ib, jb)' w_ib.  Rank 0 takes the block right above (its next system), rank tw >= 1 block tw - 1
+    const int jb = (tw == 0) ? ib - 1 : tw - 1;
+    if (jb < ib - (tw == 0 ? 0 : 1)) {
+      const int c0 = 4 * jb;
+      double wl[4], v[4][4], y[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int i = min(i0 + r, m - 1);
+        wl[r] = (i0 + r < m) ? cv[i * 32] : 0.0;
+        const double *pr = A + (i * (i - 1) / 2 + c0) * 32;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[r][c] = pr[c * 32];
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) y[c] = cv[(c0 + c) * 32];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) y[c] = fma(-v[r][c], wl[r], y[c]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) cv[(c0 + c) * 32] = y[c];
+    }
+  }
+  *F_out = F;
+  return ok;
+}
+
 template <int MC, bool kSlim>
 __device__ __forceinline__ bool tri_solve_unrolled(double *A, double *cv, double *dv, int mi, double diag, double *F_out) {
   double Fsum;
@@ -427,6 +609,9 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
   const TriGeom G = tri_geometry(m, P.tri_want4 != 0);
   const int S = G.S, NC = G.NC;
   const int loader_warp = (NC == 4) ? 4 : 3, first_producer = loader_warp + 1, nprod = 12 - first_producer;
+  // single stage (m >= 27): the phases of a tile cannot overlap, so every warp but the loader joins the solve (tri_solve_team)
+  const bool wide = (S == 1);
+  constexpr int kTeamThreads = 11 * 32;
   const double *__restrict__ resid = th.resid;
   const bool with_cur = th.Bcur != nullptr && resid != nullptr;
   const long long nloc = (long long)P.loc_end - P.loc_begin;
@@ -460,7 +645,8 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
     const int nrows = m * (m + 1) / 2, nb = nrows / kTriUnr<COV>;
     // tri_cw: the consumer's weight in tenths (its dependent chains suffer from sharing a scheduler more than its
     // instruction count says)
-    const float C = ((float)(m * m * m) / 6.f + 2.f * m * m + 25.f * m) * 0.1f * (float)P.tri_cw, Tp = (float)nrows * kTriRowCost<COV>;
+    const float C = wide ? 0.f : ((float)(m * m * m) / 6.f + 2.f * m * m + 25.f * m) * 0.1f * (float)P.tri_cw;
+    const float Tp = (float)nrows * kTriRowCost<COV>;
     int np[4] = {0, 0, 0, 0};
     for (int w = first_producer; w < 12; ++w) np[w & 3]++;
     float f[4], fs = 0.f;
@@ -542,6 +728,8 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
         const long long base = P.loc_begin + t_cur * 32;
         if (lane == 0) {
           ring[s] = t_cur;
+          // a single stage cannot hide the copy behind the solve: have the NEXT tile's block in L2 by then
+          if (S == 1 && t_nxt < ntiles) bulk_prefetch_l2(P.tri + (size_t)t_nxt * tile_doubles, tri_bytes);
           mbar_expect_tx(bar_full(s), tri_bytes);
           // c rows and the packed triangle are adjacent in the cache and in the stage: one copy
           bulk_g2s(smem_u32(st + G.off_cv), P.tri + (size_t)t_cur * tile_doubles, tri_bytes, bar_full(s));
@@ -578,15 +766,16 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
     else asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     if (warp == loader_warp) {
       run_loader();
-    } else if (warp < NC) {
+    } else if (warp < NC || wide) {
       // ================================ consumers ======================================================
-      unsigned char *cons = smem + G.off_cons + warp * G.cons_bytes;
+      // (wide: warp 0 is the tile's consumer, warps 1 and 2 only take part in the team solve)
+      unsigned char *cons = smem + G.off_cons + (wide ? 0 : warp) * G.cons_bytes;
       double *dv = reinterpret_cast<double *>(cons) + lane;  // [k][lane]: 1 / V(k,k) during the solve ...
       double *bo = reinterpret_cast<double *>(cons);         // ... then [lane][k], the image of the tile's block of B
       const double diag = th.sigmaSq + th.tauSq;
       int failed = INT_MAX;
       bool store_pending = false;
-      int s = warp, use = 0;
+      int s = wide ? 0 : warp, use = 0;
       while (s >= S) {  // (NC <= S always; kept general)
         s -= S;
         ++use;
@@ -605,6 +794,13 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
         const int mi = nn_count(i, m);
         const long long off = nn_offset(i, m);
         const bool full = tri_tile_is_full(base, m, P.loc_end);
+        if (wide && warp != 0) {  // helper of the team solve
+          double Fh;
+          team_bar(kTeamThreads);
+          tri_solve_team(A, cv, dv, m, mi, diag, &Fh, warp, kTeamThreads);
+          ++use;
+          continue;
+        }
         double fcur = 1.0;
         if (with_cur) fcur = __ldg(&th.Fcur[i]);
         const unsigned rr_parity = use & 1;
@@ -640,6 +836,10 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
         // chains), in spite of its instruction-fetch stalls.  Every other m: the rolled blocked solve.
         double Fv;
         bool ok;
+        if (wide) {
+          team_bar(kTeamThreads);  // the unit rows of a ragged tile are in place
+          ok = tri_solve_team(A, cv, dv, m, mi, diag, &Fv, 0, kTeamThreads);
+        } else
         switch (m) {
 #ifndef NNGP_TRI_ROLLED_ONLY
           case 10: ok = tri_solve_unrolled<10, kTriSlim<COV>>(A, cv, dv, mi, diag, &Fv); break;
@@ -747,6 +947,17 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_built(s));
+      if (wide && tile >= 0) {  // single stage: nothing to build until this tile is solved -- join the solve
+        mbar_wait(bar_built(s), use & 1);
+        unsigned char *st = smem + s * G.stage_bytes;
+        const long long base = P.loc_begin + tile * 32;
+        const long long i = (base + lane < P.loc_end) ? base + lane : (long long)P.loc_end - 1;
+        double Fh;
+        team_bar(kTeamThreads);
+        tri_solve_team(reinterpret_cast<double *>(st + G.off_a) + lane, reinterpret_cast<double *>(st + G.off_cv) + lane,
+                       reinterpret_cast<double *>(smem + G.off_cons) + lane, m, nn_count(i, m), th.sigmaSq + th.tauSq, &Fh,
+                       warp - 1, kTeamThreads);
+      }
       if (tile < 0 && ++markers == NC) break;  // the markers pass through, so that every consumer sees one
       if (++s == S) {
         s = 0;
@@ -854,7 +1065,7 @@ static cudaError_t tri_launch_one(const BfLaunch &P0, int grid_x, cudaStream_t s
 // Small m: per-tile hand-offs outweigh the saved distance arithmetic; 16: the rolled solve loses to bf_ws_kernel's
 // unrolled one; from 20 on only one consumer and two or three stages fit (tri_geometry) and bf_ws_kernel's two-stage
 // CTA wins until its capacities end at 24.  nngp_set_option("tri_force", 1) serves every 2 <= m <= 26 (tests).
-static bool tri_is_fastest(int m) { return (m >= 13 && m <= 15) || (m >= 17 && m <= 19) || m == 25 || m == 26; }
+static bool tri_is_fastest(int m) { return (m >= 13 && m <= 15) || (m >= 17 && m <= 19) || (m >= 25 && m <= kTriMaxM); }
 static int g_tri_force = 0;
 void tri_set_force(int on) { g_tri_force = on; }
 int tri_capacity_for_m(int m) {

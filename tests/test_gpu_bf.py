@@ -303,7 +303,7 @@ def test_matern_short_series_variant(engine, port, nu, m):
 def test_fused_current_q_launch(engine, port, cov, theta, m):
     """nngp_bf_loglik_cur: one launch returns the candidate's (logDet, Q) and Q of the factors resident in the other
     slot -- equal to nngp_bf_loglik of the candidate and nngp_q_resid of the resident slot (src/rNNGP.cpp:297-306,
-    src/util.cpp:261-280); m = 30 takes the kernels without the fused path (falls back to the separate pass)."""
+    src/util.cpp:261-280); m = 30 runs the distance-triangle kernel with a single stage."""
     n = 5000
     prob = make_problem(n, m, seed=11, port=port, domain=1.0)
     engine.set_data(prob["coords"], prob["nnIndx"], prob["nnIndxLU"], prob["X"], prob["y"], m)
@@ -322,9 +322,10 @@ def test_fused_current_q_launch(engine, port, cov, theta, m):
 
 
 @pytest.mark.parametrize("cov", [0, 1, 2, 3])
-@pytest.mark.parametrize("n,m", [(700, 3), (2500, 9), (3000, 12), (2100, 16), (1900, 20), (1500, 26), (40, 14), (33, 2)])
+@pytest.mark.parametrize("n,m", [(700, 3), (2500, 9), (3000, 12), (2100, 16), (1900, 20), (1500, 26), (40, 14), (33, 2),
+                                 (1700, 27), (1300, 29), (2200, 32), (45, 32)])
 def test_distance_triangle_kernel_every_m(engine, port, cov, n, m):
-    """bf_tri_kernel serves 2 <= m <= 26 (run-time geometry, rolled blocked Cholesky; unrolled sweep at 10 / 15 / 20) but is
+    """bf_tri_kernel serves 2 <= m <= 32 (run-time geometry, rolled blocked Cholesky; unrolled sweep at 10 / 15 / 20) but is
     selected only where it is the fastest kernel: `tri_force` routes every m through it -- B, F, logDet, Q vs the oracle."""
     prob = make_problem(n, m, seed=2 * n + m, port=port, domain=np.sqrt(n / 5000.0))
     engine.set_option("tri_force", 1)
