@@ -1,4 +1,4 @@
-// bf_tri_kernel.cu -- B/F + log-likelihood kernel over the resident DISTANCE TRIANGLE (2 <= m <= 26).
+// bf_tri_kernel.cu -- B/F + log-likelihood kernel over the resident DISTANCE TRIANGLE (2 <= m <= 32).
 //
 // Same mathematics as the other B/F kernels (reference: updateBF src/rNNGP.cpp:46-101, updateConjBF
 // src/cNNGP.cpp:24-69, Q src/util.cpp:261-280), different data path.  The distances between a location's
@@ -177,6 +177,24 @@ struct FromDist<NNGP_COV_GAUSSIAN> {
   __device__ __forceinline__ FromDist(const BfTheta &t, const double *) : nphi2(-(t.phi * t.phi)), sig(t.sigmaSq) {}
   __device__ __forceinline__ double operator()(double D) const { return sig * nngp_exp_nonpos(nphi2 * (D * D)); }
 };
+// the same with the table-driven exp (kExpTab32 in shared memory, fastmath.cuh: 12 FP64 instructions instead of 19): used
+// where the producers' phase is not hidden behind the consumers (team geometries)
+template <int COV>
+struct FromDistTab;
+template <>
+struct FromDistTab<NNGP_COV_EXPONENTIAL> {
+  double nphi, sig;
+  const double *tab;
+  __device__ __forceinline__ FromDistTab(const BfTheta &t, const double *tab_) : nphi(-t.phi), sig(t.sigmaSq), tab(tab_) {}
+  __device__ __forceinline__ double operator()(double D) const { return sig * nngp_exp_tab(nphi * D, tab); }
+};
+template <>
+struct FromDistTab<NNGP_COV_GAUSSIAN> {
+  double nphi2, sig;
+  const double *tab;
+  __device__ __forceinline__ FromDistTab(const BfTheta &t, const double *tab_) : nphi2(-(t.phi * t.phi)), sig(t.sigmaSq), tab(tab_) {}
+  __device__ __forceinline__ double operator()(double D) const { return sig * nngp_exp_tab(nphi2 * (D * D), tab); }
+};
 template <>
 struct FromDist<NNGP_COV_SPHERICAL> {
   double phi, rng, sig;
@@ -189,8 +207,8 @@ struct FromDist<NNGP_COV_SPHERICAL> {
 };
 
 // One batch of NU rows of 32 doubles (this lane's element of each): all loads, NU independent chains, all stores.
-template <int COV, int NU>
-__device__ __forceinline__ void tri_rows(unsigned char *const (&p)[NU], const FromDist<COV> &f) {
+template <int COV, int NU, typename F>
+__device__ __forceinline__ void tri_rows(unsigned char *const (&p)[NU], const F &f) {
   double v[NU];
 #pragma unroll
   for (int u = 0; u < NU; ++u) v[u] = *reinterpret_cast<const double *>(p[u]);
@@ -609,8 +627,9 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
   const TriGeom G = tri_geometry(m, P.tri_want4 != 0);
   const int S = G.S, NC = G.NC;
   const int loader_warp = (NC == 4) ? 4 : 3, first_producer = loader_warp + 1, nprod = 12 - first_producer;
-  // single stage (m >= 27): the phases of a tile cannot overlap, so every warp but the loader joins the solve (tri_solve_team)
-  const bool wide = (S == 1);
+  // one consumer only (m >= 20; from 27 on a single stage, where the phases of a tile cannot overlap at all): a lone warp
+  // needs tens of thousands of cycles per factorisation, so every warp but the loader joins the solve (tri_solve_team)
+  const bool wide = (NC == 1);
   constexpr int kTeamThreads = 11 * 32;
   const double *__restrict__ resid = th.resid;
   const bool with_cur = th.Bcur != nullptr && resid != nullptr;
@@ -674,9 +693,10 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
     bbeg[0] = 0;
     for (int w = 0; w < kTriProducers; ++w) bbeg[w + 1] = bbeg[w] + cnt[w];
   }
-  if (kMat) {
+  if (kMat || wide) {
     for (int x = tid; x < 32; x += kTriThreads) s_tab[x] = kExpTab32[x];
-    for (int x = tid; x < 128; x += kTriThreads) s_tab[32 + x] = kLogTab64[x];
+    if (kMat)
+      for (int x = tid; x < 128; x += kTriThreads) s_tab[32 + x] = kLogTab64[x];
   }
   for (int s = 0; s < S; ++s) {  // residual rows: stay zero when the launch has no quadratic form
     double *rr = reinterpret_cast<double *>(smem + s * G.stage_bytes + G.off_rr);
@@ -798,7 +818,10 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
           double Fh;
           team_bar(kTeamThreads);
           tri_solve_team(A, cv, dv, m, mi, diag, &Fh, warp, kTeamThreads);
-          ++use;
+          if (++s >= S) {
+            s = 0;
+            ++use;
+          }
           continue;
         }
         double fcur = 1.0;
@@ -939,10 +962,24 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
             default: body(std::integral_constant<int, 3>()); break;
           }
         } else {
-          const FromDist<COV> f(th, nullptr);
-          tri_transform<COV>(
-              st, lane, b0, b1, tail, m, [&](unsigned char *const(&p)[1]) { tri_rows<COV, 1>(p, f); },
-              [&](unsigned char *const(&p)[kTriUnr<COV>]) { tri_rows<COV, kTriUnr<COV>>(p, f); });
+          if constexpr (COV == NNGP_COV_EXPONENTIAL || COV == NNGP_COV_GAUSSIAN) {
+            if (wide) {
+              const FromDistTab<COV> f(th, s_tab);
+              tri_transform<COV>(
+                  st, lane, b0, b1, tail, m, [&](unsigned char *const(&p)[1]) { tri_rows<COV, 1>(p, f); },
+                  [&](unsigned char *const(&p)[kTriUnr<COV>]) { tri_rows<COV, kTriUnr<COV>>(p, f); });
+            } else {
+              const FromDist<COV> f(th, nullptr);
+              tri_transform<COV>(
+                  st, lane, b0, b1, tail, m, [&](unsigned char *const(&p)[1]) { tri_rows<COV, 1>(p, f); },
+                  [&](unsigned char *const(&p)[kTriUnr<COV>]) { tri_rows<COV, kTriUnr<COV>>(p, f); });
+            }
+          } else {
+            const FromDist<COV> f(th, nullptr);
+            tri_transform<COV>(
+                st, lane, b0, b1, tail, m, [&](unsigned char *const(&p)[1]) { tri_rows<COV, 1>(p, f); },
+                [&](unsigned char *const(&p)[kTriUnr<COV>]) { tri_rows<COV, kTriUnr<COV>>(p, f); });
+          }
         }
       }
       __syncwarp();
@@ -1064,8 +1101,13 @@ static cudaError_t tri_launch_one(const BfLaunch &P0, int grid_x, cudaStream_t s
 // 18: 0.564 / 0.694 vs 0.717 / 0.880; 20 (n = 3 x 10^5): 0.50 / 0.56 vs 0.44 / 0.56; 24: 1.13 vs 0.70; 26: 1.17 / 1.27 vs 1.75 / 2.48.
 // Small m: per-tile hand-offs outweigh the saved distance arithmetic; 16: the rolled solve loses to bf_ws_kernel's
 // unrolled one; from 20 on only one consumer and two or three stages fit (tri_geometry) and bf_ws_kernel's two-stage
-// CTA wins until its capacities end at 24.  nngp_set_option("tri_force", 1) serves every 2 <= m <= 26 (tests).
-static bool tri_is_fastest(int m) { return (m >= 13 && m <= 15) || (m >= 17 && m <= 19) || (m >= 25 && m <= kTriMaxM); }
+// CTA wins at its capacities 20 and 24.  nngp_set_option("tri_force", 1) serves every 2 <= m <= 32 (tests).
+// With the team solve (one-consumer geometries, m >= 20; n = 5 x 10^5, exponential / Matern): 20: 0.908 / 1.156 vs 0.718 / 0.915
+// (bf_ws_kernel, capacity 20); 22: 0.963 / 1.293 vs 1.139 / 1.377 (capacity 24); 24: 1.165 / 1.516 vs 1.150 / 1.427; 26: 1.226 /
+// 1.699 (lone consumer: 1.95 / 2.12); 28: 1.708 / 2.207; 32: 2.217 / 2.853 vs 3.43 / 4.93 (cooperative bf_kernel).
+static bool tri_is_fastest(int m) {
+  return (m >= 13 && m <= 15) || (m >= 17 && m <= 19) || (m >= 21 && m <= 23) || (m >= 25 && m <= kTriMaxM);
+}
 static int g_tri_force = 0;
 void tri_set_force(int on) { g_tri_force = on; }
 int tri_capacity_for_m(int m) {

@@ -239,7 +239,7 @@ int nngp_set_option(nngp_ctx *c, const char *name, int value) {
     c->opt_tri = value ? 1 : 0;
     return NNGP_OK;
   }
-  if (!strcmp(name, "tri_force")) {  // 1: the distance-triangle kernel for every 2 <= m <= 26, not only where it is fastest
+  if (!strcmp(name, "tri_force")) {  // 1: the distance-triangle kernel for every 2 <= m <= 32, not only where it is fastest
     tri_set_force(value ? 1 : 0);    // (process-wide; takes effect at the next nngp_set_data)
     return NNGP_OK;
   }
