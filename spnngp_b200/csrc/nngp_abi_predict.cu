@@ -69,8 +69,11 @@ int upload_chunk(nngp_ctx *c, SiteChunk &ch, int q, int i0, int i1, const double
 }
 
 // kriging weights W (cs x m column-major) and conditional variances F for theta = (s2, t2, phi, nu),
-// followed by the per-site reductions a = w.y_N and U = x0 - X_N'w.  Synchronises the stream.
-int site_solve(nngp_ctx *c, int cov, const double *t, SiteChunk &ch) {
+// followed by the per-site reductions a = w.y_N and U = x0 - X_N'w.  Enqueues only: `mc` / `d_mc` are the Matern tables
+// of this theta on the host and (already uploaded) on the device, `fail_dev` the device view of a mapped host int that
+// receives the 1-based failing site (INT_MAX: none) when the launch has finished.
+int site_solve_enqueue(nngp_ctx *c, int cov, const double *t, SiteChunk &ch, const MaternConsts *mc, const MaternConsts *d_mc,
+                       int *fail_dev) {
   BfLaunch P;
   memset(&P, 0, sizeof P);
   P.coords = c->d_coords;
@@ -89,17 +92,12 @@ int site_solve(nngp_ctx *c, int cov, const double *t, SiteChunk &ch) {
   th.phi = t[2];
   th.mat = nullptr;
   if (cov == NNGP_COV_MATERN) {
-    matern_prepare(t[3], &c->h_mat[0]);
-    matern_series_params(c->h_mat[0], &th.ms);
+    matern_series_params(*mc, &th.ms);
     matern_set_phi(&th.ms, t[2]);
-    NNGP_CUDA(c, cudaMemcpyAsync(c->d_mat, c->h_mat, sizeof(MaternConsts), cudaMemcpyHostToDevice, c->stream));
-    c->d_mat_nu[0] = t[3];  // what slot 0 of the device tables holds now (prepare_bf skips uploads it believes current)
-    th.mat = c->d_mat;
+    th.mat = d_mc;
   }
   double *out_dev = nullptr;
-  int *fail_dev = nullptr;
   NNGP_CUDA(c, cudaHostGetDevicePointer((void **)&out_dev, c->h_out, 0));
-  NNGP_CUDA(c, cudaHostGetDevicePointer((void **)&fail_dev, c->h_fail, 0));
   th.B = ch.W.as<double>();
   th.F = ch.F.as<double>();
   th.resid = nullptr;
@@ -114,6 +112,20 @@ int site_solve(nngp_ctx *c, int cov, const double *t, SiteChunk &ch) {
   NNGP_CUDA(c, site_reduce_launch(ch.W.as<double>(), ch.nn0.as<int>(), c->d_X, c->d_y, ch.X0.as<double>(), c->n, c->p,
                                   c->m, ch.cs, ch.a.as<double>(), ch.U.as<double>(), c->stream));
   c->launches += 2;
+  return NNGP_OK;
+}
+
+// The same, synchronous (the conjugate model's one solve per parameter set): tables through the context's slot 0.
+int site_solve(nngp_ctx *c, int cov, const double *t, SiteChunk &ch) {
+  if (cov == NNGP_COV_MATERN) {
+    matern_prepare(t[3], &c->h_mat[0]);
+    NNGP_CUDA(c, cudaMemcpyAsync(c->d_mat, c->h_mat, sizeof(MaternConsts), cudaMemcpyHostToDevice, c->stream));
+    c->d_mat_nu[0] = t[3];  // what slot 0 of the device tables holds now (prepare_bf skips uploads it believes current)
+  }
+  int *fail_dev = nullptr;
+  NNGP_CUDA(c, cudaHostGetDevicePointer((void **)&fail_dev, c->h_fail, 0));
+  int rc = site_solve_enqueue(c, cov, t, ch, c->h_mat, c->d_mat, fail_dev);
+  if (rc) return rc;
   NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
   if (c->h_fail[0] != INT_MAX) return ctx_fail(c, c->h_fail[0], "c++ error: dpotrf failed (prediction neighbour covariance)");
   return NNGP_OK;
@@ -157,7 +169,7 @@ int nngp_rnngp_predict(nngp_ctx *c, int cov, int q, const double *X0, const doub
     }
   }
 
-  Dev d_beta, d_samples, d_z;
+  Dev d_beta, d_samples;
   NNGP_CUDA(c, d_beta.alloc((size_t)p * S * sizeof(double)));
   NNGP_CUDA(c, cudaStreamSynchronize(c->stream));  // pool blocks are recycled in stream order; the copies below are not
   NNGP_CUDA(c, cudaMemcpy(d_beta.p, betaSamples, (size_t)p * S * sizeof(double), cudaMemcpyHostToDevice));
@@ -170,7 +182,7 @@ int nngp_rnngp_predict(nngp_ctx *c, int cov, int q, const double *X0, const doub
   NNGP_CUDA(c, d_samples.alloc(flat.size() * sizeof(int)));
   NNGP_CUDA(c, cudaMemcpy(d_samples.p, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice));
 
-  // chunk of sites: keep z and y0 of a chunk (2 x cs x S doubles) within ~2 GiB
+  // chunk of sites: z and y0 of a chunk are 2 x cs x S doubles, both double-buffered (4 x 1 GiB at most)
   long long cs_max = ((long long)1 << 30) / ((long long)8 * S);
   if (cs_max < 1024) cs_max = 1024;
   if (cs_max > 1 << 20) cs_max = 1 << 20;
@@ -178,9 +190,12 @@ int nngp_rnngp_predict(nngp_ctx *c, int cov, int q, const double *X0, const doub
     const long long v = atoll(e);
     if (v >= 32 && v < cs_max) cs_max = v;
   }
-  // Full duplex: the draws of chunk k leave through a second pinned ring on their own thread while the normals of
-  // chunk k + 1 arrive and its solves run (two result buffers); src/rNNGPPredict.cpp:131-137,176-181 are these two
-  // q x S streams, and they, not the solves, bound a 10^6 x 1,000 job.
+  if (cs_max > site_end - site_begin) cs_max = std::max(1, site_end - site_begin);
+  // Full duplex, and nothing but launches between two chunk boundaries: the normals of chunk k + 1 arrive (first pinned
+  // ring, or straight from the caller's page-locked array) and the draws of chunk k - 1 leave (second ring) on their own
+  // threads while the solves and draws of chunk k run; src/rNNGPPredict.cpp:131-137,176-181 are these two q x S
+  // streams.  The Matern tables of every distinct theta are prepared and uploaded once, every launch reports its failing
+  // site into its own mapped slot, and the stream is synchronised once per chunk.
   if (!c->stager) {
     c->stager = new HostStager();
     NNGP_CUDA(c, c->stager->init(c->device));
@@ -191,30 +206,68 @@ int nngp_rnngp_predict(nngp_ctx *c, int cov, int q, const double *X0, const doub
   }
   const char *dup_env = getenv("NNGP_PREDICT_DUPLEX");
   const bool duplex = !(dup_env && dup_env[0] == '0');
-  Dev d_y0b[2];
-  std::thread dl;
-  cudaError_t dl_err = cudaSuccess;
-  struct Joiner {  // never leave the download thread running behind an early return
+  const int G = (int)groups.size();
+  std::vector<MaternConsts> h_mc;
+  Dev d_mc;
+  if (cov == NNGP_COV_MATERN) {
+    h_mc.resize((size_t)G);
+    for (int g = 0; g < G; g++) matern_prepare(thetas[g][3], &h_mc[g]);
+    NNGP_CUDA(c, d_mc.alloc((size_t)G * sizeof(MaternConsts)));
+    NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
+    NNGP_CUDA(c, cudaMemcpy(d_mc.p, h_mc.data(), (size_t)G * sizeof(MaternConsts), cudaMemcpyHostToDevice));
+  }
+  struct Mapped {  // one fail slot per distinct theta, written by the kernels through the mapped pointer
+    int *h = nullptr;
+    ~Mapped() { if (h) cudaFreeHost(h); }
+  } failg;
+  NNGP_CUDA(c, cudaHostAlloc((void **)&failg.h, (size_t)G * sizeof(int), cudaHostAllocMapped));
+  int *failg_dev = nullptr;
+  NNGP_CUDA(c, cudaHostGetDevicePointer((void **)&failg_dev, failg.h, 0));
+  for (int g = 0; g < G; g++) failg.h[g] = INT_MAX;
+
+  Dev d_zb[2], d_y0b[2];
+  for (int b = 0; b < 2; b++) {
+    NNGP_CUDA(c, d_zb[b].alloc((size_t)cs_max * S * sizeof(double)));
+    NNGP_CUDA(c, d_y0b[b].alloc((size_t)cs_max * S * sizeof(double)));
+  }
+  NNGP_CUDA(c, cudaStreamSynchronize(c->stream));  // pool blocks are recycled in stream order; the staged copies are not
+  std::thread dl, ul;
+  cudaError_t dl_err = cudaSuccess, ul_err = cudaSuccess;
+  struct Joiner {  // never leave a transfer thread running behind an early return
     std::thread &t;
     ~Joiner() { if (t.joinable()) t.join(); }
-  } joiner{dl};
+  } join_dl{dl}, join_ul{ul};
+  HostStager *st1 = c->stager, *st2 = c->stager2;
+  auto start_upload = [&](int k, int i0, int cs) {
+    void *dst = d_zb[k & 1].p;
+    ul = std::thread([=, &ul_err] {
+      std::vector<StageJob> up{{StageJob::RAW, dst, z + (size_t)i0 * S, (size_t)cs * S * sizeof(double), 0}};
+      ul_err = st1->run(up, nullptr);
+    });
+  };
+  const int first_cs = (int)std::min<long long>(cs_max, site_end - site_begin);
+  if (site_end > site_begin) start_upload(0, site_begin, first_cs);
   int kchunk = 0;
   for (int i0 = site_begin; i0 < site_end; i0 += (int)cs_max, ++kchunk) {
     const int i1 = (int)std::min<long long>(site_end, (long long)i0 + cs_max);
     const int cs = i1 - i0;
-    Dev &d_y0 = d_y0b[kchunk & 1];
+    Dev &d_z = d_zb[kchunk & 1];
+    Dev &d_y0 = d_y0b[kchunk & 1];  // its previous content left with the download of chunk k - 2
     SiteChunk ch;
     int rc = upload_chunk(c, ch, q, i0, i1, X0, coords0, nnIndx0);
     if (rc) return rc;
-    NNGP_CUDA(c, d_z.alloc((size_t)cs * S * sizeof(double)));
-    NNGP_CUDA(c, d_y0.alloc((size_t)cs * S * sizeof(double)));  // its previous content left with the download of chunk k - 2
-    NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
-    {
-      std::vector<StageJob> up{{StageJob::RAW, d_z.p, z + (size_t)i0 * S, (size_t)cs * S * sizeof(double), 0}};
-      NNGP_CUDA(c, c->stager->run(up, nullptr));
+    if (ul.joinable()) ul.join();  // the normals of this chunk
+    NNGP_CUDA(c, ul_err);
+    if (i1 < site_end) {  // the next chunk's normals travel while this one is solved (its buffer was read by chunk k - 1)
+      start_upload(kchunk + 1, i1, (int)std::min<long long>(cs_max, site_end - i1));
+      if (!duplex) {
+        ul.join();
+        NNGP_CUDA(c, ul_err);
+      }
     }
-    for (size_t g = 0; g < groups.size(); g++) {
-      rc = site_solve(c, cov, thetas[g].data(), ch);
+    for (int g = 0; g < G; g++) {
+      rc = site_solve_enqueue(c, cov, thetas[g].data(), ch, h_mc.empty() ? nullptr : &h_mc[g],
+                              h_mc.empty() ? nullptr : d_mc.as<MaternConsts>() + g, failg_dev + g);
       if (rc) return rc;
       NNGP_CUDA(c, predict_emit_launch(ch.a.as<double>(), ch.U.as<double>(), ch.F.as<double>(), d_beta.as<double>(),
                                        d_z.as<double>(), d_samples.as<int>() + gofs[g], (int)groups[g].size(), p, cs, S,
@@ -222,11 +275,12 @@ int nngp_rnngp_predict(nngp_ctx *c, int cov, int q, const double *X0, const doub
       c->launches++;
     }
     NNGP_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (dl.joinable()) dl.join();  // the download of chunk k - 1 ran alongside this chunk's upload and solves
+    for (int g = 0; g < G; g++)
+      if (failg.h[g] != INT_MAX) return ctx_fail(c, failg.h[g], "c++ error: dpotrf failed (prediction neighbour covariance)");
+    if (dl.joinable()) dl.join();  // the download of chunk k - 1 ran alongside this chunk's solves
     NNGP_CUDA(c, dl_err);
     // y0 is q x S column-major on the host: column s of the chunk is contiguous on both sides
     const double *src = d_y0.as<double>();
-    HostStager *st2 = c->stager2;
     dl = std::thread([=, &dl_err] {
       std::vector<StageJob> down((size_t)S);
       for (int s = 0; s < S; s++)
