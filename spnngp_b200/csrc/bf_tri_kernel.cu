@@ -52,6 +52,7 @@ namespace nngp {
 #endif
 
 constexpr int kTriMaxM = 32;       // 27..32: ONE stage fits shared memory (loader, producers and the consumer take turns)
+constexpr int kTriNarrowMaxM = 19;  // largest m with two or more consumers (tri_geometry): the narrow instantiation
 constexpr int kTriMaxStages = 6;
 constexpr int kTriThreads = 384;
 constexpr int kTriProducers = 8;  // at most (seven when the loader takes warp 4)
@@ -617,7 +618,10 @@ __device__ __forceinline__ bool tri_solve_unrolled(double *A, double *cv, double
   return ok;
 }
 
-template <int COV>
+// WIDE: the one-consumer geometries (m >= 20) with the team solve -- an instantiation of its own, so that the hot
+// configurations (m <= 19: two to four consumers, six stages at m = 15) keep exactly the registers and the code they had
+// before the team path existed (sharing one instantiation cost the m = 15 Matern launch 13 %: 0.664 -> 0.753 ms).
+template <int COV, bool WIDE>
 __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_constant__ BfLaunch P) {
   constexpr bool kMat = kIsMatern<COV>;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -629,7 +633,8 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
   const int loader_warp = (NC == 4) ? 4 : 3, first_producer = loader_warp + 1, nprod = 12 - first_producer;
   // one consumer only (m >= 20; from 27 on a single stage, where the phases of a tile cannot overlap at all): a lone warp
   // needs tens of thousands of cycles per factorisation, so every warp but the loader joins the solve (tri_solve_team)
-  const bool wide = (NC == 1);
+  constexpr bool wide = WIDE;   // host side: WIDE == (tri_geometry(m).NC == 1)
+  constexpr int kMaxM = WIDE ? kTriMaxM : kTriNarrowMaxM;
   constexpr int kTeamThreads = 11 * 32;
   const double *__restrict__ resid = th.resid;
   const bool with_cur = th.Bcur != nullptr && resid != nullptr;
@@ -712,12 +717,12 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
     // j - 1, the ids of T(j+1) are requested, and the atomic that claims T(j+2) is outstanding in lane 0.
     const unsigned tri_bytes = (unsigned)(ne + m) * 256u;
     const size_t tile_doubles = (size_t)(ne + m) * 32;
-    int ids_a[kTriMaxM], ids_b[kTriMaxM];  // ping-pong: the ids a trip loads are first READ one trip later (a register
+    int ids_a[kMaxM], ids_b[kMaxM];  // ping-pong: the ids a trip loads are first READ one trip later (a register
                                            // copy at the end of the trip would wait for the loads right away)
-    auto load_ids = [&](long long tile, int(&ids)[kTriMaxM]) {
+    auto load_ids = [&](long long tile, int(&ids)[kMaxM]) {
       const int *src = P.nnT + (size_t)tile * m * 32 + lane;
 #pragma unroll
-      for (int k = 0; k < kTriMaxM; ++k) ids[k] = (k < m) ? __ldg(src + k * 32) : -1;
+      for (int k = 0; k < kMaxM; ++k) ids[k] = (k < m) ? __ldg(src + k * 32) : -1;
     };
     long long t_cur = blockIdx.x, t_nxt = (long long)blockIdx.x + gridDim.x;
     unsigned claim = 0u;
@@ -725,7 +730,7 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
     if (resid != nullptr && t_cur < ntiles) load_ids(t_cur, ids_a);
     int done_markers = 0, s = 0, use = 0, j = 0;  // stage of trip j, and how often it has been used before
     // one trip: issue T(j) with `ids_use`, request the ids of T(j+1) into `ids_load`; false when the work is over
-    auto trip = [&](int(&ids_use)[kTriMaxM], int(&ids_load)[kTriMaxM]) -> bool {
+    auto trip = [&](int(&ids_use)[kMaxM], int(&ids_load)[kMaxM]) -> bool {
       if (j > 0) {  // T(j+1): static, or the claim issued one trip ago
         if (pending) t_nxt = (long long)S * gridDim.x + __shfl_sync(0xffffffffu, claim, 0);
         else t_nxt = (long long)blockIdx.x + (long long)(j + 1) * gridDim.x;
@@ -761,7 +766,7 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
           long long i = base + lane;
           if (i >= P.loc_end) i = (long long)P.loc_end - 1;
 #pragma unroll
-          for (int k = 0; k < kTriMaxM; ++k)
+          for (int k = 0; k < kMaxM; ++k)
             if (k < m) cp_async8_zfill(&rr[k * 32], &resid[ids_use[k] >= 0 ? ids_use[k] : 0], ids_use[k] >= 0);
           cp_async8(&rr[m * 32], &resid[i]);
         }
@@ -842,11 +847,11 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
           // claims the registers (fused launch, exponential: 0.550 -> 0.515 ms together with the loader's L2 prefetch).
           // Forming this sum in the loader warp instead, one trip behind its gathers, was measured and dropped: the
           // loader then paces the tiles (0.918 ms).
-          double bc[kTriMaxM];
+          double bc[kMaxM];
 #pragma unroll
-          for (int k = 0; k < kTriMaxM; ++k) bc[k] = (k < mi) ? __ldg(&th.Bcur[off + k]) : 0.0;
+          for (int k = 0; k < kMaxM; ++k) bc[k] = (k < mi) ? __ldg(&th.Bcur[off + k]) : 0.0;
 #pragma unroll
-          for (int k = 0; k < kTriMaxM; ++k)
+          for (int k = 0; k < kMaxM; ++k)
             if (k < m) qcur_part = fma(bc[k], rr[k * 32], qcur_part);
         }
         if (store_pending) {  // the staging area doubles as the solve's 1 / diag rows: the last bulk store must have read it
@@ -867,7 +872,6 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
 #ifndef NNGP_TRI_ROLLED_ONLY
           case 10: ok = tri_solve_unrolled<10, kTriSlim<COV>>(A, cv, dv, mi, diag, &Fv); break;
           case 15: ok = tri_solve_unrolled<15, kTriSlim<COV>>(A, cv, dv, mi, diag, &Fv); break;
-          case 20: ok = tri_solve_unrolled<20, kTriSlim<COV>>(A, cv, dv, mi, diag, &Fv); break;
 #endif
           default: ok = tri_solve(A, cv, dv, m, mi, diag, &Fv); break;
         }
@@ -1081,16 +1085,20 @@ static cudaError_t tri_launch_one(const BfLaunch &P0, int grid_x, cudaStream_t s
   // (exponential 0.498 vs 0.466 ms, spherical 0.446 vs 0.412), without it four consumers win (0.416 vs 0.433, 0.331 vs 0.366)
   P.tri_want4 = want4_env >= 0 ? want4_env : ((kTriWant4<COV> && P.th[0].resid == nullptr) ? 1 : 0);
   const TriGeom G = tri_geometry(P.m, P.tri_want4 != 0);
-  static bool configured[64] = {};  // the attribute is per device; setting it costs a few microseconds of every launch
+  const bool wide = (G.NC == 1);
+  if (!wide && P.m > kTriNarrowMaxM) return cudaErrorInvalidValue;  // (cannot happen: NC == 1 from m = 20 on)
+  static bool configured[2][64] = {};  // the attribute is per device; setting it costs a few microseconds of every launch
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(bf_tri_kernel<COV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+  if (dev < 0 || dev >= 64 || !configured[wide][dev]) {
+    cudaError_t e = wide ? cudaFuncSetAttribute(bf_tri_kernel<COV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)
+                         : cudaFuncSetAttribute(bf_tri_kernel<COV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
     if (e != cudaSuccess) return e;
-    if (dev >= 0 && dev < 64) configured[dev] = true;
+    if (dev >= 0 && dev < 64) configured[wide][dev] = true;
   }
   dim3 grid(grid_x, P.nbatch, 1);
-  bf_tri_kernel<COV><<<grid, kTriThreads, G.smem_bytes, stream>>>(P);
+  if (wide) bf_tri_kernel<COV, true><<<grid, kTriThreads, G.smem_bytes, stream>>>(P);
+  else bf_tri_kernel<COV, false><<<grid, kTriThreads, G.smem_bytes, stream>>>(P);
   return cudaGetLastError();
 }
 
