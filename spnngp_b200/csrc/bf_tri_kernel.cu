@@ -621,7 +621,9 @@ __device__ __forceinline__ bool tri_solve_unrolled(double *A, double *cv, double
 // WIDE: the one-consumer geometries (m >= 20) with the team solve -- an instantiation of its own, so that the hot
 // configurations (m <= 19: two to four consumers, six stages at m = 15) keep exactly the registers and the code they had
 // before the team path existed (sharing one instantiation cost the m = 15 Matern launch 13 %: 0.664 -> 0.753 ms).
-template <int COV, bool WIDE>
+// MS: the consumer's solve -- 10 / 15: the fully unrolled sweep for exactly that m, 0: the rolled blocked solve (any m).
+// One solve per instantiation: the unused ones were dead weight in the hot kernels (code size, register allocation).
+template <int COV, bool WIDE, int MS>
 __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_constant__ BfLaunch P) {
   constexpr bool kMat = kIsMatern<COV>;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -868,12 +870,10 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
           team_bar(kTeamThreads);  // the unit rows of a ragged tile are in place
           ok = tri_solve_team(A, cv, dv, m, mi, diag, &Fv, 0, kTeamThreads);
         } else
-        switch (m) {
-#ifndef NNGP_TRI_ROLLED_ONLY
-          case 10: ok = tri_solve_unrolled<10, kTriSlim<COV>>(A, cv, dv, mi, diag, &Fv); break;
-          case 15: ok = tri_solve_unrolled<15, kTriSlim<COV>>(A, cv, dv, mi, diag, &Fv); break;
-#endif
-          default: ok = tri_solve(A, cv, dv, m, mi, diag, &Fv); break;
+        {
+          if constexpr (MS == 10) ok = tri_solve_unrolled<10, kTriSlim<COV>>(A, cv, dv, mi, diag, &Fv);
+          else if constexpr (MS == 15) ok = tri_solve_unrolled<15, kTriSlim<COV>>(A, cv, dv, mi, diag, &Fv);
+          else ok = tri_solve(A, cv, dv, m, mi, diag, &Fv);
         }
         if (!ok && active) failed = min(failed, (int)min(i + 1, (long long)INT_MAX - 1));
         if (!with_cur) mbar_wait(bar_rr(s), rr_parity);  // long landed by now: the solve took microseconds
@@ -1087,18 +1087,26 @@ static cudaError_t tri_launch_one(const BfLaunch &P0, int grid_x, cudaStream_t s
   const TriGeom G = tri_geometry(P.m, P.tri_want4 != 0);
   const bool wide = (G.NC == 1);
   if (!wide && P.m > kTriNarrowMaxM) return cudaErrorInvalidValue;  // (cannot happen: NC == 1 from m = 20 on)
-  static bool configured[2][64] = {};  // the attribute is per device; setting it costs a few microseconds of every launch
+  // one instantiation per (geometry class, solve): 0 narrow / rolled, 1 narrow / unrolled 10, 2 narrow / unrolled 15, 3 wide
+#ifndef NNGP_TRI_ROLLED_ONLY
+  const int kind = wide ? 3 : (P.m == 15 ? 2 : (P.m == 10 ? 1 : 0));
+#else
+  const int kind = wide ? 3 : 0;
+#endif
+  void (*kern)(BfLaunch) = kind == 3   ? bf_tri_kernel<COV, true, 0>
+                           : kind == 2 ? bf_tri_kernel<COV, false, 15>
+                           : kind == 1 ? bf_tri_kernel<COV, false, 10>
+                                       : bf_tri_kernel<COV, false, 0>;
+  static bool configured[4][64] = {};  // the attribute is per device; setting it costs a few microseconds of every launch
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !configured[wide][dev]) {
-    cudaError_t e = wide ? cudaFuncSetAttribute(bf_tri_kernel<COV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024)
-                         : cudaFuncSetAttribute(bf_tri_kernel<COV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+  if (dev < 0 || dev >= 64 || !configured[kind][dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
     if (e != cudaSuccess) return e;
-    if (dev >= 0 && dev < 64) configured[wide][dev] = true;
+    if (dev >= 0 && dev < 64) configured[kind][dev] = true;
   }
   dim3 grid(grid_x, P.nbatch, 1);
-  if (wide) bf_tri_kernel<COV, true><<<grid, kTriThreads, G.smem_bytes, stream>>>(P);
-  else bf_tri_kernel<COV, false><<<grid, kTriThreads, G.smem_bytes, stream>>>(P);
+  kern<<<grid, kTriThreads, G.smem_bytes, stream>>>(P);
   return cudaGetLastError();
 }
 
