@@ -730,6 +730,9 @@ __global__ void __launch_bounds__(kTriThreads, 1) bf_tri_kernel(const __grid_con
     unsigned claim = 0u;
     bool pending = false;
     if (resid != nullptr && t_cur < ntiles) load_ids(t_cur, ids_a);
+    // launched beside the residual kernel (BfLaunch::pdl): everything up to here -- barriers, tables, zeroed residual rows,
+    // the first neighbour ids -- needed nothing of it; the gathers below do
+    if (P.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
     int done_markers = 0, s = 0, use = 0, j = 0;  // stage of trip j, and how often it has been used before
     // one trip: issue T(j) with `ids_use`, request the ids of T(j+1) into `ids_load`; false when the work is over
     auto trip = [&](int(&ids_use)[kMaxM], int(&ids_load)[kMaxM]) -> bool {
@@ -1106,6 +1109,19 @@ static cudaError_t tri_launch_one(const BfLaunch &P0, int grid_x, cudaStream_t s
     if (dev >= 0 && dev < 64) configured[kind][dev] = true;
   }
   dim3 grid(grid_x, P.nbatch, 1);
+  if (P.pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kTriThreads, 1, 1);
+    cfg.dynamicSmemBytes = (size_t)G.smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, P);
+  }
   kern<<<grid, kTriThreads, G.smem_bytes, stream>>>(P);
   return cudaGetLastError();
 }

@@ -68,7 +68,8 @@ class HostStager {
 
   // Runs all jobs; returns when every byte is on the device.  *bad_id is set if an INT_RANGE job saw an id
   // outside [0, n) (the upload still completes).
-  cudaError_t run(const std::vector<StageJob> &jobs, bool *bad_id) {
+  // *min_id / *max_id (optional): the smallest / largest id any INT_RANGE job saw (INT_MAX / -1 if none).
+  cudaError_t run(const std::vector<StageJob> &jobs, bool *bad_id, int *min_id = nullptr, int *max_id = nullptr) {
     struct Chunk { int job; size_t off, len; };
     std::vector<Chunk> chunks;
     bool direct = false;
@@ -85,10 +86,13 @@ class HostStager {
     }
     if (chunks.empty()) {
       if (bad_id) *bad_id = false;
+      if (min_id) *min_id = 2147483647;
+      if (max_id) *max_id = -1;
       return direct ? cudaStreamSynchronize(st_[0]) : cudaSuccess;
     }
     std::atomic<int> err{(int)cudaSuccess};
     std::atomic<bool> bad{false};
+    std::atomic<int> lowest{2147483647}, highest{-1};
     auto worker = [&](int t) {
       cudaSetDevice(device_);
       int b = 0;
@@ -113,12 +117,21 @@ class HostStager {
           int *o = (int *)pin;
           const size_t cnt = ch.len / 4;
           unsigned worst = 0;  // as unsigned, a negative id is huge
+          int low = 2147483647;
           for (size_t i = 0; i < cnt; i++) {
             const int v = s[i];
             o[i] = v;
             worst = (unsigned)v > worst ? (unsigned)v : worst;
+            low = v < low ? v : low;
           }
           if ((long long)worst >= J.n) bad = true;
+          int cur = lowest.load();
+          while (low < cur && !lowest.compare_exchange_weak(cur, low)) {
+          }
+          const int high = (worst > 2147483647u) ? 2147483647 : (int)worst;
+          cur = highest.load();
+          while (high > cur && !highest.compare_exchange_weak(cur, high)) {
+          }
         }
         e = cudaMemcpyAsync((char *)J.dst + ch.off, pin, ch.len, cudaMemcpyHostToDevice, st_[t]);
         if (e == cudaSuccess) e = cudaEventRecord(ev_[t][b], st_[t]);
@@ -132,6 +145,8 @@ class HostStager {
     worker(0);
     for (auto &x : th) x.join();
     if (bad_id) *bad_id = bad.load();
+    if (min_id) *min_id = lowest.load();
+    if (max_id) *max_id = highest.load();
     return (cudaError_t)err.load();
   }
 

@@ -411,8 +411,17 @@ int nngp_set_data(nngp_ctx *c, int n, int m, int p, const double *coords, const 
       jobs.push_back({StageJob::RAW, c->d_y + s0, y + s0, (size_t)(s1 - s0) * sizeof(double), 0});
     }
     bool bad_id = false;
+    int min_id = INT_MAX, max_id = -1;
     tr.mark("buffers");
-    NNGP_CUDA(c, c->stager->run(jobs, &bad_id));
+    NNGP_CUDA(c, c->stager->run(jobs, &bad_id, &min_id, &max_id));
+    // residuals are read at the shard's own locations and at their neighbours (in the reference's ordered lists: earlier
+    // locations, so the range ends at loc_end; taken from the ids themselves, not assumed)
+    c->resid_begin = (min_id >= 0 && min_id < loc_begin) ? min_id : loc_begin;
+    c->resid_end = (max_id >= loc_end && max_id < n) ? max_id + 1 : loc_end;
+    if (!c->has_nn || c->csr_end <= c->csr_begin) {
+      c->resid_begin = 0;
+      c->resid_end = n;
+    }
     tr.mark("staged upload");
     if (gather) {
       rc = comm_exchange_replicated(c, c->d_coords, c->d_X, c->d_y, n, p);
@@ -602,7 +611,9 @@ static int prepare_bf(nngp_ctx *c, int cov, int nbatch, const double *theta, con
   return NNGP_OK;
 }
 
-static int enqueue_bf(nngp_ctx *c, int cov, const BfLaunch &P, int grid, bool with_resid) {
+static int enqueue_bf(nngp_ctx *c, int cov, const BfLaunch &P0, int grid, bool with_resid) {
+  BfLaunch P = P0;
+  bool resid_launched = false;
   if (with_resid) {
     for (int b = 0; b < P.nbatch; b++) {
       // identical betas share one residual vector
@@ -611,12 +622,19 @@ static int enqueue_bf(nngp_ctx *c, int cov, const BfLaunch &P, int grid, bool wi
         if (memcmp(c->h_beta + (size_t)a * c->p, c->h_beta + (size_t)b * c->p, c->p * sizeof(double)) == 0) dup = true;
       if (dup) continue;
       if (c->p <= kResidBetaMax)
-        NNGP_CUDA(c, resid_launch_val(c->d_X, c->d_y, c->h_beta + (size_t)b * c->p, c->n, c->p, c->d_resid[b], c->sms, c->stream));
+        NNGP_CUDA(c, resid_launch_val(c->d_X, c->d_y, c->h_beta + (size_t)b * c->p, c->n, c->p, c->d_resid[b], c->resid_begin, c->resid_end, c->sms, c->stream));
       else
-        NNGP_CUDA(c, resid_launch(c->d_X, c->d_y, c->d_beta + (size_t)b * c->p, c->n, c->p, c->d_resid[b], c->sms, c->stream));
+        NNGP_CUDA(c, resid_launch(c->d_X, c->d_y, c->d_beta + (size_t)b * c->p, c->n, c->p, c->d_resid[b], c->resid_begin, c->resid_end, c->sms, c->stream));
       c->launches++;
+      resid_launched = true;
     }
   }
+  // NNGP_PDL=1: the first B/F launch behind a residual kernel starts beside it (programmatic dependent launch).  Opt-in:
+  // measured per sampler iteration on one GPU (tools/iter_probe.py), it buys 2.5 % on an inner 125k-location shard (Matern
+  // 139.8 -> 136.4 us, exponential 106.9 -> 104.2), nothing at n = 10^6, and COSTS 10 % on the Matern head shard
+  // [0, 125000) (151.9 -> 168.2 us) -- the rank that paces a sharded fit.
+  static const bool use_pdl = getenv("NNGP_PDL") != nullptr;
+  P.pdl = (resid_launched && use_pdl) ? 1 : 0;
   // Matern: one launch per series variant present in the batch (0 full, 1 short, 2 tiny), so that the result of a
   // parameter set never depends on what it was batched with (the sampler's current and candidate phi may straddle a
   // variant's range); a homogeneous batch -- the usual case -- is one launch
@@ -642,6 +660,7 @@ static int enqueue_bf(nngp_ctx *c, int cov, const BfLaunch &P, int grid, bool wi
     Pv.matern_short = v;
     NNGP_CUDA(c, bf_launch(Pv, cov, grid, c->stream));
     c->launches++;
+    P.pdl = 0;  // only the launch right behind the residual kernel
   }
   return NNGP_OK;
 }
@@ -840,10 +859,10 @@ int nngp_q_resid(nngp_ctx *c, int slot, const double *beta, double *out) {
   NNGP_CUDA(c, cudaSetDevice(c->device));
   memcpy(c->h_beta, beta, c->p * sizeof(double));
   if (c->p <= kResidBetaMax) {
-    NNGP_CUDA(c, resid_launch_val(c->d_X, c->d_y, c->h_beta, c->n, c->p, c->d_resid[0], c->sms, c->stream));
+    NNGP_CUDA(c, resid_launch_val(c->d_X, c->d_y, c->h_beta, c->n, c->p, c->d_resid[0], c->resid_begin, c->resid_end, c->sms, c->stream));
   } else {
     NNGP_CUDA(c, cudaMemcpyAsync(c->d_beta, c->h_beta, c->p * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    NNGP_CUDA(c, resid_launch(c->d_X, c->d_y, c->d_beta, c->n, c->p, c->d_resid[0], c->sms, c->stream));
+    NNGP_CUDA(c, resid_launch(c->d_X, c->d_y, c->d_beta, c->n, c->p, c->d_resid[0], c->resid_begin, c->resid_end, c->sms, c->stream));
   }
   NNGP_CUDA(c, q_resid_launch(c->d_B[slot], c->d_F[slot], c->d_nnIndx, c->d_resid[0], c->m, c->loc_begin, c->loc_end,
                               c->d_partials, c->d_out, c->sms, c->stream));

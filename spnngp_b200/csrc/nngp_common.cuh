@@ -59,6 +59,9 @@ struct BfLaunch {
   // short one (bf_ws_kernel, bf_tri_kernel), 2 = the tiny one (bf_tri_kernel; bf_ws_kernel runs the short one instead);
   // the other kernels ignore the flag (their t_fast_max is 1)
   int matern_short;
+  // 1: the launch directly follows the residual kernel of the same evaluation in the stream and may start beside it
+  // (programmatic dependent launch; bf_tri_kernel waits with griddepcontrol.wait before its first residual gather)
+  int pdl;
   // resident distance triangle (tri_cache.cu) of the locations [loc_begin, loc_end): tile t (32 locations) holds
   // m(m+1)/2 rows of 32 doubles -- m rows location <-> neighbour k, then the packed pairs (k, l), l < k.  NULL: gather kernels.
   const double *tri;

@@ -86,6 +86,7 @@ struct nngp_ctx {
 
   // Matern short series (matern_series.cuh): chosen per parameter set when phi^2/4 * pair_d2_q99 <= t_short_max(nu)
   int opt_matern_short = 2;      // nngp_set_option("matern_short", 0/1/2): 0 full series, 1 at most the short one, 2 tiny allowed
+  int resid_begin = 0, resid_end = 0;  // residuals are formed for [resid_begin, resid_end): the shard's locations and every neighbour of theirs
   double pair_d2_q99 = 1e300;    // 99 % quantile over this shard's locations of the largest squared pair distance
   unsigned int *d_hist = nullptr;
   unsigned int *h_hist = nullptr;   // pinned copy, filled asynchronously behind the histogram kernel
@@ -226,9 +227,9 @@ int mbox_wait_payload(nngp_ctx *c, unsigned long long seq, int len, double *sum)
 int mbox_host_allreduce(nngp_ctx *c, double *buf, int len);
 
 // q_kernels.cu
-cudaError_t resid_launch(const double *X, const double *y, const double *beta, int n, int p, double *r, int sms,
+cudaError_t resid_launch(const double *X, const double *y, const double *beta, int n, int p, double *r, int i0, int i1, int sms,
                          cudaStream_t stream);
-cudaError_t resid_launch_val(const double *X, const double *y, const double *beta_host, int n, int p, double *r, int sms,
+cudaError_t resid_launch_val(const double *X, const double *y, const double *beta_host, int n, int p, double *r, int i0, int i1, int sms,
                              cudaStream_t stream);
 int q_resid_grid(int m, long long nloc, int sms);
 cudaError_t q_resid_launch(const double *B, const double *F, const int *nnIndx, const double *resid, int m,

@@ -20,9 +20,11 @@ struct ResidBeta {
 };
 __global__ void __launch_bounds__(256) resid_val_kernel(const double *__restrict__ X, const double *__restrict__ y,
                                                         const __grid_constant__ ResidBeta beta, int n, int p,
-                                                        double *__restrict__ r) {
+                                                        double *__restrict__ r, int i0, int i1) {
+  // the B/F launch behind this kernel may set itself up meanwhile (it waits for this grid before it reads r)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  for (long long i = i0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += stride) {
     double acc = 0.0;
     for (int c = 0; c < p; ++c) acc = fma(__ldg(&X[(size_t)c * n + i]), beta.b[c], acc);
     r[i] = acc - __ldg(&y[i]);
@@ -31,9 +33,10 @@ __global__ void __launch_bounds__(256) resid_val_kernel(const double *__restrict
 
 __global__ void __launch_bounds__(256) resid_kernel(const double *__restrict__ X, const double *__restrict__ y,
                                                     const double *__restrict__ beta, int n, int p,
-                                                    double *__restrict__ r) {
+                                                    double *__restrict__ r, int i0, int i1) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  for (long long i = i0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += stride) {
     double acc = 0.0;
     for (int c = 0; c < p; ++c) acc = fma(__ldg(&X[(size_t)c * n + i]), __ldg(&beta[c]), acc);
     r[i] = acc - __ldg(&y[i]);
@@ -267,24 +270,26 @@ __global__ void __launch_bounds__(256) q_forms_kernel(const double *__restrict__
 // ---- launchers --------------------------------------------------------------------------------------
 static int lanes_for_m(int m) { return m <= 8 ? 8 : (m <= 16 ? 16 : 32); }
 
-cudaError_t resid_launch(const double *X, const double *y, const double *beta, int n, int p, double *r, int sms,
+// r[i] = x_i' beta - y_i for i in [i0, i1): a shard only needs its own locations and their neighbours (all earlier in the
+// ordering), so a sharded fit does not recompute the whole vector on every rank and every iteration
+cudaError_t resid_launch(const double *X, const double *y, const double *beta, int n, int p, double *r, int i0, int i1, int sms,
                          cudaStream_t stream) {
-  int grid = (n + 255) / 256;
+  int grid = (i1 - i0 + 255) / 256;
   if (grid > sms * 8) grid = sms * 8;
   if (grid < 1) grid = 1;
-  resid_kernel<<<grid, 256, 0, stream>>>(X, y, beta, n, p, r);
+  resid_kernel<<<grid, 256, 0, stream>>>(X, y, beta, n, p, r, i0, i1);
   return cudaGetLastError();
 }
 
 // beta_host: p <= kResidBetaMax doubles on the host
-cudaError_t resid_launch_val(const double *X, const double *y, const double *beta_host, int n, int p, double *r, int sms,
-                             cudaStream_t stream) {
-  int grid = (n + 255) / 256;
+cudaError_t resid_launch_val(const double *X, const double *y, const double *beta_host, int n, int p, double *r, int i0, int i1,
+                             int sms, cudaStream_t stream) {
+  int grid = (i1 - i0 + 255) / 256;
   if (grid > sms * 8) grid = sms * 8;
   if (grid < 1) grid = 1;
   ResidBeta b;
   for (int c = 0; c < kResidBetaMax; ++c) b.b[c] = c < p ? beta_host[c] : 0.0;
-  resid_val_kernel<<<grid, 256, 0, stream>>>(X, y, b, n, p, r);
+  resid_val_kernel<<<grid, 256, 0, stream>>>(X, y, b, n, p, r, i0, i1);
   return cudaGetLastError();
 }
 
