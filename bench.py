@@ -28,9 +28,29 @@ import time
 
 import numpy as np
 
-# stdout carries ONE JSON line: NCCL_DEBUG=VERSION makes libnccl print its banner there
-if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+# stdout carries ONE JSON line: NCCL_DEBUG=VERSION (from the environment or from /etc/nccl.conf) makes libnccl print its
+# banner there.  Two guards: the variable is pinned to WARN unless the caller asked for more, and file descriptor 1 points at
+# stderr for the whole run -- the JSON line is written to the saved descriptor (emit_line).
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
     os.environ["NCCL_DEBUG"] = "WARN"
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -249,7 +269,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     return 0
 
 
@@ -456,7 +476,7 @@ def run_b200(args, rank, world, local_rank):
                 "knn_cb_setup_s": t_knn, **ab,
             },
         }
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     eng.close()
     if world > 1:
         dist.barrier()
@@ -501,7 +521,7 @@ def cpu_baseline_other_configs(args):
     from oracle import pyoracle as po
     cores = os.cpu_count() or 1
     if not po.Ref.available():
-        print(json.dumps({"impl": "reference", "cpu_configs": None, "unavailable": "oracle/_ref not built"}))
+        emit_line({"impl": "reference", "cpu_configs": None, "unavailable": "oracle/_ref not built"})
         return 0
     ref = po.Ref(); port = po.Port(); port.set_threads(cores)
     rng = np.random.default_rng(11)
@@ -545,7 +565,7 @@ def cpu_baseline_other_configs(args):
     out["spConjNNGP_kfold_5x25_extrapolated_s"] = 5 * (t_nn + 25 * t_fit)
     out["note"] = ("reference C++ (oracle/_ref) with OpenMP on the box's host cores; the prediction and k-fold figures are "
                    "bounded samples, linear in q*S and in folds*sets; the RANN query search is not included")
-    print(json.dumps({"impl": "reference", "cpu_configs": out}), flush=True)
+    emit_line({"impl": "reference", "cpu_configs": out})
     return 0
 
 
@@ -567,6 +587,7 @@ def main():
     ap.add_argument("--cpu-configs", action="store_true",
                     help="time the reference's CPU code on samples of BASELINE configs[1], [3], [4] (no GPU work)")
     args = ap.parse_args()
+    protect_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
