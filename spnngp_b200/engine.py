@@ -240,9 +240,10 @@ class Engine:
 
     # ---- entry points ------------------------------------------------------------------------------
     def rnngp(self, cov, sigmaSqIG, tauSqIG, phiUnif, nuUnif, starting, tuning, n_samples, rnorm, runif, mode=1,
-              verbose=False, n_report=100, printer=None, allreduce=None, rep_indx=None):
+              verbose=False, n_report=100, printer=None, allreduce=None, rep_indx=None, interrupt=None):
         """Response-model sampler on the data given to set_data (reference `rNNGP`, src/rNNGP.cpp:105).
         rnorm/runif: ctypes function pointers or Python callables (mu, sd) / (a, b).
+        interrupt: callable polled once per iteration (R_CheckUserInterrupt's place); a nonzero return stops the chain.
         rep_indx: 0/1 per iteration (fit.rep, src/rNNGP.cpp:203-208); then a 4th result, y.rep n x nRep, is returned."""
         a = RnngpArgs()
         a.cov_model = cov
@@ -258,6 +259,8 @@ class Engine:
         a.runif = _as_cfunc(runif, _lib.RUNIF_FN)
         if printer is not None:
             a.print = _lib.PRINT_FN(lambda s: printer(s.decode()))
+        if interrupt is not None:
+            a.interrupt = _lib.INTERRUPT_FN(lambda: int(interrupt() or 0))
         if allreduce is not None:
             def _ar(buf, n, _user):
                 arr = np.ctypeslib.as_array(buf, shape=(n,))
