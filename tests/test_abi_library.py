@@ -74,3 +74,30 @@ def test_tools_do_not_use_the_oracle():
             if re.search(r"from oracle|import oracle|pyoracle|oracle/", txt):
                 bad.append(f)
     assert not bad, bad
+
+
+def test_bench_reference_arm_prints_one_json_line(tmp_path):
+    """bench.py --impl reference (the reference's own CPU path through oracle/_ref, no GPU): stdout carries exactly one
+    JSON line with the contract's keys even when a library would print a banner there (NCCL_DEBUG=VERSION), and without a
+    CUDA device the GPU arm refuses to run instead of falling back."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.exists(os.path.join(root, "oracle", "_ref", "libspnngp_ref.so")):
+        pytest.skip("oracle/_ref not built")
+    env = dict(os.environ, NCCL_DEBUG="VERSION")
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--ref-budget-s", "5"], capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert p.returncode == 0, p.stderr[-500:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, p.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "rNNGP_mcmc_iter_per_s" and d["unit"] == "iter/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["cpu_baseline"]["kind"] == "reference"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["config"]["workload"].endswith("(BASELINE.json configs[2])")
+    import torch
+    if not torch.cuda.is_available():
+        q = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1"], capture_output=True, text=True,
+                           timeout=600, cwd=root)
+        assert q.returncode != 0 and "no CPU fallback" in (q.stderr + q.stdout)
