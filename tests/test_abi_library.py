@@ -101,3 +101,15 @@ def test_bench_reference_arm_prints_one_json_line(tmp_path):
         q = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1"], capture_output=True, text=True,
                            timeout=600, cwd=root)
         assert q.returncode != 0 and "no CPU fallback" in (q.stderr + q.stdout)
+
+
+def test_every_python_tool_parses():
+    """tools/*.py, bench.py and the package are never imported by the CPU suite as a whole (they need a GPU): at least
+    every file must be valid Python."""
+    import ast
+    import glob
+    files = glob.glob(os.path.join(ROOT, "tools", "*.py")) + glob.glob(os.path.join(ROOT, "spnngp_b200", "*.py"))
+    files += [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")]
+    assert len(files) > 20
+    for f in files:
+        ast.parse(open(f).read(), filename=f)
